@@ -1,0 +1,226 @@
+"""Pin the CPU oracle: NumPy known-answer files, live NumPy draws, and the reference's golden outputs."""
+import csv
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from oracle import np_port as npp
+
+PAY_ATOL = 1e-12  # payoff = S_T - K cancels: a few ulp of the price scale (ulp(100)=1.4e-14, S_T up to ~1e3)
+ULP2 = 5e-16  # 2 ulp relative: exp/log1p may come from a different libm/SIMD kernel than NumPy's
+
+
+def _kat(name):
+    path = os.path.join(os.path.dirname(np.__file__), "random", "tests", "data", name)
+    with open(path) as f:
+        rows = list(csv.reader(f))
+    seed = int(rows[0][1], 0)
+    vals = np.array([int(r[1], 0) for r in rows[1:]], dtype=np.uint64)
+    return seed, vals
+
+
+@pytest.mark.parametrize("fname", ["pcg64-testset-1.csv", "pcg64-testset-2.csv"])
+def test_pcg64_numpy_known_answers(fname):
+    seed, vals = _kat(fname)
+    assert np.array_equal(co.Gen.pcg64(seed).raw64(vals.size), vals)
+
+
+@pytest.mark.parametrize("fname", ["philox-testset-1.csv", "philox-testset-2.csv"])
+def test_philox_numpy_known_answers(fname):
+    seed, vals = _kat(fname)
+    assert np.array_equal(co.Gen.philox(seed).raw64(vals.size), vals)
+
+
+def test_seedsequence_and_spawn_tree(golden):
+    j, _ = golden
+    assert co.seedseq_state(123, (), 4).tolist() == j["G0"]["seedseq123_state4"]
+    assert co.Gen.pcg64(123).raw64(3).tolist() == j["G0"]["pcg64_123_first3"]
+    for k in range(2):
+        assert co.seedseq_state(123, (k,), 2).tolist() == j["G0"]["philox_child_keys"][k]
+    assert co.Gen.philox(123, (0,)).raw64(4).tolist() == j["G0"]["philox_child0_first4"]
+    for ent, sk in [(0, ()), (2**64 + 17, (5,)), (2**130 + 3, (1, 2, 3)), (42, (70000,))]:
+        assert np.array_equal(co.seedseq_state(ent, sk, 4),
+                              np.random.SeedSequence(ent, spawn_key=sk).generate_state(4, np.uint64))
+
+
+def test_draw_streams_match_numpy_bit_for_bit():
+    g, r = co.Gen.pcg64(7), np.random.default_rng(7)
+    assert np.array_equal(g.standard_normal(200_000), r.standard_normal(200_000))
+    assert np.array_equal(g.integers(0, 100_000_000, 100_001), r.integers(0, 100_000_000, 100_001))
+    assert np.array_equal(g.uniform(-1, 1, 7), r.uniform(-1, 1, 7))
+    assert np.array_equal(g.integers(1, 7, 9), r.integers(1, 7, 9))  # leaves a buffered half word
+    assert np.array_equal(g.standard_normal(5), r.standard_normal(5))
+    assert np.array_equal(g.integers(0, 3, 4), r.integers(0, 3, 4))  # ... which is used here
+    g, r = co.Gen.philox(99, (4,)), np.random.Generator(np.random.Philox(np.random.SeedSequence(99).spawn(5)[4]))
+    assert np.array_equal(g.standard_normal(50_000), r.standard_normal(50_000))
+    assert np.array_equal(g.random(11), r.random(11))
+    g = co.Gen.pcg64(9).advance(123456789012345)
+    assert np.array_equal(g.raw64(4), np.random.PCG64(9).advance(123456789012345).random_raw(4))
+    st = np.random.default_rng(5)
+    st.integers(0, 10, 3)
+    g = co.Gen.pcg64_from_state(st.bit_generator.state)
+    assert np.array_equal(g.integers(0, 10, 5), st.integers(0, 10, 5))
+
+
+def test_pairwise_sum_is_numpy_sum():
+    r = np.random.default_rng(1)
+    for n in (1, 7, 8, 9, 127, 128, 129, 252, 2520, 10_001):
+        x = r.normal(size=n)
+        assert co.np_sum(x) == float(np.sum(x))
+
+
+def test_pi_golden_config1(golden):
+    j, a = golden
+    out, hits = co.Gen.pcg64(123).pi(10_000, 5000)
+    assert int(hits.sum()) == j["G1"]["sum_hits"] == 39_268_872
+    assert np.array_equal(out, a["G1_pi_results"])
+    port = npp.Runner("pi", seed=123).run(200, parallel=True, n_points=5000)
+    assert np.array_equal(port, a["G1_pi_results"][:200])
+
+
+def _blocks(n, w):
+    return npp.make_blocks(n, max(1, n // (8 * w)))
+
+
+def test_pi_golden_philox_blocks_and_antithetic(golden):
+    j, a = golden
+    parts = [co.Gen.philox(123, (k,)).pi(b - a_, 100)[0] for k, (a_, b) in enumerate(_blocks(20_000, 8))]
+    assert np.array_equal(np.concatenate(parts), a["G2_pi_parallel_results"])
+    parts = [co.Gen.philox(5, (k,)).pi(b - a_, 33, True)[0] for k, (a_, b) in enumerate(_blocks(20_001, 3))]
+    assert np.array_equal(np.concatenate(parts), a["G2b_pi_antithetic_parallel_results"])
+    g = co.Gen.pcg64(6)
+    assert np.array_equal(g.pi(500, 101, True)[0], a["G2c_pi_antithetic_seq_results"])
+    assert np.array_equal(g.pi(300, 64)[0], a["G2d_pi_seq_second_run_results"])  # stream continues
+
+
+def test_dice_golden(golden):
+    _, a = golden
+    assert np.array_equal(co.Gen.pcg64(42).dice_sums(10_000), a["G3_dice_seq"])
+    parts = [co.Gen.philox(42, (k,)).dice_sums(b - a_) for k, (a_, b) in enumerate(_blocks(20_000, 4))]
+    assert np.array_equal(np.concatenate(parts), a["G3_dice_par"])
+
+
+def test_black_scholes_golden(golden):
+    _, a = golden
+    np.testing.assert_allclose(co.Gen.pcg64(42).gbm_terminal(1000, 252, co.BS_EURO_CALL, [100, 100, 1, .05, .2]),
+                               a["G4_bs_call_seq"], rtol=ULP2, atol=PAY_ATOL)
+    np.testing.assert_allclose(co.Gen.pcg64(42).gbm_terminal(777, 61, co.BS_EURO_PUT, [95, 105, .5, .03, .35]),
+                               a["G4_bs_put_seq"], rtol=ULP2, atol=PAY_ATOL)
+    np.testing.assert_allclose(co.Gen.pcg64(42).gbm_terminal(1000, 252, co.BS_AMER_PUT, [100, 100, 1, .05, .2]),
+                               a["G4_bs_amer_put_seq"], rtol=4 * ULP2, atol=PAY_ATOL)
+    np.testing.assert_allclose(co.Gen.pcg64(42).gbm_terminal(400, 40, co.BS_AMER_CALL, [100, 100, 1, .05, .2]),
+                               a["G4_bs_amer_call_seq"], rtol=4 * ULP2, atol=PAY_ATOL)
+    parts = [co.Gen.philox(11, (k,)).gbm_terminal(b - a_, 64, co.BS_EURO_CALL, [100, 100, 1, .05, .2])
+             for k, (a_, b) in enumerate(_blocks(20_000, 4))]
+    np.testing.assert_allclose(np.concatenate(parts), a["G4_bs_call_par"], rtol=ULP2, atol=PAY_ATOL)
+    parts = [co.Gen.philox(11, (k,)).gbm_terminal(b - a_, 16, co.BS_AMER_PUT, [100, 100, 1, .05, .2])
+             for k, (a_, b) in enumerate(_blocks(20_000, 2))]
+    np.testing.assert_allclose(np.concatenate(parts), a["G4_bs_amer_put_par"], rtol=4 * ULP2, atol=PAY_ATOL)
+    # the NumPy-level port is the same call sequence as the reference => bit-exact
+    assert np.array_equal(npp.Runner("black_scholes", seed=42).run(1000), a["G4_bs_call_seq"])
+    assert np.array_equal(npp.Runner("black_scholes", seed=11).run(20_000, parallel=True, n_workers=4, n_steps=64),
+                          a["G4_bs_call_par"])
+
+
+def test_portfolio_golden(golden):
+    _, a = golden
+    np.testing.assert_allclose(co.Gen.pcg64(42).gbm_terminal(500, 1260, co.PORTFOLIO_GBM, [1e4, .07, .2]),
+                               a["G5_portfolio_gbm_seq"], rtol=ULP2, atol=0)
+    np.testing.assert_allclose(co.Gen.pcg64(42).gbm_terminal(500, 504, co.PORTFOLIO_LOG1P, [1e4, .07, .2]),
+                               a["G5_portfolio_log1p_seq"], rtol=4 * ULP2, atol=0)
+    parts = [co.Gen.philox(3, (k,)).gbm_terminal(b - a_, 252, co.PORTFOLIO_GBM, [1e4, .07, .2])
+             for k, (a_, b) in enumerate(_blocks(20_000, 8))]
+    np.testing.assert_allclose(np.concatenate(parts), a["G5_portfolio_gbm_par"], rtol=ULP2, atol=0)
+    assert np.array_equal(npp.Runner("portfolio", seed=42).run(500, years=5), a["G5_portfolio_gbm_seq"])
+
+
+def test_paths_and_lsm_golden(golden):
+    j, a = golden
+    np.testing.assert_allclose(co.Gen.pcg64(5).gbm_terminal(300, 30, co.PATH_TERMINAL, [100, .05, .2, 1.0]),
+                               a["G6_path_terminal_seq"], rtol=4 * ULP2, atol=0)
+    paths = co.Gen.pcg64(1).gbm_paths(4000, 50, 100.0, 0.05, 0.2, 1.0)
+    np.testing.assert_allclose(paths[:8], a["G6_paths_head"], rtol=4 * ULP2, atol=0)
+    np.testing.assert_allclose(paths[-1], a["G6_paths_tail_row"], rtol=4 * ULP2, atol=0)
+    ref_paths = npp.Runner("path_terminal", seed=1).simulate_paths(4000, n_steps=50)
+    assert float(ref_paths.sum()) == j["G6"]["paths_checksum"]
+    assert npp.lsm_price(ref_paths, 100.0, 0.05, 1 / 50, "put")[0] == j["G6"]["lsm_put"]
+    assert npp.lsm_price(ref_paths, 100.0, 0.05, 1 / 50, "call")[0] == j["G6"]["lsm_call"]
+    assert npp.lsm_price(ref_paths, 110.0, 0.05, 1 / 50, "put")[0] == j["G6"]["lsm_put_K110"]
+
+
+def test_greeks_port_golden(golden):
+    j, _ = golden
+    g = npp.greeks(1000)
+    for k, v in j["G4_greeks_call"].items():
+        assert g[k] == v, k
+    g = npp.greeks(20_000, option_type="put", n_steps=12, parallel=True, n_workers=j["G4_greeks_put_par_cpu_count"])
+    for k, v in j["G4_greeks_put_par"].items():
+        assert g[k] == v, k
+
+
+def _cmp_metrics(mine, ref):
+    for k, v in ref.items():
+        if isinstance(v, dict):
+            for kk, vv in v.items():
+                got = mine[k][int(kk) if k == "percentiles" else kk]
+                assert got == vv or (isinstance(vv, float) and np.isnan(vv) and np.isnan(got)), (k, kk, got, vv)
+        else:
+            assert mine[k] == v, (k, mine[k], v)
+
+
+def test_stats_port_golden(golden):
+    j, a = golden
+    x = np.random.default_rng(0).normal(5, 2, 100_000)
+    _cmp_metrics(npp.default_metrics(x, percentiles=(1, 5, 50, 95, 99), rng=7, n_bootstrap=1000, bootstrap="bca",
+                                     target=5.0, eps=0.01), j["G7"])
+    _cmp_metrics(npp.default_metrics(a["G7_omit_x"], nan_policy="omit", rng=11, n_bootstrap=500, confidence=0.9,
+                                     target=2.0, eps=0.1, ci_method="t"), j["G7_omit"])
+    six = np.linspace(0, 1, 6)
+    m = npp.default_metrics(six, rng=123, n_bootstrap=200)
+    assert m["ci_mean_bootstrap"] == j["G8"]["percentile_rng123_B200"]["ci_mean_bootstrap"]
+    m = npp.default_metrics(six, rng=321, n_bootstrap=200, bootstrap="bca")
+    assert m["ci_mean_bootstrap"] == j["G8"]["bca_rng321_B200"]["ci_mean_bootstrap"]
+
+
+def test_bootstrap_index_stream_c_oracle_matches_numpy():
+    x = np.random.default_rng(0).normal(5, 2, 20_000)
+    means, idx = co.Gen.pcg64(7).bootstrap_means(x, 20, keep_idx=50_000)
+    r = np.random.default_rng(7)
+    ref_idx = r.integers(0, x.size, size=(20, x.size))
+    assert np.array_equal(idx, ref_idx.ravel()[:50_000])
+    assert np.array_equal(means, x[ref_idx].mean(axis=1))
+    r = np.random.default_rng(7)
+    assert np.array_equal(npp.bootstrap_means_chunked(x, 20, r), means)
+
+
+def test_stats_of_config1_golden(golden):
+    j, a = golden
+    m = npp.default_metrics(a["G1_pi_results"], n=10_000, rng=7, target=float(np.pi), eps=0.01)
+    ref = j["G1"]["stats"]
+    assert m["mean"] == ref["mean"] and m["std"] == ref["std"]
+    assert m["skew"] == ref["skew"] and m["kurtosis"] == ref["kurtosis"]
+    assert m["ci_mean"] == ref["ci_mean"]
+    assert m["ci_mean_bootstrap"] == ref["ci_mean_bootstrap"]
+    assert m["ci_mean_chebyshev"] == ref["ci_mean_chebyshev"]
+    assert {str(k): v for k, v in m["percentiles"].items()} == j["G1"]["percentiles"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/mcframework"), reason="reference mount absent")
+def test_port_against_live_reference():
+    import sys
+    sys.path.insert(0, "/root/reference/src")
+    try:
+        import logging
+        import mcframework as ref
+        logging.getLogger("mcframework.core").setLevel(logging.WARNING)
+        s = ref.PortfolioSimulation()
+        s.set_seed(77)
+        want = s.run(20_500, years=1, use_gbm=False, parallel=True, n_workers=5, compute_stats=False).results
+        got = npp.Runner("portfolio", seed=77).run(20_500, parallel=True, n_workers=5, years=1, use_gbm=False)
+        assert np.array_equal(got, want)
+    finally:
+        sys.path.remove("/root/reference/src")
+        for k in [k for k in sys.modules if k.startswith("mcframework") and not k.startswith("mcframework_b200")]:
+            del sys.modules[k]
