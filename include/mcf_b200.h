@@ -1,0 +1,129 @@
+/*
+ * mcf_b200.h -- C ABI of the B200-native replication + statistics hot path of mcframework.
+ *
+ * The reference (milanfusco/mcFramework) is pure Python and has NO FFI for this path; the
+ * entry points below are what a binding for it would call.  Each one cites the reference
+ * code it replaces (paths under the reference's src/mcframework/).  A ctypes stub a
+ * maintainer would add on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, no exceptions, no torch types.  Return value: MCF_OK (0) or a negative error.
+ *   - every `d_*` pointer is DEVICE memory owned by the caller; `h_*` is HOST memory.
+ *   - no allocation inside the library: scratch comes from a caller-provided device workspace
+ *     whose size the matching `*_workspace_bytes` function returns.
+ *   - all launches go to the caller's `cudaStream_t` (passed as void*), nothing synchronises
+ *     unless stated.  Kernels report data-dependent problems (e.g. an under-provisioned
+ *     stream window) through a status word inside the workspace: read it with
+ *     mcf_workspace_status() AFTER synchronising the stream.
+ *   - `gen_kind` (MCF_GEN_*) names the generator of ALL records of a call (a launch never mixes
+ *     generators); `sims_per_stream_hint` is the uniform block size (0 = unknown) that lets a
+ *     thread find its stream record without a search.
+ *   - random streams are described by `mcf_stream` records produced on the host from NumPy's
+ *     own SeedSequence / bit_generator.state, so the device walks exactly the streams the
+ *     reference would (core.py:363-364 PCG64; core.py:102-103,637,659 Philox per block).
+ */
+#ifndef MCF_B200_H
+#define MCF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCF_ABI_VERSION 1
+
+enum {
+    MCF_OK = 0,
+    MCF_ERR_BAD_ARG = -1,
+    MCF_ERR_CUDA = -2,
+    MCF_ERR_WORKSPACE_TOO_SMALL = -3,
+    MCF_ERR_WINDOW_TOO_SMALL = -4, /* stream window under-provisioned: re-plan with a larger slack */
+    MCF_ERR_NOT_CONVERGED = -5     /* chunk-entry fix-up needs more iterations (practically never) */
+};
+
+enum { MCF_GEN_PCG64 = 0, MCF_GEN_PHILOX = 1 };
+
+/* One reference random stream and the replications that consume it back to back.
+ * PCG64  (np.random.default_rng, core.py:364): s = {state_hi, state_lo, inc_hi, inc_lo, 0, 0}
+ * Philox (np.random.Philox(child), core.py:659): s = {key0, key1, ctr0, ctr1, ctr2, ctr3}
+ * buf_pos: Philox output-buffer position (4 = empty, the state right after construction).
+ * has_uint32/uinteger: NumPy's buffered upper half for next_uint32 (Generator.integers). */
+typedef struct mcf_stream {
+    uint32_t kind;
+    uint32_t buf_pos;
+    uint32_t has_uint32;
+    uint32_t uinteger;
+    uint64_t s[6];
+    int64_t first_sim; /* index of this stream's first replication in the result vector */
+    int64_t n_sims;    /* replications drawn from this stream, consecutively */
+} mcf_stream;
+
+/* Per-replication bodies that consume standard normals (ziggurat, variable stream consumption). */
+enum {
+    MCF_BS_EURO_CALL = 0,    /* p={S0,K,T,r,sigma}   sims/black_scholes.py:237-243 */
+    MCF_BS_EURO_PUT = 1,
+    MCF_BS_AMER_CALL = 2,    /* max_k intrinsic_k*exp(-r*dt*k)  sims/black_scholes.py:245-255 */
+    MCF_BS_AMER_PUT = 3,
+    MCF_PATH_TERMINAL = 4,   /* p={S0,r,sigma,T}     sims/black_scholes.py:399-401 */
+    MCF_PORTFOLIO_GBM = 5,   /* p={V0,mu,sigma}      sims/portfolio.py:79-82 */
+    MCF_PORTFOLIO_LOG1P = 6, /* p={V0,mu,sigma}      sims/portfolio.py:83-84 */
+    MCF_NORMAL_SUM = 7       /* sum of the n_steps standard normals (building block / tests) */
+};
+
+typedef struct mcf_gbm_spec {
+    int32_t mode;
+    int32_t reserved;
+    double p[6];
+} mcf_gbm_spec;
+
+/* ---- library info -------------------------------------------------------------------- */
+int mcf_abi_version(void);
+const char *mcf_build_info(void); /* "sm_100a, nvcc 12.9, ..." */
+int mcf_last_cuda_error(void);    /* cudaError_t behind the last MCF_ERR_CUDA */
+
+/* ---- (1) Pi estimation: fixed draw count => exact jump-ahead, no planning pass ---------
+ * replaces PiEstimationSimulation.single_simulation looped by _run_sequential/_work
+ * (sims/pi.py:69-82; core.py:593-594,661-662).
+ * d_hits[i]  : points with x*x+y*y<=1 of replication i (bit-exact integer)
+ * d_out[i]   : 4.0*hits/n_points (what single_simulation returns); may be NULL */
+int mcf_pi_hits(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total, int64_t n_points,
+                int32_t antithetic, int64_t sims_per_stream_hint, int64_t *d_hits, double *d_out, void *cuda_stream);
+
+/* ---- (2) normal-consuming replications -------------------------------------------------
+ * Step A, mcf_normal_plan: locate, for every replication, the position in its reference
+ * stream where its first standard_normal() call starts.  The ziggurat consumes a data
+ * dependent number of 64-bit draws, so this is a speculative chunked scan of each stream
+ * (64 draws per thread) + entry fix-up + prefix sum + locate.  The plan depends only on the
+ * streams and draws_per_sim, not on model parameters: Greeks re-use one plan for all bumps
+ * (sims/black_scholes.py:286-362 re-seed with 42 before every revaluation).
+ * Step B, mcf_gbm_terminal / mcf_gbm_paths: one thread per replication replays its
+ * n_steps normals from the planned position, path state in registers. */
+int64_t mcf_normal_plan_workspace_bytes(int32_t n_streams, int64_t max_sims_per_stream, int64_t normals_per_sim,
+                                        double slack);
+int mcf_normal_plan(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total,
+                    int64_t max_sims_per_stream, int64_t normals_per_sim, double slack, int32_t resolve_iters, void *d_workspace,
+                    int64_t workspace_bytes, uint64_t *d_sim_start /* [n_total] */,
+                    uint64_t *d_stream_end /* [n_streams] draws consumed per stream; may be NULL */, void *cuda_stream);
+/* 0 if the last plan in this workspace was valid, else MCF_ERR_WINDOW_TOO_SMALL / MCF_ERR_NOT_CONVERGED.
+ * Synchronises the stream (reads one word back). */
+int mcf_workspace_status(const void *d_workspace, void *cuda_stream);
+
+/* d_out[k*n_total + i] = value of replication i under specs[k] (common random numbers).
+ * replaces BlackScholesSimulation / BlackScholesPathSimulation / PortfolioSimulation
+ * .single_simulation under the replication loop. */
+int mcf_gbm_terminal(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total,
+                     int64_t n_steps, int64_t sims_per_stream_hint, const uint64_t *d_sim_start, const mcf_gbm_spec *h_specs, int32_t n_specs, double *d_out,
+                     void *cuda_stream);
+
+/* Full GBM paths, (n_total, n_steps+1) row-major when time_major==0 (what simulate_paths returns,
+ * sims/black_scholes.py:415-418) or (n_steps+1, n_total) when time_major==1 (LSM layout).
+ * p={S0,r,sigma,T}. */
+int mcf_gbm_paths(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total, int64_t n_steps,
+                  int64_t sims_per_stream_hint, const uint64_t *d_sim_start, const double *h_p4, int32_t time_major, double *d_paths,
+                  void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCF_B200_H */

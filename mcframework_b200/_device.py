@@ -1,0 +1,138 @@
+"""Device-side operations behind the public API: thin Python over the C ABI.
+
+All functions take/return ``torch`` CUDA tensors (ownership only) and launch on torch's current
+stream.  Nothing here computes on the CPU; a missing library or device raises
+(see :mod:`mcframework_b200._native`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native as N
+from ._streams import StreamLayout
+
+#: counters for bench.py's ``gpu_launches`` (kernels launched by this library, by entry point)
+LAUNCHES = {"pi": 0, "plan": 0, "gbm": 0, "paths": 0, "stats": 0, "lsm": 0}
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _stream_ptr():
+    return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def upload_records(layout: StreamLayout):
+    """Copy the ``mcf_stream`` records to the device (a few KB)."""
+    torch = _torch()
+    host = torch.from_numpy(np.ascontiguousarray(layout.records).view(np.uint8).copy())
+    return host.to("cuda", non_blocking=False)
+
+
+@dataclass
+class DeviceLayout:
+    layout: StreamLayout
+    records: "object"  # torch uint8 tensor on device
+
+    @classmethod
+    def of(cls, layout: StreamLayout) -> "DeviceLayout":
+        N.lib()
+        return cls(layout, upload_records(layout))
+
+
+def pi_hits(dl: DeviceLayout, n_points: int, antithetic: bool = False):
+    """(hits int64[n], estimates float64[n]) on device -- sims/pi.py:69-82 under the replication loop."""
+    torch = _torch()
+    lay = dl.layout
+    hits = torch.empty(lay.n_total, dtype=torch.int64, device="cuda")
+    out = torch.empty(lay.n_total, dtype=torch.float64, device="cuda")
+    rc = N.lib().mcf_pi_hits(lay.kind, _ptr(dl.records), lay.n_streams, lay.n_total, int(n_points), int(bool(antithetic)),
+                             lay.hint, _ptr(hits), _ptr(out), _stream_ptr())
+    N.check("mcf_pi_hits", rc)
+    LAUNCHES["pi"] += 2
+    return hits, out
+
+
+@dataclass
+class NormalPlan:
+    """Where every replication's first ``standard_normal`` draw sits in its reference stream."""
+
+    sim_start: "object"  # torch int64 (bit pattern of uint64) [n_total]
+    stream_end: "object"  # torch int64 [n_streams]: 64-bit draws consumed per stream
+    normals_per_sim: int
+
+
+def normal_plan(dl: DeviceLayout, normals_per_sim: int, slack: float = 0.03, resolve_iters: int = 3,
+                max_retries: int = 4) -> NormalPlan:
+    """Planning pass for ziggurat-consuming replications ("stream-exact planning")."""
+    torch = _torch()
+    lay = dl.layout
+    lib = N.lib()
+    sim_start = torch.empty(lay.n_total, dtype=torch.int64, device="cuda")
+    stream_end = torch.zeros(lay.n_streams, dtype=torch.int64, device="cuda")
+    for _ in range(max_retries):
+        nbytes = lib.mcf_normal_plan_workspace_bytes(lay.n_streams, lay.max_sims, int(normals_per_sim), float(slack))
+        if nbytes < 0:
+            N.check("mcf_normal_plan_workspace_bytes", int(nbytes))
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda")
+        rc = lib.mcf_normal_plan(lay.kind, _ptr(dl.records), lay.n_streams, lay.n_total, lay.max_sims,
+                                 int(normals_per_sim), float(slack), int(resolve_iters), _ptr(ws), int(nbytes),
+                                 _ptr(sim_start), _ptr(stream_end), _stream_ptr())
+        N.check("mcf_normal_plan", rc)
+        LAUNCHES["plan"] += 5 + resolve_iters
+        status = lib.mcf_workspace_status(_ptr(ws), _stream_ptr())
+        del ws
+        if status == N.OK:
+            return NormalPlan(sim_start, stream_end, int(normals_per_sim))
+        if status == N.ERR_WINDOW_TOO_SMALL:
+            slack = slack * 2 + 0.02
+        elif status == N.ERR_NOT_CONVERGED:
+            resolve_iters = min(resolve_iters + 3, 12)
+        else:
+            N.check("mcf_workspace_status", status)
+    raise N.NativeError("mcf_normal_plan", status, "planning did not succeed after retries")
+
+
+def _spec_array(specs):
+    arr = (N.GbmSpec * len(specs))()
+    for i, (mode, params) in enumerate(specs):
+        arr[i].mode = int(mode)
+        for k, v in enumerate(params):
+            arr[i].p[k] = float(v)
+    return arr
+
+
+def gbm_terminal(dl: DeviceLayout, n_steps: int, plan: NormalPlan, specs):
+    """float64[(len(specs), n)] terminal values; ``specs`` = [(mode, params), ...] on common random numbers."""
+    torch = _torch()
+    lay = dl.layout
+    out = torch.empty((len(specs), lay.n_total), dtype=torch.float64, device="cuda")
+    rc = N.lib().mcf_gbm_terminal(lay.kind, _ptr(dl.records), lay.n_streams, lay.n_total, int(n_steps), lay.hint,
+                                  _ptr(plan.sim_start), _spec_array(specs), len(specs), _ptr(out), _stream_ptr())
+    N.check("mcf_gbm_terminal", rc)
+    LAUNCHES["gbm"] += 1
+    return out
+
+
+def gbm_paths(dl: DeviceLayout, n_steps: int, plan: NormalPlan, S0: float, r: float, sigma: float, T: float,
+              time_major: bool = False):
+    torch = _torch()
+    lay = dl.layout
+    shape = (n_steps + 1, lay.n_total) if time_major else (lay.n_total, n_steps + 1)
+    out = torch.empty(shape, dtype=torch.float64, device="cuda")
+    p4 = (C.c_double * 4)(float(S0), float(r), float(sigma), float(T))
+    rc = N.lib().mcf_gbm_paths(lay.kind, _ptr(dl.records), lay.n_streams, lay.n_total, int(n_steps), lay.hint,
+                               _ptr(plan.sim_start), p4, int(bool(time_major)), _ptr(out), _stream_ptr())
+    N.check("mcf_gbm_paths", rc)
+    LAUNCHES["paths"] += 1
+    return out

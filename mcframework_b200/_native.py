@@ -1,0 +1,88 @@
+"""ctypes binding of ``libmcf_b200.so`` (the C ABI declared in ``include/mcf_b200.h``).
+
+There is NO CPU fallback: every device operation goes through :func:`lib`, which raises
+``RuntimeError`` when the CUDA library is not built or no CUDA device is visible.
+PyTorch is used only for device-memory ownership and the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmcf_b200.so")
+
+OK, ERR_BAD_ARG, ERR_CUDA, ERR_WORKSPACE_TOO_SMALL, ERR_WINDOW_TOO_SMALL, ERR_NOT_CONVERGED = 0, -1, -2, -3, -4, -5
+_ERR_NAMES = {
+    ERR_BAD_ARG: "MCF_ERR_BAD_ARG",
+    ERR_CUDA: "MCF_ERR_CUDA",
+    ERR_WORKSPACE_TOO_SMALL: "MCF_ERR_WORKSPACE_TOO_SMALL",
+    ERR_WINDOW_TOO_SMALL: "MCF_ERR_WINDOW_TOO_SMALL",
+    ERR_NOT_CONVERGED: "MCF_ERR_NOT_CONVERGED",
+}
+
+# replication bodies (enum in include/mcf_b200.h)
+BS_EURO_CALL, BS_EURO_PUT, BS_AMER_CALL, BS_AMER_PUT, PATH_TERMINAL, PORTFOLIO_GBM, PORTFOLIO_LOG1P, NORMAL_SUM = range(8)
+
+
+class NativeError(RuntimeError):
+    def __init__(self, fn: str, code: int, detail: str = ""):
+        self.code = code
+        super().__init__(f"{fn} failed: {_ERR_NAMES.get(code, code)}{(' -- ' + detail) if detail else ''}")
+
+
+class GbmSpec(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32), ("p", C.c_double * 6)]
+
+
+_i32, _i64, _u32, _f64, _vp = C.c_int32, C.c_int64, C.c_uint32, C.c_double, C.c_void_p
+
+#: name -> (restype, argtypes); every symbol include/mcf_b200.h declares
+SIGNATURES = {
+    "mcf_abi_version": (C.c_int, []),
+    "mcf_build_info": (C.c_char_p, []),
+    "mcf_last_cuda_error": (C.c_int, []),
+    "mcf_pi_hits": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i32, _i64, _vp, _vp, _vp]),
+    "mcf_normal_plan_workspace_bytes": (_i64, [_i32, _i64, _i64, _f64]),
+    "mcf_normal_plan": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i64, _f64, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "mcf_workspace_status": (C.c_int, [_vp, _vp]),
+    "mcf_gbm_terminal": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i64, _vp, C.POINTER(GbmSpec), _i32, _vp, _vp]),
+    "mcf_gbm_paths": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i64, _vp, C.POINTER(_f64), _i32, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH):
+    """dlopen the C-ABI library and attach signatures (no CUDA call is made)."""
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"CUDA library not built: {path} is missing. Run `python -m mcframework_b200.build` "
+            "(needs nvcc; targets sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def lib():
+    """The loaded library, after checking that a CUDA device is usable.  Fails loudly otherwise."""
+    global _lib
+    if _lib is None:
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("mcframework_b200 needs a CUDA device (B200, sm_100a); none is visible. "
+                               "There is no CPU fallback.")
+        _lib = load_library()
+    return _lib
+
+
+def check(fn: str, code: int):
+    if code != OK:
+        detail = ""
+        if code == ERR_CUDA and _lib is not None:
+            detail = f"cudaError {_lib.mcf_last_cuda_error()}"
+        raise NativeError(fn, code, detail)

@@ -1,0 +1,114 @@
+"""Host-side description of the reference's random streams for the device kernels.
+
+The reference seeds everything through NumPy (``core.py:363-364`` ``SeedSequence`` ->
+``default_rng`` = PCG64; ``core.py:637,659`` ``seed_seq.spawn`` -> ``Philox`` per block).  We call
+NumPy's *own* ``SeedSequence.spawn`` / ``generate_state`` / ``bit_generator.state`` here, so the
+spawn tree (including the parent's ``n_children_spawned`` side effect) is identical by
+construction, and hand the raw generator states to the GPU as ``mcf_stream`` records
+(``include/mcf_b200.h``).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+GEN_PCG64 = 0
+GEN_PHILOX = 1
+
+#: mirrors ``struct mcf_stream`` (80 bytes)
+STREAM_DTYPE = np.dtype(
+    [
+        ("kind", np.uint32),
+        ("buf_pos", np.uint32),
+        ("has_uint32", np.uint32),
+        ("uinteger", np.uint32),
+        ("s", np.uint64, (6,)),
+        ("first_sim", np.int64),
+        ("n_sims", np.int64),
+    ],
+    align=True,
+)
+assert STREAM_DTYPE.itemsize == 80, STREAM_DTYPE.itemsize
+
+_M64 = (1 << 64) - 1
+
+
+def block_edges(n: int, block_size: int) -> list[tuple[int, int]]:
+    """Half-open blocks covering ``[0, n)`` (same partition as ``make_blocks``, core.py:107-134)."""
+    if block_size <= 0:
+        raise ValueError("block_size must be positive")
+    starts = range(0, n, block_size)
+    return [(a, min(a + block_size, n)) for a in starts]
+
+
+def pcg64_record(state: dict, first_sim: int, n_sims: int) -> np.ndarray:
+    """One record from ``Generator.bit_generator.state`` of a PCG64."""
+    if state.get("bit_generator") != "PCG64":
+        raise TypeError(f"expected a PCG64 state, got {state.get('bit_generator')!r}")
+    rec = np.zeros(1, dtype=STREAM_DTYPE)
+    st, inc = int(state["state"]["state"]), int(state["state"]["inc"])
+    rec["kind"] = GEN_PCG64
+    rec["buf_pos"] = 0
+    rec["has_uint32"] = int(state["has_uint32"])
+    rec["uinteger"] = int(state["uinteger"])
+    rec["s"][0, :4] = [st >> 64, st & _M64, inc >> 64, inc & _M64]
+    rec["first_sim"] = first_sim
+    rec["n_sims"] = n_sims
+    return rec
+
+
+def philox_records(children, blocks) -> np.ndarray:
+    """Records for ``Philox(child)`` of every spawned child (core.py:659): key from
+    ``child.generate_state(2, uint64)``, counter 0, empty output buffer."""
+    rec = np.zeros(len(children), dtype=STREAM_DTYPE)
+    rec["kind"] = GEN_PHILOX
+    rec["buf_pos"] = 4
+    for k, (child, (a, b)) in enumerate(zip(children, blocks)):
+        rec["s"][k, :2] = child.generate_state(2, np.uint64)
+        rec["first_sim"][k] = a
+        rec["n_sims"][k] = b - a
+    return rec
+
+
+@dataclass
+class StreamLayout:
+    """Which reference streams a run consumes and which replications each one feeds."""
+
+    kind: int
+    records: np.ndarray  # STREAM_DTYPE[n_streams]
+    n_total: int
+    hint: int  # uniform block size (0 when there is a single stream)
+
+    @property
+    def n_streams(self) -> int:
+        return int(self.records.size)
+
+    @property
+    def max_sims(self) -> int:
+        return int(self.records["n_sims"].max())
+
+    def shard(self, rank: int, world: int) -> "StreamLayout":
+        """Contiguous range of stream records for one GPU; results concatenate in reference order."""
+        k = self.n_streams
+        lo, hi = rank * k // world, (rank + 1) * k // world
+        part = self.records[lo:hi].copy()
+        if part.size:
+            part["first_sim"] -= part["first_sim"][0]
+        return StreamLayout(self.kind, part, int(part["n_sims"].sum()), self.hint)
+
+
+def sequential_layout(rng: np.random.Generator, n: int) -> StreamLayout:
+    """``_run_sequential`` (core.py:583-597): every replication draws from ``self.rng`` in turn."""
+    return StreamLayout(GEN_PCG64, pcg64_record(rng.bit_generator.state, 0, n), n, 0)
+
+
+def parallel_layout(seed_seq, n: int, n_workers: int, chunks_per_worker: int = 8) -> StreamLayout:
+    """``_prepare_parallel_blocks`` (core.py:622-641): ``max(1, n // (8*W))``-sized blocks, one spawned
+    child per block (a fresh OS-entropy SeedSequence per block when the simulation is unseeded)."""
+    blocks = block_edges(n, max(1, n // (n_workers * chunks_per_worker)))
+    if seed_seq is not None:
+        children = seed_seq.spawn(len(blocks))
+    else:
+        children = [np.random.SeedSequence() for _ in blocks]
+    return StreamLayout(GEN_PHILOX, philox_records(children, blocks), n, blocks[0][1] - blocks[0][0])

@@ -1,0 +1,456 @@
+// mcf_device.cuh -- per-thread building blocks of the B200 replication kernels.
+//
+// Everything here is `__host__ __device__` so that tests/hostemu can compile the SAME source
+// with g++ and check the stream logic on a CPU-only box (the product never runs that build).
+// The kernels in mcf_kernels.cu are thin grid/block wrappers around these functions.
+//
+// Algorithms restated (NumPy 2.3.x, the reference's pinned dependency):
+//   PCG64 XSL-RR 128/64      numpy/random/src/pcg64/pcg64.h      (reference: core.py:315,364)
+//   Philox4x64-10            numpy/random/src/philox/philox.h    (reference: core.py:102-103,659)
+//   next_double              (u64 >> 11) * 2^-53
+//   random_standard_normal   256-layer ziggurat, distributions.c (reference: black_scholes.py:103,239)
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+
+#include "../../include/mcf_b200.h"
+
+#if defined(__CUDACC__)
+#define MCF_HD __host__ __device__ __forceinline__
+#else
+#define MCF_HD inline
+#endif
+
+namespace mcf {
+
+// ---------------------------------------------------------------------------------------
+// exact-rounding helpers: the reference's results come from separately rounded mul/add
+// (no FMA in NumPy's x86-64 wheels), so nothing on the parity path may be contracted.
+// ---------------------------------------------------------------------------------------
+MCF_HD double xmul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b;  // host build also uses -ffp-contract=off
+    return r;
+#endif
+}
+MCF_HD double xadd(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b;
+    return r;
+#endif
+}
+MCF_HD double xsub(double a, double b) { return xadd(a, -b); }
+
+MCF_HD double bits_to_double(uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+
+// exact conversion of an integer < 2^52 (one FP64 add instead of a 64-bit I2F)
+MCF_HD double u52_to_double(uint64_t v) { return bits_to_double(0x4330000000000000ULL | v) - 4503599627370496.0; }
+
+// next_double: 53-bit integer * 2^-53 (exact)
+MCF_HD double u64_to_unit_double(uint64_t v) {
+    uint64_t k = v >> 11;  // < 2^53
+    // split so both halves fit the 2^52 trick; every step is exact
+    double hi = u52_to_double(k >> 32);          // < 2^21
+    double lo = u52_to_double(k & 0xFFFFFFFFULL);  // < 2^32
+    return (hi * 4294967296.0 + lo) * (1.0 / 9007199254740992.0);
+}
+
+MCF_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+MCF_HD int popc64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(v);
+#else
+    return __builtin_popcountll(v);
+#endif
+}
+MCF_HD int ctz64(uint64_t v) {  // v != 0
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)v) - 1;
+#else
+    return __builtin_ctzll(v);
+#endif
+}
+// position of the k-th (0-based) set bit of m; requires k < popc(m)
+MCF_HD int select_bit64(uint64_t m, int k) {
+    int pos = 0;
+#pragma unroll
+    for (int w = 32; w >= 1; w >>= 1) {
+        uint64_t low = m & ((1ULL << w) - 1ULL);
+        int c = popc64(low);
+        if (k >= c) {
+            k -= c;
+            m >>= w;
+            pos += w;
+        } else {
+            m = low;
+        }
+    }
+    return pos;
+}
+MCF_HD uint64_t mask_from(unsigned e) { return e >= 64 ? 0ULL : ~((1ULL << e) - 1ULL); }  // bits >= e
+
+// ---------------------------------------------------------------------------------------
+// 128-bit helpers for the PCG64 LCG
+// ---------------------------------------------------------------------------------------
+struct u128 {
+    uint64_t hi, lo;
+};
+MCF_HD u128 mk128(uint64_t hi, uint64_t lo) {
+    u128 r;
+    r.hi = hi;
+    r.lo = lo;
+    return r;
+}
+MCF_HD u128 mul128(u128 a, u128 b) {  // low 128 bits of a*b
+    u128 r;
+    r.lo = a.lo * b.lo;
+    r.hi = mulhi64(a.lo, b.lo) + a.lo * b.hi + a.hi * b.lo;
+    return r;
+}
+MCF_HD u128 add128(u128 a, u128 b) {
+    u128 r;
+    r.lo = a.lo + b.lo;
+    r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ULL : 0ULL);
+    return r;
+}
+
+#define MCF_PCG_MULT_HI 0x2360ED051FC65DA4ULL
+#define MCF_PCG_MULT_LO 0x4385DF649FCCF645ULL
+
+MCF_HD u128 pcg_step(u128 s, u128 inc) { return add128(mul128(s, mk128(MCF_PCG_MULT_HI, MCF_PCG_MULT_LO)), inc); }
+MCF_HD uint64_t pcg_output(u128 s) {
+    uint64_t v = s.hi ^ s.lo;
+    unsigned rot = (unsigned)(s.hi >> 58);
+    return (v >> rot) | (v << ((64u - rot) & 63u));
+}
+// state after `delta` steps (pcg_advance_lcg_128, O(log delta))
+MCF_HD u128 pcg_advance(u128 s, u128 inc, uint64_t delta) {
+    u128 cur_mult = mk128(MCF_PCG_MULT_HI, MCF_PCG_MULT_LO), cur_plus = inc;
+    u128 acc_mult = mk128(0, 1), acc_plus = mk128(0, 0);
+    while (delta > 0) {
+        if (delta & 1ULL) {
+            acc_mult = mul128(acc_mult, cur_mult);
+            acc_plus = add128(mul128(acc_plus, cur_mult), cur_plus);
+        }
+        cur_plus = mul128(add128(cur_mult, mk128(0, 1)), cur_plus);
+        cur_mult = mul128(cur_mult, cur_mult);
+        delta >>= 1;
+    }
+    return add128(mul128(acc_mult, s), acc_plus);
+}
+
+// ---------------------------------------------------------------------------------------
+// Philox4x64-10
+// ---------------------------------------------------------------------------------------
+#define MCF_PHILOX_M0 0xD2E7470EE14C6C93ULL
+#define MCF_PHILOX_M1 0xCA5A826395121157ULL
+#define MCF_PHILOX_W0 0x9E3779B97F4A7C15ULL
+#define MCF_PHILOX_W1 0xBB67AE8584CAA73BULL
+
+MCF_HD void philox4x64_10(uint64_t c0, uint64_t c1, uint64_t c2, uint64_t c3, uint64_t k0, uint64_t k1,
+                          uint64_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint64_t hi0 = mulhi64(MCF_PHILOX_M0, c0), lo0 = MCF_PHILOX_M0 * c0;
+        uint64_t hi1 = mulhi64(MCF_PHILOX_M1, c2), lo1 = MCF_PHILOX_M1 * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += MCF_PHILOX_W0;
+        k1 += MCF_PHILOX_W1;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+// ---------------------------------------------------------------------------------------
+// Cursors: random access into a reference stream.  `pos` counts 64-bit draws from the
+// state captured in the mcf_stream record (pos 0 = the next value NumPy would return).
+// ---------------------------------------------------------------------------------------
+template <int KIND>
+struct Cursor;
+
+template <>
+struct Cursor<MCF_GEN_PCG64> {
+    u128 state, inc;
+    uint64_t pos;
+    MCF_HD void init(const mcf_stream &s, uint64_t p) {
+        inc = mk128(s.s[2], s.s[3]);
+        state = pcg_advance(mk128(s.s[0], s.s[1]), inc, p);
+        pos = p;
+    }
+    MCF_HD uint64_t next64() {
+        state = pcg_step(state, inc);  // NumPy steps first, then outputs from the new state
+        pos++;
+        return pcg_output(state);
+    }
+};
+
+template <>
+struct Cursor<MCF_GEN_PHILOX> {
+    uint64_t k0, k1, b0, b1, b2, b3;  // key and base counter
+    uint64_t q;                       // buf_pos + pos: block = base + (q >> 2), lane = q & 3
+    uint64_t pos;
+    uint64_t v0, v1, v2, v3;  // current block
+    uint64_t have;            // block index held in v*, ~0 = none
+    MCF_HD void init(const mcf_stream &s, uint64_t p) {
+        k0 = s.s[0];
+        k1 = s.s[1];
+        b0 = s.s[2];
+        b1 = s.s[3];
+        b2 = s.s[4];
+        b3 = s.s[5];
+        q = (uint64_t)s.buf_pos + p;
+        pos = p;
+        have = ~0ULL;
+        v0 = v1 = v2 = v3 = 0;
+    }
+    MCF_HD void load_block(uint64_t blk) {
+        uint64_t c0 = b0 + blk;
+        uint64_t carry = c0 < b0 ? 1ULL : 0ULL;
+        uint64_t c1 = b1 + carry;
+        uint64_t c2 = b2 + ((carry && c1 == 0) ? 1ULL : 0ULL);
+        uint64_t out[4];
+        philox4x64_10(c0, c1, c2, b3, k0, k1, out);
+        v0 = out[0];
+        v1 = out[1];
+        v2 = out[2];
+        v3 = out[3];
+        have = blk;
+    }
+    MCF_HD uint64_t next64() {
+        uint64_t blk = q >> 2;
+        if (blk != have) load_block(blk);
+        unsigned lane = (unsigned)(q & 3ULL);
+        uint64_t v = lane == 0 ? v0 : (lane == 1 ? v1 : (lane == 2 ? v2 : v3));
+        q++;
+        pos++;
+        return v;
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// Ziggurat
+// ---------------------------------------------------------------------------------------
+struct ZigTables {
+    const uint64_t *ki;
+    const double *wi;
+    const double *fi;
+};
+#define MCF_ZIG_R 3.6541528853610088
+#define MCF_ZIG_INV_R 0.27366123732975828
+
+// One pass through NumPy's `for (;;)` body.  Returns true when a normal is produced (x).
+// Consumption: 1 draw (fast accept), 2 draws (wedge, accepted or not), 1+2k draws (tail).
+template <class Cur>
+MCF_HD bool zig_attempt(Cur &cur, const ZigTables &t, double &x) {
+    uint64_t r = cur.next64();
+    unsigned idx = (unsigned)(r & 0xffULL);
+    r >>= 8;
+    unsigned sign = (unsigned)(r & 1ULL);
+    uint64_t rabs = (r >> 1) & 0x000fffffffffffffULL;
+    double v = xmul(u52_to_double(rabs), t.wi[idx]);
+    x = sign ? -v : v;
+    if (rabs < t.ki[idx]) return true;
+    if (idx == 0) {
+        for (;;) {
+            double xx = xmul(-MCF_ZIG_INV_R, log1p(-u64_to_unit_double(cur.next64())));
+            double yy = -log1p(-u64_to_unit_double(cur.next64()));
+            if (xadd(yy, yy) > xmul(xx, xx)) {
+                double m = xadd(MCF_ZIG_R, xx);
+                x = ((rabs >> 8) & 1ULL) ? -m : m;
+                return true;
+            }
+        }
+    }
+    double f1 = t.fi[idx - 1], f0 = t.fi[idx];
+    double lhs = xadd(xmul(xsub(f1, f0), u64_to_unit_double(cur.next64())), f0);
+    return lhs < exp(xmul(xmul(-0.5, x), x));
+}
+
+template <class Cur>
+MCF_HD double zig_normal(Cur &cur, const ZigTables &t) {
+    double x;
+    while (!zig_attempt(cur, t, x)) {
+    }
+    return x;
+}
+
+// ---------------------------------------------------------------------------------------
+// Stream lookup: replication index -> stream record (streams sorted by first_sim)
+// ---------------------------------------------------------------------------------------
+MCF_HD int find_stream(const mcf_stream *streams, int n_streams, int64_t sim) {
+    int lo = 0, hi = n_streams - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (streams[mid].first_sim <= sim)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return lo;
+}
+
+// ---------------------------------------------------------------------------------------
+// Pi: hits among `npts` consecutive points starting at the cursor (sims/pi.py:71-72)
+// ---------------------------------------------------------------------------------------
+template <class Cur>
+MCF_HD int64_t pi_count_hits(Cur &cur, int64_t npts) {
+    int64_t hits = 0;
+    for (int64_t i = 0; i < npts; i++) {
+        double x = xadd(-1.0, xmul(2.0, u64_to_unit_double(cur.next64())));
+        double y = xadd(-1.0, xmul(2.0, u64_to_unit_double(cur.next64())));
+        hits += (xadd(xmul(x, x), xmul(y, y)) <= 1.0) ? 1 : 0;
+    }
+    return hits;
+}
+
+// ---------------------------------------------------------------------------------------
+// Planning pass over a stream window.  A chunk is 64 consecutive draw positions.
+//   startmask bit j : a ziggurat attempt starts at chunk_base + j
+//   emitmask  bit j : ... and that attempt produces a normal
+//   exit            : first attempt start at or beyond the chunk end, minus the chunk end
+//   gen_entry       : offset the masks were generated from (0 = speculative)
+// ---------------------------------------------------------------------------------------
+#define MCF_CHUNK 64
+#define MCF_EXIT_OVERFLOW 255
+
+struct ChunkInfo {
+    uint64_t startmask, emitmask;
+    uint32_t exit, gen_entry;
+};
+
+// cursor must be positioned at chunk_base + entry
+template <class Cur>
+MCF_HD ChunkInfo scan_chunk(Cur &cur, uint64_t chunk_base, uint32_t entry, const ZigTables &t) {
+    ChunkInfo ci;
+    ci.startmask = 0;
+    ci.emitmask = 0;
+    ci.gen_entry = entry;
+    const uint64_t end = chunk_base + MCF_CHUNK;
+    while (cur.pos < end) {
+        unsigned j = (unsigned)(cur.pos - chunk_base);
+        double x;
+        bool emitted = zig_attempt(cur, t, x);
+        ci.startmask |= 1ULL << j;
+        if (emitted) ci.emitmask |= 1ULL << j;
+    }
+    uint64_t over = cur.pos - end;
+    ci.exit = over >= MCF_EXIT_OVERFLOW ? MCF_EXIT_OVERFLOW : (uint32_t)over;
+    return ci;
+}
+
+// Is a chunk generated from `gen_entry` valid for true entry offset `e`?
+MCF_HD bool chunk_valid_for_entry(uint64_t startmask, uint32_t gen_entry, uint32_t e) {
+    if (e == gen_entry) return true;
+    return e < MCF_CHUNK && ((startmask >> e) & 1ULL);
+}
+
+// For a chunk whose emissions have stream-local ordinals [E, E+count): find every replication
+// boundary inside.  Replication m (m >= 1) starts right after the attempt that emitted normal
+// number m*nps-1.  `visit(m, position)` is called for m in [1, n_sims]; m == n_sims marks the
+// end of the stream's last replication (total consumption).
+template <class F>
+MCF_HD void locate_in_chunk(uint64_t chunk_base, uint64_t eff_start, uint64_t eff_emit, uint32_t exit_, uint64_t E,
+                            uint64_t nps, uint64_t n_sims, F visit) {
+    uint64_t cnt = (uint64_t)popc64(eff_emit);
+    if (cnt == 0) return;
+    uint64_t m = (E + nps) / nps;  // smallest m with m*nps - 1 >= E
+    for (; m <= n_sims; m++) {
+        uint64_t k = m * nps - 1;
+        if (k >= E + cnt) break;
+        int j = select_bit64(eff_emit, (int)(k - E));
+        uint64_t later = (j >= 63) ? 0ULL : (eff_start & ~((2ULL << j) - 1ULL));
+        uint64_t endpos = later ? (uint64_t)ctz64(later) : (uint64_t)MCF_CHUNK + exit_;
+        visit(m, chunk_base + endpos);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Replication bodies (pass 2): the cursor sits where the replication's first draw starts.
+// ---------------------------------------------------------------------------------------
+struct GbmDerived {  // host-precomputed exactly as the reference computes them in Python floats
+    int32_t mode;
+    double a;      // per-step drift      (r - 0.5*sigma^2)*dt   | loc of rng.normal
+    double b;      // per-step vol scale  sigma*sqrt(dt)          | scale of rng.normal
+    double s0;     // S0 | V0
+    double logs0;  // log(S0)
+    double K;
+    double disc;   // exp(-r*T)
+    double rdt;    // r*dt   (discount exponent per step, "american")
+};
+
+// European / portfolio terminal value from a stream of normals; sum in fp64, sequential order
+// (the reference sums pairwise; the difference is covered by the stated tolerance).
+template <class Cur>
+MCF_HD double run_terminal(Cur &cur, const ZigTables &t, int64_t n_steps, const GbmDerived &g) {
+    switch (g.mode) {
+    case MCF_NORMAL_SUM: {
+        double acc = 0.0;
+        for (int64_t k = 0; k < n_steps; k++) acc = xadd(acc, zig_normal(cur, t));
+        return acc;
+    }
+    case MCF_BS_EURO_CALL:
+    case MCF_BS_EURO_PUT:
+    case MCF_PORTFOLIO_GBM: {
+        double acc = 0.0;
+        for (int64_t k = 0; k < n_steps; k++) acc = xadd(acc, xadd(g.a, xmul(g.b, zig_normal(cur, t))));
+        double st = xmul(g.s0, exp(acc));
+        if (g.mode == MCF_PORTFOLIO_GBM) return st;
+        double pay = g.mode == MCF_BS_EURO_CALL ? fmax(xsub(st, g.K), 0.0) : fmax(xsub(g.K, st), 0.0);
+        return xmul(pay, g.disc);
+    }
+    case MCF_PORTFOLIO_LOG1P: {
+        double acc = 0.0;
+        for (int64_t k = 0; k < n_steps; k++) acc = xadd(acc, log1p(xadd(g.a, xmul(g.b, zig_normal(cur, t)))));
+        return xmul(g.s0, exp(acc));
+    }
+    case MCF_PATH_TERMINAL: {
+        double acc = 0.0;  // np.cumsum of log-returns, then exp(log(S0) + cumsum[-1])
+        for (int64_t k = 0; k < n_steps; k++) acc = xadd(acc, xadd(g.a, xmul(g.b, zig_normal(cur, t))));
+        return exp(xadd(g.logs0, acc));
+    }
+    case MCF_BS_AMER_CALL:
+    case MCF_BS_AMER_PUT: {
+        const bool call = g.mode == MCF_BS_AMER_CALL;
+        double s = exp(g.logs0);
+        double best = call ? fmax(xsub(s, g.K), 0.0) : fmax(xsub(g.K, s), 0.0);  // k = 0, discount 1
+        double acc = 0.0;
+        for (int64_t k = 1; k <= n_steps; k++) {
+            acc = xadd(acc, xadd(g.a, xmul(g.b, zig_normal(cur, t))));
+            s = exp(xadd(g.logs0, acc));
+            double intr = call ? fmax(xsub(s, g.K), 0.0) : fmax(xsub(g.K, s), 0.0);
+            double v = xmul(intr, exp(xmul(-g.rdt, (double)k)));
+            best = fmax(best, v);
+        }
+        return best;
+    }
+    default:
+        return bits_to_double(0x7ff8000000000000ULL);
+    }
+}
+
+}  // namespace mcf

@@ -1,0 +1,518 @@
+// mcf_kernels.cu -- sm_100a kernels + C ABI (include/mcf_b200.h) for the replication hot path.
+//
+// Layout of the work (DESIGN.md has the long form):
+//   * Pi: one warp per (replication, slice); every lane jumps to its own position in the
+//     reference stream (PCG64 advance / Philox counter), counts hits in registers, the warp
+//     reduces with shuffles and lane 0 adds one integer per slice.
+//   * Normal-consuming replications: the ziggurat makes stream consumption data dependent,
+//     so a planning pass finds where each replication starts (scan 64-draw chunks
+//     speculatively -> fix chunk entries -> tile sums -> per-stream scan -> locate), then one
+//     thread per replication replays its draws with all path state in registers.
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "mcf_device.cuh"
+#include "mcf_host.h"
+#include "zig_tables.h"
+
+using namespace mcf;
+
+// ------------------------------------------------------------------ ziggurat tables in HBM
+__device__ const unsigned long long g_zig_ki[256] = {MCF_ZIG_KI_LIST};
+__device__ const unsigned long long g_zig_wi[256] = {MCF_ZIG_WI_BITS_LIST};
+__device__ const unsigned long long g_zig_fi[256] = {MCF_ZIG_FI_BITS_LIST};
+
+struct ZigShared {
+    uint64_t ki[256];
+    double wi[256];
+    double fi[256];
+};
+
+__device__ __forceinline__ ZigTables load_zig_tables(ZigShared &sh) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        sh.ki[i] = g_zig_ki[i];
+        sh.wi[i] = __longlong_as_double((long long)g_zig_wi[i]);
+        sh.fi[i] = __longlong_as_double((long long)g_zig_fi[i]);
+    }
+    __syncthreads();
+    ZigTables t;
+    t.ki = sh.ki;
+    t.wi = sh.wi;
+    t.fi = sh.fi;
+    return t;
+}
+
+__device__ __forceinline__ int stream_of(const mcf_stream *streams, int n_streams, int64_t sim, int64_t hint) {
+    int64_t g = hint > 0 ? sim / hint : 0;
+    if (g < n_streams) {
+        int64_t f = streams[g].first_sim;
+        if (f <= sim && sim < f + streams[g].n_sims) return (int)g;
+    }
+    return find_stream(streams, n_streams, sim);
+}
+
+// ===================================================================================== Pi
+template <int KIND>
+__global__ void __launch_bounds__(256) pi_kernel(const mcf_stream *__restrict__ streams, int n_streams, int64_t n_total,
+                                                 int64_t m, int64_t draws_per_sim, int64_t ppt, int64_t parts,
+                                                 int weight, int extra_point, int64_t hint,
+                                                 unsigned long long *__restrict__ hits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_units = n_total * parts;
+    for (int64_t unit = warp0; unit < n_units; unit += n_warps) {
+        const int64_t sim = unit / parts, part = unit - sim * parts;
+        const int si = stream_of(streams, n_streams, sim, hint);
+        const mcf_stream st = streams[si];
+        const uint64_t base = (uint64_t)(sim - st.first_sim) * (uint64_t)draws_per_sim;
+        const int64_t p0 = (part * 32 + lane) * ppt;
+        int64_t cnt = m - p0;
+        cnt = cnt < 0 ? 0 : (cnt > ppt ? ppt : cnt);
+        int64_t h = 0;
+        if (cnt > 0) {
+            Cursor<KIND> cur;
+            cur.init(st, base + 2ULL * (uint64_t)p0);
+            h = pi_count_hits(cur, cnt) * weight;
+        }
+        if (extra_point && part == 0 && lane == 0) {  // odd n_points with antithetic pairs (sims/pi.py:79-80)
+            Cursor<KIND> cur;
+            cur.init(st, base + 2ULL * (uint64_t)m);
+            h += pi_count_hits(cur, 1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+        if (lane == 0) atomicAdd(&hits[sim], (unsigned long long)h);
+    }
+}
+
+__global__ void pi_finalize_kernel(const unsigned long long *__restrict__ hits, int64_t n_total, double n_points,
+                                   double *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_total) out[i] = __ddiv_rn(__dmul_rn(4.0, (double)(long long)hits[i]), n_points);
+}
+
+// ========================================================================== planning pass
+__global__ void plan_init_kernel(int *hdr, int iters) {
+    if (threadIdx.x < MCF_HDR_WORDS) hdr[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) hdr[MCF_HDR_WORDS - 1] = iters;
+}
+
+// one thread scans RUN consecutive chunks of one stream, carrying the ziggurat chain through
+template <int KIND, int RUN>
+__global__ void __launch_bounds__(256) plan_scan_kernel(const mcf_stream *__restrict__ streams, int64_t cps,
+                                                        int64_t n_runs, uint64_t *__restrict__ startmask,
+                                                        uint64_t *__restrict__ emitmask, uint8_t *__restrict__ exit_,
+                                                        uint8_t *__restrict__ gen, int *hdr) {
+    __shared__ ZigShared sh;
+    const ZigTables t = load_zig_tables(sh);
+    const int64_t run = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (run >= n_runs) return;
+    const int64_t runs_per_stream = cps / RUN;
+    const int64_t si = run / runs_per_stream;
+    const int64_t c0 = (run - si * runs_per_stream) * RUN;
+    const mcf_stream st = streams[si];
+    Cursor<KIND> cur;
+    cur.init(st, (uint64_t)c0 * MCF_CHUNK);
+    uint32_t entry = 0;
+#pragma unroll 1
+    for (int c = 0; c < RUN; c++) {
+        const int64_t id = si * cps + c0 + c;
+        ChunkInfo ci = scan_chunk(cur, (uint64_t)(c0 + c) * MCF_CHUNK, entry, t);
+        startmask[id] = ci.startmask;
+        emitmask[id] = ci.emitmask;
+        exit_[id] = (uint8_t)ci.exit;
+        gen[id] = (uint8_t)ci.gen_entry;
+        if (ci.exit == MCF_EXIT_OVERFLOW) atomicExch(&hdr[0], MCF_ERR_NOT_CONVERGED);
+        entry = ci.exit;
+    }
+}
+
+// fix chunk entries: a chunk's true entry offset is its predecessor's exit
+template <int KIND>
+__global__ void __launch_bounds__(256) plan_resolve_kernel(const mcf_stream *__restrict__ streams, int64_t cps,
+                                                           int64_t n_chunks, uint64_t *__restrict__ startmask,
+                                                           uint64_t *__restrict__ emitmask, uint8_t *exit_,
+                                                           uint8_t *__restrict__ gen, uint8_t *__restrict__ entry_true,
+                                                           int *hdr, int iter) {
+    __shared__ ZigShared sh;
+    const ZigTables t = load_zig_tables(sh);
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_chunks) return;
+    const int64_t si = id / cps, c = id - si * cps;
+    const uint32_t e = c == 0 ? 0u : (uint32_t)((volatile uint8_t *)exit_)[id - 1];
+    if (!chunk_valid_for_entry(startmask[id], gen[id], e)) {
+        const mcf_stream st = streams[si];
+        Cursor<KIND> cur;
+        cur.init(st, (uint64_t)c * MCF_CHUNK + e);
+        ChunkInfo ci = scan_chunk(cur, (uint64_t)c * MCF_CHUNK, e, t);
+        startmask[id] = ci.startmask;
+        emitmask[id] = ci.emitmask;
+        gen[id] = (uint8_t)ci.gen_entry;
+        if (ci.exit != exit_[id]) {
+            ((volatile uint8_t *)exit_)[id] = (uint8_t)ci.exit;
+            atomicExch(&hdr[1 + iter], 1);
+        }
+        if (ci.exit == MCF_EXIT_OVERFLOW) atomicExch(&hdr[0], MCF_ERR_NOT_CONVERGED);
+    }
+    entry_true[id] = (uint8_t)e;
+}
+
+__device__ __forceinline__ uint32_t block_reduce_sum(uint32_t v, uint32_t *sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t r = 0;
+    if (threadIdx.x < 32) {
+        r = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    return r;  // valid in thread 0
+}
+
+// 256 threads x 4 chunks = one tile
+__global__ void __launch_bounds__(256) plan_tile_count_kernel(const uint64_t *__restrict__ emitmask,
+                                                              const uint8_t *__restrict__ entry_true,
+                                                              uint64_t *__restrict__ tile_sum) {
+    __shared__ uint32_t sh[8];
+    const int64_t base = (int64_t)blockIdx.x * MCF_TILE + threadIdx.x * 4;
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) c += (uint32_t)popc64(emitmask[base + k] & mask_from(entry_true[base + k]));
+    uint32_t s = block_reduce_sum(c, sh);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = s;
+}
+
+// one CTA per stream: exclusive scan of that stream's tile sums; also checks the window was large enough
+__global__ void __launch_bounds__(1024) plan_tile_scan_kernel(const mcf_stream *__restrict__ streams, int64_t tps,
+                                                              int64_t nps, const uint64_t *__restrict__ tile_sum,
+                                                              uint64_t *__restrict__ tile_pre, int *hdr) {
+    __shared__ uint64_t warp_tot[32];
+    __shared__ uint64_t carry_sh;
+    const int64_t si = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_sh = 0;
+    __syncthreads();
+    for (int64_t t0 = 0; t0 < tps; t0 += blockDim.x) {
+        const int64_t i = t0 + threadIdx.x;
+        uint64_t v = i < tps ? tile_sum[si * tps + i] : 0ULL, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_tot[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint64_t w = warp_tot[lane], z = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint64_t y = __shfl_up_sync(0xffffffffu, z, o);
+                if (lane >= o) z += y;
+            }
+            warp_tot[lane] = z - w;  // exclusive prefix of warp totals
+        }
+        __syncthreads();
+        const uint64_t carry = carry_sh;
+        const uint64_t incl = carry + warp_tot[wid] + x;
+        if (i < tps) tile_pre[si * tps + i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_sh = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const uint64_t need = (uint64_t)streams[si].n_sims * (uint64_t)nps;
+        if (carry_sh < need) atomicExch(&hdr[0], MCF_ERR_WINDOW_TOO_SMALL);
+    }
+}
+
+// one CTA per tile: exclusive scan of the chunk counts, then find replication boundaries
+__global__ void __launch_bounds__(256) plan_locate_kernel(const mcf_stream *__restrict__ streams, int64_t cps,
+                                                          int64_t tps, int64_t nps,
+                                                          const uint64_t *__restrict__ startmask,
+                                                          const uint64_t *__restrict__ emitmask,
+                                                          const uint8_t *__restrict__ exit_,
+                                                          const uint8_t *__restrict__ entry_true,
+                                                          const uint64_t *__restrict__ tile_pre,
+                                                          uint64_t *__restrict__ sim_start,
+                                                          uint64_t *__restrict__ stream_end) {
+    __shared__ uint32_t warp_tot[8];
+    const int64_t tile = blockIdx.x;
+    const int64_t si = tile / tps;
+    const int64_t base = tile * MCF_TILE + threadIdx.x * 4;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t es[4], ee[4];
+    uint32_t cnt[4], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint64_t m = mask_from(entry_true[base + k]);
+        es[k] = startmask[base + k] & m;
+        ee[k] = emitmask[base + k] & m;
+        cnt[k] = (uint32_t)popc64(ee[k]);
+        tot += cnt[k];
+    }
+    uint32_t x = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[wid] = x;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int w = 0; w < wid; w++) wbase += warp_tot[w];
+    uint64_t E = tile_pre[tile] + wbase + (x - tot);
+    const mcf_stream st = streams[si];
+    const int64_t first_chunk = base - si * cps;
+    if (first_chunk == 0) sim_start[st.first_sim] = 0ULL;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint64_t chunk_base = (uint64_t)(first_chunk + k) * MCF_CHUNK;
+        locate_in_chunk(chunk_base, es[k], ee[k], exit_[base + k], E, (uint64_t)nps, (uint64_t)st.n_sims,
+                        [&](uint64_t m, uint64_t pos) {
+                            if (m < (uint64_t)st.n_sims)
+                                sim_start[st.first_sim + (int64_t)m] = pos;
+                            else if (stream_end)
+                                stream_end[si] = pos;
+                        });
+        E += cnt[k];
+    }
+}
+
+// ====================================================================== replication pass
+template <int KIND>
+__global__ void __launch_bounds__(256) gbm_terminal_kernel(const mcf_stream *__restrict__ streams, int n_streams,
+                                                           int64_t n_total, int64_t n_steps, int64_t hint,
+                                                           const uint64_t *__restrict__ sim_start, SpecPack specs,
+                                                           double *__restrict__ out) {
+    __shared__ ZigShared sh;
+    const ZigTables t = load_zig_tables(sh);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    const int si = stream_of(streams, n_streams, i, hint);
+    const mcf_stream st = streams[si];
+    Cursor<KIND> cur;
+    cur.init(st, sim_start[i]);
+    if (specs.n == 1) {
+        out[i] = run_terminal(cur, t, n_steps, specs.g[0]);
+        return;
+    }
+    // several parameter sets on common random numbers (Greeks): the terminal log-price is affine
+    // in sum(Z), so one pass over the normals serves every set (all sets are affine-sum modes).
+    double zsum = 0.0;
+    for (int64_t k = 0; k < n_steps; k++) zsum = xadd(zsum, zig_normal(cur, t));
+    for (int s = 0; s < specs.n; s++) {
+        const GbmDerived &g = specs.g[s];
+        const double acc = xadd(xmul((double)n_steps, g.a), xmul(g.b, zsum));
+        double v;
+        if (g.mode == MCF_NORMAL_SUM) {
+            v = zsum;
+        } else if (g.mode == MCF_PATH_TERMINAL) {
+            v = exp(xadd(g.logs0, acc));
+        } else {
+            const double stv = xmul(g.s0, exp(acc));
+            if (g.mode == MCF_PORTFOLIO_GBM)
+                v = stv;
+            else
+                v = xmul(g.mode == MCF_BS_EURO_CALL ? fmax(xsub(stv, g.K), 0.0) : fmax(xsub(g.K, stv), 0.0), g.disc);
+        }
+        out[(int64_t)s * n_total + i] = v;
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) gbm_paths_kernel(const mcf_stream *__restrict__ streams, int n_streams,
+                                                        int64_t n_total, int64_t n_steps, int64_t hint,
+                                                        const uint64_t *__restrict__ sim_start, GbmDerived g,
+                                                        int time_major, double *__restrict__ paths) {
+    __shared__ ZigShared sh;
+    const ZigTables t = load_zig_tables(sh);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    const int si = stream_of(streams, n_streams, i, hint);
+    const mcf_stream st = streams[si];
+    Cursor<KIND> cur;
+    cur.init(st, sim_start[i]);
+    const int64_t stride = time_major ? n_total : 1;
+    double *p = paths + (time_major ? i : i * (n_steps + 1));
+    double acc = 0.0;
+    p[0] = exp(g.logs0);
+    for (int64_t k = 1; k <= n_steps; k++) {
+        acc = xadd(acc, xadd(g.a, xmul(g.b, zig_normal(cur, t))));
+        p[k * stride] = exp(xadd(g.logs0, acc));
+    }
+}
+
+// ================================================================================= C ABI
+static int g_last_cuda_error = 0;
+#define MCF_STR2(x) #x
+#define MCF_STR(x) MCF_STR2(x)
+#define MCF_CUDA_OK(x)                                   \
+    do {                                                 \
+        cudaError_t e__ = (x);                           \
+        if (e__ != cudaSuccess) {                        \
+            g_last_cuda_error = (int)e__;                \
+            return MCF_ERR_CUDA;                         \
+        }                                                \
+    } while (0)
+
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+template <int KIND>
+static int normal_plan_impl(const mcf_stream *d_streams, const PlanGeom &g, int64_t nps, int32_t iters, char *ws,
+                            uint64_t *d_sim_start, uint64_t *d_stream_end, cudaStream_t cs) {
+    int *hdr = (int *)ws;
+    uint64_t *sm = (uint64_t *)(ws + g.off_start), *em = (uint64_t *)(ws + g.off_emit);
+    uint64_t *tsum = (uint64_t *)(ws + g.off_tsum), *tpre = (uint64_t *)(ws + g.off_tpre);
+    uint8_t *ex = (uint8_t *)(ws + g.off_exit), *gen = (uint8_t *)(ws + g.off_gen), *ent = (uint8_t *)(ws + g.off_entry);
+    plan_init_kernel<<<1, 32, 0, cs>>>(hdr, iters);
+    constexpr int RUN = KIND == MCF_GEN_PCG64 ? 8 : 1;  // PCG64 pays an O(log n) jump per thread
+    const int64_t n_runs = g.n_chunks / RUN;
+    plan_scan_kernel<KIND, RUN><<<grid_for(n_runs, 256), 256, 0, cs>>>(d_streams, g.cps, n_runs, sm, em, ex, gen, hdr);
+    MCF_CUDA_OK(cudaGetLastError());
+    for (int it = 0; it < iters; it++) {
+        plan_resolve_kernel<KIND><<<grid_for(g.n_chunks, 256), 256, 0, cs>>>(d_streams, g.cps, g.n_chunks, sm, em, ex,
+                                                                             gen, ent, hdr, it);
+        MCF_CUDA_OK(cudaGetLastError());
+    }
+    plan_tile_count_kernel<<<(unsigned)g.n_tiles, 256, 0, cs>>>(em, ent, tsum);
+    MCF_CUDA_OK(cudaGetLastError());
+    plan_tile_scan_kernel<<<(unsigned)(g.n_chunks / g.cps), 1024, 0, cs>>>(d_streams, g.tps, nps, tsum, tpre, hdr);
+    MCF_CUDA_OK(cudaGetLastError());
+    plan_locate_kernel<<<(unsigned)g.n_tiles, 256, 0, cs>>>(d_streams, g.cps, g.tps, nps, sm, em, ex, ent, tpre,
+                                                           d_sim_start, d_stream_end);
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+extern "C" {
+
+int mcf_abi_version(void) { return MCF_ABI_VERSION; }
+
+const char *mcf_build_info(void) {
+    return "mcf_b200: sm_100a, CUDA " MCF_STR(CUDART_VERSION) ", built " __DATE__;
+}
+
+int mcf_last_cuda_error(void) { return g_last_cuda_error; }
+
+int mcf_pi_hits(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total, int64_t n_points,
+                  int32_t antithetic, int64_t sims_per_stream_hint, int64_t *d_hits, double *d_out, void *cuda_stream) {
+    if (!d_streams || n_streams <= 0 || n_total <= 0 || n_points <= 0 || !d_hits) return MCF_ERR_BAD_ARG;
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    const PiGeom pg = pi_geom(n_points, antithetic);
+    MCF_CUDA_OK(cudaMemsetAsync(d_hits, 0, sizeof(int64_t) * (size_t)n_total, cs));
+    const int64_t n_units = n_total * pg.parts;
+    int64_t blocks = (n_units + 7) / 8;  // 8 warps per CTA
+    const int64_t max_blocks = 148LL * 8 * 64;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (gen_kind == MCF_GEN_PCG64)
+        pi_kernel<MCF_GEN_PCG64><<<(unsigned)blocks, 256, 0, cs>>>(
+            d_streams, n_streams, n_total, pg.m, pg.draws_per_sim, pg.ppt, pg.parts, pg.weight, pg.extra,
+            sims_per_stream_hint, (unsigned long long *)d_hits);
+    else
+        pi_kernel<MCF_GEN_PHILOX><<<(unsigned)blocks, 256, 0, cs>>>(
+            d_streams, n_streams, n_total, pg.m, pg.draws_per_sim, pg.ppt, pg.parts, pg.weight, pg.extra,
+            sims_per_stream_hint, (unsigned long long *)d_hits);
+    MCF_CUDA_OK(cudaGetLastError());
+    if (d_out) {
+        pi_finalize_kernel<<<grid_for(n_total, 256), 256, 0, cs>>>((const unsigned long long *)d_hits, n_total,
+                                                                   (double)n_points, d_out);
+        MCF_CUDA_OK(cudaGetLastError());
+    }
+    return MCF_OK;
+}
+
+
+int64_t mcf_normal_plan_workspace_bytes(int32_t n_streams, int64_t max_sims_per_stream, int64_t normals_per_sim,
+                                        double slack) {
+    if (n_streams <= 0 || max_sims_per_stream <= 0 || normals_per_sim <= 0 || slack < 0) return MCF_ERR_BAD_ARG;
+    return plan_geom(n_streams, max_sims_per_stream, normals_per_sim, slack).total;
+}
+
+int mcf_normal_plan(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total,
+                      int64_t max_sims_per_stream, int64_t normals_per_sim, double slack, int32_t resolve_iters,
+                      void *d_workspace, int64_t workspace_bytes, uint64_t *d_sim_start, uint64_t *d_stream_end,
+                      void *cuda_stream) {
+    if (!d_streams || n_streams <= 0 || n_total <= 0 || max_sims_per_stream <= 0 || normals_per_sim <= 0 ||
+        !d_workspace || !d_sim_start || resolve_iters < 1 || resolve_iters > MCF_HDR_WORDS - 3)
+        return MCF_ERR_BAD_ARG;
+    const PlanGeom g = plan_geom(n_streams, max_sims_per_stream, normals_per_sim, slack);
+    if (workspace_bytes < g.total) return MCF_ERR_WORKSPACE_TOO_SMALL;
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    if (gen_kind == MCF_GEN_PCG64)
+        return normal_plan_impl<MCF_GEN_PCG64>(d_streams, g, normals_per_sim, resolve_iters, (char *)d_workspace,
+                                               d_sim_start, d_stream_end, cs);
+    return normal_plan_impl<MCF_GEN_PHILOX>(d_streams, g, normals_per_sim, resolve_iters, (char *)d_workspace,
+                                            d_sim_start, d_stream_end, cs);
+}
+
+
+int mcf_workspace_status(const void *d_workspace, void *cuda_stream) {
+    int hdr[MCF_HDR_WORDS];
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    MCF_CUDA_OK(cudaMemcpyAsync(hdr, d_workspace, sizeof(hdr), cudaMemcpyDeviceToHost, cs));
+    MCF_CUDA_OK(cudaStreamSynchronize(cs));
+    if (hdr[0] != 0) return hdr[0];
+    const int iters = hdr[MCF_HDR_WORDS - 1];
+    if (iters >= 1 && hdr[1 + iters - 1] != 0) return MCF_ERR_NOT_CONVERGED;
+    return MCF_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int mcf_gbm_terminal(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total, int64_t n_steps,
+                       int64_t sims_per_stream_hint, const uint64_t *d_sim_start, const mcf_gbm_spec *h_specs,
+                       int32_t n_specs, double *d_out, void *cuda_stream) {
+    if (!d_streams || n_streams <= 0 || n_total <= 0 || n_steps <= 0 || !d_sim_start || !h_specs || n_specs < 1 ||
+        n_specs > MCF_MAX_SPECS || !d_out)
+        return MCF_ERR_BAD_ARG;
+    SpecPack pack;
+    pack.n = n_specs;
+    for (int s = 0; s < n_specs; s++) {
+        int rc = derive_spec(h_specs[s], n_steps, &pack.g[s]);
+        if (rc) return rc;
+        const int m = h_specs[s].mode;
+        if (n_specs > 1 && (m == MCF_BS_AMER_CALL || m == MCF_BS_AMER_PUT || m == MCF_PORTFOLIO_LOG1P))
+            return MCF_ERR_BAD_ARG;  // path-dependent bodies take one parameter set per launch
+    }
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    if (gen_kind == MCF_GEN_PCG64)
+        gbm_terminal_kernel<MCF_GEN_PCG64><<<grid_for(n_total, 256), 256, 0, cs>>>(
+            d_streams, n_streams, n_total, n_steps, sims_per_stream_hint, d_sim_start, pack, d_out);
+    else
+        gbm_terminal_kernel<MCF_GEN_PHILOX><<<grid_for(n_total, 256), 256, 0, cs>>>(
+            d_streams, n_streams, n_total, n_steps, sims_per_stream_hint, d_sim_start, pack, d_out);
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+
+int mcf_gbm_paths(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total, int64_t n_steps,
+                    int64_t sims_per_stream_hint, const uint64_t *d_sim_start, const double *h_p4, int32_t time_major,
+                    double *d_paths, void *cuda_stream) {
+    if (!d_streams || n_streams <= 0 || n_total <= 0 || n_steps <= 0 || !d_sim_start || !h_p4 || !d_paths)
+        return MCF_ERR_BAD_ARG;
+    mcf_gbm_spec s;
+    memset(&s, 0, sizeof(s));
+    s.mode = MCF_PATH_TERMINAL;
+    for (int k = 0; k < 4; k++) s.p[k] = h_p4[k];
+    GbmDerived g;
+    derive_spec(s, n_steps, &g);
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    if (gen_kind == MCF_GEN_PCG64)
+        gbm_paths_kernel<MCF_GEN_PCG64><<<grid_for(n_total, 256), 256, 0, cs>>>(
+            d_streams, n_streams, n_total, n_steps, sims_per_stream_hint, d_sim_start, g, time_major, d_paths);
+    else
+        gbm_paths_kernel<MCF_GEN_PHILOX><<<grid_for(n_total, 256), 256, 0, cs>>>(
+            d_streams, n_streams, n_total, n_steps, sims_per_stream_hint, d_sim_start, g, time_major, d_paths);
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+
+}  // extern "C"

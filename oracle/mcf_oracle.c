@@ -32,6 +32,9 @@
 #include <string.h>
 
 #include "zig_tables_oracle.h"
+static const unsigned long long MCF_ZIG_KI[256] = {MCF_ZIG_KI_LIST};
+static const unsigned long long MCF_ZIG_WI_BITS[256] = {MCF_ZIG_WI_BITS_LIST};
+static const unsigned long long MCF_ZIG_FI_BITS[256] = {MCF_ZIG_FI_BITS_LIST};
 
 typedef unsigned __int128 u128;
 
