@@ -123,6 +123,88 @@ int mcf_gbm_paths(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_stre
                   int64_t sims_per_stream_hint, const uint64_t *d_sim_start, const double *h_p4, int32_t time_major, double *d_paths,
                   void *cuda_stream);
 
+/* ---- (3) Longstaff-Schwartz backward induction ------------------------------------------
+ * replaces _american_exercise_lsm (sims/black_scholes.py:109-193).  `d_paths_tm` is TIME-MAJOR:
+ * element (step t, path i) at d_paths_tm[t*n_paths + i] (what mcf_gbm_paths writes with
+ * time_major=1; mcf_transpose converts the (n_paths, n_steps+1) row-major matrix simulate_paths
+ * returns).  Per step t = n_steps-1 .. 1: mcf_lsm_reduce leaves the 8 normal-equation sums of the
+ * in-the-money paths in the first 8 doubles of the workspace (sum them across ranks when paths are
+ * sharded), mcf_lsm_apply solves the 3x3 system (pseudo-inverse, like lstsq) and exercises where
+ * intrinsic > fitted.  mcf_lsm runs the whole loop on one GPU. */
+int64_t mcf_lsm_workspace_bytes(int64_t n_paths);
+int mcf_lsm_begin(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K, int32_t is_put, void *d_workspace,
+                  int64_t workspace_bytes, void *cuda_stream);
+int mcf_lsm_reduce(const double *d_paths_tm, int64_t n_paths, int64_t t, double K, double r, double dt, int32_t is_put,
+                   void *d_workspace, void *cuda_stream);
+int mcf_lsm_apply(const double *d_paths_tm, int64_t n_paths, int64_t t, double K, int32_t is_put, void *d_workspace,
+                  void *cuda_stream);
+/* d_price_sum[0] = sum_i cash_flow_i*exp(-r*dt*exercise_i) over this rank's paths; d_price[0] = that / n_paths.
+ * Either may be NULL.  d_exercise_times (int32[n_paths], may be NULL) receives the exercise step of every path. */
+int mcf_lsm_finish(int64_t n_paths, double r, double dt, void *d_workspace, double *d_price_sum, double *d_price,
+                   int32_t *d_exercise_times, void *cuda_stream);
+int mcf_lsm(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K, double r, double dt, int32_t is_put,
+            void *d_workspace, int64_t workspace_bytes, double *d_price, int32_t *d_exercise_times, void *cuda_stream);
+/* (n_rows, n_cols) row-major -> (n_cols, n_rows) row-major */
+int mcf_transpose(const double *d_in, int64_t n_rows, int64_t n_cols, double *d_out, void *cuda_stream);
+
+/* ---- (4) StatsEngine reductions --------------------------------------------------------
+ * mcf_moments: ONE pass over x (stats_engine.py:734-742 isfinite mask folded into the load) giving
+ * everything mean/std/skew/kurtosis/ci_mean/chebyshev/markov/bias/mse need (stats_engine.py:767-1472):
+ *   out[0] n_finite  out[1] n_nan  out[2] n_posinf  out[3] n_neginf
+ *   out[4] mean      out[5] M2=sum (x-mean)^2   out[6] M3   out[7] M4      (finite values only)
+ *   out[8] sum (x-target)^2   out[9] sum x   out[10] min   out[11] max      (finite values only)
+ * Per-rank outputs merge on the host with the pairwise update formulas (see _stats_host.py). */
+#define MCF_MOMENTS_OUT 12
+int64_t mcf_moments_workspace_bytes(int64_t n);
+int mcf_moments(const double *d_x, int64_t n, double target, double *d_out, void *d_workspace, int64_t workspace_bytes,
+                void *cuda_stream);
+
+/* mcf_select: k order statistics (0-based ranks in the sorted order np.percentile uses: NaN last) by
+ * MSD radix selection, replaces the sort inside np.percentile (stats_engine.py:865,1197,1286;
+ * core.py:757).  With omit_nonfinite != 0, NaN and +-inf are excluded (nan_policy="omit").
+ * Multi-GPU: call begin, then per pass {hist on every rank; all-reduce(SUM, int64) the histogram
+ * block [mcf_select_hist_offset, +mcf_select_hist_bytes) of the workspace; choose}, then finish. */
+#define MCF_SELECT_MAX_RANKS 32
+int64_t mcf_select_workspace_bytes(void);
+int64_t mcf_select_hist_offset(void);
+int64_t mcf_select_hist_bytes(void);
+int32_t mcf_select_passes(void);
+int mcf_select_begin(const int64_t *h_ranks, int32_t k, void *d_workspace, int64_t workspace_bytes, void *cuda_stream);
+int mcf_select_hist(const double *d_x, int64_t n, int32_t omit_nonfinite, void *d_workspace, void *cuda_stream);
+int mcf_select_choose(void *d_workspace, void *cuda_stream);
+int mcf_select_finish(const void *d_workspace, double *d_out, void *cuda_stream);
+int mcf_select(const double *d_x, int64_t n, int32_t omit_nonfinite, const int64_t *h_ranks, int32_t k, double *d_out,
+               void *d_workspace, int64_t workspace_bytes, void *cuda_stream);
+
+/* Bootstrap means, replaces _bootstrap_means (stats_engine.py:1019-1041):
+ *   idx = rng.integers(0, n, size=(B, n)); means = x[idx].mean(axis=1)
+ * The index matrix is the sequence of ACCEPTED 32-bit slots of the stream (Lemire rejection decides each
+ * slot on its own value), so slots [slot_lo, slot_hi) can be processed independently:
+ *   mcf_bootstrap_count      : accepted slots per chunk + their scan; *d_total = accepted in the range
+ *   mcf_bootstrap_accumulate : regenerate the slots, gather x[idx], add into d_sums[ordinal / n] where
+ *                              ordinal = ordinal_base + (accepted slots before it in the range);
+ *                              ordinals >= B*n are ignored; the thread that produces ordinal B*n-1
+ *                              stores (slot index + 1) in *d_end_slot (stream consumption of the call).
+ * Multi-GPU: shard the slot range, all-gather the per-rank totals to get each rank's ordinal_base,
+ * all-reduce d_sums.  d_sums must be zeroed by the caller; mcf_bootstrap_finalize divides by n.
+ * Needs 2 <= n < 2^32 (NumPy's 32-bit path; n == 1 consumes no randomness). */
+int64_t mcf_bootstrap_workspace_bytes(int64_t n_slots, int32_t chunk_slots);
+int mcf_bootstrap_count(uint32_t gen_kind, const mcf_stream *d_stream, int64_t n, uint64_t slot_lo, uint64_t slot_hi,
+                        int32_t chunk_slots, void *d_workspace, int64_t workspace_bytes, uint64_t *d_total,
+                        void *cuda_stream);
+int mcf_bootstrap_accumulate(uint32_t gen_kind, const mcf_stream *d_stream, const double *d_x, int64_t n,
+                             int64_t n_resamples, uint64_t slot_lo, uint64_t slot_hi, int32_t chunk_slots,
+                             uint64_t ordinal_base, const void *d_workspace, int64_t workspace_bytes, double *d_sums,
+                             uint64_t *d_end_slot, void *cuda_stream);
+int mcf_bootstrap_finalize(double *d_sums, int64_t n_resamples, int64_t n, void *cuda_stream);
+/* *d_count = #{i : d_x[i] < value}  (BCa bias correction z0, stats_engine.py:1075-1078) */
+int mcf_count_less(const double *d_x, int64_t n, double value, int64_t *d_count, void *cuda_stream);
+/* nan_policy="omit" (_clean, stats_engine.py:734-742): d_out[0..*d_count) = finite values of d_x, order kept. */
+int64_t mcf_compact_workspace_bytes(int64_t n);
+int mcf_compact_finite(const double *d_x, int64_t n, double *d_out, int64_t *d_count, void *d_workspace,
+                       int64_t workspace_bytes, void *cuda_stream);
+int mcf_stats_last_cuda_error(void);
+
 #ifdef __cplusplus
 }
 #endif

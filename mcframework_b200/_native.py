@@ -35,7 +35,7 @@ class GbmSpec(C.Structure):
     _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32), ("p", C.c_double * 6)]
 
 
-_i32, _i64, _u32, _f64, _vp = C.c_int32, C.c_int64, C.c_uint32, C.c_double, C.c_void_p
+_i32, _i64, _u32, _u64, _f64, _vp = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_double, C.c_void_p
 
 #: name -> (restype, argtypes); every symbol include/mcf_b200.h declares
 SIGNATURES = {
@@ -48,6 +48,34 @@ SIGNATURES = {
     "mcf_workspace_status": (C.c_int, [_vp, _vp]),
     "mcf_gbm_terminal": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i64, _vp, C.POINTER(GbmSpec), _i32, _vp, _vp]),
     "mcf_gbm_paths": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i64, _vp, C.POINTER(_f64), _i32, _vp, _vp]),
+    # Longstaff-Schwartz
+    "mcf_lsm_workspace_bytes": (_i64, [_i64]),
+    "mcf_lsm_begin": (C.c_int, [_vp, _i64, _i64, _f64, _i32, _vp, _i64, _vp]),
+    "mcf_lsm_reduce": (C.c_int, [_vp, _i64, _i64, _f64, _f64, _f64, _i32, _vp, _vp]),
+    "mcf_lsm_apply": (C.c_int, [_vp, _i64, _i64, _f64, _i32, _vp, _vp]),
+    "mcf_lsm_finish": (C.c_int, [_i64, _f64, _f64, _vp, _vp, _vp, _vp, _vp]),
+    "mcf_lsm": (C.c_int, [_vp, _i64, _i64, _f64, _f64, _f64, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "mcf_transpose": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
+    # StatsEngine reductions
+    "mcf_moments_workspace_bytes": (_i64, [_i64]),
+    "mcf_moments": (C.c_int, [_vp, _i64, _f64, _vp, _vp, _i64, _vp]),
+    "mcf_select_workspace_bytes": (_i64, []),
+    "mcf_select_hist_offset": (_i64, []),
+    "mcf_select_hist_bytes": (_i64, []),
+    "mcf_select_passes": (_i32, []),
+    "mcf_select_begin": (C.c_int, [C.POINTER(_i64), _i32, _vp, _i64, _vp]),
+    "mcf_select_hist": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "mcf_select_choose": (C.c_int, [_vp, _vp]),
+    "mcf_select_finish": (C.c_int, [_vp, _vp, _vp]),
+    "mcf_select": (C.c_int, [_vp, _i64, _i32, C.POINTER(_i64), _i32, _vp, _vp, _i64, _vp]),
+    "mcf_bootstrap_workspace_bytes": (_i64, [_i64, _i32]),
+    "mcf_bootstrap_count": (C.c_int, [_u32, _vp, _i64, _u64, _u64, _i32, _vp, _i64, _vp, _vp]),
+    "mcf_bootstrap_accumulate": (C.c_int, [_u32, _vp, _vp, _i64, _i64, _u64, _u64, _i32, _u64, _vp, _i64, _vp, _vp, _vp]),
+    "mcf_bootstrap_finalize": (C.c_int, [_vp, _i64, _i64, _vp]),
+    "mcf_count_less": (C.c_int, [_vp, _i64, _f64, _vp, _vp]),
+    "mcf_compact_workspace_bytes": (_i64, [_i64]),
+    "mcf_compact_finite": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "mcf_stats_last_cuda_error": (C.c_int, []),
 }
 
 _lib = None
@@ -84,5 +112,5 @@ def check(fn: str, code: int):
     if code != OK:
         detail = ""
         if code == ERR_CUDA and _lib is not None:
-            detail = f"cudaError {_lib.mcf_last_cuda_error()}"
+            detail = f"cudaError {_lib.mcf_last_cuda_error() or _lib.mcf_stats_last_cuda_error()}"
         raise NativeError(fn, code, detail)

@@ -112,3 +112,51 @@ def parallel_layout(seed_seq, n: int, n_workers: int, chunks_per_worker: int = 8
     else:
         children = [np.random.SeedSequence() for _ in blocks]
     return StreamLayout(GEN_PHILOX, philox_records(children, blocks), n, blocks[0][1] - blocks[0][0])
+
+
+def generator_record(gen: np.random.Generator, first_sim: int = 0, n_sims: int = 1) -> tuple[int, np.ndarray]:
+    """``mcf_stream`` record of a Generator's CURRENT state (PCG64 or Philox bit generators)."""
+    st = gen.bit_generator.state
+    name = st.get("bit_generator")
+    if name == "PCG64":
+        return GEN_PCG64, pcg64_record(st, first_sim, n_sims)
+    if name == "Philox":
+        rec = np.zeros(1, dtype=STREAM_DTYPE)
+        rec["kind"] = GEN_PHILOX
+        # the device cursor addresses block (counter + (buffer_pos + p) // 4), lane (buffer_pos + p) % 4
+        rec["buf_pos"] = int(st["buffer_pos"])
+        rec["has_uint32"] = int(st["has_uint32"])
+        rec["uinteger"] = int(st["uinteger"])
+        rec["s"][0, :2] = st["state"]["key"]
+        rec["s"][0, 2:6] = st["state"]["counter"]
+        rec["first_sim"] = first_sim
+        rec["n_sims"] = n_sims
+        return GEN_PHILOX, rec
+    raise NotImplementedError(f"device streams support PCG64 and Philox bit generators, got {name!r}")
+
+
+def consume_draws(gen: np.random.Generator, draws: int) -> int:
+    """Advance ``gen`` by ``draws`` 64-bit outputs without producing them; returns the LAST of those outputs
+    (NumPy's buffered ``next_uint32`` needs its upper half).  PCG64: O(log n) jump.  Philox: counter arithmetic."""
+    if draws <= 0:
+        return 0
+    bg = gen.bit_generator
+    st = bg.state
+    if st["bit_generator"] == "PCG64":
+        bg.advance(draws - 1)
+        return int(bg.random_raw())
+    if st["bit_generator"] == "Philox":
+        q = int(st["buffer_pos"]) + draws  # position after consumption, in units of 64-bit outputs
+        ctr = sum(int(c) << (64 * i) for i, c in enumerate(st["state"]["counter"]))
+        blk = (q - 1) // 4  # block (relative to the counter) holding the last consumed output
+        if blk == 0:  # still inside the buffered block
+            last = int(st["buffer"][q - 1])
+            st["buffer_pos"] = q
+            bg.state = st
+            return last
+        new_ctr = (ctr + blk - 1) % (1 << 256)  # pre-increment: the next generated block is new_ctr + 1
+        st["state"]["counter"] = np.array([(new_ctr >> (64 * i)) & _M64 for i in range(4)], dtype=np.uint64)
+        st["buffer_pos"] = 4
+        bg.state = st
+        return int(bg.random_raw((q - 1) % 4 + 1)[-1])
+    raise NotImplementedError(st["bit_generator"])

@@ -1,0 +1,1136 @@
+// mcf_stats.cu -- sm_100a kernels + C ABI for the StatsEngine reductions and the Longstaff-Schwartz sweep.
+//
+//   moments   : one HBM pass (8 B/element): per-thread shifted power sums -> Chan/Pebay merges in
+//               warp shuffles, shared memory and a one-CTA final merge (deterministic order).
+//   select    : k simultaneous order statistics by MSD radix selection on order-preserving keys;
+//               8 passes x 8-bit digits, histograms in shared memory with warp-aggregated atomics,
+//               rank/prefix bookkeeping stays on the device (no host round trip between passes).
+//   bootstrap : NumPy's (B, n) Lemire index matrix is "the accepted 32-bit slots of one stream, in
+//               order"; pass A counts accepted slots per chunk, a scan gives every chunk its first
+//               ordinal, pass B regenerates the slots, gathers x[idx] (8 independent loads in
+//               flight per thread) and adds into the resample the ordinal belongs to.  Indices
+//               never touch HBM.
+//   lsm       : per time step one reduction sweep (8 sums of the normal equations in a shifted
+//               basis) + a 3x3 pseudo-inverse solve + one decision sweep; state per path is
+//               (exercise step, cash flow at exercise).
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "mcf_stats_device.cuh"
+
+using namespace mcf;
+
+static int g_stats_last_cuda_error = 0;
+extern "C" int mcf_stats_last_cuda_error(void) { return g_stats_last_cuda_error; }
+#define MCF_CUDA_OK(x)                          \
+    do {                                        \
+        cudaError_t e__ = (x);                  \
+        if (e__ != cudaSuccess) {               \
+            g_stats_last_cuda_error = (int)e__; \
+            return MCF_ERR_CUDA;                \
+        }                                       \
+    } while (0)
+
+static inline int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
+static inline int grid_cap(int64_t work_items, int per_block, int cap) {
+    int64_t g = (work_items + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+#define MCF_SM_COUNT 148
+
+// ======================================================================================= moments
+struct MomentsPartial {
+    Moments m;
+    double sq_target, sum, n_nan, n_pinf, n_ninf, vmin, vmax;
+};
+
+__device__ __forceinline__ double shfl_xor_d(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+
+__device__ __forceinline__ MomentsPartial partial_shfl_xor(const MomentsPartial &p, int o) {
+    MomentsPartial q;
+    q.m.n = shfl_xor_d(p.m.n, o);
+    q.m.mean = shfl_xor_d(p.m.mean, o);
+    q.m.m2 = shfl_xor_d(p.m.m2, o);
+    q.m.m3 = shfl_xor_d(p.m.m3, o);
+    q.m.m4 = shfl_xor_d(p.m.m4, o);
+    q.sq_target = shfl_xor_d(p.sq_target, o);
+    q.sum = shfl_xor_d(p.sum, o);
+    q.n_nan = shfl_xor_d(p.n_nan, o);
+    q.n_pinf = shfl_xor_d(p.n_pinf, o);
+    q.n_ninf = shfl_xor_d(p.n_ninf, o);
+    q.vmin = shfl_xor_d(p.vmin, o);
+    q.vmax = shfl_xor_d(p.vmax, o);
+    return q;
+}
+
+// merge(lower-indexed, higher-indexed): the same operand order on every lane keeps the result
+// bit-identical across lanes (the update formulas are not symmetric in rounding).
+__device__ __forceinline__ MomentsPartial partial_merge(const MomentsPartial &a, const MomentsPartial &b) {
+    MomentsPartial r;
+    r.m = moments_merge(a.m, b.m);
+    r.sq_target = a.sq_target + b.sq_target;
+    r.sum = a.sum + b.sum;
+    r.n_nan = a.n_nan + b.n_nan;
+    r.n_pinf = a.n_pinf + b.n_pinf;
+    r.n_ninf = a.n_ninf + b.n_ninf;
+    r.vmin = fmin(a.vmin, b.vmin);
+    r.vmax = fmax(a.vmax, b.vmax);
+    return r;
+}
+
+__device__ __forceinline__ MomentsPartial partial_warp_reduce(MomentsPartial p) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        MomentsPartial q = partial_shfl_xor(p, o);
+        p = (lane & o) ? partial_merge(q, p) : partial_merge(p, q);
+    }
+    return p;
+}
+
+struct MomAcc {
+    double c, n, s1, s2, s3, s4, sq, n_nan, n_pinf, n_ninf, vmin, vmax;
+    bool have_c;
+};
+
+__device__ __forceinline__ void mom_add(MomAcc &a, double x, double target) {
+    const uint64_t b = double_bits(x);
+    if (bits_nonfinite(b)) {
+        if (b & 0x000fffffffffffffULL)
+            a.n_nan += 1.0;
+        else if (b >> 63)
+            a.n_ninf += 1.0;
+        else
+            a.n_pinf += 1.0;
+        return;
+    }
+    if (!a.have_c) {
+        a.c = x;
+        a.have_c = true;
+    }
+    const double d = x - a.c, d2 = d * d, e = x - target;
+    a.n += 1.0;
+    a.s1 += d;
+    a.s2 += d2;
+    a.s3 = fma(d2, d, a.s3);
+    a.s4 = fma(d2, d2, a.s4);
+    a.sq = fma(e, e, a.sq);
+    a.vmin = fmin(a.vmin, x);
+    a.vmax = fmax(a.vmax, x);
+}
+
+__global__ void __launch_bounds__(256) moments_kernel(const double *__restrict__ x, int64_t n, double target,
+                                                      MomentsPartial *__restrict__ partials) {
+    MomAcc a;
+    a.c = 0.0;
+    a.have_c = false;
+    a.n = a.s1 = a.s2 = a.s3 = a.s4 = a.sq = a.n_nan = a.n_pinf = a.n_ninf = 0.0;
+    a.vmin = bits_to_double(0x7ff0000000000000ULL);
+    a.vmax = bits_to_double(0xfff0000000000000ULL);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    // 16-byte vector loads when the base pointer allows it
+    if ((((uintptr_t)x) & 15) == 0) {
+        const double2 *x2 = reinterpret_cast<const double2 *>(x);
+        const int64_t n2 = n >> 1;
+        int64_t i = tid;
+        for (; i + 3 * nthr < n2; i += 4 * nthr) {  // 4 independent 16 B loads in flight
+            const double2 v0 = __ldg(&x2[i]), v1 = __ldg(&x2[i + nthr]), v2 = __ldg(&x2[i + 2 * nthr]),
+                          v3 = __ldg(&x2[i + 3 * nthr]);
+            mom_add(a, v0.x, target);
+            mom_add(a, v0.y, target);
+            mom_add(a, v1.x, target);
+            mom_add(a, v1.y, target);
+            mom_add(a, v2.x, target);
+            mom_add(a, v2.y, target);
+            mom_add(a, v3.x, target);
+            mom_add(a, v3.y, target);
+        }
+        for (; i < n2; i += nthr) {
+            const double2 v = __ldg(&x2[i]);
+            mom_add(a, v.x, target);
+            mom_add(a, v.y, target);
+        }
+        if ((n & 1) && tid == 0) mom_add(a, x[n - 1], target);
+    } else {
+        for (int64_t i = tid; i < n; i += nthr) mom_add(a, x[i], target);
+    }
+    MomentsPartial p;
+    p.m = moments_from_shifted(a.n, a.c, a.s1, a.s2, a.s3, a.s4);
+    p.sq_target = a.sq;
+    p.sum = a.n > 0.0 ? fma(a.n, a.c, a.s1) : 0.0;
+    p.n_nan = a.n_nan;
+    p.n_pinf = a.n_pinf;
+    p.n_ninf = a.n_ninf;
+    p.vmin = a.vmin;
+    p.vmax = a.vmax;
+    p = partial_warp_reduce(p);
+    __shared__ MomentsPartial sh[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sh[wid] = p;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        MomentsPartial r = sh[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = partial_merge(r, sh[w]);
+        partials[blockIdx.x] = r;
+    }
+}
+
+__global__ void __launch_bounds__(32) moments_final_kernel(const MomentsPartial *__restrict__ partials, int n_partials,
+                                                           double *__restrict__ out) {
+    // one warp: lane l merges partials l, l+32, ... in order, then the warp tree (fixed order => deterministic)
+    const int lane = threadIdx.x;
+    MomentsPartial p;
+    p.m = moments_empty();
+    p.sq_target = p.sum = p.n_nan = p.n_pinf = p.n_ninf = 0.0;
+    p.vmin = bits_to_double(0x7ff0000000000000ULL);
+    p.vmax = bits_to_double(0xfff0000000000000ULL);
+    for (int i = lane; i < n_partials; i += 32) p = partial_merge(p, partials[i]);
+    p = partial_warp_reduce(p);
+    if (lane == 0) {
+        out[0] = p.m.n;
+        out[1] = p.n_nan;
+        out[2] = p.n_pinf;
+        out[3] = p.n_ninf;
+        out[4] = p.m.mean;
+        out[5] = p.m.m2;
+        out[6] = p.m.m3;
+        out[7] = p.m.m4;
+        out[8] = p.sq_target;
+        out[9] = p.sum;
+        out[10] = p.vmin;
+        out[11] = p.vmax;
+    }
+}
+
+// ======================================================================================== select
+#define SEL_BITS 8
+#define SEL_BINS (1 << SEL_BITS)
+#define SEL_PASSES (64 / SEL_BITS)
+
+struct SelectState {
+    int32_t k, n_uniq, pass, pad;
+    int64_t rank[MCF_SELECT_MAX_RANKS];      // remaining rank inside the current prefix
+    uint64_t prefix[MCF_SELECT_MAX_RANKS];   // bits decided so far (right aligned)
+    int32_t uniq_of[MCF_SELECT_MAX_RANKS];   // rank -> index into uniq[]
+    uint64_t uniq[MCF_SELECT_MAX_RANKS];     // sorted distinct prefixes
+};
+
+struct SelectGeom {
+    int64_t off_state, off_hist, hist_bytes, total;
+};
+static inline SelectGeom select_geom() {
+    SelectGeom g;
+    g.off_state = 0;
+    g.off_hist = align256((int64_t)sizeof(SelectState));
+    g.hist_bytes = (int64_t)MCF_SELECT_MAX_RANKS * SEL_BINS * 8;
+    g.total = align256(g.off_hist + g.hist_bytes);
+    return g;
+}
+
+__global__ void select_init_kernel(SelectState *st, unsigned long long *hist, SelectState init) {
+    for (int i = threadIdx.x; i < MCF_SELECT_MAX_RANKS * SEL_BINS; i += blockDim.x) hist[i] = 0ULL;
+    if (threadIdx.x == 0) *st = init;
+}
+
+__global__ void __launch_bounds__(512) select_hist_kernel(const double *__restrict__ x, int64_t n, int omit,
+                                                          const SelectState *__restrict__ st,
+                                                          unsigned long long *__restrict__ hist) {
+    __shared__ unsigned int sh_hist[MCF_SELECT_MAX_RANKS * SEL_BINS];
+    __shared__ uint64_t sh_uniq[MCF_SELECT_MAX_RANKS];
+    const int n_uniq = st->n_uniq, pass = st->pass;
+    for (int i = threadIdx.x; i < n_uniq * SEL_BINS; i += blockDim.x) sh_hist[i] = 0u;
+    if (threadIdx.x < n_uniq) sh_uniq[threadIdx.x] = st->uniq[threadIdx.x];
+    __syncthreads();
+    const int shift = 64 - SEL_BITS * (pass + 1);  // digit position of this pass
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = tid - (threadIdx.x & 31); i0 < n; i0 += nthr) {  // warp-uniform trip count
+        const int64_t i = i0 + (threadIdx.x & 31);
+        int slot = -1;
+        if (i < n) {
+            const uint64_t key = select_key(__ldg(&x[i]), omit);
+            const unsigned digit = (unsigned)(key >> shift) & (SEL_BINS - 1);
+            if (pass == 0) {
+                slot = (int)digit;
+            } else {
+                const uint64_t pre = key >> (shift + SEL_BITS);
+                int lo = 0, hi = n_uniq - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (sh_uniq[mid] < pre)
+                        lo = mid + 1;
+                    else
+                        hi = mid;
+                }
+                if (sh_uniq[lo] == pre) slot = lo * SEL_BINS + (int)digit;
+            }
+        }
+        // warp-aggregated shared-memory atomics: one add per distinct bin per warp
+        const unsigned peers = __match_any_sync(0xffffffffu, slot);
+        if (slot >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh_hist[slot], __popc(peers));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_uniq * SEL_BINS; i += blockDim.x) {
+        const unsigned v = sh_hist[i];
+        if (v) atomicAdd(&hist[i], (unsigned long long)v);
+    }
+}
+
+// one CTA: every rank walks the histogram of its prefix, picks its digit, then prefixes are re-uniqued
+__global__ void select_choose_kernel(SelectState *st, unsigned long long *hist) {
+    __shared__ SelectState s;
+    if (threadIdx.x == 0) s = *st;
+    __syncthreads();
+    if (threadIdx.x < s.k) {
+        const int r = threadIdx.x;
+        const unsigned long long *h = hist + (size_t)s.uniq_of[r] * SEL_BINS;
+        int64_t rem = s.rank[r];
+        int d = 0;
+        for (; d < SEL_BINS - 1; d++) {
+            const int64_t c = (int64_t)h[d];
+            if (rem < c) break;
+            rem -= c;
+        }
+        s.rank[r] = rem;
+        s.prefix[r] = (s.prefix[r] << SEL_BITS) | (uint64_t)d;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // insertion sort of the distinct prefixes (k <= 32)
+        int nu = 0;
+        for (int r = 0; r < s.k; r++) {
+            const uint64_t p = s.prefix[r];
+            int pos = 0;
+            bool found = false;
+            for (; pos < nu; pos++) {
+                if (s.uniq[pos] == p) {
+                    found = true;
+                    break;
+                }
+                if (s.uniq[pos] > p) break;
+            }
+            if (!found) {
+                for (int j = nu; j > pos; j--) s.uniq[j] = s.uniq[j - 1];
+                s.uniq[pos] = p;
+                nu++;
+            }
+        }
+        for (int r = 0; r < s.k; r++)
+            for (int u = 0; u < nu; u++)
+                if (s.uniq[u] == s.prefix[r]) s.uniq_of[r] = u;
+        s.n_uniq = nu;
+        s.pass += 1;
+        *st = s;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < MCF_SELECT_MAX_RANKS * SEL_BINS; i += blockDim.x) hist[i] = 0ULL;
+}
+
+__global__ void select_finish_kernel(const SelectState *st, double *out) {
+    if (threadIdx.x < st->k) out[threadIdx.x] = select_unkey(st->prefix[threadIdx.x]);
+}
+
+// ===================================================================================== bootstrap
+struct BootGeom {
+    int64_t n_chunks, n_blocks;
+    int64_t off_counts, off_bsum, off_bbase, off_total, total;
+};
+#define BOOT_THREADS 256
+static inline BootGeom boot_geom(int64_t n_slots, int32_t chunk_slots) {
+    BootGeom g;
+    g.n_chunks = (n_slots + chunk_slots - 1) / chunk_slots;
+    g.n_blocks = (g.n_chunks + BOOT_THREADS - 1) / BOOT_THREADS;
+    int64_t o = 0;
+    g.off_total = o;
+    o += 256;
+    g.off_counts = o;
+    o = align256(o + g.n_blocks * BOOT_THREADS * 4);
+    g.off_bsum = o;
+    o = align256(o + g.n_blocks * 8);
+    g.off_bbase = o;
+    o = align256(o + g.n_blocks * 8);
+    g.total = o;
+    return g;
+}
+
+// Walks the 32-bit slots [s0, s1) of one stream in order.
+template <int KIND>
+struct SlotWalker {
+    Cursor<KIND> cur;
+    uint64_t v;
+    uint32_t has, uinteger;
+    bool have_v;
+    __device__ __forceinline__ void init(const mcf_stream &st, uint64_t s0) {
+        has = st.has_uint32 ? 1u : 0u;
+        uinteger = st.uinteger;
+        const uint64_t t0 = s0 >= has ? s0 - has : 0;
+        cur.init(st, t0 >> 1);
+        have_v = false;
+        v = 0;
+    }
+    __device__ __forceinline__ uint32_t get(uint64_t s) {
+        if (has && s == 0) return uinteger;
+        const uint64_t t = s - has;
+        if (!(t & 1ULL) || !have_v) {
+            v = cur.next64();
+            have_v = true;
+        }
+        return (t & 1ULL) ? (uint32_t)(v >> 32) : (uint32_t)v;
+    }
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(BOOT_THREADS) boot_count_kernel(const mcf_stream *__restrict__ stream, uint32_t n,
+                                                                  uint64_t slot_lo, uint64_t slot_hi, int chunk_slots,
+                                                                  int64_t n_chunks, uint32_t *__restrict__ counts,
+                                                                  unsigned long long *__restrict__ block_sum) {
+    const int64_t chunk = (int64_t)blockIdx.x * BOOT_THREADS + threadIdx.x;
+    uint32_t cnt = 0;
+    if (chunk < n_chunks) {
+        const SlotRule rule = slot_rule(n);
+        const uint64_t s0 = slot_lo + (uint64_t)chunk * (uint64_t)chunk_slots;
+        uint64_t s1 = s0 + (uint64_t)chunk_slots;
+        if (s1 > slot_hi) s1 = slot_hi;
+        if (rule.threshold == 0) {
+            cnt = (uint32_t)(s1 - s0);
+        } else {
+            const mcf_stream st = *stream;
+            SlotWalker<KIND> w;
+            w.init(st, s0);
+            for (uint64_t s = s0; s < s1; s++) {
+                uint32_t idx;
+                cnt += slot_accept(rule, w.get(s), idx) ? 1u : 0u;
+            }
+        }
+    }
+    counts[chunk] = cnt;  // counts[] is padded to n_blocks * BOOT_THREADS
+    __shared__ uint32_t sh[BOOT_THREADS / 32];
+    uint32_t v = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w2 = 0; w2 < BOOT_THREADS / 32; w2++) t += sh[w2];
+        block_sum[blockIdx.x] = t;
+    }
+}
+
+// one CTA: exclusive scan of u64 values; total written to *total
+__global__ void __launch_bounds__(1024) scan_u64_kernel(const unsigned long long *__restrict__ in, int64_t n,
+                                                        unsigned long long *__restrict__ out,
+                                                        unsigned long long *__restrict__ total) {
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long carry_sh;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_sh = 0;
+    __syncthreads();
+    for (int64_t t0 = 0; t0 < n; t0 += blockDim.x) {
+        const int64_t i = t0 + threadIdx.x;
+        const unsigned long long v = i < n ? in[i] : 0ULL;
+        unsigned long long x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_tot[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            const unsigned long long w = warp_tot[lane];
+            unsigned long long z = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xffffffffu, z, o);
+                if (lane >= o) z += y;
+            }
+            warp_tot[lane] = z - w;
+        }
+        __syncthreads();
+        const unsigned long long incl = carry_sh + warp_tot[wid] + x;
+        if (i < n) out[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_sh = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry_sh;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(BOOT_THREADS) boot_accumulate_kernel(
+    const mcf_stream *__restrict__ stream, const double *__restrict__ x, uint32_t n, uint64_t n_resamples,
+    uint64_t slot_lo, uint64_t slot_hi, int chunk_slots, int64_t n_chunks, uint64_t ordinal_base,
+    const uint32_t *__restrict__ counts, const unsigned long long *__restrict__ block_base, double *__restrict__ sums,
+    unsigned long long *__restrict__ end_slot) {
+    __shared__ uint32_t warp_tot[BOOT_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t chunk = (int64_t)blockIdx.x * BOOT_THREADS + threadIdx.x;
+    // block-exclusive scan of the per-chunk accepted counts
+    const uint32_t cnt = counts[chunk];
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int w2 = 0; w2 < wid; w2++) wbase += warp_tot[w2];
+    uint64_t ord = ordinal_base + block_base[blockIdx.x] + wbase + (incl - cnt);
+    const uint64_t total_needed = n_resamples * (uint64_t)n;
+
+    double acc = 0.0;
+    uint64_t b = 0;
+    bool touched = false, flushed = false;
+    if (chunk < n_chunks && cnt > 0 && ord < total_needed) {
+        const SlotRule rule = slot_rule(n);
+        const mcf_stream st = *stream;
+        const uint64_t s0 = slot_lo + (uint64_t)chunk * (uint64_t)chunk_slots;
+        uint64_t s1 = s0 + (uint64_t)chunk_slots;
+        if (s1 > slot_hi) s1 = slot_hi;
+        b = ord / n;
+        uint64_t next_boundary = (b + 1) * (uint64_t)n;
+        SlotWalker<KIND> w;
+        w.init(st, s0);
+        bool done = false;
+        for (uint64_t sb = s0; sb < s1 && !done; sb += 8) {
+            uint32_t idx[8];
+            bool ok[8];
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint64_t s = sb + j;
+                ok[j] = false;
+                idx[j] = 0;
+                if (s < s1) ok[j] = slot_accept(rule, w.get(s), idx[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = ok[j] ? __ldg(&x[idx[j]]) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (ok[j] && !done) {
+                    if (ord == next_boundary) {
+                        atomicAdd(&sums[b], acc);
+                        acc = 0.0;
+                        flushed = true;
+                        b++;
+                        next_boundary += n;
+                    }
+                    acc += v[j];
+                    touched = true;
+                    ord++;
+                    if (ord == total_needed) {
+                        *end_slot = sb + j + 1;  // slots consumed by the whole (B, n) draw
+                        done = true;
+                    }
+                }
+            }
+        }
+    }
+    // common case: the whole warp stayed inside one resample -> one atomic per warp
+    const uint64_t b0 = __shfl_sync(0xffffffffu, b, 0);
+    const bool simple = __all_sync(0xffffffffu, !touched || (b == b0 && !flushed));
+    if (simple) {
+        double t = touched ? acc : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        // lanes that did not touch anything may carry a stale b; use the first touched lane's resample
+        const unsigned tm = __ballot_sync(0xffffffffu, touched);
+        if (tm) {
+            const uint64_t bt = __shfl_sync(0xffffffffu, b, __ffs(tm) - 1);
+            if (lane == 0) atomicAdd(&sums[bt], t);
+        }
+    } else if (touched) {
+        atomicAdd(&sums[b], acc);
+    }
+}
+
+__global__ void boot_finalize_kernel(double *__restrict__ sums, int64_t B, double n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) sums[i] = __ddiv_rn(sums[i], n);
+}
+
+// =========================================================================================== lsm
+struct LsmState {
+    double sums[8];    // n, Su, Su2, Su3, Su4, Sy, Suy, Su2y   (u = (S-K)/K)
+    double coef[3];    // fitted = coef0 + coef1*u + coef2*u^2
+    int32_t have_fit;  // 0: no in-the-money path at this step (or fit skipped)
+    int32_t pad;
+    double price_sum;
+};
+
+struct LsmGeom {
+    int64_t off_state, off_partials, off_ex, off_cf, total;
+    int n_blocks;
+};
+#define LSM_THREADS 256
+static inline LsmGeom lsm_geom(int64_t n_paths) {
+    LsmGeom g;
+    g.n_blocks = grid_cap(n_paths, LSM_THREADS * 4, MCF_SM_COUNT * 8);
+    int64_t o = 0;
+    g.off_state = o;
+    o = align256(o + (int64_t)sizeof(LsmState));
+    g.off_partials = o;
+    o = align256(o + (int64_t)g.n_blocks * 8 * 8);
+    g.off_ex = o;
+    o = align256(o + n_paths * 4);
+    g.off_cf = o;
+    o = align256(o + n_paths * 8);
+    g.total = o;
+    return g;
+}
+
+__device__ __forceinline__ double lsm_intrinsic(double s, double K, int is_put) {
+    return is_put ? fmax(K - s, 0.0) : fmax(s - K, 0.0);
+}
+
+__global__ void __launch_bounds__(LSM_THREADS) lsm_init_kernel(const double *__restrict__ s_T, int64_t n_paths,
+                                                               int32_t n_steps, double K, int is_put,
+                                                               int32_t *__restrict__ ex, double *__restrict__ cf) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_paths; i += (int64_t)gridDim.x * blockDim.x) {
+        ex[i] = n_steps;
+        cf[i] = lsm_intrinsic(s_T[i], K, is_put);
+    }
+}
+
+// sweep 1 of step t: sums of the normal equations over in-the-money paths
+__global__ void __launch_bounds__(LSM_THREADS) lsm_reduce_kernel(const double *__restrict__ s_t, int64_t n_paths,
+                                                                 int32_t t, double K, double rdt, int is_put,
+                                                                 const int32_t *__restrict__ ex,
+                                                                 const double *__restrict__ cf,
+                                                                 double *__restrict__ partials) {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = 0.0;
+    const double invK = 1.0 / K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_paths; i += (int64_t)gridDim.x * blockDim.x) {
+        const double s = __ldg(&s_t[i]);
+        if (lsm_intrinsic(s, K, is_put) > 0.0) {
+            const double y = cf[i] * exp(-rdt * (double)(ex[i] - t));
+            const double u = (s - K) * invK, u2 = u * u;
+            a[0] += 1.0;
+            a[1] += u;
+            a[2] += u2;
+            a[3] = fma(u2, u, a[3]);
+            a[4] = fma(u2, u2, a[4]);
+            a[5] += y;
+            a[6] = fma(u, y, a[6]);
+            a[7] = fma(u2, y, a[7]);
+        }
+    }
+    __shared__ double sh[LSM_THREADS / 32][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        double v = a[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[wid][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double v = 0.0;
+        for (int w2 = 0; w2 < LSM_THREADS / 32; w2++) v += sh[w2][threadIdx.x];
+        partials[(size_t)blockIdx.x * 8 + threadIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) lsm_sum_partials_kernel(const double *__restrict__ partials, int n_blocks,
+                                                               LsmState *__restrict__ st) {
+    // 8 warps, warp k sums column k in a fixed order
+    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+    double v = 0.0;
+    for (int b = lane; b < n_blocks; b += 32) v += partials[(size_t)b * 8 + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) st->sums[k] = v;
+}
+
+// symmetric 3x3 eigen-decomposition (cyclic Jacobi) -> pseudo-inverse solve with lstsq's rcond=eps*max(M,N) spirit
+__device__ void lsm_solve3(const double G[3][3], const double rhs[3], double n_rows, double coef[3]) {
+    double A[3][3], V[3][3];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            A[i][j] = G[i][j];
+            V[i][j] = i == j ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < 30; sweep++) {
+        const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        if (off == 0.0) break;
+        for (int p = 0; p < 2; p++)
+            for (int q = p + 1; q < 3; q++) {
+                if (A[p][q] == 0.0) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+                const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
+                for (int k = 0; k < 3; k++) {
+                    const double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - s * akq;
+                    A[k][q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < 3; k++) {
+                    const double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - s * aqk;
+                    A[q][k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; k++) {
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - s * vkq;
+                    V[k][q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    double lmax = fmax(fmax(fabs(A[0][0]), fabs(A[1][1])), fabs(A[2][2]));
+    // singular values of X are sqrt(eigenvalues of X^T X); lstsq drops s < eps*max(M,N)*s_max
+    const double rc = 2.220446049250313e-16 * fmax(n_rows, 3.0);
+    const double cutoff = lmax * rc * rc;
+    coef[0] = coef[1] = coef[2] = 0.0;
+    for (int e = 0; e < 3; e++) {
+        const double lam = A[e][e];
+        if (lam > cutoff && lam > 0.0) {
+            const double proj = (V[0][e] * rhs[0] + V[1][e] * rhs[1] + V[2][e] * rhs[2]) / lam;
+            for (int i = 0; i < 3; i++) coef[i] += V[i][e] * proj;
+        }
+    }
+}
+
+__global__ void lsm_solve_kernel(LsmState *st) {
+    if (threadIdx.x != 0) return;
+    const double *s = st->sums;
+    if (s[0] <= 0.0) {
+        st->have_fit = 0;
+        return;
+    }
+    // rescale u by its rms so the Gram matrix is well conditioned; fitted values are basis independent
+    const double scale = s[2] > 0.0 ? sqrt(s[2] / s[0]) : 1.0;
+    const double i1 = 1.0 / scale, i2 = i1 * i1, i3 = i2 * i1, i4 = i2 * i2;
+    const double G[3][3] = {{s[0], s[1] * i1, s[2] * i2}, {s[1] * i1, s[2] * i2, s[3] * i3}, {s[2] * i2, s[3] * i3, s[4] * i4}};
+    const double rhs[3] = {s[5], s[6] * i1, s[7] * i2};
+    double c[3];
+    lsm_solve3(G, rhs, s[0], c);
+    st->coef[0] = c[0];
+    st->coef[1] = c[1] * i1;
+    st->coef[2] = c[2] * i2;
+    st->have_fit = 1;
+}
+
+// sweep 2 of step t: exercise where intrinsic > fitted continuation
+__global__ void __launch_bounds__(LSM_THREADS) lsm_apply_kernel(const double *__restrict__ s_t, int64_t n_paths, int32_t t,
+                                                                double K, int is_put, const LsmState *__restrict__ st,
+                                                                int32_t *__restrict__ ex, double *__restrict__ cf) {
+    if (!st->have_fit) return;
+    const double c0 = st->coef[0], c1 = st->coef[1], c2 = st->coef[2], invK = 1.0 / K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_paths; i += (int64_t)gridDim.x * blockDim.x) {
+        const double s = __ldg(&s_t[i]);
+        const double intr = lsm_intrinsic(s, K, is_put);
+        if (intr > 0.0) {
+            const double u = (s - K) * invK;
+            const double fitted = fma(fma(c2, u, c1), u, c0);
+            if (intr > fitted) {
+                ex[i] = t;
+                cf[i] = intr;
+            }
+        }
+    }
+}
+
+// discounted cash flows: per-block partial sums (column 0 of partials)
+__global__ void __launch_bounds__(LSM_THREADS) lsm_price_kernel(int64_t n_paths, double rdt, const int32_t *__restrict__ ex,
+                                                                const double *__restrict__ cf,
+                                                                double *__restrict__ partials) {
+    double a = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_paths; i += (int64_t)gridDim.x * blockDim.x)
+        a += cf[i] * exp(-rdt * (double)ex[i]);
+    __shared__ double sh[LSM_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double v = 0.0;
+        if (threadIdx.x == 0)
+            for (int w2 = 0; w2 < LSM_THREADS / 32; w2++) v += sh[w2];
+        partials[(size_t)blockIdx.x * 8 + threadIdx.x] = v;
+    }
+}
+
+__global__ void lsm_price_final_kernel(const LsmState *st, double n_paths, double *price_sum_out, double *price_out) {
+    if (threadIdx.x == 0) {
+        if (price_sum_out) *price_sum_out = st->sums[0];
+        if (price_out) *price_out = st->sums[0] / n_paths;
+    }
+}
+
+// (n_rows, n_cols) row-major -> (n_cols, n_rows) row-major, 32x32 tiles through shared memory
+__global__ void __launch_bounds__(256) transpose_kernel(const double *__restrict__ in, int64_t n_rows, int64_t n_cols,
+                                                        int64_t tiles_x, double *__restrict__ out) {
+    __shared__ double tile[32][33];
+    const int64_t tile_id = blockIdx.x;  // 1-D grid: either dimension may exceed the 65535 limit of grid.y
+    const int64_t r0 = (tile_id / tiles_x) * 32, c0 = (tile_id % tiles_x) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int k = ty; k < 32; k += 8) {
+        const int64_t r = r0 + k, c = c0 + tx;
+        if (r < n_rows && c < n_cols) tile[k][tx] = in[r * n_cols + c];
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int64_t c = c0 + k, r = r0 + tx;
+        if (r < n_rows && c < n_cols) out[c * n_rows + r] = tile[tx][k];
+    }
+}
+
+
+// ================================================================================ small helpers
+// number of elements strictly below v (NaN compares false, like NumPy's `means < m_hat`)
+__global__ void __launch_bounds__(256) count_less_kernel(const double *__restrict__ x, int64_t n, double v,
+                                                         unsigned long long *__restrict__ out) {
+    unsigned long long c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        c += (__ldg(&x[i]) < v) ? 1ULL : 0ULL;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// order-preserving compaction of the finite values (nan_policy="omit"): tile = 1024 elements per CTA
+#define COMPACT_TILE 1024
+__global__ void __launch_bounds__(256) compact_count_kernel(const double *__restrict__ x, int64_t n,
+                                                            unsigned long long *__restrict__ tile_count) {
+    const int64_t base = (int64_t)blockIdx.x * COMPACT_TILE;
+    unsigned c = 0;
+    for (int k = 0; k < 4; k++) {
+        const int64_t i = base + k * 256 + threadIdx.x;
+        if (i < n) c += bits_nonfinite(double_bits(x[i])) ? 0u : 1u;
+    }
+    __shared__ unsigned sh[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int w = 0; w < 8; w++) t += sh[w];
+        tile_count[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) compact_scatter_kernel(const double *__restrict__ x, int64_t n,
+                                                              const unsigned long long *__restrict__ tile_base,
+                                                              double *__restrict__ out) {
+    // each thread owns 4 CONSECUTIVE elements so that the in-tile order is preserved by a plain scan
+    const int64_t base = (int64_t)blockIdx.x * COMPACT_TILE + (int64_t)threadIdx.x * 4;
+    double v[4];
+    bool keep[4];
+    unsigned c = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int64_t i = base + k;
+        keep[k] = false;
+        v[k] = 0.0;
+        if (i < n) {
+            v[k] = x[i];
+            keep[k] = !bits_nonfinite(double_bits(v[k]));
+        }
+        c += keep[k] ? 1u : 0u;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    __shared__ unsigned sh[8];
+    if (lane == 31) sh[wid] = incl;
+    __syncthreads();
+    unsigned wbase = 0;
+    for (int w = 0; w < wid; w++) wbase += sh[w];
+    unsigned long long pos = tile_base[blockIdx.x] + wbase + (incl - c);
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (keep[k]) out[pos++] = v[k];
+}
+
+// ========================================================================================= C ABI
+extern "C" {
+
+int64_t mcf_moments_workspace_bytes(int64_t n) {
+    if (n < 0) return MCF_ERR_BAD_ARG;
+    return align256((int64_t)sizeof(MomentsPartial) * MCF_SM_COUNT * 8);
+}
+
+int mcf_moments(const double *d_x, int64_t n, double target, double *d_out, void *d_workspace, int64_t workspace_bytes,
+                void *cuda_stream) {
+    if (!d_x || n <= 0 || !d_out || !d_workspace) return MCF_ERR_BAD_ARG;
+    if (workspace_bytes < mcf_moments_workspace_bytes(n)) return MCF_ERR_WORKSPACE_TOO_SMALL;
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    const int blocks = grid_cap(n, 256 * 8, MCF_SM_COUNT * 8);
+    moments_kernel<<<blocks, 256, 0, cs>>>(d_x, n, target, (MomentsPartial *)d_workspace);
+    MCF_CUDA_OK(cudaGetLastError());
+    moments_final_kernel<<<1, 32, 0, cs>>>((const MomentsPartial *)d_workspace, blocks, d_out);
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+int64_t mcf_select_workspace_bytes(void) { return select_geom().total; }
+int64_t mcf_select_hist_offset(void) { return select_geom().off_hist; }
+int64_t mcf_select_hist_bytes(void) { return select_geom().hist_bytes; }
+int32_t mcf_select_passes(void) { return SEL_PASSES; }
+
+int mcf_select_begin(const int64_t *h_ranks, int32_t k, void *d_workspace, int64_t workspace_bytes, void *cuda_stream) {
+    if (!h_ranks || k < 1 || k > MCF_SELECT_MAX_RANKS || !d_workspace) return MCF_ERR_BAD_ARG;
+    const SelectGeom g = select_geom();
+    if (workspace_bytes < g.total) return MCF_ERR_WORKSPACE_TOO_SMALL;
+    SelectState init;
+    memset(&init, 0, sizeof(init));
+    init.k = k;
+    init.n_uniq = 1;
+    for (int r = 0; r < k; r++) {
+        if (h_ranks[r] < 0) return MCF_ERR_BAD_ARG;
+        init.rank[r] = h_ranks[r];
+    }
+    char *ws = (char *)d_workspace;
+    select_init_kernel<<<1, 256, 0, (cudaStream_t)cuda_stream>>>((SelectState *)(ws + g.off_state),
+                                                                 (unsigned long long *)(ws + g.off_hist), init);
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+int mcf_select_hist(const double *d_x, int64_t n, int32_t omit_nonfinite, void *d_workspace, void *cuda_stream) {
+    if (!d_x || n <= 0 || !d_workspace) return MCF_ERR_BAD_ARG;
+    const SelectGeom g = select_geom();
+    char *ws = (char *)d_workspace;
+    const int blocks = grid_cap(n, 512 * 8, MCF_SM_COUNT * 4);
+    select_hist_kernel<<<blocks, 512, 0, (cudaStream_t)cuda_stream>>>(d_x, n, omit_nonfinite,
+                                                                      (const SelectState *)(ws + g.off_state),
+                                                                      (unsigned long long *)(ws + g.off_hist));
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+int mcf_select_choose(void *d_workspace, void *cuda_stream) {
+    if (!d_workspace) return MCF_ERR_BAD_ARG;
+    const SelectGeom g = select_geom();
+    char *ws = (char *)d_workspace;
+    select_choose_kernel<<<1, 256, 0, (cudaStream_t)cuda_stream>>>((SelectState *)(ws + g.off_state),
+                                                                   (unsigned long long *)(ws + g.off_hist));
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+int mcf_select_finish(const void *d_workspace, double *d_out, void *cuda_stream) {
+    if (!d_workspace || !d_out) return MCF_ERR_BAD_ARG;
+    const SelectGeom g = select_geom();
+    select_finish_kernel<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(
+        (const SelectState *)((const char *)d_workspace + g.off_state), d_out);
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+int mcf_select(const double *d_x, int64_t n, int32_t omit_nonfinite, const int64_t *h_ranks, int32_t k, double *d_out,
+               void *d_workspace, int64_t workspace_bytes, void *cuda_stream) {
+    int rc = mcf_select_begin(h_ranks, k, d_workspace, workspace_bytes, cuda_stream);
+    if (rc) return rc;
+    for (int p = 0; p < SEL_PASSES; p++) {
+        rc = mcf_select_hist(d_x, n, omit_nonfinite, d_workspace, cuda_stream);
+        if (rc) return rc;
+        rc = mcf_select_choose(d_workspace, cuda_stream);
+        if (rc) return rc;
+    }
+    return mcf_select_finish(d_workspace, d_out, cuda_stream);
+}
+
+int64_t mcf_bootstrap_workspace_bytes(int64_t n_slots, int32_t chunk_slots) {
+    if (n_slots <= 0 || chunk_slots < 8) return MCF_ERR_BAD_ARG;
+    return boot_geom(n_slots, chunk_slots).total;
+}
+
+int mcf_bootstrap_count(uint32_t gen_kind, const mcf_stream *d_stream, int64_t n, uint64_t slot_lo, uint64_t slot_hi,
+                        int32_t chunk_slots, void *d_workspace, int64_t workspace_bytes, uint64_t *d_total,
+                        void *cuda_stream) {
+    if (!d_stream || n < 2 || n > 0xFFFFFFFFLL || slot_hi <= slot_lo || chunk_slots < 8 || !d_workspace)
+        return MCF_ERR_BAD_ARG;
+    const BootGeom g = boot_geom((int64_t)(slot_hi - slot_lo), chunk_slots);
+    if (workspace_bytes < g.total) return MCF_ERR_WORKSPACE_TOO_SMALL;
+    char *ws = (char *)d_workspace;
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    uint32_t *counts = (uint32_t *)(ws + g.off_counts);
+    unsigned long long *bsum = (unsigned long long *)(ws + g.off_bsum), *bbase = (unsigned long long *)(ws + g.off_bbase);
+    unsigned long long *total = (unsigned long long *)(ws + g.off_total);
+    if (gen_kind == MCF_GEN_PCG64)
+        boot_count_kernel<MCF_GEN_PCG64><<<(unsigned)g.n_blocks, BOOT_THREADS, 0, cs>>>(
+            d_stream, (uint32_t)n, slot_lo, slot_hi, chunk_slots, g.n_chunks, counts, bsum);
+    else
+        boot_count_kernel<MCF_GEN_PHILOX><<<(unsigned)g.n_blocks, BOOT_THREADS, 0, cs>>>(
+            d_stream, (uint32_t)n, slot_lo, slot_hi, chunk_slots, g.n_chunks, counts, bsum);
+    MCF_CUDA_OK(cudaGetLastError());
+    scan_u64_kernel<<<1, 1024, 0, cs>>>(bsum, g.n_blocks, bbase, total);
+    MCF_CUDA_OK(cudaGetLastError());
+    if (d_total) MCF_CUDA_OK(cudaMemcpyAsync(d_total, total, 8, cudaMemcpyDeviceToDevice, cs));
+    return MCF_OK;
+}
+
+int mcf_bootstrap_accumulate(uint32_t gen_kind, const mcf_stream *d_stream, const double *d_x, int64_t n, int64_t n_resamples,
+                             uint64_t slot_lo, uint64_t slot_hi, int32_t chunk_slots, uint64_t ordinal_base,
+                             const void *d_workspace, int64_t workspace_bytes, double *d_sums, uint64_t *d_end_slot,
+                             void *cuda_stream) {
+    if (!d_stream || !d_x || n < 2 || n > 0xFFFFFFFFLL || n_resamples <= 0 || slot_hi <= slot_lo || chunk_slots < 8 ||
+        !d_workspace || !d_sums || !d_end_slot)
+        return MCF_ERR_BAD_ARG;
+    const BootGeom g = boot_geom((int64_t)(slot_hi - slot_lo), chunk_slots);
+    if (workspace_bytes < g.total) return MCF_ERR_WORKSPACE_TOO_SMALL;
+    const char *ws = (const char *)d_workspace;
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    const uint32_t *counts = (const uint32_t *)(ws + g.off_counts);
+    const unsigned long long *bbase = (const unsigned long long *)(ws + g.off_bbase);
+    if (gen_kind == MCF_GEN_PCG64)
+        boot_accumulate_kernel<MCF_GEN_PCG64><<<(unsigned)g.n_blocks, BOOT_THREADS, 0, cs>>>(
+            d_stream, d_x, (uint32_t)n, (uint64_t)n_resamples, slot_lo, slot_hi, chunk_slots, g.n_chunks, ordinal_base,
+            counts, bbase, d_sums, (unsigned long long *)d_end_slot);
+    else
+        boot_accumulate_kernel<MCF_GEN_PHILOX><<<(unsigned)g.n_blocks, BOOT_THREADS, 0, cs>>>(
+            d_stream, d_x, (uint32_t)n, (uint64_t)n_resamples, slot_lo, slot_hi, chunk_slots, g.n_chunks, ordinal_base,
+            counts, bbase, d_sums, (unsigned long long *)d_end_slot);
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+int mcf_bootstrap_finalize(double *d_sums, int64_t n_resamples, int64_t n, void *cuda_stream) {
+    if (!d_sums || n_resamples <= 0 || n <= 0) return MCF_ERR_BAD_ARG;
+    boot_finalize_kernel<<<(unsigned)((n_resamples + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(d_sums, n_resamples,
+                                                                                                    (double)n);
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+int64_t mcf_lsm_workspace_bytes(int64_t n_paths) {
+    if (n_paths <= 0) return MCF_ERR_BAD_ARG;
+    return lsm_geom(n_paths).total;
+}
+int64_t mcf_lsm_sums_offset(void) { return 0; }
+
+int mcf_lsm_begin(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K, int32_t is_put, void *d_workspace,
+                  int64_t workspace_bytes, void *cuda_stream) {
+    if (!d_paths_tm || n_paths <= 0 || n_steps < 1 || n_steps > 0x7fffffff || !d_workspace) return MCF_ERR_BAD_ARG;
+    const LsmGeom g = lsm_geom(n_paths);
+    if (workspace_bytes < g.total) return MCF_ERR_WORKSPACE_TOO_SMALL;
+    char *ws = (char *)d_workspace;
+    lsm_init_kernel<<<g.n_blocks, LSM_THREADS, 0, (cudaStream_t)cuda_stream>>>(
+        d_paths_tm + (size_t)n_steps * (size_t)n_paths, n_paths, (int32_t)n_steps, K, is_put, (int32_t *)(ws + g.off_ex),
+        (double *)(ws + g.off_cf));
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+// sums of step t -> workspace[0..8) doubles (all-reduce them across ranks when paths are sharded)
+int mcf_lsm_reduce(const double *d_paths_tm, int64_t n_paths, int64_t t, double K, double r, double dt, int32_t is_put,
+                   void *d_workspace, void *cuda_stream) {
+    if (!d_paths_tm || n_paths <= 0 || t < 0 || !d_workspace) return MCF_ERR_BAD_ARG;
+    const LsmGeom g = lsm_geom(n_paths);
+    char *ws = (char *)d_workspace;
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    lsm_reduce_kernel<<<g.n_blocks, LSM_THREADS, 0, cs>>>(d_paths_tm + (size_t)t * (size_t)n_paths, n_paths, (int32_t)t, K,
+                                                          r * dt, is_put, (const int32_t *)(ws + g.off_ex),
+                                                          (const double *)(ws + g.off_cf), (double *)(ws + g.off_partials));
+    MCF_CUDA_OK(cudaGetLastError());
+    lsm_sum_partials_kernel<<<1, 256, 0, cs>>>((const double *)(ws + g.off_partials), g.n_blocks,
+                                               (LsmState *)(ws + g.off_state));
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+int mcf_lsm_apply(const double *d_paths_tm, int64_t n_paths, int64_t t, double K, int32_t is_put, void *d_workspace,
+                  void *cuda_stream) {
+    if (!d_paths_tm || n_paths <= 0 || t < 0 || !d_workspace) return MCF_ERR_BAD_ARG;
+    const LsmGeom g = lsm_geom(n_paths);
+    char *ws = (char *)d_workspace;
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    lsm_solve_kernel<<<1, 32, 0, cs>>>((LsmState *)(ws + g.off_state));
+    MCF_CUDA_OK(cudaGetLastError());
+    lsm_apply_kernel<<<g.n_blocks, LSM_THREADS, 0, cs>>>(d_paths_tm + (size_t)t * (size_t)n_paths, n_paths, (int32_t)t, K,
+                                                         is_put, (const LsmState *)(ws + g.off_state),
+                                                         (int32_t *)(ws + g.off_ex), (double *)(ws + g.off_cf));
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+// sum of discounted cash flows over this rank's paths -> d_price_sum[0]; price = sum / n_paths -> d_price[0]
+int mcf_lsm_finish(int64_t n_paths, double r, double dt, void *d_workspace, double *d_price_sum, double *d_price,
+                   int32_t *d_exercise_times, void *cuda_stream) {
+    if (n_paths <= 0 || !d_workspace) return MCF_ERR_BAD_ARG;
+    const LsmGeom g = lsm_geom(n_paths);
+    char *ws = (char *)d_workspace;
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    lsm_price_kernel<<<g.n_blocks, LSM_THREADS, 0, cs>>>(n_paths, r * dt, (const int32_t *)(ws + g.off_ex),
+                                                         (const double *)(ws + g.off_cf), (double *)(ws + g.off_partials));
+    MCF_CUDA_OK(cudaGetLastError());
+    lsm_sum_partials_kernel<<<1, 256, 0, cs>>>((const double *)(ws + g.off_partials), g.n_blocks,
+                                               (LsmState *)(ws + g.off_state));
+    MCF_CUDA_OK(cudaGetLastError());
+    lsm_price_final_kernel<<<1, 32, 0, cs>>>((const LsmState *)(ws + g.off_state), (double)n_paths, d_price_sum, d_price);
+    MCF_CUDA_OK(cudaGetLastError());
+    if (d_exercise_times)
+        MCF_CUDA_OK(cudaMemcpyAsync(d_exercise_times, ws + g.off_ex, (size_t)n_paths * 4, cudaMemcpyDeviceToDevice, cs));
+    return MCF_OK;
+}
+
+int mcf_lsm(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K, double r, double dt, int32_t is_put,
+            void *d_workspace, int64_t workspace_bytes, double *d_price, int32_t *d_exercise_times, void *cuda_stream) {
+    int rc = mcf_lsm_begin(d_paths_tm, n_paths, n_steps, K, is_put, d_workspace, workspace_bytes, cuda_stream);
+    if (rc) return rc;
+    for (int64_t t = n_steps - 1; t >= 1; t--) {
+        rc = mcf_lsm_reduce(d_paths_tm, n_paths, t, K, r, dt, is_put, d_workspace, cuda_stream);
+        if (rc) return rc;
+        rc = mcf_lsm_apply(d_paths_tm, n_paths, t, K, is_put, d_workspace, cuda_stream);
+        if (rc) return rc;
+    }
+    return mcf_lsm_finish(n_paths, r, dt, d_workspace, NULL, d_price, d_exercise_times, cuda_stream);
+}
+
+int mcf_transpose(const double *d_in, int64_t n_rows, int64_t n_cols, double *d_out, void *cuda_stream) {
+    if (!d_in || !d_out || n_rows <= 0 || n_cols <= 0) return MCF_ERR_BAD_ARG;
+    const int64_t gx = (n_cols + 31) / 32, gy = (n_rows + 31) / 32;
+    if (gx * gy > 0x7fffffffLL) return MCF_ERR_BAD_ARG;
+    transpose_kernel<<<(unsigned)(gx * gy), 256, 0, (cudaStream_t)cuda_stream>>>(d_in, n_rows, n_cols, gx, d_out);
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+int mcf_count_less(const double *d_x, int64_t n, double value, int64_t *d_count, void *cuda_stream) {
+    if (!d_x || n <= 0 || !d_count) return MCF_ERR_BAD_ARG;
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    MCF_CUDA_OK(cudaMemsetAsync(d_count, 0, 8, cs));
+    count_less_kernel<<<grid_cap(n, 256 * 8, MCF_SM_COUNT * 4), 256, 0, cs>>>(d_x, n, value, (unsigned long long *)d_count);
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+int64_t mcf_compact_workspace_bytes(int64_t n) {
+    if (n <= 0) return MCF_ERR_BAD_ARG;
+    const int64_t tiles = (n + COMPACT_TILE - 1) / COMPACT_TILE;
+    return align256(tiles * 8) * 2 + 256;
+}
+
+// d_out[0 .. *d_count) = the finite values of d_x in their original order (d_out needs room for n doubles)
+int mcf_compact_finite(const double *d_x, int64_t n, double *d_out, int64_t *d_count, void *d_workspace,
+                       int64_t workspace_bytes, void *cuda_stream) {
+    if (!d_x || n <= 0 || !d_out || !d_count || !d_workspace) return MCF_ERR_BAD_ARG;
+    if (workspace_bytes < mcf_compact_workspace_bytes(n)) return MCF_ERR_WORKSPACE_TOO_SMALL;
+    const int64_t tiles = (n + COMPACT_TILE - 1) / COMPACT_TILE;
+    char *ws = (char *)d_workspace;
+    unsigned long long *cnt = (unsigned long long *)ws, *base = (unsigned long long *)(ws + align256(tiles * 8));
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    compact_count_kernel<<<(unsigned)tiles, 256, 0, cs>>>(d_x, n, cnt);
+    MCF_CUDA_OK(cudaGetLastError());
+    scan_u64_kernel<<<1, 1024, 0, cs>>>(cnt, tiles, base, (unsigned long long *)d_count);
+    MCF_CUDA_OK(cudaGetLastError());
+    compact_scatter_kernel<<<(unsigned)tiles, 256, 0, cs>>>(d_x, n, base, d_out);
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+}  // extern "C"

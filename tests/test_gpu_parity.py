@@ -170,3 +170,144 @@ def test_large_run_sum_of_normals_matches_oracle_blockwise(dev):
         f = int(rec["first_sim"])
         np.testing.assert_allclose(sums[f:f + n], z.sum(axis=1), rtol=0, atol=1e-11)
     assert abs(sums.mean()) < 5 * np.sqrt(252 / sums.size)
+
+
+# ======================================================================= StatsEngine kernels
+STAT_RTOL = 1e-11  # device one-pass sums vs NumPy's pairwise sums / SciPy's two-pass moments
+
+
+def _dev_tensor(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+@pytest.fixture(scope="module")
+def sd():
+    from mcframework_b200 import _stats_device
+    return _stats_device
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 1000, 100_003, 4_000_001])
+def test_moments_vs_numpy_scipy(sd, n):
+    import scipy.stats as st
+    x = np.random.default_rng(n).normal(5.0, 2.0, n) ** 1
+    m = sd.moments(_dev_tensor(x), target=4.5)
+    assert m.n == n and m.n_nonfinite == 0
+    np.testing.assert_allclose(m.mean, x.mean(), rtol=1e-14)
+    np.testing.assert_allclose(m.total, x.sum(), rtol=1e-13)
+    np.testing.assert_allclose(m.sq_target, ((x - 4.5) ** 2).sum(), rtol=1e-13)
+    assert m.vmin == x.min() and m.vmax == x.max()
+    if n > 1:
+        np.testing.assert_allclose(np.sqrt(m.m2 / (n - 1)), x.std(ddof=1), rtol=1e-13)
+    if n > 3:
+        m2, m3, m4 = m.m2 / n, m.m3 / n, m.m4 / n
+        g1 = np.sqrt(n * (n - 1.0)) / (n - 2.0) * m3 / m2 ** 1.5
+        g2 = 1.0 / (n - 2) / (n - 3) * ((n * n - 1.0) * m4 / m2 ** 2.0 - 3 * (n - 1) ** 2.0)
+        np.testing.assert_allclose(g1, st.skew(x, bias=False), rtol=STAT_RTOL, atol=1e-13)
+        np.testing.assert_allclose(g2, st.kurtosis(x, fisher=True, bias=False), rtol=STAT_RTOL, atol=1e-12)
+
+
+def test_moments_nonfinite_and_skewed(sd):
+    x = np.random.default_rng(0).lognormal(0, 1.5, 300_001)
+    x[[5, 77, 1000]] = [np.nan, np.inf, -np.inf]
+    x[2000] = np.nan
+    m = sd.moments(_dev_tensor(x[1:]), target=0.0)  # odd offset: exercises the unaligned path
+    f = x[1:][np.isfinite(x[1:])]
+    assert (m.n, m.n_nan, m.n_posinf, m.n_neginf) == (f.size, 2, 1, 1)
+    np.testing.assert_allclose(m.mean, f.mean(), rtol=1e-13)
+    np.testing.assert_allclose(m.m2, ((f - f.mean()) ** 2).sum(), rtol=1e-12)
+    np.testing.assert_allclose(m.m3, ((f - f.mean()) ** 3).sum(), rtol=1e-10)
+    np.testing.assert_allclose(m.m4, ((f - f.mean()) ** 4).sum(), rtol=1e-10)
+
+
+@pytest.mark.parametrize("n,dist", [(1, "normal"), (2, "normal"), (1001, "normal"), (250_000, "payoff"), (3_000_000, "normal"),
+                                    (100_000, "const"), (65_537, "ints")])
+def test_percentiles_bit_exact_vs_numpy(sd, n, dist):
+    rng = np.random.default_rng(n)
+    if dist == "normal":
+        x = rng.normal(5, 2, n)
+    elif dist == "payoff":
+        x = np.maximum(rng.normal(0, 10, n), 0.0)  # ~50% exact zeros, like option payoffs
+        x[::7] *= -0.0
+    elif dist == "const":
+        x = np.full(n, 3.25)
+    else:
+        x = rng.integers(-5, 5, n).astype(float)
+    pcts = (0, 1, 5, 25, 50, 75, 95, 99, 100, 33.3)
+    got = sd.percentiles(_dev_tensor(x), pcts)
+    want = np.percentile(x, pcts)
+    assert np.array_equal(got, want), (got, want)
+
+
+def test_percentiles_nan_policies(sd):
+    x = np.random.default_rng(3).normal(0, 1, 50_000)
+    x[[3, 99, 4000]] = [np.nan, np.inf, -np.inf]
+    xd = _dev_tensor(x)
+    assert np.all(np.isnan(sd.percentiles(xd, (5, 50), has_nan=True)))
+    f = x[np.isfinite(x)]
+    assert np.array_equal(sd.percentiles(xd, (5, 50, 95), n_valid=f.size, omit_nonfinite=True), np.percentile(f, (5, 50, 95)))
+    y = x.copy()
+    y[3] = 1.0  # infinities only: they take part in the order
+    assert np.array_equal(sd.percentiles(_dev_tensor(y), (0, 50, 100)), np.percentile(y, (0, 50, 100)))
+
+
+@pytest.mark.parametrize("n,B", [(6, 200), (1000, 150), (10_000, 100), (65_536, 30), (100_000, 50), (3_000_000, 4)])
+def test_bootstrap_means_vs_numpy_stream(sd, n, B):
+    """Indices are bit-exact (same accepted slots), so the means agree to summation-order rounding;
+    the generator is left exactly where NumPy leaves it."""
+    x = np.random.default_rng(1).normal(5, 2, n)
+    g_ref, g_dev = np.random.default_rng(321), np.random.default_rng(321)
+    want = np.stack([x[g_ref.integers(0, n, size=n)].mean() for _ in range(B)])
+    got = sd.bootstrap_means(_dev_tensor(x), B, g_dev).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-13, atol=0)
+    assert g_dev.bit_generator.state == g_ref.bit_generator.state
+    # integer-valued data: sums are exact in fp64, so any index difference would show
+    xi = np.random.default_rng(2).integers(0, 1 << 20, n).astype(float)
+    g_ref, g_dev = np.random.default_rng(5), np.random.default_rng(5)
+    g_ref.integers(0, 10, size=3), g_dev.integers(0, 10, size=3)  # leaves a buffered upper half (has_uint32 = 1)
+    want = np.stack([xi[g_ref.integers(0, n, size=n)].sum() for _ in range(B)])
+    got = sd.bootstrap_means(_dev_tensor(xi), B, g_dev).cpu().numpy() * n
+    assert np.array_equal(np.rint(got), want)
+    assert g_dev.bit_generator.state == g_ref.bit_generator.state
+
+
+def test_bootstrap_philox_generator(sd):
+    n, B = 5000, 120
+    x = np.random.default_rng(1).integers(0, 1000, n).astype(float)
+    g_ref, g_dev = (np.random.Generator(np.random.Philox(9)) for _ in range(2))
+    g_ref.random(3), g_dev.random(3)  # mid-buffer start
+    want = np.stack([x[g_ref.integers(0, n, size=n)].sum() for _ in range(B)])
+    got = sd.bootstrap_means(_dev_tensor(x), B, g_dev).cpu().numpy() * n
+    assert np.array_equal(np.rint(got), want)
+    assert np.array_equal(g_dev.integers(0, 1 << 30, 5), g_ref.integers(0, 1 << 30, 5))
+
+
+@pytest.mark.parametrize("n_paths,n_steps,put", [(100, 50, True), (100, 50, False), (20_000, 252, True), (3, 10, True), (5000, 12, False)])
+def test_lsm_vs_oracle(sd, n_paths, n_steps, put):
+    from oracle import np_port
+    rng = np.random.default_rng(42)
+    T, r, sigma, S0, K = 1.0, 0.05, 0.2, 100.0, 100.0
+    dt = T / n_steps
+    z = rng.standard_normal((n_paths, n_steps))
+    paths = S0 * np.exp(np.concatenate([np.zeros((n_paths, 1)), np.cumsum((r - 0.5 * sigma ** 2) * dt + sigma * np.sqrt(dt) * z, axis=1)], axis=1))
+    want, want_ex = np_port.lsm_price(paths, K, r, dt, "put" if put else "call")
+    tm = sd.transpose(_dev_tensor(paths))
+    assert np.array_equal(tm.cpu().numpy(), paths.T)
+    price, ex = sd.lsm_price(tm, K, r, dt, put, return_exercise=True)
+    np.testing.assert_allclose(float(price.cpu().numpy()[0]), want, rtol=1e-9)
+    assert np.mean(ex.cpu().numpy() == want_ex) >= 0.9999  # exercise decisions: borderline flips only
+
+
+def test_lsm_deep_otm_is_zero(sd):
+    paths = np.full((500, 20), 100.0) * np.exp(np.random.default_rng(0).normal(0, 0.01, (500, 20)))
+    got = float(sd.lsm_price(sd.transpose(_dev_tensor(paths)), 10.0, 0.05, 0.05, True).cpu().numpy()[0])
+    assert got == 0.0
+
+
+def test_count_less_and_compact(sd):
+    x = np.random.default_rng(8).normal(0, 1, 70_001)
+    x[::13] = np.nan
+    x[5::101] = np.inf
+    xd = _dev_tensor(x)
+    assert sd.count_less(xd, 0.25) == int(np.sum(x < 0.25))
+    assert np.array_equal(sd.compact_finite(xd).cpu().numpy(), x[np.isfinite(x)])
