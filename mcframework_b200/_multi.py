@@ -23,3 +23,23 @@ def gather_results(local, group):
     parts = [torch.empty(width, dtype=local.dtype, device=local.device) for _ in range(world)]
     dist.all_gather(parts, padded, group=group)
     return torch.cat([p[:k] for p, k in zip(parts, sizes)])
+
+
+def gather_results_to_root(local, group):
+    """Rank 0 receives the concatenation (rank order); other ranks get ``None``."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_local = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    sizes = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(sizes, n_local, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    width = max(sizes)
+    padded = torch.zeros(width, dtype=local.dtype, device=local.device)
+    padded[: local.numel()] = local
+    parts = [torch.empty(width, dtype=local.dtype, device=local.device) for _ in range(world)] if rank == 0 else None
+    dist.gather(padded, parts, dst=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    if rank != 0:
+        return None
+    return torch.cat([p[:k] for p, k in zip(parts, sizes)])

@@ -25,6 +25,10 @@ _ERR_NAMES = {
 BS_EURO_CALL, BS_EURO_PUT, BS_AMER_CALL, BS_AMER_PUT, PATH_TERMINAL, PORTFOLIO_GBM, PORTFOLIO_LOG1P, NORMAL_SUM = range(8)
 
 
+class DeviceUnavailableError(RuntimeError):
+    """The CUDA library is not built or no CUDA device is visible.  Never swallowed: there is no CPU fallback."""
+
+
 class NativeError(RuntimeError):
     def __init__(self, fn: str, code: int, detail: str = ""):
         self.code = code
@@ -84,7 +88,7 @@ _lib = None
 def load_library(path: str = LIB_PATH):
     """dlopen the C-ABI library and attach signatures (no CUDA call is made)."""
     if not os.path.exists(path):
-        raise RuntimeError(
+        raise DeviceUnavailableError(
             f"CUDA library not built: {path} is missing. Run `python -m mcframework_b200.build` "
             "(needs nvcc; targets sm_100a). There is no CPU fallback.")
     lib = C.CDLL(path)
@@ -102,7 +106,7 @@ def lib():
         import torch
 
         if not torch.cuda.is_available():
-            raise RuntimeError("mcframework_b200 needs a CUDA device (B200, sm_100a); none is visible. "
+            raise DeviceUnavailableError("mcframework_b200 needs a CUDA device (B200, sm_100a); none is visible. "
                                "There is no CPU fallback.")
         _lib = load_library()
     return _lib

@@ -29,6 +29,7 @@ from typing import Any, Callable, Iterable, Mapping
 
 import numpy as np
 
+from ._native import DeviceUnavailableError, NativeError
 from .stats_engine import DEFAULT_ENGINE, DeviceSample, StatsContext, StatsEngine, _ensure_ctx, ci_mean, mean, std
 from .stats_engine import percentiles as pct
 from .utils import autocrit
@@ -189,6 +190,8 @@ class MonteCarloSimulation(ABC):
         try:
             outcome = eng.compute(sample, ctx)
             stats = outcome.metrics if hasattr(outcome, "metrics") else {}
+        except (DeviceUnavailableError, NativeError):
+            raise
         except Exception as exc:  # noqa: BLE001
             logger.error("Stats engine failed: %s", exc)
             stats = {}
@@ -253,11 +256,16 @@ class MonteCarloSimulation(ABC):
         import torch
 
         if group is not None:
-            from ._multi import gather_results
+            from . import _multi
 
+            # "all": every rank returns the full vector (reference semantics on every rank);
+            # "root": only rank 0 does, the others return their own shard (saves N-1 host copies)
             local = values_dev
-            full = gather_results(local, group)
-            host = full.cpu().numpy()
+            if getattr(self, "gather_mode", "all") == "root":
+                full = _multi.gather_results_to_root(local, group)
+                host = (full if full is not None else local).cpu().numpy()
+            else:
+                host = _multi.gather_results(local, group).cpu().numpy()
             self._device_sample = DeviceSample(local, host, group)
         else:
             host = torch.empty(values_dev.shape, dtype=torch.float64, pin_memory=values_dev.numel() >= (1 << 20))

@@ -105,7 +105,7 @@ class BlackScholesSimulation(MonteCarloSimulation):
     def calculate_greeks(self, n_simulations: int, S0: float = 100.0, K: float = 100.0, T: float = 1.0, r: float = 0.05,
                          sigma: float = 0.20, option_type: str = "call", exercise_type: str = "european",
                          n_steps: int = 252, parallel: bool = False, bump_pct: float = 0.01,
-                         time_bump_days: float = 1.0) -> dict[str, float]:
+                         time_bump_days: float = 1.0, *, n_workers: int | None = None) -> dict[str, float]:
         """Central-difference delta, gamma, vega, theta, rho on common random numbers (:257-374)."""
         from .. import _stats_device as SD
 
@@ -122,19 +122,26 @@ class BlackScholesSimulation(MonteCarloSimulation):
             sets.append([S0, K, T - dT, r, sigma])
 
         self.set_seed(42)  # the reference re-seeds with 42 before EVERY revaluation: one stream layout serves all
-        n_workers = mp.cpu_count()
+        if n_workers is None:
+            n_workers = mp.cpu_count()  # what run(parallel=True) defaults to in the reference (core.py:547-548)
+        group = None
         if parallel and n_workers > 1 and n_simulations >= self._PARALLEL_THRESHOLD:
             blocks, children = self._prepare_parallel_blocks(n_simulations, n_workers)
             lay = S.StreamLayout(S.GEN_PHILOX, S.philox_records(children, blocks), n_simulations, blocks[0][1] - blocks[0][0])
+            group = self._shard_group()
+            if group is not None:
+                import torch.distributed as dist
+
+                lay = lay.shard(dist.get_rank(group), dist.get_world_size(group))
         else:
             lay = S.sequential_layout(self.rng, n_simulations)
         dl = D.DeviceLayout.of(lay)
         plan = D.normal_plan(dl, int(n_steps))
         if exercise_type == "european":
             values = D.gbm_terminal(dl, int(n_steps), plan, [(mode, p) for p in sets])
-            means = [SD.moments(values[k]).mean for k in range(len(sets))]
+            means = [SD.moments(values[k], group=group).mean for k in range(len(sets))]
         else:  # path-dependent payoff: one replay per parameter set, same plan
-            means = [SD.moments(D.gbm_terminal(dl, int(n_steps), plan, [(mode, p)])[0]).mean for p in sets]
+            means = [SD.moments(D.gbm_terminal(dl, int(n_steps), plan, [(mode, p)])[0], group=group).mean for p in sets]
         v0, v_up, v_dn, v_sig_up, v_sig_dn, v_r_up, v_r_dn = means[:7]
         greeks = {
             "price": float(v0),

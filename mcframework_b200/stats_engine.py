@@ -22,6 +22,7 @@ import numpy as np
 from scipy.special import erfinv
 from scipy.stats import norm
 
+from ._native import DeviceUnavailableError, NativeError
 from .utils import autocrit
 
 logger = logging.getLogger(__name__)
@@ -627,6 +628,8 @@ class StatsEngine:
                         res = m(host_view, ctx)
                     else:
                         res = m(x, ctx)
+            except (DeviceUnavailableError, NativeError):
+                raise  # a broken device path is never recorded as a "metric error"
             except MissingContextError as exc:
                 skipped.append((m.name, str(exc)))
                 logger.debug("Skipping metric %s: %s", m.name, exc)

@@ -1,0 +1,214 @@
+"""Public-API parity on the GPU: the scenarios of tools/gen_golden.py (run there on the UNMODIFIED reference)
+replayed through ``mcframework_b200`` -- same calls, same seeds -- and compared with the committed fixtures.
+
+Bars: Pi results (multiples of 4/n_points, i.e. integer hit counts) bit-exact; every float within RES_RTOL of
+the reference result vector; statistics within STAT_RTOL (one-pass device sums vs NumPy pairwise sums);
+bootstrap intervals within BOOT_RTOL (identical index stream, different summation order).
+"""
+import logging
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import have_cuda
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_cuda(), reason="needs a CUDA device")]
+
+RES_RTOL, PAY_ATOL = 1e-12, 1e-11
+STAT_RTOL = 1e-10
+BOOT_RTOL = 1e-11
+
+
+@pytest.fixture(scope="module")
+def m():
+    import mcframework_b200 as mod
+    logging.getLogger("mcframework_b200.core").setLevel(logging.WARNING)
+    return mod
+
+
+def _close_stats(got, want, rtol=STAT_RTOL):
+    assert set(got) == set(want), (sorted(got), sorted(want))
+    for k, w in want.items():
+        g = got[k]
+        if isinstance(w, dict):
+            assert set(g) == set(w), k
+            for kk, ww in w.items():
+                if isinstance(ww, str):
+                    assert g[kk] == ww, (k, kk)
+                else:
+                    np.testing.assert_allclose(g[kk], ww, rtol=BOOT_RTOL if "bootstrap" in k else rtol, err_msg=f"{k}.{kk}")
+        elif isinstance(w, (list, tuple)):
+            np.testing.assert_allclose(g, w, rtol=rtol, err_msg=k)
+        elif isinstance(w, str):
+            assert g == w, k
+        else:
+            np.testing.assert_allclose(g, w, rtol=rtol, atol=1e-13, err_msg=k)
+
+
+def test_config1_pi_run_simulation_end_to_end(m, golden):
+    """BASELINE config 1 exactly as the README runs it (parallel=True falls back to the sequential stream)."""
+    j, a = golden
+    sim = m.PiEstimationSimulation()
+    sim.set_seed(123)
+    fw = m.MonteCarloFramework()
+    fw.register_simulation(sim)
+    seen = []
+    res = fw.run_simulation("Pi Estimation", 10_000, n_points=5000, parallel=True,
+                            extra_context=j["G1"]["extra_context"], progress_callback=lambda d, t: seen.append((d, t)))
+    assert isinstance(res.results, np.ndarray) and res.results.dtype == np.float64
+    assert np.array_equal(res.results, a["G1_pi_results"])  # hit counts bit-exact
+    assert int(round(res.results.sum() * 5000 / 4)) == j["G1"]["sum_hits"] == 39_268_872
+    np.testing.assert_allclose(res.mean, j["G1"]["mean"], rtol=1e-14)
+    np.testing.assert_allclose(res.std, j["G1"]["std"], rtol=1e-12)
+    assert res.percentiles == {int(k): v for k, v in j["G1"]["percentiles"].items()}  # order statistics bit-exact
+    _close_stats(res.stats, j["G1"]["stats"])
+    assert seen[-1] == (10_000, 10_000) and len(seen) == 100
+    assert res.metadata["seed_entropy"] == 123 and res.metadata["engine_defaults_used"] is True
+    assert fw.compare_results(["Pi Estimation"], "mean")["Pi Estimation"] == res.mean
+
+
+def test_pi_layouts_and_stream_continuation(m, golden):
+    _, a = golden
+    sim = m.PiEstimationSimulation()
+    sim.set_seed(123)
+    assert np.array_equal(sim.run(20_000, n_points=100, parallel=True, n_workers=8, compute_stats=False).results,
+                          a["G2_pi_parallel_results"])
+    sim.set_seed(5)
+    assert np.array_equal(sim.run(20_001, n_points=33, antithetic=True, parallel=True, n_workers=3, compute_stats=False).results,
+                          a["G2b_pi_antithetic_parallel_results"])
+    sim.set_seed(6)
+    assert np.array_equal(sim.run(500, n_points=101, antithetic=True, compute_stats=False).results,
+                          a["G2c_pi_antithetic_seq_results"])
+    # a second run WITHOUT re-seeding continues the PCG64 stream where the first one stopped
+    assert np.array_equal(sim.run(300, n_points=64, compute_stats=False).results, a["G2d_pi_seq_second_run_results"])
+
+
+def test_user_hook_runs_as_plugin_code(m, golden):
+    """Arbitrary Python hooks are user code: looped on the host with the reference's stream layout (G3)."""
+    _, a = golden
+
+    class Dice(m.MonteCarloSimulation):
+        def single_simulation(self, _rng=None, **kw):
+            rng = self._rng(_rng, self.rng)
+            return float(rng.integers(1, 7, size=2).sum())
+
+    d = Dice("2d6")
+    d.set_seed(42)
+    assert np.array_equal(d.run(10_000, compute_stats=False).results, a["G3_dice_seq"])
+    d.set_seed(42)
+    r = d.run(20_000, parallel=True, n_workers=4)
+    assert np.array_equal(r.results, a["G3_dice_par"])
+    np.testing.assert_allclose(r.mean, a["G3_dice_par"].mean(), rtol=1e-13)  # statistics still come from the kernels
+    assert r.percentiles[50] == np.percentile(a["G3_dice_par"], 50)
+
+
+def test_black_scholes_runs(m, golden):
+    _, a = golden
+    bs = m.BlackScholesSimulation()
+    bs.set_seed(42)
+    np.testing.assert_allclose(bs.run(1000, compute_stats=False).results, a["G4_bs_call_seq"], rtol=RES_RTOL, atol=PAY_ATOL)
+    bs.set_seed(42)
+    r = bs.run(777, option_type="put", S0=95.0, K=105.0, T=0.5, r=0.03, sigma=0.35, n_steps=61, compute_stats=False)
+    np.testing.assert_allclose(r.results, a["G4_bs_put_seq"], rtol=RES_RTOL, atol=PAY_ATOL)
+    bs.set_seed(42)
+    r = bs.run(1000, option_type="put", exercise_type="american", compute_stats=False)
+    np.testing.assert_allclose(r.results, a["G4_bs_amer_put_seq"], rtol=RES_RTOL, atol=PAY_ATOL)
+    bs.set_seed(11)
+    r = bs.run(20_000, parallel=True, n_workers=4, n_steps=64, compute_stats=False)
+    np.testing.assert_allclose(r.results, a["G4_bs_call_par"], rtol=RES_RTOL, atol=PAY_ATOL)
+    with pytest.raises(ValueError, match="exercise_type must be 'european' or 'american'"):
+        bs.run(10, exercise_type="bermudan")
+
+
+def test_greeks(m, golden):
+    j, _ = golden
+    bs = m.BlackScholesSimulation()
+    bs.set_seed(9)
+    before = bs.rng.bit_generator.state
+    g = bs.calculate_greeks(1000)
+    for k, w in j["G4_greeks_call"].items():
+        np.testing.assert_allclose(g[k], w, rtol=1e-9, err_msg=k)  # differences of means: cancellation
+    assert bs.rng.bit_generator.state == before and bs.seed_seq.entropy == 42
+    g = bs.calculate_greeks(20_000, option_type="put", n_steps=12, parallel=True, n_workers=j["G4_greeks_put_par_cpu_count"])
+    for k, w in j["G4_greeks_put_par"].items():
+        np.testing.assert_allclose(g[k], w, rtol=1e-9, err_msg=k)
+
+
+def test_portfolio_and_paths_and_lsm(m, golden):
+    j, a = golden
+    pf = m.PortfolioSimulation()
+    pf.set_seed(42)
+    np.testing.assert_allclose(pf.run(500, years=5, compute_stats=False).results, a["G5_portfolio_gbm_seq"], rtol=RES_RTOL)
+    pf.set_seed(42)
+    np.testing.assert_allclose(pf.run(500, years=2, use_gbm=False, compute_stats=False).results,
+                               a["G5_portfolio_log1p_seq"], rtol=RES_RTOL)
+    ps = m.BlackScholesPathSimulation()
+    ps.set_seed(5)
+    np.testing.assert_allclose(ps.run(300, n_steps=30, compute_stats=False).results, a["G6_path_terminal_seq"], rtol=RES_RTOL)
+    ps.set_seed(1)
+    paths = ps.simulate_paths(4000, n_steps=50)
+    assert paths.shape == (4000, 51)
+    np.testing.assert_allclose(paths[:8], a["G6_paths_head"], rtol=RES_RTOL)
+    np.testing.assert_allclose(paths[-1], a["G6_paths_tail_row"], rtol=RES_RTOL)
+    from mcframework_b200.sims import _american_exercise_lsm, _simulate_gbm_path
+
+    np.testing.assert_allclose(_american_exercise_lsm(paths, 100.0, 0.05, 1.0 / 50, "put"), j["G6"]["lsm_put"], rtol=1e-9)
+    np.testing.assert_allclose(_american_exercise_lsm(paths, 100.0, 0.05, 1.0 / 50, "call"), j["G6"]["lsm_call"], rtol=1e-9)
+    np.testing.assert_allclose(_american_exercise_lsm(paths, 110.0, 0.05, 1.0 / 50, "put"), j["G6"]["lsm_put_K110"], rtol=1e-9)
+    rng = np.random.default_rng(42)
+    small = np.array([_simulate_gbm_path(100.0, 0.05, 0.2, 1.0, 50, rng) for _ in range(100)])
+    np.testing.assert_allclose(_american_exercise_lsm(small, 100.0, 0.05, 1.0 / 50, "put"), j["G6"]["lsm_small_put"], rtol=1e-9)
+    np.testing.assert_allclose(_american_exercise_lsm(small, 100.0, 0.05, 1.0 / 50, "call"), j["G6"]["lsm_small_call"], rtol=1e-9)
+    # device-resident variant: time-major paths straight into the LSM sweep
+    ps.set_seed(1)
+    tm = ps.simulate_paths(4000, n_steps=50, device=True, time_major=True)
+    np.testing.assert_allclose(_american_exercise_lsm(tm, 100.0, 0.05, 1.0 / 50, "put", time_major=True), j["G6"]["lsm_put"], rtol=1e-9)
+
+
+def test_stats_engine_golden(m, golden):
+    j, a = golden
+    from mcframework_b200.stats_engine import build_default_engine
+
+    eng = build_default_engine()
+    x = np.random.default_rng(0).normal(5, 2, 100_000)
+    ctx = m.StatsContext(n=x.size, percentiles=(1, 5, 50, 95, 99), rng=7, n_bootstrap=1000, bootstrap="bca", target=5.0, eps=0.01)
+    out = eng.compute(x, ctx)
+    assert not out.errors and not out.skipped
+    want = dict(j["G7"])
+    want["percentiles"] = {int(k): v for k, v in want["percentiles"].items()}
+    assert out.metrics["percentiles"] == want["percentiles"]
+    _close_stats(out.metrics, want)
+    xs = a["G7_omit_x"]
+    ctx = m.StatsContext(n=xs.size, nan_policy="omit", rng=11, n_bootstrap=500, bootstrap="percentile", confidence=0.9,
+                         target=2.0, eps=0.1, ci_method="t")
+    want = dict(j["G7_omit"])
+    want["percentiles"] = {int(k): v for k, v in want["percentiles"].items()}
+    _close_stats(eng.compute(xs, ctx).metrics, want)
+    six = np.linspace(0, 1, 6)
+    got = eng.compute(six, m.StatsContext(n=6, rng=123, n_bootstrap=200), select=["ci_mean_bootstrap"]).metrics
+    _close_stats(got, j["G8"]["percentile_rng123_B200"])
+    got = eng.compute(six, m.StatsContext(n=6, rng=321, n_bootstrap=200, bootstrap="bca"), select=["ci_mean_bootstrap"]).metrics
+    _close_stats(got, j["G8"]["bca_rng321_B200"])
+
+
+def test_engine_taxonomy_and_small_samples(m):
+    from mcframework_b200 import stats_engine as se
+
+    eng = se.build_default_engine()
+    out = eng.compute(np.array([1.0, 2.0, 3.0, 4.0]), m.StatsContext(n=4, rng=1, n_bootstrap=100))
+    skipped = dict(out.skipped)
+    assert set(skipped) == {"chebyshev_required_n", "markov_error_prob", "bias_to_target", "mse_to_target"}
+    assert out.metrics["mean"] == 2.5 and out.metrics["percentiles"] == {5: 1.15, 25: 1.75, 50: 2.5, 75: 3.25, 95: 3.85}
+    assert out.metrics["skew"] == 0.0 and out.metrics["ci_mean"]["method"] == "t"
+    assert se.std(np.array([1.0]), m.StatsContext(n=1)) is None and se.mean(np.array([]), {"n": 0}) is None
+    assert se.skew(np.array([1.0, 2.0]), None) == 0.0 and se.kurtosis(np.array([1.0, 2.0, 3.0]), None) == 0.0
+    assert math.isnan(se.mean(np.array([1.0, np.nan]), None))
+    assert se.mean(np.array([1.0, np.nan, 3.0]), {"nan_policy": "omit"}) == 2.0
+    with pytest.raises(ValueError, match="method must be 'auto', 'z', or 't'"):
+        se.ci_mean(np.arange(10.0), m.StatsContext(n=10, ci_method="bootstrap"))
+    assert se.ci_mean_bootstrap(np.array([]), {"n": 0}) is None
+    # a user metric gets the host array and can sit next to device metrics
+    eng2 = m.StatsEngine([m.FnMetric("mean", se.mean), m.FnMetric("peak", lambda x, ctx: float(np.max(x)))])
+    assert eng2.compute(np.array([1.0, 5.0, 3.0])).metrics == {"mean": 3.0, "peak": 5.0}

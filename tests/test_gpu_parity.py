@@ -89,44 +89,35 @@ def test_normal_plan_positions_bit_exact(dev):
         assert np.array_equal(starts[f:f + len(want)], np.array(want, dtype=np.uint64))
 
 
-def test_black_scholes_golden(dev, golden):
+def _terminal(D, lay, steps, mode, p):
+    dl = D.DeviceLayout.of(lay)
+    return D.gbm_terminal(dl, steps, D.normal_plan(dl, steps), [(mode, p)])[0].cpu().numpy()
+
+
+PF = [1e4, 0.07, 0.2]
+TERMINAL_CASES = {
+    "G4_bs_call_seq": (("seq", 42, 1000), 252, "BS_EURO_CALL", BS),
+    "G4_bs_put_seq": (("seq", 42, 777), 61, "BS_EURO_PUT", [95, 105, .5, .03, .35]),
+    "G4_bs_amer_put_seq": (("seq", 42, 1000), 252, "BS_AMER_PUT", BS),
+    "G4_bs_amer_call_seq": (("seq", 42, 400), 40, "BS_AMER_CALL", BS),
+    "G4_bs_call_par": (("par", 11, 20_000, 4), 64, "BS_EURO_CALL", BS),
+    "G4_bs_amer_put_par": (("par", 11, 20_000, 2), 16, "BS_AMER_PUT", BS),
+    "G5_portfolio_gbm_seq": (("seq", 42, 500), 1260, "PORTFOLIO_GBM", PF),
+    "G5_portfolio_log1p_seq": (("seq", 42, 500), 504, "PORTFOLIO_LOG1P", PF),
+    "G5_portfolio_gbm_par": (("par", 3, 20_000, 8), 252, "PORTFOLIO_GBM", PF),
+    "G6_path_terminal_seq": (("seq", 5, 300), 30, "PATH_TERMINAL", [100, .05, .2, 1.0]),
+}
+
+
+@pytest.mark.parametrize("key", sorted(TERMINAL_CASES))
+def test_terminal_values_golden(dev, golden, key):
+    """Payoffs / terminal values of the reference run (tests/golden, produced by tools/gen_golden.py)."""
     D, N, S = dev
     _, a = golden
-
-    def run(lay, steps, mode, p):
-        dl = D.DeviceLayout.of(lay)
-        return D.gbm_terminal(dl, steps, D.normal_plan(dl, steps), [(mode, p)])[0].cpu().numpy()
-
-    np.testing.assert_allclose(run(_seq(S, 42, 1000), 252, N.BS_EURO_CALL, BS), a["G4_bs_call_seq"],
-                               rtol=FP_RTOL, atol=PAY_ATOL)
-    np.testing.assert_allclose(run(_seq(S, 42, 777), 61, N.BS_EURO_PUT, [95, 105, .5, .03, .35]), a["G4_bs_put_seq"],
-                               rtol=FP_RTOL, atol=PAY_ATOL)
-    np.testing.assert_allclose(run(_seq(S, 42, 1000), 252, N.BS_AMER_PUT, BS), a["G4_bs_amer_put_seq"],
-                               rtol=FP_RTOL, atol=PAY_ATOL)
-    np.testing.assert_allclose(run(_seq(S, 42, 400), 40, N.BS_AMER_CALL, BS), a["G4_bs_amer_call_seq"],
-                               rtol=FP_RTOL, atol=PAY_ATOL)
-    np.testing.assert_allclose(run(S.parallel_layout(np.random.SeedSequence(11), 20_000, 4), 64, N.BS_EURO_CALL, BS),
-                               a["G4_bs_call_par"], rtol=FP_RTOL, atol=PAY_ATOL)
-    np.testing.assert_allclose(run(S.parallel_layout(np.random.SeedSequence(11), 20_000, 2), 16, N.BS_AMER_PUT, BS),
-                               a["G4_bs_amer_put_par"], rtol=FP_RTOL, atol=PAY_ATOL)
-
-
-def test_portfolio_and_path_golden(dev, golden):
-    D, N, S = dev
-    _, a = golden
-
-    def run(lay, steps, mode, p):
-        dl = D.DeviceLayout.of(lay)
-        return D.gbm_terminal(dl, steps, D.normal_plan(dl, steps), [(mode, p)])[0].cpu().numpy()
-
-    PF = [1e4, 0.07, 0.2]
-    np.testing.assert_allclose(run(_seq(S, 42, 500), 1260, N.PORTFOLIO_GBM, PF), a["G5_portfolio_gbm_seq"], rtol=FP_RTOL)
-    np.testing.assert_allclose(run(_seq(S, 42, 500), 504, N.PORTFOLIO_LOG1P, PF), a["G5_portfolio_log1p_seq"],
-                               rtol=FP_RTOL)
-    np.testing.assert_allclose(run(S.parallel_layout(np.random.SeedSequence(3), 20_000, 8), 252, N.PORTFOLIO_GBM, PF),
-                               a["G5_portfolio_gbm_par"], rtol=FP_RTOL)
-    np.testing.assert_allclose(run(_seq(S, 5, 300), 30, N.PATH_TERMINAL, [100, .05, .2, 1.0]),
-                               a["G6_path_terminal_seq"], rtol=FP_RTOL)
+    how, steps, mode, p = TERMINAL_CASES[key]
+    lay = _seq(S, how[1], how[2]) if how[0] == "seq" else S.parallel_layout(np.random.SeedSequence(how[1]), how[2], how[3])
+    got = _terminal(D, lay, steps, getattr(N, mode), p)
+    np.testing.assert_allclose(got, a[key], rtol=FP_RTOL, atol=PAY_ATOL if key.startswith("G4") else 0)
 
 
 def test_paths_golden_both_layouts(dev, golden):

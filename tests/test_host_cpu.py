@@ -1,0 +1,199 @@
+"""CPU-only tests: host logic, C-ABI surface, and the device functions compiled for the host (tests/hostemu).
+
+Nothing here launches a kernel.  The hostemu harness compiles the SAME ``__host__ __device__`` functions the
+kernels call (mcf_device.cuh) with g++ and walks them with the kernels' work decomposition, so stream
+positions, jump-ahead and the planning pass are checked against the oracle without a GPU.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+# ------------------------------------------------------------------------------------- C ABI surface
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mcf_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mcf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mcframework_b200 import _native, build
+
+    build.build_native()
+    lib = _native.load_library()  # dlopen only; no CUDA call
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/mcf_b200.h but not exported"
+        assert name in _native.SIGNATURES, f"{name} has no ctypes signature"
+    assert lib.mcf_abi_version() == 1
+    assert lib.mcf_select_workspace_bytes() > 0 and lib.mcf_lsm_workspace_bytes(1000) > 0
+    assert lib.mcf_bootstrap_workspace_bytes(10 ** 6, 64) > 0 and lib.mcf_moments_workspace_bytes(5) > 0
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import mcframework_b200 as m
+
+    sim = m.PiEstimationSimulation()
+    sim.set_seed(1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sim.run(10, n_points=100)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.DEFAULT_ENGINE.compute(np.arange(10.0), m.StatsContext(n=10))
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "mcframework_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+# ------------------------------------------------------------------------------------- stream layouts
+def test_layouts_match_reference_block_rule():
+    from mcframework_b200 import _streams as S
+
+    lay = S.parallel_layout(np.random.SeedSequence(123), 20_000, 8)
+    assert lay.n_streams == 65 and lay.hint == 312 and int(lay.records["n_sims"][-1]) == 32
+    kids = np.random.SeedSequence(123).spawn(65)
+    assert np.array_equal(lay.records["s"][:, :2], np.stack([k.generate_state(2, np.uint64) for k in kids]))
+    parts = [lay.shard(r, 4) for r in range(4)]
+    assert sum(p.n_total for p in parts) == 20_000 and all(int(p.records["first_sim"][0]) == 0 for p in parts)
+    seq = S.sequential_layout(np.random.default_rng(5), 10)
+    st = np.random.default_rng(5).bit_generator.state["state"]
+    assert int(seq.records["s"][0, 0]) == st["state"] >> 64 and int(seq.records["s"][0, 3]) == st["inc"] & (2 ** 64 - 1)
+
+
+def test_consume_draws_matches_numpy():
+    from mcframework_b200._streams import consume_draws
+
+    for mk in (lambda: np.random.default_rng(5), lambda: np.random.Generator(np.random.Philox(7))):
+        for pre in (0, 1, 3, 6):
+            for d in (1, 2, 4, 5, 9, 1000):
+                a, b = mk(), mk()
+                a.bit_generator.random_raw(pre), b.bit_generator.random_raw(pre)
+                want = int(np.atleast_1d(a.bit_generator.random_raw(d))[-1])
+                assert consume_draws(b, d) == want
+                assert a.bit_generator.random_raw(6).tolist() == b.bit_generator.random_raw(6).tolist()
+
+
+# ------------------------------------------------------------------------------------- quantile rule
+def test_quantile_plan_and_lerp_are_numpy_percentile():
+    from mcframework_b200._stats_device import lerp_like_numpy, quantile_plan
+
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 10, 1001, 65_536):
+        x = np.sort(rng.normal(0, 3, n))
+        pcts = [0, 1, 2.5, 5, 25, 33.3, 50, 75, 95, 97.5, 99, 100]
+        lo, hi, g = quantile_plan(n, pcts)
+        assert np.array_equal(lerp_like_numpy(x[lo], x[hi], g), np.percentile(x, pcts))
+
+
+def test_summary_merge_is_chan():
+    from mcframework_b200._stats_device import MomentSummary, merge_summaries
+
+    rng = np.random.default_rng(1)
+    x = rng.lognormal(0, 1, 10_000)
+
+    def summ(a):
+        m = a.mean()
+        return MomentSummary(a.size, 0, 0, 0, m, ((a - m) ** 2).sum(), ((a - m) ** 3).sum(), ((a - m) ** 4).sum(),
+                             ((a - 1.0) ** 2).sum(), a.sum(), a.min(), a.max())
+
+    whole = summ(x)
+    merged = merge_summaries([summ(x[:100]), summ(x[100:7000]), summ(x[7000:7000]) if False else summ(x[7000:])])
+    for f in ("n", "mean", "m2", "m3", "m4", "sq_target", "total", "vmin", "vmax"):
+        np.testing.assert_allclose(getattr(merged, f), getattr(whole, f), rtol=1e-11)
+
+
+# ------------------------------------------------------------------------------------- host API logic
+def test_validation_messages_and_context():
+    import mcframework_b200 as m
+    from mcframework_b200.core import make_blocks
+
+    sim = m.PiEstimationSimulation()
+    for kw, msg in ((dict(n_simulations=0), "n_simulations must be positive"),
+                    (dict(n_simulations=5, n_workers=0), "n_workers must be positive"),
+                    (dict(n_simulations=5, confidence=1.0), r"confidence must be in the interval \(0, 1\)"),
+                    (dict(n_simulations=5, ci_method="x"), "ci_method must be one of")):
+        with pytest.raises(ValueError, match=msg):
+            sim.run(**kw)
+    assert make_blocks(10, 4) == [(0, 4), (4, 8), (8, 10)] and make_blocks(0, 3) == []
+    with pytest.raises(ValueError, match="n_bootstrap .* should be >= 100"):
+        m.StatsContext(n=10, n_bootstrap=50)
+    with pytest.raises(ValueError, match="ess .* cannot exceed n"):
+        m.StatsContext(n=10, ess=11)
+    ctx = m.StatsContext(n=100, confidence=0.9, nan_policy="omit")
+    assert ctx.q_bound() == (100.0 * ((1 - 0.9) / 2), 100.0 * (1 - (1 - 0.9) / 2)) and ctx.eff_n(7, 5) == 5
+    fw = m.MonteCarloFramework()
+    with pytest.raises(ValueError, match="Simulation 'nope' not found"):
+        fw.run_simulation("nope", 10)
+    fw.results["a"] = m.SimulationResult(np.zeros(4), 4, 0.0, 1.0, 2.0, {50: 1.5}, {}, {"requested_percentiles": [50]})
+    assert fw.compare_results(["a"], "var") == {"a": 4.0} and fw.compare_results(["a"], "p50") == {"a": 1.5}
+    with pytest.raises(ValueError, match="Percentile 75 not computed"):
+        fw.compare_results(["a"], "p75")
+    assert m.z_crit(0.95) == pytest.approx(1.959964, abs=1e-5) and m.autocrit(0.95, 10)[1] == "t"
+
+
+def test_builtin_hooks_map_to_programs():
+    import mcframework_b200 as m
+    from mcframework_b200 import _native as N
+
+    p = m.PortfolioSimulation()._program_for(dict(years=5, use_gbm=False))
+    assert p.kind == "normals" and p.n_steps == int(5 / (1.0 / 252.0)) and p.specs[0][0] == N.PORTFOLIO_LOG1P
+    b = m.BlackScholesSimulation()._program_for(dict(option_type="put", exercise_type="american", n_steps=10))
+    assert b.specs[0][0] == N.BS_AMER_PUT and b.n_steps == 10
+    with pytest.raises(ValueError, match="option_type must be 'call' or 'put'"):
+        m.BlackScholesSimulation()._program_for(dict(option_type="straddle"))
+
+    class Custom(m.PiEstimationSimulation):
+        def single_simulation(self, **kw):
+            return 1.0
+
+    assert Custom()._program_for({}) is None  # replaced hook => user Python code, looped on the host
+
+
+# ------------------------------------------------------------------------------------- hostemu
+@pytest.fixture(scope="module")
+def emu():
+    import hostemu
+
+    hostemu.build()
+    return hostemu
+
+
+def test_hostemu_pi_matches_oracle(emu):
+    from mcframework_b200 import _streams as S
+    from oracle import c_oracle as co
+
+    for n_points, anti in ((100, False), (33, True), (8193, False)):
+        lay = S.sequential_layout(np.random.default_rng(np.random.SeedSequence(77)), 23)
+        assert np.array_equal(emu.pi_hits(lay, n_points, anti), co.Gen.pcg64(77).pi(23, n_points, anti)[1])
+    lay = S.parallel_layout(np.random.SeedSequence(123), 20_000, 8)
+    hits = emu.pi_hits(lay, 100)
+    assert int(hits.sum()) == 1_570_354
+
+
+def test_hostemu_normal_plan_matches_oracle(emu):
+    from mcframework_b200 import _streams as S
+    from oracle import c_oracle as co
+
+    for seed, n, steps in ((42, 300, 252), (3, 2000, 7)):
+        lay = S.sequential_layout(np.random.default_rng(np.random.SeedSequence(seed)), n)
+        rc, starts, end, _ = emu.normal_plan(lay, steps)
+        assert rc == 0
+        g, want = co.Gen.pcg64(seed), []
+        for _ in range(n):
+            want.append(g.consumed)
+            g.standard_normal(steps)
+        assert np.array_equal(starts, np.array(want, dtype=np.uint64)) and int(end[0]) == g.consumed

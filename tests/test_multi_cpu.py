@@ -1,0 +1,122 @@
+"""World-size-2 gloo tests (CPU): the host side of the N>1 path -- block sharding, result gathering, and the
+combination of per-rank statistical partials.  Kernels are not involved (those are covered by ``-m gpu``)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _summary_of(a):
+    from mcframework_b200._stats_device import MomentSummary
+
+    m = a.mean() if a.size else 0.0
+    return MomentSummary(a.size, 0, 0, 0, m, ((a - m) ** 2).sum(), ((a - m) ** 3).sum(), ((a - m) ** 4).sum(),
+                         ((a - 2.0) ** 2).sum(), a.sum(), a.min() if a.size else np.inf, a.max() if a.size else -np.inf)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mcframework_b200 import _multi, _streams as S
+        from mcframework_b200._stats_device import MomentSummary, merge_summaries, quantile_plan
+
+        # (1) every rank derives the SAME block layout from the seed and takes a contiguous range of blocks
+        n = 20_011
+        full = S.parallel_layout(np.random.SeedSequence(7), n, 8)
+        mine = full.shard(rank, world)
+        lo = full.n_streams * rank // world
+        assert np.array_equal(mine.records["s"], full.records["s"][lo:lo + mine.n_streams])
+        assert int(mine.records["first_sim"][0]) == 0 and mine.n_total == int(mine.records["n_sims"].sum())
+
+        # (2) results come back in reference order on every rank (and on the root only)
+        first = int(full.records["first_sim"][lo])
+        local = torch.arange(first, first + mine.n_total, dtype=torch.float64)
+        everyone = _multi.gather_results(local, dist.group.WORLD)
+        assert torch.equal(everyone, torch.arange(n, dtype=torch.float64))
+        root = _multi.gather_results_to_root(local, dist.group.WORLD)
+        assert (root is None) == (rank != 0)
+        if rank == 0:
+            assert torch.equal(root, torch.arange(n, dtype=torch.float64))
+
+        # (3) moment partials: all-gather 12 doubles per rank, merge with the pairwise update formulas
+        x = np.random.default_rng(0).lognormal(0, 1, n)
+        part = torch.from_numpy(_summary_of(x[first:first + mine.n_total]).to_array())
+        parts = [torch.empty_like(part) for _ in range(world)]
+        dist.all_gather(parts, part)
+        merged = merge_summaries(MomentSummary.from_array(p.numpy()) for p in parts)
+        whole = _summary_of(x)
+        for f in ("n", "mean", "m2", "m3", "m4", "sq_target", "total", "vmin", "vmax"):
+            np.testing.assert_allclose(getattr(merged, f), getattr(whole, f), rtol=1e-11)
+
+        # (4) radix-select combine: summed per-rank digit histograms select the global order statistic
+        keys = np.sort(x).view(np.uint64)  # positive doubles: bit patterns are already order-preserving
+        ranks, _, _ = quantile_plan(n, [50])
+        want = np.sort(x)[ranks[0]]
+        mykeys = x[first:first + mine.n_total].view(np.uint64)
+        prefix, rem = np.uint64(0), int(ranks[0])
+        for p in range(8):
+            shift = np.uint64(64 - 8 * (p + 1))
+            sel = mykeys if p == 0 else mykeys[(mykeys >> (shift + np.uint64(8))) == prefix]
+            hist = torch.from_numpy(np.bincount(((sel >> shift) & np.uint64(255)).astype(np.int64), minlength=256))
+            dist.all_reduce(hist)
+            c = np.cumsum(hist.numpy())
+            d = int(np.searchsorted(c, rem, side="right"))
+            rem -= int(c[d - 1]) if d else 0
+            prefix = (prefix << np.uint64(8)) | np.uint64(d)
+        assert np.array([prefix], dtype=np.uint64).view(np.float64)[0] == want and keys.size == n
+
+        # (5) bootstrap slot-range sharding: ordinal bases from an all-gather of accepted counts
+        from oracle import c_oracle as co
+
+        npop, B = 1000, 7
+        g = co.Gen.pcg64(5)
+        slots = g.raw32(2 * 6000)
+        thr = (1 << 32) % npop
+        acc = ((slots.astype(np.uint64) * np.uint64(npop)) & np.uint64(0xFFFFFFFF)) >= thr
+        total = slots.size
+        a, b = total * rank // world, total * (rank + 1) // world
+        cnt = torch.tensor([int(acc[a:b].sum())])
+        cnts = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(cnts, cnt)
+        base = sum(int(c) for c in cnts[:rank])
+        idx = ((slots[a:b].astype(np.uint64) * np.uint64(npop)) >> np.uint64(32))[acc[a:b]]
+        ords = base + np.arange(idx.size)
+        keep = ords < B * npop
+        xs = np.random.default_rng(1).integers(0, 1000, npop).astype(float)
+        sums = torch.zeros(B, dtype=torch.float64)
+        sums.index_add_(0, torch.from_numpy(ords[keep] // npop), torch.from_numpy(xs[idx[keep].astype(np.int64)]))
+        dist.all_reduce(sums)
+        ref = np.random.default_rng(5)
+        want = np.array([xs[ref.integers(0, npop, size=npop)].sum() for _ in range(B)])
+        assert np.array_equal(sums.numpy(), want)
+        q.put((rank, "ok"))
+    except Exception as exc:  # noqa: BLE001
+        import traceback
+
+        q.put((rank, traceback.format_exc() + repr(exc)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_host_logic_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert out == {0: "ok", 1: "ok"}, out
