@@ -202,11 +202,8 @@ def _advance_generator(gen: np.random.Generator, slots_consumed: int) -> None:
         return
     last = consume_draws(gen, (t + 1) // 2)  # the draw whose halves were (partly) used
     st = bg.state
-    if t & 1:
-        st["has_uint32"] = 1
-        st["uinteger"] = last >> 32
-    else:
-        st["has_uint32"] = 0
+    st["has_uint32"] = 1 if (t & 1) else 0
+    st["uinteger"] = last >> 32  # NumPy keeps the (possibly already consumed) upper half in the state
     bg.state = st
 
 

@@ -294,16 +294,21 @@ __global__ void __launch_bounds__(256) gbm_terminal_kernel(const mcf_stream *__r
     if (i >= n_total) return;
     const int si = stream_of(streams, n_streams, i, hint);
     const mcf_stream st = streams[si];
+    const uint64_t start = sim_start[i];
     Cursor<KIND> cur;
-    cur.init(st, sim_start[i]);
+    cur.init(st, start);
+    // Per-thread trip count (start < 2^63 always): keeps the step counter in a per-thread register.  With a
+    // warp-uniform counter, ptxas 12.9 emitted a uniform-datapath loop (BSSY.RELIABLE / BRA.U.ANY) around the
+    // divergent ziggurat slow path that never terminated on sm_100a for the bodies with exp() inside the loop.
+    const int64_t steps = n_steps + (int64_t)(start >> 63);
     if (specs.n == 1) {
-        out[i] = run_terminal(cur, t, n_steps, specs.g[0]);
+        out[i] = run_terminal(cur, t, steps, specs.g[0]);
         return;
     }
     // several parameter sets on common random numbers (Greeks): the terminal log-price is affine
     // in sum(Z), so one pass over the normals serves every set (all sets are affine-sum modes).
     double zsum = 0.0;
-    for (int64_t k = 0; k < n_steps; k++) zsum = xadd(zsum, zig_normal(cur, t));
+    for (int64_t k = 0; k < steps; k++) zsum = xadd(zsum, zig_normal(cur, t));
     for (int s = 0; s < specs.n; s++) {
         const GbmDerived &g = specs.g[s];
         const double acc = xadd(xmul((double)n_steps, g.a), xmul(g.b, zsum));
@@ -334,13 +339,15 @@ __global__ void __launch_bounds__(256) gbm_paths_kernel(const mcf_stream *__rest
     if (i >= n_total) return;
     const int si = stream_of(streams, n_streams, i, hint);
     const mcf_stream st = streams[si];
+    const uint64_t start = sim_start[i];
     Cursor<KIND> cur;
-    cur.init(st, sim_start[i]);
+    cur.init(st, start);
+    const int64_t steps = n_steps + (int64_t)(start >> 63);  // per-thread trip count, see gbm_terminal_kernel
     const int64_t stride = time_major ? n_total : 1;
     double *p = paths + (time_major ? i : i * (n_steps + 1));
     double acc = 0.0;
     p[0] = exp(g.logs0);
-    for (int64_t k = 1; k <= n_steps; k++) {
+    for (int64_t k = 1; k <= steps; k++) {
         acc = xadd(acc, xadd(g.a, xmul(g.b, zig_normal(cur, t))));
         p[k * stride] = exp(xadd(g.logs0, acc));
     }
