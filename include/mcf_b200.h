@@ -123,6 +123,15 @@ int mcf_gbm_paths(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_stre
                   int64_t sims_per_stream_hint, const uint64_t *d_sim_start, const double *h_p4, int32_t time_major, double *d_paths,
                   void *cuda_stream);
 
+/* Stored path slices (BASELINE config 3; the reference stores either nothing, sims/portfolio.py:77-84, or every
+ * step, sims/black_scholes.py:415-418): values at steps 0, slice_stride, 2*slice_stride, ... <= n_steps, i.e.
+ * n_slices = n_steps/slice_stride + 1 per replication.  h_spec->mode is MCF_PORTFOLIO_GBM (p={V0,mu,sigma}, value
+ * V0*exp(cumulative log-return)) or MCF_PATH_TERMINAL (p={S0,r,sigma,T}).  Output (n_slices, n_total) when
+ * time_major (coalesced stores) else (n_total, n_slices). */
+int mcf_gbm_slices(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total, int64_t n_steps,
+                   int64_t sims_per_stream_hint, const uint64_t *d_sim_start, const mcf_gbm_spec *h_spec,
+                   int64_t slice_stride, int32_t time_major, double *d_out, void *cuda_stream);
+
 /* ---- (3) Longstaff-Schwartz backward induction ------------------------------------------
  * replaces _american_exercise_lsm (sims/black_scholes.py:109-193).  `d_paths_tm` is TIME-MAJOR:
  * element (step t, path i) at d_paths_tm[t*n_paths + i] (what mcf_gbm_paths writes with

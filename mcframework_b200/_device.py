@@ -136,3 +136,19 @@ def gbm_paths(dl: DeviceLayout, n_steps: int, plan: NormalPlan, S0: float, r: fl
     N.check("mcf_gbm_paths", rc)
     LAUNCHES["paths"] += 1
     return out
+
+
+def gbm_slices(dl: DeviceLayout, n_steps: int, plan: NormalPlan, mode: int, params, slice_stride: int,
+               time_major: bool = True):
+    """Path values at steps 0, stride, 2*stride, ...: float64 (n_slices, n) when time_major else (n, n_slices)."""
+    torch = _torch()
+    lay = dl.layout
+    n_slices = int(n_steps) // int(slice_stride) + 1
+    shape = (n_slices, lay.n_total) if time_major else (lay.n_total, n_slices)
+    out = torch.empty(shape, dtype=torch.float64, device="cuda")
+    rc = N.lib().mcf_gbm_slices(lay.kind, _ptr(dl.records), lay.n_streams, lay.n_total, int(n_steps), lay.hint,
+                                _ptr(plan.sim_start), _spec_array([(mode, params)]), int(slice_stride),
+                                int(bool(time_major)), _ptr(out), _stream_ptr())
+    N.check("mcf_gbm_slices", rc)
+    LAUNCHES["paths"] += 1
+    return out

@@ -353,6 +353,42 @@ __global__ void __launch_bounds__(256) gbm_paths_kernel(const mcf_stream *__rest
     }
 }
 
+
+// Stored path slices (BASELINE cfg 3): value at steps 0, stride, 2*stride, ... <= n_steps.  Time-major output
+// (n_slices, n_total) gives fully coalesced 8-byte stores per warp; row-major (n_total, n_slices) is what a
+// host caller reshapes most easily.  mode: MCF_PORTFOLIO_GBM -> V0*exp(sum), MCF_PATH_TERMINAL -> exp(log S0 + sum).
+template <int KIND>
+__global__ void __launch_bounds__(256) gbm_slices_kernel(const mcf_stream *__restrict__ streams, int n_streams,
+                                                         int64_t n_total, int64_t n_steps, int64_t hint,
+                                                         const uint64_t *__restrict__ sim_start, GbmDerived g,
+                                                         int64_t slice_stride, int64_t n_slices, int time_major,
+                                                         double *__restrict__ out) {
+    __shared__ ZigShared sh;
+    const ZigTables t = load_zig_tables(sh);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    const int si = stream_of(streams, n_streams, i, hint);
+    const mcf_stream st = streams[si];
+    const uint64_t start = sim_start[i];
+    Cursor<KIND> cur;
+    cur.init(st, start);
+    const int64_t steps = n_steps + (int64_t)(start >> 63);  // per-thread trip count, see gbm_terminal_kernel
+    const int64_t stride = time_major ? n_total : 1;
+    double *p = out + (time_major ? i : i * n_slices);
+    const bool path_mode = g.mode == MCF_PATH_TERMINAL;
+    double acc = 0.0;
+    p[0] = path_mode ? exp(g.logs0) : g.s0;
+    int64_t next = slice_stride, slot = 1;
+    for (int64_t k = 1; k <= steps; k++) {
+        acc = xadd(acc, xadd(g.a, xmul(g.b, zig_normal(cur, t))));
+        if (k == next) {
+            p[slot * stride] = path_mode ? exp(xadd(g.logs0, acc)) : xmul(g.s0, exp(acc));
+            slot++;
+            next += slice_stride;
+        }
+    }
+}
+
 // ================================================================================= C ABI
 static int g_last_cuda_error = 0;
 #define MCF_STR2(x) #x
@@ -523,3 +559,27 @@ int mcf_gbm_paths(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_stre
 
 
 }  // extern "C"
+
+extern "C" int mcf_gbm_slices(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total,
+                              int64_t n_steps, int64_t sims_per_stream_hint, const uint64_t *d_sim_start,
+                              const mcf_gbm_spec *h_spec, int64_t slice_stride, int32_t time_major, double *d_out,
+                              void *cuda_stream) {
+    if (!d_streams || n_streams <= 0 || n_total <= 0 || n_steps <= 0 || !d_sim_start || !h_spec || slice_stride <= 0 ||
+        !d_out || (h_spec->mode != MCF_PORTFOLIO_GBM && h_spec->mode != MCF_PATH_TERMINAL))
+        return MCF_ERR_BAD_ARG;
+    GbmDerived g;
+    int rc = derive_spec(*h_spec, n_steps, &g);
+    if (rc) return rc;
+    const int64_t n_slices = n_steps / slice_stride + 1;
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    if (gen_kind == MCF_GEN_PCG64)
+        gbm_slices_kernel<MCF_GEN_PCG64><<<grid_for(n_total, 256), 256, 0, cs>>>(
+            d_streams, n_streams, n_total, n_steps, sims_per_stream_hint, d_sim_start, g, slice_stride, n_slices,
+            time_major, d_out);
+    else
+        gbm_slices_kernel<MCF_GEN_PHILOX><<<grid_for(n_total, 256), 256, 0, cs>>>(
+            d_streams, n_streams, n_total, n_steps, sims_per_stream_hint, d_sim_start, g, slice_stride, n_slices,
+            time_major, d_out);
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}

@@ -200,7 +200,8 @@ def test_engine_taxonomy_and_small_samples(m):
     out = eng.compute(np.array([1.0, 2.0, 3.0, 4.0]), m.StatsContext(n=4, rng=1, n_bootstrap=100))
     skipped = dict(out.skipped)
     assert set(skipped) == {"chebyshev_required_n", "markov_error_prob", "bias_to_target", "mse_to_target"}
-    assert out.metrics["mean"] == 2.5 and out.metrics["percentiles"] == {5: 1.15, 25: 1.75, 50: 2.5, 75: 3.25, 95: 3.85}
+    want = dict(zip((5, 25, 50, 75, 95), map(float, np.percentile([1.0, 2.0, 3.0, 4.0], (5, 25, 50, 75, 95)))))
+    assert out.metrics["mean"] == 2.5 and out.metrics["percentiles"] == want
     assert out.metrics["skew"] == 0.0 and out.metrics["ci_mean"]["method"] == "t"
     assert se.std(np.array([1.0]), m.StatsContext(n=1)) is None and se.mean(np.array([]), {"n": 0}) is None
     assert se.skew(np.array([1.0, 2.0]), None) == 0.0 and se.kurtosis(np.array([1.0, 2.0, 3.0]), None) == 0.0

@@ -303,3 +303,20 @@ def test_count_less_and_compact(sd):
     xd = _dev_tensor(x)
     assert sd.count_less(xd, 0.25) == int(np.sum(x < 0.25))
     assert np.array_equal(sd.compact_finite(xd).cpu().numpy(), x[np.isfinite(x)])
+
+
+def test_path_slices_are_strided_paths(dev):
+    """mcf_gbm_slices == every stride-th column of mcf_gbm_paths (same stream, same plan); portfolio mode
+    == V0*exp(cumulative log-return) and its last slice equals the PortfolioSimulation terminal value."""
+    D, N, S = dev
+    dl = D.DeviceLayout.of(S.parallel_layout(np.random.SeedSequence(21), 20_000, 4))
+    plan = D.normal_plan(dl, 48)
+    full = D.gbm_paths(dl, 48, plan, 100.0, 0.05, 0.2, 1.0).cpu().numpy()
+    tm = D.gbm_slices(dl, 48, plan, N.PATH_TERMINAL, [100.0, 0.05, 0.2, 1.0], 12, time_major=True).cpu().numpy()
+    rm = D.gbm_slices(dl, 48, plan, N.PATH_TERMINAL, [100.0, 0.05, 0.2, 1.0], 12, time_major=False).cpu().numpy()
+    assert tm.shape == (5, 20_000) and np.array_equal(tm.T, rm) and np.array_equal(rm, full[:, ::12])
+    odd = D.gbm_slices(dl, 48, plan, N.PATH_TERMINAL, [100.0, 0.05, 0.2, 1.0], 7).cpu().numpy()
+    assert np.array_equal(odd.T, full[:, ::7])
+    pf = D.gbm_slices(dl, 48, plan, N.PORTFOLIO_GBM, [1e4, 0.07, 0.2], 48).cpu().numpy()
+    term = D.gbm_terminal(dl, 48, plan, [(N.PORTFOLIO_GBM, [1e4, 0.07, 0.2])])[0].cpu().numpy()
+    assert np.all(pf[0] == 1e4) and np.array_equal(pf[1], term)
