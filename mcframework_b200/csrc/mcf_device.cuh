@@ -253,6 +253,49 @@ struct Cursor<MCF_GEN_PHILOX> {
 };
 
 // ---------------------------------------------------------------------------------------
+// Draw delivery.  `consume_draws(cur, f)` hands consecutive 64-bit draws to `f` until it returns false.
+// For Philox the draws come in blocks of four that are generated ONCE per loop trip by every lane of the
+// warp together: lanes whose ziggurat chains have drifted apart still execute the (expensive) block function
+// converged, instead of each lane regenerating blocks at its own iteration (4x divergence waste).
+// ---------------------------------------------------------------------------------------
+template <class F>
+MCF_HD void consume_draws(Cursor<MCF_GEN_PCG64> &cur, F f) {
+    while (f(cur.next64())) {
+    }
+}
+
+template <class F>
+MCF_HD void consume_draws(Cursor<MCF_GEN_PHILOX> &cur, F f) {
+    for (;;) {
+        const unsigned first = (unsigned)(cur.q & 3ULL);
+        cur.load_block(cur.q >> 2);
+        const uint64_t v0 = cur.v0, v1 = cur.v1, v2 = cur.v2, v3 = cur.v3;
+        bool go = true;
+        if (first == 0) {
+            cur.q++;
+            cur.pos++;
+            go = f(v0);
+        }
+        if (go && first <= 1) {
+            cur.q++;
+            cur.pos++;
+            go = f(v1);
+        }
+        if (go && first <= 2) {
+            cur.q++;
+            cur.pos++;
+            go = f(v2);
+        }
+        if (go) {
+            cur.q++;
+            cur.pos++;
+            go = f(v3);
+        }
+        if (!go) return;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Ziggurat
 // ---------------------------------------------------------------------------------------
 struct ZigTables {
@@ -263,32 +306,95 @@ struct ZigTables {
 #define MCF_ZIG_R 3.6541528853610088
 #define MCF_ZIG_INV_R 0.27366123732975828
 
-// One pass through NumPy's `for (;;)` body.  Returns true when a normal is produced (x).
-// Consumption: 1 draw (fast accept), 2 draws (wedge, accepted or not), 1+2k draws (tail).
+// NumPy's random_standard_normal as a state machine over single draws (distributions.c):
+//   state 0: the draw starts an attempt (1 draw when rabs < ki[idx]: 98.5 %)
+//   state 1: wedge -- the draw is the uniform of the acceptance test; accepted or not, back to state 0
+//   state 2/3: tail (idx == 0) -- draws come in (xx, yy) pairs until 2*yy > xx*xx
+struct ZigFsm {
+    uint32_t state, idx;
+    uint64_t rabs;
+    double x, xx;
+};
+MCF_HD void zig_reset(ZigFsm &s) {
+    s.state = 0;
+    s.idx = 0;
+    s.rabs = 0;
+    s.x = 0.0;
+    s.xx = 0.0;
+}
+
+// Feed one draw.  Returns true when a normal is produced (in `out`).
+MCF_HD bool zig_feed(ZigFsm &s, uint64_t r, const ZigTables &t, double &out) {
+    if (s.state == 0) {
+        const unsigned idx = (unsigned)(r & 0xffULL);
+        r >>= 8;
+        const unsigned sign = (unsigned)(r & 1ULL);
+        const uint64_t rabs = (r >> 1) & 0x000fffffffffffffULL;
+        const double v = xmul(u52_to_double(rabs), t.wi[idx]);
+        const double x = sign ? -v : v;
+        if (rabs < t.ki[idx]) {
+            out = x;
+            return true;
+        }
+        s.idx = idx;
+        s.rabs = rabs;
+        s.x = x;
+        s.state = idx == 0 ? 2u : 1u;
+        return false;
+    }
+    if (s.state == 1) {
+        s.state = 0;
+        const double f1 = t.fi[s.idx - 1], f0 = t.fi[s.idx];
+        const double lhs = xadd(xmul(xsub(f1, f0), u64_to_unit_double(r)), f0);
+        if (lhs < exp(xmul(xmul(-0.5, s.x), s.x))) {
+            out = s.x;
+            return true;
+        }
+        return false;
+    }
+    if (s.state == 2) {
+        s.xx = xmul(-MCF_ZIG_INV_R, log1p(-u64_to_unit_double(r)));
+        s.state = 3;
+        return false;
+    }
+    const double yy = -log1p(-u64_to_unit_double(r));
+    if (xadd(yy, yy) > xmul(s.xx, s.xx)) {
+        const double m = xadd(MCF_ZIG_R, s.xx);
+        out = ((s.rabs >> 8) & 1ULL) ? -m : m;
+        s.state = 0;
+        return true;
+    }
+    s.state = 2;
+    return false;
+}
+
+// the next `n` standard normals of the stream, in order: f(z) for each
+template <class Cur, class F>
+MCF_HD void for_each_normal(Cur &cur, const ZigTables &t, int64_t n, F f) {
+    if (n <= 0) return;
+    ZigFsm s;
+    zig_reset(s);
+    int64_t left = n;
+    consume_draws(cur, [&](uint64_t r) {
+        double z;
+        if (zig_feed(s, r, t, z)) {
+            f(z);
+            left--;
+        }
+        return left > 0;
+    });
+}
+
+// One pass through NumPy's `for (;;)` body (cursor-driven form; tests and single draws).
 template <class Cur>
 MCF_HD bool zig_attempt(Cur &cur, const ZigTables &t, double &x) {
-    uint64_t r = cur.next64();
-    unsigned idx = (unsigned)(r & 0xffULL);
-    r >>= 8;
-    unsigned sign = (unsigned)(r & 1ULL);
-    uint64_t rabs = (r >> 1) & 0x000fffffffffffffULL;
-    double v = xmul(u52_to_double(rabs), t.wi[idx]);
-    x = sign ? -v : v;
-    if (rabs < t.ki[idx]) return true;
-    if (idx == 0) {
-        for (;;) {
-            double xx = xmul(-MCF_ZIG_INV_R, log1p(-u64_to_unit_double(cur.next64())));
-            double yy = -log1p(-u64_to_unit_double(cur.next64()));
-            if (xadd(yy, yy) > xmul(xx, xx)) {
-                double m = xadd(MCF_ZIG_R, xx);
-                x = ((rabs >> 8) & 1ULL) ? -m : m;
-                return true;
-            }
-        }
-    }
-    double f1 = t.fi[idx - 1], f0 = t.fi[idx];
-    double lhs = xadd(xmul(xsub(f1, f0), u64_to_unit_double(cur.next64())), f0);
-    return lhs < exp(xmul(xmul(-0.5, x), x));
+    ZigFsm s;
+    zig_reset(s);
+    bool emitted = false;
+    do {
+        emitted = zig_feed(s, cur.next64(), t, x);
+    } while (s.state != 0);
+    return emitted;
 }
 
 template <class Cur>
@@ -319,12 +425,19 @@ MCF_HD int find_stream(const mcf_stream *streams, int n_streams, int64_t sim) {
 // ---------------------------------------------------------------------------------------
 template <class Cur>
 MCF_HD int64_t pi_count_hits(Cur &cur, int64_t npts) {
-    int64_t hits = 0;
-    for (int64_t i = 0; i < npts; i++) {
-        double x = xadd(-1.0, xmul(2.0, u64_to_unit_double(cur.next64())));
-        double y = xadd(-1.0, xmul(2.0, u64_to_unit_double(cur.next64())));
-        hits += (xadd(xmul(x, x), xmul(y, y)) <= 1.0) ? 1 : 0;
-    }
+    if (npts <= 0) return 0;
+    int64_t hits = 0, left = 2 * npts;
+    double x = 0.0;
+    consume_draws(cur, [&](uint64_t r) {
+        const double c = xadd(-1.0, xmul(2.0, u64_to_unit_double(r)));
+        if (left & 1) {  // second coordinate of the point
+            hits += (xadd(xmul(x, x), xmul(c, c)) <= 1.0) ? 1 : 0;
+        } else {
+            x = c;
+        }
+        left--;
+        return left > 0;
+    });
     return hits;
 }
 
@@ -351,14 +464,21 @@ MCF_HD ChunkInfo scan_chunk(Cur &cur, uint64_t chunk_base, uint32_t entry, const
     ci.emitmask = 0;
     ci.gen_entry = entry;
     const uint64_t end = chunk_base + MCF_CHUNK;
-    while (cur.pos < end) {
-        unsigned j = (unsigned)(cur.pos - chunk_base);
-        double x;
-        bool emitted = zig_attempt(cur, t, x);
-        ci.startmask |= 1ULL << j;
-        if (emitted) ci.emitmask |= 1ULL << j;
+    if (cur.pos < end) {
+        ZigFsm s;
+        zig_reset(s);
+        unsigned js = 0;  // offset (in the chunk) where the attempt in progress started
+        consume_draws(cur, [&](uint64_t r) {
+            if (s.state == 0) {
+                js = (unsigned)(cur.pos - 1 - chunk_base);  // pos was advanced before the draw was handed over
+                ci.startmask |= 1ULL << js;
+            }
+            double x;
+            if (zig_feed(s, r, t, x)) ci.emitmask |= 1ULL << js;
+            return !(s.state == 0 && cur.pos >= end);  // go on inside the chunk, or until the straddling attempt ends
+        });
     }
-    uint64_t over = cur.pos - end;
+    const uint64_t over = cur.pos - end;
     ci.exit = over >= MCF_EXIT_OVERFLOW ? MCF_EXIT_OVERFLOW : (uint32_t)over;
     return ci;
 }
@@ -410,42 +530,42 @@ MCF_HD double run_terminal(Cur &cur, const ZigTables &t, int64_t n_steps, const 
     switch (g.mode) {
     case MCF_NORMAL_SUM: {
         double acc = 0.0;
-        for (int64_t k = 0; k < n_steps; k++) acc = xadd(acc, zig_normal(cur, t));
+        for_each_normal(cur, t, n_steps, [&](double z) { acc = xadd(acc, z); });
         return acc;
     }
     case MCF_BS_EURO_CALL:
     case MCF_BS_EURO_PUT:
-    case MCF_PORTFOLIO_GBM: {
+    case MCF_PORTFOLIO_GBM:
+    case MCF_PATH_TERMINAL: {
         double acc = 0.0;
-        for (int64_t k = 0; k < n_steps; k++) acc = xadd(acc, xadd(g.a, xmul(g.b, zig_normal(cur, t))));
-        double st = xmul(g.s0, exp(acc));
+        const double a = g.a, b = g.b;
+        for_each_normal(cur, t, n_steps, [&](double z) { acc = xadd(acc, xadd(a, xmul(b, z))); });
+        if (g.mode == MCF_PATH_TERMINAL) return exp(xadd(g.logs0, acc));  // exp(log(S0) + cumsum[-1])
+        const double st = xmul(g.s0, exp(acc));
         if (g.mode == MCF_PORTFOLIO_GBM) return st;
-        double pay = g.mode == MCF_BS_EURO_CALL ? fmax(xsub(st, g.K), 0.0) : fmax(xsub(g.K, st), 0.0);
+        const double pay = g.mode == MCF_BS_EURO_CALL ? fmax(xsub(st, g.K), 0.0) : fmax(xsub(g.K, st), 0.0);
         return xmul(pay, g.disc);
     }
     case MCF_PORTFOLIO_LOG1P: {
         double acc = 0.0;
-        for (int64_t k = 0; k < n_steps; k++) acc = xadd(acc, log1p(xadd(g.a, xmul(g.b, zig_normal(cur, t)))));
+        const double a = g.a, b = g.b;
+        for_each_normal(cur, t, n_steps, [&](double z) { acc = xadd(acc, log1p(xadd(a, xmul(b, z)))); });
         return xmul(g.s0, exp(acc));
-    }
-    case MCF_PATH_TERMINAL: {
-        double acc = 0.0;  // np.cumsum of log-returns, then exp(log(S0) + cumsum[-1])
-        for (int64_t k = 0; k < n_steps; k++) acc = xadd(acc, xadd(g.a, xmul(g.b, zig_normal(cur, t))));
-        return exp(xadd(g.logs0, acc));
     }
     case MCF_BS_AMER_CALL:
     case MCF_BS_AMER_PUT: {
         const bool call = g.mode == MCF_BS_AMER_CALL;
-        double s = exp(g.logs0);
-        double best = call ? fmax(xsub(s, g.K), 0.0) : fmax(xsub(g.K, s), 0.0);  // k = 0, discount 1
-        double acc = 0.0;
-        for (int64_t k = 1; k <= n_steps; k++) {
-            acc = xadd(acc, xadd(g.a, xmul(g.b, zig_normal(cur, t))));
-            s = exp(xadd(g.logs0, acc));
-            double intr = call ? fmax(xsub(s, g.K), 0.0) : fmax(xsub(g.K, s), 0.0);
-            double v = xmul(intr, exp(xmul(-g.rdt, (double)k)));
-            best = fmax(best, v);
-        }
+        const double a = g.a, b = g.b, K = g.K, logs0 = g.logs0, nrdt = -g.rdt;
+        const double s0 = exp(logs0);
+        double best = call ? fmax(xsub(s0, K), 0.0) : fmax(xsub(K, s0), 0.0);  // k = 0, discount 1
+        double acc = 0.0, kf = 0.0;
+        for_each_normal(cur, t, n_steps, [&](double z) {
+            kf += 1.0;  // exact for every representable step count
+            acc = xadd(acc, xadd(a, xmul(b, z)));
+            const double s = exp(xadd(logs0, acc));
+            const double intr = call ? fmax(xsub(s, K), 0.0) : fmax(xsub(K, s), 0.0);
+            best = fmax(best, xmul(intr, exp(xmul(nrdt, kf))));
+        });
         return best;
     }
     default:

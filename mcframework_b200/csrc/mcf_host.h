@@ -110,7 +110,8 @@ static inline PiGeom pi_geom(int64_t n_points, int antithetic) {
     g.weight = antithetic ? 2 : 1;
     g.draws_per_sim = 2 * g.m + (g.extra ? 2 : 0);
     g.ppt = (g.m + 31) / 32;
-    if (g.ppt < 1) g.ppt = 1;
+    g.ppt += g.ppt & 1;  // even: every lane then starts on the same Philox block phase (2 draws per point, 4 per block)
+    if (g.ppt < 2) g.ppt = 2;
     if (g.ppt > 256) g.ppt = 256;  // long replications are cut into slices of 32*256 points
     g.parts = (g.m + 32 * g.ppt - 1) / (32 * g.ppt);
     if (g.parts < 1) g.parts = 1;

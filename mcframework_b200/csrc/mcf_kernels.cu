@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(256) gbm_terminal_kernel(const mcf_stream *__r
     // several parameter sets on common random numbers (Greeks): the terminal log-price is affine
     // in sum(Z), so one pass over the normals serves every set (all sets are affine-sum modes).
     double zsum = 0.0;
-    for (int64_t k = 0; k < steps; k++) zsum = xadd(zsum, zig_normal(cur, t));
+    for_each_normal(cur, t, steps, [&](double z) { zsum = xadd(zsum, z); });
     for (int s = 0; s < specs.n; s++) {
         const GbmDerived &g = specs.g[s];
         const double acc = xadd(xmul((double)n_steps, g.a), xmul(g.b, zsum));
@@ -346,11 +346,13 @@ __global__ void __launch_bounds__(256) gbm_paths_kernel(const mcf_stream *__rest
     const int64_t stride = time_major ? n_total : 1;
     double *p = paths + (time_major ? i : i * (n_steps + 1));
     double acc = 0.0;
-    p[0] = exp(g.logs0);
-    for (int64_t k = 1; k <= steps; k++) {
-        acc = xadd(acc, xadd(g.a, xmul(g.b, zig_normal(cur, t))));
-        p[k * stride] = exp(xadd(g.logs0, acc));
-    }
+    const double a = g.a, b = g.b, logs0 = g.logs0;
+    p[0] = exp(logs0);
+    for_each_normal(cur, t, steps, [&](double z) {
+        acc = xadd(acc, xadd(a, xmul(b, z)));
+        p += stride;
+        *p = exp(xadd(logs0, acc));
+    });
 }
 
 
@@ -377,16 +379,17 @@ __global__ void __launch_bounds__(256) gbm_slices_kernel(const mcf_stream *__res
     double *p = out + (time_major ? i : i * n_slices);
     const bool path_mode = g.mode == MCF_PATH_TERMINAL;
     double acc = 0.0;
-    p[0] = path_mode ? exp(g.logs0) : g.s0;
-    int64_t next = slice_stride, slot = 1;
-    for (int64_t k = 1; k <= steps; k++) {
-        acc = xadd(acc, xadd(g.a, xmul(g.b, zig_normal(cur, t))));
-        if (k == next) {
-            p[slot * stride] = path_mode ? exp(xadd(g.logs0, acc)) : xmul(g.s0, exp(acc));
-            slot++;
-            next += slice_stride;
+    const double a = g.a, b = g.b, logs0 = g.logs0, s0 = g.s0;
+    p[0] = path_mode ? exp(logs0) : s0;
+    int64_t until_store = slice_stride;
+    for_each_normal(cur, t, steps, [&](double z) {
+        acc = xadd(acc, xadd(a, xmul(b, z)));
+        if (--until_store == 0) {
+            p += stride;
+            *p = path_mode ? exp(xadd(logs0, acc)) : xmul(s0, exp(acc));
+            until_store = slice_stride;
         }
-    }
+    });
 }
 
 // ================================================================================= C ABI
