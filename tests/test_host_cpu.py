@@ -197,3 +197,32 @@ def test_hostemu_normal_plan_matches_oracle(emu):
             want.append(g.consumed)
             g.standard_normal(steps)
         assert np.array_equal(starts, np.array(want, dtype=np.uint64)) and int(end[0]) == g.consumed
+
+
+def test_hostemu_terminal_values_match_reference_golden(emu, golden):
+    """Plan + replay (block-synchronous Philox consumption, ziggurat state machine) on the host build of the
+    device functions reproduces the reference's result vectors."""
+    from mcframework_b200 import _native as N, _streams as S
+
+    _, a = golden
+    BS = [100.0, 100.0, 1.0, 0.05, 0.2]
+
+    def seq(seed, n):
+        return S.sequential_layout(np.random.default_rng(np.random.SeedSequence(seed)), n)
+
+    cases = [(seq(42, 1000), 252, N.BS_EURO_CALL, BS, "G4_bs_call_seq"),
+             (seq(42, 1000), 252, N.BS_AMER_PUT, BS, "G4_bs_amer_put_seq"),
+             (S.parallel_layout(np.random.SeedSequence(11), 20_000, 4), 64, N.BS_EURO_CALL, BS, "G4_bs_call_par"),
+             (S.parallel_layout(np.random.SeedSequence(11), 20_000, 2), 16, N.BS_AMER_PUT, BS, "G4_bs_amer_put_par"),
+             (seq(42, 500), 504, N.PORTFOLIO_LOG1P, [1e4, .07, .2], "G5_portfolio_log1p_seq")]
+    for lay, steps, mode, p, key in cases:
+        rc, starts, _, _ = emu.normal_plan(lay, steps)
+        assert rc == 0
+        np.testing.assert_allclose(emu.gbm_terminal(lay, steps, starts, [(mode, p)])[0], a[key], rtol=1e-12, atol=1e-11)
+    lay = S.parallel_layout(np.random.SeedSequence(5), 20_001, 3)
+    assert np.array_equal(emu.pi_hits(lay, 33, True) * 4.0 / 33, a["G2b_pi_antithetic_parallel_results"])
+    g = np.random.Generator(np.random.Philox(9))
+    g.random(3)  # mid-buffer Philox state
+    _, rec = S.generator_record(g)
+    z, _ = emu.normals(rec, 0, 1000)
+    assert np.array_equal(z, g.standard_normal(1000))
