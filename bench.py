@@ -308,8 +308,9 @@ def b200_arm(args):
     else:
         wi = inst.get(dominant + "_warp_inst_per_path_step")
         ach = (wi * P * N_STEPS / (dom_ms / 1e3)) if (wi and dom_ms) else None
+        tr = inst.get(dominant + "_dram_bytes_per_path_step")
         roof.update({"achieved": ach / 1e9 if ach else None, "peak": issue_peak / 1e9, "unit": "Gwarp-inst/s",
-                     "frac": (ach / issue_peak) if ach else None, "traffic": inst.get(dominant + "_dram_bytes_per_launch"),
+                     "frac": (ach / issue_peak) if ach else None, "traffic": tr * P * N_STEPS if tr else None,
                      "peak_source": f"148 SM x 4 schedulers x {sm_mhz:.0f} MHz (median SM clock under load)",
                      "inst_source": inst.get("source"),
                      "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak if hbm_ach else None,
