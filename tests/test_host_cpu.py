@@ -226,3 +226,19 @@ def test_hostemu_terminal_values_match_reference_golden(emu, golden):
     _, rec = S.generator_record(g)
     z, _ = emu.normals(rec, 0, 1000)
     assert np.array_equal(z, g.standard_normal(1000))
+
+
+def test_hostemu_ziggurat_with_certified_wedge_bounds_is_numpy_bit_for_bit(emu):
+    """2e6 normals per generator (~3e4 wedge tests, ~600 tail draws): every value equals NumPy's, so every
+    accept/reject decision taken from the polynomial bounds instead of exp() was NumPy's decision."""
+    from mcframework_b200 import _streams as S
+
+    for gen in (np.random.default_rng(2024), np.random.Generator(np.random.Philox(77))):
+        _, rec = S.generator_record(gen)
+        z, end = emu.normals(rec, 0, 2_000_000)
+        before = gen.bit_generator.state
+        assert np.array_equal(z, gen.standard_normal(2_000_000))
+        probe = np.random.Generator(type(gen.bit_generator)())
+        probe.bit_generator.state = before
+        S.consume_draws(probe, int(end))
+        assert probe.bit_generator.random_raw(4).tolist() == gen.bit_generator.random_raw(4).tolist()
