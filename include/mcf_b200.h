@@ -97,8 +97,10 @@ int mcf_pi_hits(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_stream
  * (64 draws per thread) + entry fix-up + prefix sum + locate.  The plan depends only on the
  * streams and draws_per_sim, not on model parameters: Greeks re-use one plan for all bumps
  * (sims/black_scholes.py:286-362 re-seed with 42 before every revaluation).
- * Step B, mcf_gbm_terminal / mcf_gbm_paths: one thread per replication replays its
- * n_steps normals from the planned position, path state in registers. */
+ * Step B, mcf_gbm_terminal / mcf_gbm_paths / mcf_gbm_slices: one thread per replication replays the draws of
+ * its stream range; the plan workspace (`d_plan_workspace`, the one mcf_normal_plan filled -- keep it alive)
+ * holds one bit per draw saying "an attempt starting here emits a normal", so the replay is branch-light:
+ * no acceptance tests are repeated, only emitted draws are converted.  Path state stays in registers. */
 int64_t mcf_normal_plan_workspace_bytes(int32_t n_streams, int64_t max_sims_per_stream, int64_t normals_per_sim,
                                         double slack);
 int mcf_normal_plan(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total,
@@ -113,15 +115,16 @@ int mcf_workspace_status(const void *d_workspace, void *cuda_stream);
  * replaces BlackScholesSimulation / BlackScholesPathSimulation / PortfolioSimulation
  * .single_simulation under the replication loop. */
 int mcf_gbm_terminal(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total,
-                     int64_t n_steps, int64_t sims_per_stream_hint, const uint64_t *d_sim_start, const mcf_gbm_spec *h_specs, int32_t n_specs, double *d_out,
+                     int64_t n_steps, int64_t sims_per_stream_hint, const uint64_t *d_sim_start,
+                     const void *d_plan_workspace, const mcf_gbm_spec *h_specs, int32_t n_specs, double *d_out,
                      void *cuda_stream);
 
 /* Full GBM paths, (n_total, n_steps+1) row-major when time_major==0 (what simulate_paths returns,
  * sims/black_scholes.py:415-418) or (n_steps+1, n_total) when time_major==1 (LSM layout).
  * p={S0,r,sigma,T}. */
 int mcf_gbm_paths(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total, int64_t n_steps,
-                  int64_t sims_per_stream_hint, const uint64_t *d_sim_start, const double *h_p4, int32_t time_major, double *d_paths,
-                  void *cuda_stream);
+                  int64_t sims_per_stream_hint, const uint64_t *d_sim_start, const void *d_plan_workspace,
+                  const double *h_p4, int32_t time_major, double *d_paths, void *cuda_stream);
 
 /* Stored path slices (BASELINE config 3; the reference stores either nothing, sims/portfolio.py:77-84, or every
  * step, sims/black_scholes.py:415-418): values at steps 0, slice_stride, 2*slice_stride, ... <= n_steps, i.e.
@@ -129,8 +132,9 @@ int mcf_gbm_paths(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_stre
  * V0*exp(cumulative log-return)) or MCF_PATH_TERMINAL (p={S0,r,sigma,T}).  Output (n_slices, n_total) when
  * time_major (coalesced stores) else (n_total, n_slices). */
 int mcf_gbm_slices(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total, int64_t n_steps,
-                   int64_t sims_per_stream_hint, const uint64_t *d_sim_start, const mcf_gbm_spec *h_spec,
-                   int64_t slice_stride, int32_t time_major, double *d_out, void *cuda_stream);
+                   int64_t sims_per_stream_hint, const uint64_t *d_sim_start, const void *d_plan_workspace,
+                   const mcf_gbm_spec *h_spec, int64_t slice_stride, int32_t time_major, double *d_out,
+                   void *cuda_stream);
 
 /* ---- (3) Longstaff-Schwartz backward induction ------------------------------------------
  * replaces _american_exercise_lsm (sims/black_scholes.py:109-193).  `d_paths_tm` is TIME-MAJOR:
@@ -141,12 +145,12 @@ int mcf_gbm_slices(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_str
  * sharded), mcf_lsm_apply solves the 3x3 system (pseudo-inverse, like lstsq) and exercises where
  * intrinsic > fitted.  mcf_lsm runs the whole loop on one GPU. */
 int64_t mcf_lsm_workspace_bytes(int64_t n_paths);
-int mcf_lsm_begin(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K, int32_t is_put, void *d_workspace,
-                  int64_t workspace_bytes, void *cuda_stream);
+int mcf_lsm_begin(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K, double r, double dt,
+                  int32_t is_put, void *d_workspace, int64_t workspace_bytes, void *cuda_stream);
 int mcf_lsm_reduce(const double *d_paths_tm, int64_t n_paths, int64_t t, double K, double r, double dt, int32_t is_put,
                    void *d_workspace, void *cuda_stream);
-int mcf_lsm_apply(const double *d_paths_tm, int64_t n_paths, int64_t t, double K, int32_t is_put, void *d_workspace,
-                  void *cuda_stream);
+int mcf_lsm_apply(const double *d_paths_tm, int64_t n_paths, int64_t t, double K, double r, double dt, int32_t is_put,
+                  void *d_workspace, void *cuda_stream);
 /* d_price_sum[0] = sum_i cash_flow_i*exp(-r*dt*exercise_i) over this rank's paths; d_price[0] = that / n_paths.
  * Either may be NULL.  d_exercise_times (int32[n_paths], may be NULL) receives the exercise step of every path. */
 int mcf_lsm_finish(int64_t n_paths, double r, double dt, void *d_workspace, double *d_price_sum, double *d_price,
@@ -161,7 +165,7 @@ int mcf_transpose(const double *d_in, int64_t n_rows, int64_t n_cols, double *d_
  * everything mean/std/skew/kurtosis/ci_mean/chebyshev/markov/bias/mse need (stats_engine.py:767-1472):
  *   out[0] n_finite  out[1] n_nan  out[2] n_posinf  out[3] n_neginf
  *   out[4] mean      out[5] M2=sum (x-mean)^2   out[6] M3   out[7] M4      (finite values only)
- *   out[8] sum (x-target)^2   out[9] sum x   out[10] min   out[11] max      (finite values only)
+ *   out[8] sum (x-target)^2 (= M2 + n*(mean-target)^2)   out[9] sum x   out[10..11] reserved
  * Per-rank outputs merge on the host with the pairwise update formulas (see _stats_host.py). */
 #define MCF_MOMENTS_OUT 12
 int64_t mcf_moments_workspace_bytes(int64_t n);

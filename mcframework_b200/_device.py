@@ -70,6 +70,7 @@ class NormalPlan:
     sim_start: "object"  # torch int64 (bit pattern of uint64) [n_total]
     stream_end: "object"  # torch int64 [n_streams]: 64-bit draws consumed per stream
     normals_per_sim: int
+    workspace: "object" = None  # torch uint8: emit masks etc. -- the replay kernels read it
 
 
 def normal_plan(dl: DeviceLayout, normals_per_sim: int, slack: float = 0.03, resolve_iters: int = 3,
@@ -91,9 +92,9 @@ def normal_plan(dl: DeviceLayout, normals_per_sim: int, slack: float = 0.03, res
         N.check("mcf_normal_plan", rc)
         LAUNCHES["plan"] += 5 + resolve_iters
         status = lib.mcf_workspace_status(_ptr(ws), _stream_ptr())
-        del ws
         if status == N.OK:
-            return NormalPlan(sim_start, stream_end, int(normals_per_sim))
+            return NormalPlan(sim_start, stream_end, int(normals_per_sim), ws)
+        del ws
         if status == N.ERR_WINDOW_TOO_SMALL:
             slack = slack * 2 + 0.02
         elif status == N.ERR_NOT_CONVERGED:
@@ -118,7 +119,8 @@ def gbm_terminal(dl: DeviceLayout, n_steps: int, plan: NormalPlan, specs):
     lay = dl.layout
     out = torch.empty((len(specs), lay.n_total), dtype=torch.float64, device="cuda")
     rc = N.lib().mcf_gbm_terminal(lay.kind, _ptr(dl.records), lay.n_streams, lay.n_total, int(n_steps), lay.hint,
-                                  _ptr(plan.sim_start), _spec_array(specs), len(specs), _ptr(out), _stream_ptr())
+                                  _ptr(plan.sim_start), _ptr(plan.workspace), _spec_array(specs), len(specs), _ptr(out),
+                                  _stream_ptr())
     N.check("mcf_gbm_terminal", rc)
     LAUNCHES["gbm"] += 1
     return out
@@ -132,7 +134,7 @@ def gbm_paths(dl: DeviceLayout, n_steps: int, plan: NormalPlan, S0: float, r: fl
     out = torch.empty(shape, dtype=torch.float64, device="cuda")
     p4 = (C.c_double * 4)(float(S0), float(r), float(sigma), float(T))
     rc = N.lib().mcf_gbm_paths(lay.kind, _ptr(dl.records), lay.n_streams, lay.n_total, int(n_steps), lay.hint,
-                               _ptr(plan.sim_start), p4, int(bool(time_major)), _ptr(out), _stream_ptr())
+                               _ptr(plan.sim_start), _ptr(plan.workspace), p4, int(bool(time_major)), _ptr(out), _stream_ptr())
     N.check("mcf_gbm_paths", rc)
     LAUNCHES["paths"] += 1
     return out
@@ -147,7 +149,7 @@ def gbm_slices(dl: DeviceLayout, n_steps: int, plan: NormalPlan, mode: int, para
     shape = (n_slices, lay.n_total) if time_major else (lay.n_total, n_slices)
     out = torch.empty(shape, dtype=torch.float64, device="cuda")
     rc = N.lib().mcf_gbm_slices(lay.kind, _ptr(dl.records), lay.n_streams, lay.n_total, int(n_steps), lay.hint,
-                                _ptr(plan.sim_start), _spec_array([(mode, params)]), int(slice_stride),
+                                _ptr(plan.sim_start), _ptr(plan.workspace), _spec_array([(mode, params)]), int(slice_stride),
                                 int(bool(time_major)), _ptr(out), _stream_ptr())
     N.check("mcf_gbm_slices", rc)
     LAUNCHES["paths"] += 1

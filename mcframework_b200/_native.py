@@ -50,14 +50,14 @@ SIGNATURES = {
     "mcf_normal_plan_workspace_bytes": (_i64, [_i32, _i64, _i64, _f64]),
     "mcf_normal_plan": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i64, _f64, _i32, _vp, _i64, _vp, _vp, _vp]),
     "mcf_workspace_status": (C.c_int, [_vp, _vp]),
-    "mcf_gbm_terminal": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i64, _vp, C.POINTER(GbmSpec), _i32, _vp, _vp]),
-    "mcf_gbm_paths": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i64, _vp, C.POINTER(_f64), _i32, _vp, _vp]),
-    "mcf_gbm_slices": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i64, _vp, C.POINTER(GbmSpec), _i64, _i32, _vp, _vp]),
+    "mcf_gbm_terminal": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i64, _vp, _vp, C.POINTER(GbmSpec), _i32, _vp, _vp]),
+    "mcf_gbm_paths": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i64, _vp, _vp, C.POINTER(_f64), _i32, _vp, _vp]),
+    "mcf_gbm_slices": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i64, _vp, _vp, C.POINTER(GbmSpec), _i64, _i32, _vp, _vp]),
     # Longstaff-Schwartz
     "mcf_lsm_workspace_bytes": (_i64, [_i64]),
-    "mcf_lsm_begin": (C.c_int, [_vp, _i64, _i64, _f64, _i32, _vp, _i64, _vp]),
+    "mcf_lsm_begin": (C.c_int, [_vp, _i64, _i64, _f64, _f64, _f64, _i32, _vp, _i64, _vp]),
     "mcf_lsm_reduce": (C.c_int, [_vp, _i64, _i64, _f64, _f64, _f64, _i32, _vp, _vp]),
-    "mcf_lsm_apply": (C.c_int, [_vp, _i64, _i64, _f64, _i32, _vp, _vp]),
+    "mcf_lsm_apply": (C.c_int, [_vp, _i64, _i64, _f64, _f64, _f64, _i32, _vp, _vp]),
     "mcf_lsm_finish": (C.c_int, [_i64, _f64, _f64, _vp, _vp, _vp, _vp, _vp]),
     "mcf_lsm": (C.c_int, [_vp, _i64, _i64, _f64, _f64, _f64, _i32, _vp, _i64, _vp, _vp, _vp]),
     "mcf_transpose": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),

@@ -35,8 +35,8 @@ class MomentSummary:
     m4: float
     sq_target: float
     total: float
-    vmin: float
-    vmax: float
+    reserved0: float = 0.0
+    reserved1: float = 0.0
 
     @classmethod
     def from_array(cls, a) -> "MomentSummary":
@@ -44,7 +44,7 @@ class MomentSummary:
 
     def to_array(self) -> np.ndarray:
         return np.array([self.n, self.n_nan, self.n_posinf, self.n_neginf, self.mean, self.m2, self.m3, self.m4,
-                         self.sq_target, self.total, self.vmin, self.vmax], dtype=np.float64)
+                         self.sq_target, self.total, 0.0, 0.0], dtype=np.float64)
 
     @property
     def n_nonfinite(self) -> float:
@@ -72,8 +72,7 @@ def merge_summaries(parts) -> MomentSummary:
             m4 = (a.m4 + b.m4 + d * dn * dn2 * a.n * b.n * (a.n * a.n - a.n * b.n + b.n * b.n)
                   + 6.0 * dn2 * (a.n * a.n * b.m2 + b.n * b.n * a.m2) + 4.0 * dn * (a.n * b.m3 - b.n * a.m3))
         acc = MomentSummary(n, a.n_nan + b.n_nan, a.n_posinf + b.n_posinf, a.n_neginf + b.n_neginf, mean, m2, m3, m4,
-                            a.sq_target + b.sq_target, a.total + b.total, min(a.vmin, b.vmin),
-                            max(a.vmax, b.vmax))
+                            a.sq_target + b.sq_target, a.total + b.total)
     return acc
 
 
@@ -96,7 +95,6 @@ def moments(x, target: float = 0.0, group=None) -> MomentSummary:
     torch = _torch()
     if x.numel() == 0:
         out = torch.zeros(MOMENTS_OUT, dtype=torch.float64, device=x.device)
-        out[10], out[11] = math.inf, -math.inf
     else:
         out = moments_raw(x, target)
     if group is None:
@@ -310,11 +308,11 @@ def lsm_price(paths_tm, K: float, r: float, dt: float, is_put: bool, group=None,
     import torch.distributed as dist
 
     sums = ws[:64].view(torch.float64)
-    N.check("mcf_lsm_begin", lib.mcf_lsm_begin(_ptr(paths_tm), n_paths, n_steps, float(K), int(bool(is_put)), _ptr(ws), nbytes, sp))
+    N.check("mcf_lsm_begin", lib.mcf_lsm_begin(_ptr(paths_tm), n_paths, n_steps, float(K), float(r), float(dt), int(bool(is_put)), _ptr(ws), nbytes, sp))
     for t in range(n_steps - 1, 0, -1):
         N.check("mcf_lsm_reduce", lib.mcf_lsm_reduce(_ptr(paths_tm), n_paths, t, float(K), float(r), float(dt), int(bool(is_put)), _ptr(ws), sp))
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-        N.check("mcf_lsm_apply", lib.mcf_lsm_apply(_ptr(paths_tm), n_paths, t, float(K), int(bool(is_put)), _ptr(ws), sp))
+        N.check("mcf_lsm_apply", lib.mcf_lsm_apply(_ptr(paths_tm), n_paths, t, float(K), float(r), float(dt), int(bool(is_put)), _ptr(ws), sp))
     psum = torch.empty(1, dtype=torch.float64, device=paths_tm.device)
     N.check("mcf_lsm_finish", lib.mcf_lsm_finish(n_paths, float(r), float(dt), _ptr(ws), _ptr(psum), None,
                                                  _ptr(ex) if ex is not None else None, sp))

@@ -549,6 +549,101 @@ MCF_HD void locate_in_chunk(uint64_t chunk_base, uint64_t eff_start, uint64_t ef
 }
 
 // ---------------------------------------------------------------------------------------
+// Mask-driven replay.  The planning pass has already decided, for every draw position of a stream, whether an
+// attempt that STARTS there emits a normal (emitmask, valid from the chunk's true entry offset).  A normal that
+// is emitted by the attempt starting at draw v is always the fast-path value +-rabs(v)*wi[idx(v)] -- also when it
+// was accepted by the wedge test -- except in the tail (idx == 0, rabs >= ki[0]).  So the replay needs no state
+// machine, no acceptance tests and no ki/fi tables: for each set bit, convert one draw.  The stream range of
+// replication i is [sim_start[i], sim_start[i+1]) (or the stream's end), so there is no emit counter either.
+// ---------------------------------------------------------------------------------------
+struct PlanView {
+    const uint64_t *emit;  // [n_streams * cps]
+    const uint8_t *entry;  // [n_streams * cps] true entry offset of every chunk
+    int64_t cps;           // chunks per stream
+};
+
+MCF_HD uint64_t plan_emit_word(const PlanView &pv, int64_t si, uint64_t chunk) {
+    const int64_t id = si * pv.cps + (int64_t)chunk;
+    return pv.emit[id] & mask_from(pv.entry[id]);
+}
+
+// the normal emitted by the tail attempt whose first draw (at position p) carried `rabs`
+template <int KIND>
+MCF_HD double zig_tail_value(const mcf_stream &st, uint64_t p, uint64_t rabs) {
+    Cursor<KIND> c;
+    c.init(st, p + 1);
+    for (;;) {
+        const double xx = xmul(-MCF_ZIG_INV_R, log1p(-u64_to_unit_double(c.next64())));
+        const double yy = -log1p(-u64_to_unit_double(c.next64()));
+        if (xadd(yy, yy) > xmul(xx, xx)) {
+            const double m = xadd(MCF_ZIG_R, xx);
+            return ((rabs >> 8) & 1ULL) ? -m : m;
+        }
+    }
+}
+
+template <int KIND>
+MCF_HD double zig_value_of_start(const mcf_stream &st, uint64_t p, uint64_t r, const double *wi, uint64_t ki0) {
+    const unsigned idx = (unsigned)(r & 0xffULL);
+    const unsigned sign = (unsigned)((r >> 8) & 1ULL);
+    const uint64_t rabs = (r >> 9) & 0x000fffffffffffffULL;
+    if (idx == 0 && rabs >= ki0) return zig_tail_value<KIND>(st, p, rabs);  // 3e-4 of the emits
+    const double v = xmul(u52_to_double(rabs), wi[idx]);
+    return sign ? -v : v;
+}
+
+// f(z) for every normal emitted by attempts starting in [start, end) of stream `si`, in stream order
+template <class F>
+MCF_HD void replay_emits(Cursor<MCF_GEN_PCG64> &cur, const mcf_stream &st, const PlanView &pv, int64_t si, uint64_t start,
+                         uint64_t end, const double *wi, uint64_t ki0, F f) {
+    if (end <= start) return;
+    cur.init(st, start);
+    uint64_t word = plan_emit_word(pv, si, start >> 6);
+    for (uint64_t p = start; p < end; p++) {
+        if ((p & 63ULL) == 0 && p != start) word = plan_emit_word(pv, si, p >> 6);
+        const uint64_t r = cur.next64();
+        if ((word >> (p & 63ULL)) & 1ULL) f(zig_value_of_start<MCF_GEN_PCG64>(st, p, r, wi, ki0));
+    }
+}
+
+// Philox: whole blocks of four draws, every lane generating its block in the same loop trip.
+// Requires a block-aligned stream (buf_pos % 4 == 0: every stream of a parallel run); see replay_emits_any.
+template <class F>
+MCF_HD void replay_emits(Cursor<MCF_GEN_PHILOX> &cur, const mcf_stream &st, const PlanView &pv, int64_t si, uint64_t start,
+                         uint64_t end, const double *wi, uint64_t ki0, F f) {
+    if (end <= start) return;
+    cur.init(st, start);
+    const uint64_t off = (uint64_t)st.buf_pos;
+    if (off & 3ULL) {  // generator captured mid-buffer (user-supplied Philox): draw by draw
+        uint64_t w = plan_emit_word(pv, si, start >> 6);
+        for (uint64_t p = start; p < end; p++) {
+            if ((p & 63ULL) == 0 && p != start) w = plan_emit_word(pv, si, p >> 6);
+            const uint64_t r = cur.next64();
+            if ((w >> (p & 63ULL)) & 1ULL) f(zig_value_of_start<MCF_GEN_PHILOX>(st, p, r, wi, ki0));
+        }
+        return;
+    }
+    const uint64_t b_first = (start + off) >> 2, b_last = (end - 1 + off) >> 2;
+    uint64_t chunk = ~0ULL, word = 0;
+    for (uint64_t blk = b_first; blk <= b_last; blk++) {
+        const uint64_t p0 = (blk << 2) - off;  // stream position of the block's first draw (may precede `start`)
+        const uint64_t c = (p0 + 3) >> 6;      // blocks never straddle chunks when off % 4 == 0 (p0 % 4 == 0)
+        if (c != chunk) {
+            chunk = c;
+            word = plan_emit_word(pv, si, c);
+        }
+        unsigned nib = (unsigned)(word >> (p0 & 63ULL)) & 0xFu;
+        if (blk == b_first) nib &= (0xFu << (unsigned)(start - p0)) & 0xFu;
+        if (blk == b_last) nib &= 0xFu >> (unsigned)(p0 + 4 - end);
+        cur.load_block(blk);
+        if (nib & 1u) f(zig_value_of_start<MCF_GEN_PHILOX>(st, p0, cur.v0, wi, ki0));
+        if (nib & 2u) f(zig_value_of_start<MCF_GEN_PHILOX>(st, p0 + 1, cur.v1, wi, ki0));
+        if (nib & 4u) f(zig_value_of_start<MCF_GEN_PHILOX>(st, p0 + 2, cur.v2, wi, ki0));
+        if (nib & 8u) f(zig_value_of_start<MCF_GEN_PHILOX>(st, p0 + 3, cur.v3, wi, ki0));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Replication bodies (pass 2): the cursor sits where the replication's first draw starts.
 // ---------------------------------------------------------------------------------------
 struct GbmDerived {  // host-precomputed exactly as the reference computes them in Python floats
@@ -564,12 +659,13 @@ struct GbmDerived {  // host-precomputed exactly as the reference computes them 
 
 // European / portfolio terminal value from a stream of normals; sum in fp64, sequential order
 // (the reference sums pairwise; the difference is covered by the stated tolerance).
-template <class Cur>
-MCF_HD double run_terminal(Cur &cur, const ZigTables &t, int64_t n_steps, const GbmDerived &g) {
+// `each(f)` must call f(z) for every normal of the replication, in stream order.
+template <class Each>
+MCF_HD double terminal_value(Each each, const GbmDerived &g) {
     switch (g.mode) {
     case MCF_NORMAL_SUM: {
         double acc = 0.0;
-        for_each_normal(cur, t, n_steps, [&](double z) { acc = xadd(acc, z); });
+        each([&](double z) { acc = xadd(acc, z); });
         return acc;
     }
     case MCF_BS_EURO_CALL:
@@ -578,7 +674,7 @@ MCF_HD double run_terminal(Cur &cur, const ZigTables &t, int64_t n_steps, const 
     case MCF_PATH_TERMINAL: {
         double acc = 0.0;
         const double a = g.a, b = g.b;
-        for_each_normal(cur, t, n_steps, [&](double z) { acc = xadd(acc, xadd(a, xmul(b, z))); });
+        each([&](double z) { acc = xadd(acc, xadd(a, xmul(b, z))); });
         if (g.mode == MCF_PATH_TERMINAL) return exp(xadd(g.logs0, acc));  // exp(log(S0) + cumsum[-1])
         const double st = xmul(g.s0, exp(acc));
         if (g.mode == MCF_PORTFOLIO_GBM) return st;
@@ -588,7 +684,7 @@ MCF_HD double run_terminal(Cur &cur, const ZigTables &t, int64_t n_steps, const 
     case MCF_PORTFOLIO_LOG1P: {
         double acc = 0.0;
         const double a = g.a, b = g.b;
-        for_each_normal(cur, t, n_steps, [&](double z) { acc = xadd(acc, log1p(xadd(a, xmul(b, z)))); });
+        each([&](double z) { acc = xadd(acc, log1p(xadd(a, xmul(b, z)))); });
         return xmul(g.s0, exp(acc));
     }
     case MCF_BS_AMER_CALL:
@@ -598,7 +694,7 @@ MCF_HD double run_terminal(Cur &cur, const ZigTables &t, int64_t n_steps, const 
         const double s0 = exp(logs0);
         double best = call ? fmax(xsub(s0, K), 0.0) : fmax(xsub(K, s0), 0.0);  // k = 0, discount 1
         double acc = 0.0, kf = 0.0;
-        for_each_normal(cur, t, n_steps, [&](double z) {
+        each([&](double z) {
             kf += 1.0;  // exact for every representable step count
             acc = xadd(acc, xadd(a, xmul(b, z)));
             const double s = exp(xadd(logs0, acc));
@@ -610,6 +706,12 @@ MCF_HD double run_terminal(Cur &cur, const ZigTables &t, int64_t n_steps, const 
     default:
         return bits_to_double(0x7ff8000000000000ULL);
     }
+}
+
+// state-machine driven form (no plan masks needed): tests, single replications
+template <class Cur>
+MCF_HD double run_terminal(Cur &cur, const ZigTables &t, int64_t n_steps, const GbmDerived &g) {
+    return terminal_value([&](auto f) { for_each_normal(cur, t, n_steps, f); }, g);
 }
 
 }  // namespace mcf

@@ -15,7 +15,15 @@ struct PlanGeom {
     int64_t tps;        // tiles per stream
     int64_t n_chunks;   // n_streams * cps
     int64_t n_tiles;
-    int64_t off_start, off_emit, off_exit, off_gen, off_entry, off_tsum, off_tpre, total;
+    int64_t off_start, off_emit, off_exit, off_gen, off_entry, off_tsum, off_tpre, off_send, total;
+};
+
+// Device-resident description of a finished plan (at byte MCF_LAYOUT_OFFSET of the workspace): lets the replay
+// kernels find the emit masks without the host having to remember the geometry.
+#define MCF_LAYOUT_OFFSET 64
+#define MCF_LAYOUT_MAGIC 0x6d63665f706c616eLL
+struct PlanLayout {
+    int64_t magic, cps, off_emit, off_entry, off_send, n_streams;
 };
 
 static inline PlanGeom plan_geom(int32_t n_streams, int64_t max_sims, int64_t nps, double slack) {
@@ -42,6 +50,9 @@ static inline PlanGeom plan_geom(int32_t n_streams, int64_t max_sims, int64_t np
     o += g.n_chunks;
     g.off_entry = o;
     o += g.n_chunks;
+    o = (o + 255) / 256 * 256;
+    g.off_send = o;
+    o += (int64_t)n_streams * 8;
     g.total = (o + 255) / 256 * 256;
     return g;
 }

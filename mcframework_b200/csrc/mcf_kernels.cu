@@ -93,10 +93,13 @@ __global__ void pi_finalize_kernel(const unsigned long long *__restrict__ hits, 
 }
 
 // ========================================================================== planning pass
-__global__ void plan_init_kernel(int *hdr, int iters) {
+__global__ void plan_init_kernel(int *hdr, int iters, PlanLayout layout) {
     if (threadIdx.x < MCF_HDR_WORDS) hdr[threadIdx.x] = 0;
     __syncthreads();
-    if (threadIdx.x == 0) hdr[MCF_HDR_WORDS - 1] = iters;
+    if (threadIdx.x == 0) {
+        hdr[MCF_HDR_WORDS - 1] = iters;
+        *reinterpret_cast<PlanLayout *>(reinterpret_cast<char *>(hdr) + MCF_LAYOUT_OFFSET) = layout;
+    }
 }
 
 // one thread scans RUN consecutive chunks of one stream, carrying the ziggurat chain through
@@ -238,7 +241,8 @@ __global__ void __launch_bounds__(256) plan_locate_kernel(const mcf_stream *__re
                                                           const uint8_t *__restrict__ entry_true,
                                                           const uint64_t *__restrict__ tile_pre,
                                                           uint64_t *__restrict__ sim_start,
-                                                          uint64_t *__restrict__ stream_end) {
+                                                          uint64_t *__restrict__ stream_end,
+                                                          uint64_t *__restrict__ stream_end_ws) {
     __shared__ uint32_t warp_tot[8];
     const int64_t tile = blockIdx.x;
     const int64_t si = tile / tps;
@@ -273,45 +277,77 @@ __global__ void __launch_bounds__(256) plan_locate_kernel(const mcf_stream *__re
         const uint64_t chunk_base = (uint64_t)(first_chunk + k) * MCF_CHUNK;
         locate_in_chunk(chunk_base, es[k], ee[k], exit_[base + k], E, (uint64_t)nps, (uint64_t)st.n_sims,
                         [&](uint64_t m, uint64_t pos) {
-                            if (m < (uint64_t)st.n_sims)
+                            if (m < (uint64_t)st.n_sims) {
                                 sim_start[st.first_sim + (int64_t)m] = pos;
-                            else if (stream_end)
-                                stream_end[si] = pos;
+                            } else {
+                                stream_end_ws[si] = pos;
+                                if (stream_end) stream_end[si] = pos;
+                            }
                         });
         E += cnt[k];
     }
 }
 
 // ====================================================================== replication pass
+// Only the wi table (2 KB) and ki[0] are needed: acceptance decisions come from the plan's emit masks.
+struct WiShared {
+    double wi[256];
+};
+__device__ __forceinline__ const double *load_wi_table(WiShared &sh) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh.wi[i] = __longlong_as_double((long long)g_zig_wi[i]);
+    __syncthreads();
+    return sh.wi;
+}
+
+struct ReplaySetup {
+    mcf_stream st;
+    PlanView pv;
+    int64_t si;
+    uint64_t start, end;
+};
+
+// where replication i lives: its stream, its draw range [start, end), the plan's masks
+__device__ __forceinline__ ReplaySetup replay_setup(const mcf_stream *__restrict__ streams, int n_streams, int64_t hint,
+                                                    const uint64_t *__restrict__ sim_start, const char *__restrict__ plan_ws,
+                                                    int64_t i) {
+    ReplaySetup r;
+    const PlanLayout *lay = reinterpret_cast<const PlanLayout *>(plan_ws + MCF_LAYOUT_OFFSET);
+    r.si = stream_of(streams, n_streams, i, hint);
+    r.st = streams[r.si];
+    r.pv.emit = reinterpret_cast<const uint64_t *>(plan_ws + lay->off_emit);
+    r.pv.entry = reinterpret_cast<const uint8_t *>(plan_ws + lay->off_entry);
+    r.pv.cps = lay->cps;
+    r.start = sim_start[i];
+    const bool last = (i + 1 == r.st.first_sim + r.st.n_sims);
+    r.end = last ? reinterpret_cast<const uint64_t *>(plan_ws + lay->off_send)[r.si] : sim_start[i + 1];
+    return r;
+}
+
 template <int KIND>
-__global__ void __launch_bounds__(256) gbm_terminal_kernel(const mcf_stream *__restrict__ streams, int n_streams,
-                                                           int64_t n_total, int64_t n_steps, int64_t hint,
-                                                           const uint64_t *__restrict__ sim_start, SpecPack specs,
-                                                           double *__restrict__ out) {
-    __shared__ ZigShared sh;
-    const ZigTables t = load_zig_tables(sh);
+__global__ void __launch_bounds__(256, 3) gbm_terminal_kernel(const mcf_stream *__restrict__ streams, int n_streams,
+                                                              int64_t n_total, int64_t hint,
+                                                              const uint64_t *__restrict__ sim_start,
+                                                              const char *__restrict__ plan_ws, SpecPack specs,
+                                                              double n_steps_f, double *__restrict__ out) {
+    __shared__ WiShared sh;
+    const double *wi = load_wi_table(sh);
+    const uint64_t ki0 = g_zig_ki[0];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_total) return;
-    const int si = stream_of(streams, n_streams, i, hint);
-    const mcf_stream st = streams[si];
-    const uint64_t start = sim_start[i];
+    const ReplaySetup rs = replay_setup(streams, n_streams, hint, sim_start, plan_ws, i);
     Cursor<KIND> cur;
-    cur.init(st, start);
-    // Per-thread trip count (start < 2^63 always): keeps the step counter in a per-thread register.  With a
-    // warp-uniform counter, ptxas 12.9 emitted a uniform-datapath loop (BSSY.RELIABLE / BRA.U.ANY) around the
-    // divergent ziggurat slow path that never terminated on sm_100a for the bodies with exp() inside the loop.
-    const int64_t steps = n_steps + (int64_t)(start >> 63);
     if (specs.n == 1) {
-        out[i] = run_terminal(cur, t, steps, specs.g[0]);
+        out[i] = terminal_value([&](auto f) { replay_emits(cur, rs.st, rs.pv, rs.si, rs.start, rs.end, wi, ki0, f); },
+                                specs.g[0]);
         return;
     }
     // several parameter sets on common random numbers (Greeks): the terminal log-price is affine
     // in sum(Z), so one pass over the normals serves every set (all sets are affine-sum modes).
     double zsum = 0.0;
-    for_each_normal(cur, t, steps, [&](double z) { zsum = xadd(zsum, z); });
+    replay_emits(cur, rs.st, rs.pv, rs.si, rs.start, rs.end, wi, ki0, [&](double z) { zsum = xadd(zsum, z); });
     for (int s = 0; s < specs.n; s++) {
         const GbmDerived &g = specs.g[s];
-        const double acc = xadd(xmul((double)n_steps, g.a), xmul(g.b, zsum));
+        const double acc = xadd(xmul(n_steps_f, g.a), xmul(g.b, zsum));
         double v;
         if (g.mode == MCF_NORMAL_SUM) {
             v = zsum;
@@ -329,52 +365,47 @@ __global__ void __launch_bounds__(256) gbm_terminal_kernel(const mcf_stream *__r
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(256) gbm_paths_kernel(const mcf_stream *__restrict__ streams, int n_streams,
-                                                        int64_t n_total, int64_t n_steps, int64_t hint,
-                                                        const uint64_t *__restrict__ sim_start, GbmDerived g,
-                                                        int time_major, double *__restrict__ paths) {
-    __shared__ ZigShared sh;
-    const ZigTables t = load_zig_tables(sh);
+__global__ void __launch_bounds__(256, 3) gbm_paths_kernel(const mcf_stream *__restrict__ streams, int n_streams,
+                                                           int64_t n_total, int64_t n_steps, int64_t hint,
+                                                           const uint64_t *__restrict__ sim_start,
+                                                           const char *__restrict__ plan_ws, GbmDerived g, int time_major,
+                                                           double *__restrict__ paths) {
+    __shared__ WiShared sh;
+    const double *wi = load_wi_table(sh);
+    const uint64_t ki0 = g_zig_ki[0];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_total) return;
-    const int si = stream_of(streams, n_streams, i, hint);
-    const mcf_stream st = streams[si];
-    const uint64_t start = sim_start[i];
+    const ReplaySetup rs = replay_setup(streams, n_streams, hint, sim_start, plan_ws, i);
     Cursor<KIND> cur;
-    cur.init(st, start);
-    const int64_t steps = n_steps + (int64_t)(start >> 63);  // per-thread trip count, see gbm_terminal_kernel
     const int64_t stride = time_major ? n_total : 1;
     double *p = paths + (time_major ? i : i * (n_steps + 1));
     double acc = 0.0;
     const double a = g.a, b = g.b, logs0 = g.logs0;
     p[0] = exp(logs0);
-    for_each_normal(cur, t, steps, [&](double z) {
+    replay_emits(cur, rs.st, rs.pv, rs.si, rs.start, rs.end, wi, ki0, [&](double z) {
         acc = xadd(acc, xadd(a, xmul(b, z)));
         p += stride;
         *p = exp(xadd(logs0, acc));
     });
 }
 
-
 // Stored path slices (BASELINE cfg 3): value at steps 0, stride, 2*stride, ... <= n_steps.  Time-major output
 // (n_slices, n_total) gives fully coalesced 8-byte stores per warp; row-major (n_total, n_slices) is what a
 // host caller reshapes most easily.  mode: MCF_PORTFOLIO_GBM -> V0*exp(sum), MCF_PATH_TERMINAL -> exp(log S0 + sum).
 template <int KIND>
-__global__ void __launch_bounds__(256) gbm_slices_kernel(const mcf_stream *__restrict__ streams, int n_streams,
-                                                         int64_t n_total, int64_t n_steps, int64_t hint,
-                                                         const uint64_t *__restrict__ sim_start, GbmDerived g,
-                                                         int64_t slice_stride, int64_t n_slices, int time_major,
-                                                         double *__restrict__ out) {
-    __shared__ ZigShared sh;
-    const ZigTables t = load_zig_tables(sh);
+__global__ void __launch_bounds__(256, 3) gbm_slices_kernel(const mcf_stream *__restrict__ streams, int n_streams,
+                                                            int64_t n_total, int64_t hint,
+                                                            const uint64_t *__restrict__ sim_start,
+                                                            const char *__restrict__ plan_ws, GbmDerived g,
+                                                            int64_t slice_stride, int64_t n_slices, int time_major,
+                                                            double *__restrict__ out) {
+    __shared__ WiShared sh;
+    const double *wi = load_wi_table(sh);
+    const uint64_t ki0 = g_zig_ki[0];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_total) return;
-    const int si = stream_of(streams, n_streams, i, hint);
-    const mcf_stream st = streams[si];
-    const uint64_t start = sim_start[i];
+    const ReplaySetup rs = replay_setup(streams, n_streams, hint, sim_start, plan_ws, i);
     Cursor<KIND> cur;
-    cur.init(st, start);
-    const int64_t steps = n_steps + (int64_t)(start >> 63);  // per-thread trip count, see gbm_terminal_kernel
     const int64_t stride = time_major ? n_total : 1;
     double *p = out + (time_major ? i : i * n_slices);
     const bool path_mode = g.mode == MCF_PATH_TERMINAL;
@@ -382,7 +413,7 @@ __global__ void __launch_bounds__(256) gbm_slices_kernel(const mcf_stream *__res
     const double a = g.a, b = g.b, logs0 = g.logs0, s0 = g.s0;
     p[0] = path_mode ? exp(logs0) : s0;
     int64_t until_store = slice_stride;
-    for_each_normal(cur, t, steps, [&](double z) {
+    replay_emits(cur, rs.st, rs.pv, rs.si, rs.start, rs.end, wi, ki0, [&](double z) {
         acc = xadd(acc, xadd(a, xmul(b, z)));
         if (--until_store == 0) {
             p += stride;
@@ -414,7 +445,14 @@ static int normal_plan_impl(const mcf_stream *d_streams, const PlanGeom &g, int6
     uint64_t *sm = (uint64_t *)(ws + g.off_start), *em = (uint64_t *)(ws + g.off_emit);
     uint64_t *tsum = (uint64_t *)(ws + g.off_tsum), *tpre = (uint64_t *)(ws + g.off_tpre);
     uint8_t *ex = (uint8_t *)(ws + g.off_exit), *gen = (uint8_t *)(ws + g.off_gen), *ent = (uint8_t *)(ws + g.off_entry);
-    plan_init_kernel<<<1, 32, 0, cs>>>(hdr, iters);
+    PlanLayout layout;
+    layout.magic = MCF_LAYOUT_MAGIC;
+    layout.cps = g.cps;
+    layout.off_emit = g.off_emit;
+    layout.off_entry = g.off_entry;
+    layout.off_send = g.off_send;
+    layout.n_streams = g.n_chunks / g.cps;
+    plan_init_kernel<<<1, 32, 0, cs>>>(hdr, iters, layout);
     constexpr int RUN = KIND == MCF_GEN_PCG64 ? 8 : 1;  // PCG64 pays an O(log n) jump per thread
     const int64_t n_runs = g.n_chunks / RUN;
     plan_scan_kernel<KIND, RUN><<<grid_for(n_runs, 256), 256, 0, cs>>>(d_streams, g.cps, n_runs, sm, em, ex, gen, hdr);
@@ -429,7 +467,7 @@ static int normal_plan_impl(const mcf_stream *d_streams, const PlanGeom &g, int6
     plan_tile_scan_kernel<<<(unsigned)(g.n_chunks / g.cps), 1024, 0, cs>>>(d_streams, g.tps, nps, tsum, tpre, hdr);
     MCF_CUDA_OK(cudaGetLastError());
     plan_locate_kernel<<<(unsigned)g.n_tiles, 256, 0, cs>>>(d_streams, g.cps, g.tps, nps, sm, em, ex, ent, tpre,
-                                                           d_sim_start, d_stream_end);
+                                                           d_sim_start, d_stream_end, (uint64_t *)(ws + g.off_send));
     MCF_CUDA_OK(cudaGetLastError());
     return MCF_OK;
 }
@@ -512,10 +550,10 @@ int mcf_workspace_status(const void *d_workspace, void *cuda_stream) {
 extern "C" {
 
 int mcf_gbm_terminal(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total, int64_t n_steps,
-                       int64_t sims_per_stream_hint, const uint64_t *d_sim_start, const mcf_gbm_spec *h_specs,
-                       int32_t n_specs, double *d_out, void *cuda_stream) {
-    if (!d_streams || n_streams <= 0 || n_total <= 0 || n_steps <= 0 || !d_sim_start || !h_specs || n_specs < 1 ||
-        n_specs > MCF_MAX_SPECS || !d_out)
+                       int64_t sims_per_stream_hint, const uint64_t *d_sim_start, const void *d_plan_workspace,
+                       const mcf_gbm_spec *h_specs, int32_t n_specs, double *d_out, void *cuda_stream) {
+    if (!d_streams || n_streams <= 0 || n_total <= 0 || n_steps <= 0 || !d_sim_start || !d_plan_workspace || !h_specs ||
+        n_specs < 1 || n_specs > MCF_MAX_SPECS || !d_out)
         return MCF_ERR_BAD_ARG;
     SpecPack pack;
     pack.n = n_specs;
@@ -529,19 +567,22 @@ int mcf_gbm_terminal(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_s
     cudaStream_t cs = (cudaStream_t)cuda_stream;
     if (gen_kind == MCF_GEN_PCG64)
         gbm_terminal_kernel<MCF_GEN_PCG64><<<grid_for(n_total, 256), 256, 0, cs>>>(
-            d_streams, n_streams, n_total, n_steps, sims_per_stream_hint, d_sim_start, pack, d_out);
+            d_streams, n_streams, n_total, sims_per_stream_hint, d_sim_start, (const char *)d_plan_workspace, pack,
+            (double)n_steps, d_out);
     else
         gbm_terminal_kernel<MCF_GEN_PHILOX><<<grid_for(n_total, 256), 256, 0, cs>>>(
-            d_streams, n_streams, n_total, n_steps, sims_per_stream_hint, d_sim_start, pack, d_out);
+            d_streams, n_streams, n_total, sims_per_stream_hint, d_sim_start, (const char *)d_plan_workspace, pack,
+            (double)n_steps, d_out);
     MCF_CUDA_OK(cudaGetLastError());
     return MCF_OK;
 }
 
 
 int mcf_gbm_paths(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total, int64_t n_steps,
-                    int64_t sims_per_stream_hint, const uint64_t *d_sim_start, const double *h_p4, int32_t time_major,
-                    double *d_paths, void *cuda_stream) {
-    if (!d_streams || n_streams <= 0 || n_total <= 0 || n_steps <= 0 || !d_sim_start || !h_p4 || !d_paths)
+                    int64_t sims_per_stream_hint, const uint64_t *d_sim_start, const void *d_plan_workspace,
+                    const double *h_p4, int32_t time_major, double *d_paths, void *cuda_stream) {
+    if (!d_streams || n_streams <= 0 || n_total <= 0 || n_steps <= 0 || !d_sim_start || !d_plan_workspace || !h_p4 ||
+        !d_paths)
         return MCF_ERR_BAD_ARG;
     mcf_gbm_spec s;
     memset(&s, 0, sizeof(s));
@@ -552,10 +593,12 @@ int mcf_gbm_paths(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_stre
     cudaStream_t cs = (cudaStream_t)cuda_stream;
     if (gen_kind == MCF_GEN_PCG64)
         gbm_paths_kernel<MCF_GEN_PCG64><<<grid_for(n_total, 256), 256, 0, cs>>>(
-            d_streams, n_streams, n_total, n_steps, sims_per_stream_hint, d_sim_start, g, time_major, d_paths);
+            d_streams, n_streams, n_total, n_steps, sims_per_stream_hint, d_sim_start, (const char *)d_plan_workspace, g,
+            time_major, d_paths);
     else
         gbm_paths_kernel<MCF_GEN_PHILOX><<<grid_for(n_total, 256), 256, 0, cs>>>(
-            d_streams, n_streams, n_total, n_steps, sims_per_stream_hint, d_sim_start, g, time_major, d_paths);
+            d_streams, n_streams, n_total, n_steps, sims_per_stream_hint, d_sim_start, (const char *)d_plan_workspace, g,
+            time_major, d_paths);
     MCF_CUDA_OK(cudaGetLastError());
     return MCF_OK;
 }
@@ -565,9 +608,10 @@ int mcf_gbm_paths(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_stre
 
 extern "C" int mcf_gbm_slices(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total,
                               int64_t n_steps, int64_t sims_per_stream_hint, const uint64_t *d_sim_start,
-                              const mcf_gbm_spec *h_spec, int64_t slice_stride, int32_t time_major, double *d_out,
-                              void *cuda_stream) {
-    if (!d_streams || n_streams <= 0 || n_total <= 0 || n_steps <= 0 || !d_sim_start || !h_spec || slice_stride <= 0 ||
+                              const void *d_plan_workspace, const mcf_gbm_spec *h_spec, int64_t slice_stride,
+                              int32_t time_major, double *d_out, void *cuda_stream) {
+    if (!d_streams || n_streams <= 0 || n_total <= 0 || n_steps <= 0 || !d_sim_start || !d_plan_workspace || !h_spec ||
+        slice_stride <= 0 ||
         !d_out || (h_spec->mode != MCF_PORTFOLIO_GBM && h_spec->mode != MCF_PATH_TERMINAL))
         return MCF_ERR_BAD_ARG;
     GbmDerived g;
@@ -577,12 +621,12 @@ extern "C" int mcf_gbm_slices(uint32_t gen_kind, const mcf_stream *d_streams, in
     cudaStream_t cs = (cudaStream_t)cuda_stream;
     if (gen_kind == MCF_GEN_PCG64)
         gbm_slices_kernel<MCF_GEN_PCG64><<<grid_for(n_total, 256), 256, 0, cs>>>(
-            d_streams, n_streams, n_total, n_steps, sims_per_stream_hint, d_sim_start, g, slice_stride, n_slices,
-            time_major, d_out);
+            d_streams, n_streams, n_total, sims_per_stream_hint, d_sim_start, (const char *)d_plan_workspace, g,
+            slice_stride, n_slices, time_major, d_out);
     else
         gbm_slices_kernel<MCF_GEN_PHILOX><<<grid_for(n_total, 256), 256, 0, cs>>>(
-            d_streams, n_streams, n_total, n_steps, sims_per_stream_hint, d_sim_start, g, slice_stride, n_slices,
-            time_major, d_out);
+            d_streams, n_streams, n_total, sims_per_stream_hint, d_sim_start, (const char *)d_plan_workspace, g,
+            slice_stride, n_slices, time_major, d_out);
     MCF_CUDA_OK(cudaGetLastError());
     return MCF_OK;
 }

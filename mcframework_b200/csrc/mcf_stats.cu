@@ -44,7 +44,7 @@ static inline int grid_cap(int64_t work_items, int per_block, int cap) {
 // ======================================================================================= moments
 struct MomentsPartial {
     Moments m;
-    double sq_target, sum, n_nan, n_pinf, n_ninf, vmin, vmax;
+    double sum, n_nan, n_pinf, n_ninf;
 };
 
 __device__ __forceinline__ double shfl_xor_d(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
@@ -56,13 +56,10 @@ __device__ __forceinline__ MomentsPartial partial_shfl_xor(const MomentsPartial 
     q.m.m2 = shfl_xor_d(p.m.m2, o);
     q.m.m3 = shfl_xor_d(p.m.m3, o);
     q.m.m4 = shfl_xor_d(p.m.m4, o);
-    q.sq_target = shfl_xor_d(p.sq_target, o);
     q.sum = shfl_xor_d(p.sum, o);
     q.n_nan = shfl_xor_d(p.n_nan, o);
     q.n_pinf = shfl_xor_d(p.n_pinf, o);
     q.n_ninf = shfl_xor_d(p.n_ninf, o);
-    q.vmin = shfl_xor_d(p.vmin, o);
-    q.vmax = shfl_xor_d(p.vmax, o);
     return q;
 }
 
@@ -71,13 +68,10 @@ __device__ __forceinline__ MomentsPartial partial_shfl_xor(const MomentsPartial 
 __device__ __forceinline__ MomentsPartial partial_merge(const MomentsPartial &a, const MomentsPartial &b) {
     MomentsPartial r;
     r.m = moments_merge(a.m, b.m);
-    r.sq_target = a.sq_target + b.sq_target;
     r.sum = a.sum + b.sum;
     r.n_nan = a.n_nan + b.n_nan;
     r.n_pinf = a.n_pinf + b.n_pinf;
     r.n_ninf = a.n_ninf + b.n_ninf;
-    r.vmin = fmin(a.vmin, b.vmin);
-    r.vmax = fmax(a.vmax, b.vmax);
     return r;
 }
 
@@ -91,81 +85,76 @@ __device__ __forceinline__ MomentsPartial partial_warp_reduce(MomentsPartial p) 
     return p;
 }
 
+// Lean per-element work (the kernel must stay under the HBM roofline, not the FP64 pipe): 6 FP64 operations
+// and one exponent test per element.  Everything else is derived afterwards:
+//   n = elements seen - non-finite ones,  sum x = n*c + s1,  sum (x-target)^2 = M2 + n*(mean-target)^2.
 struct MomAcc {
-    double c, n, s1, s2, s3, s4, sq, n_nan, n_pinf, n_ninf, vmin, vmax;
-    bool have_c;
+    double c, s1, s2, s3, s4;
+    unsigned long long seen, n_nan, n_pinf, n_ninf;
 };
 
-__device__ __forceinline__ void mom_add(MomAcc &a, double x, double target) {
+__device__ __forceinline__ void mom_add(MomAcc &a, double x) {
     const uint64_t b = double_bits(x);
-    if (bits_nonfinite(b)) {
+    a.seen++;
+    if (bits_nonfinite(b)) {  // rare
         if (b & 0x000fffffffffffffULL)
-            a.n_nan += 1.0;
+            a.n_nan++;
         else if (b >> 63)
-            a.n_ninf += 1.0;
+            a.n_ninf++;
         else
-            a.n_pinf += 1.0;
+            a.n_pinf++;
         return;
     }
-    if (!a.have_c) {
-        a.c = x;
-        a.have_c = true;
-    }
-    const double d = x - a.c, d2 = d * d, e = x - target;
-    a.n += 1.0;
+    const double d = x - a.c, d2 = d * d;
     a.s1 += d;
     a.s2 += d2;
     a.s3 = fma(d2, d, a.s3);
     a.s4 = fma(d2, d2, a.s4);
-    a.sq = fma(e, e, a.sq);
-    a.vmin = fmin(a.vmin, x);
-    a.vmax = fmax(a.vmax, x);
 }
 
-__global__ void __launch_bounds__(256) moments_kernel(const double *__restrict__ x, int64_t n, double target,
-                                                      MomentsPartial *__restrict__ partials) {
+__global__ void __launch_bounds__(256, 4) moments_kernel(const double *__restrict__ x, int64_t n, double target,
+                                                         MomentsPartial *__restrict__ partials) {
     MomAcc a;
-    a.c = 0.0;
-    a.have_c = false;
-    a.n = a.s1 = a.s2 = a.s3 = a.s4 = a.sq = a.n_nan = a.n_pinf = a.n_ninf = 0.0;
-    a.vmin = bits_to_double(0x7ff0000000000000ULL);
-    a.vmax = bits_to_double(0xfff0000000000000ULL);
+    a.s1 = a.s2 = a.s3 = a.s4 = 0.0;
+    a.seen = a.n_nan = a.n_pinf = a.n_ninf = 0ULL;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
-    // 16-byte vector loads when the base pointer allows it
-    if ((((uintptr_t)x) & 15) == 0) {
+    // shift = a value from this thread's own neighbourhood (keeps |x - c| within the sample's spread)
+    {
+        const double probe = x[tid < n ? tid : 0];
+        a.c = bits_nonfinite(double_bits(probe)) ? 0.0 : probe;
+    }
+    if ((((uintptr_t)x) & 15) == 0) {  // 16-byte vector loads when the base pointer allows it
         const double2 *x2 = reinterpret_cast<const double2 *>(x);
         const int64_t n2 = n >> 1;
         int64_t i = tid;
         for (; i + 3 * nthr < n2; i += 4 * nthr) {  // 4 independent 16 B loads in flight
             const double2 v0 = __ldg(&x2[i]), v1 = __ldg(&x2[i + nthr]), v2 = __ldg(&x2[i + 2 * nthr]),
                           v3 = __ldg(&x2[i + 3 * nthr]);
-            mom_add(a, v0.x, target);
-            mom_add(a, v0.y, target);
-            mom_add(a, v1.x, target);
-            mom_add(a, v1.y, target);
-            mom_add(a, v2.x, target);
-            mom_add(a, v2.y, target);
-            mom_add(a, v3.x, target);
-            mom_add(a, v3.y, target);
+            mom_add(a, v0.x);
+            mom_add(a, v0.y);
+            mom_add(a, v1.x);
+            mom_add(a, v1.y);
+            mom_add(a, v2.x);
+            mom_add(a, v2.y);
+            mom_add(a, v3.x);
+            mom_add(a, v3.y);
         }
         for (; i < n2; i += nthr) {
             const double2 v = __ldg(&x2[i]);
-            mom_add(a, v.x, target);
-            mom_add(a, v.y, target);
+            mom_add(a, v.x);
+            mom_add(a, v.y);
         }
-        if ((n & 1) && tid == 0) mom_add(a, x[n - 1], target);
+        if ((n & 1) && tid == 0) mom_add(a, x[n - 1]);
     } else {
-        for (int64_t i = tid; i < n; i += nthr) mom_add(a, x[i], target);
+        for (int64_t i = tid; i < n; i += nthr) mom_add(a, x[i]);
     }
     MomentsPartial p;
-    p.m = moments_from_shifted(a.n, a.c, a.s1, a.s2, a.s3, a.s4);
-    p.sq_target = a.sq;
-    p.sum = a.n > 0.0 ? fma(a.n, a.c, a.s1) : 0.0;
-    p.n_nan = a.n_nan;
-    p.n_pinf = a.n_pinf;
-    p.n_ninf = a.n_ninf;
-    p.vmin = a.vmin;
-    p.vmax = a.vmax;
+    const double cnt = (double)(a.seen - a.n_nan - a.n_pinf - a.n_ninf);
+    p.m = moments_from_shifted(cnt, a.c, a.s1, a.s2, a.s3, a.s4);
+    p.sum = cnt > 0.0 ? fma(cnt, a.c, a.s1) : 0.0;
+    p.n_nan = (double)a.n_nan;
+    p.n_pinf = (double)a.n_pinf;
+    p.n_ninf = (double)a.n_ninf;
     p = partial_warp_reduce(p);
     __shared__ MomentsPartial sh[8];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -176,20 +165,20 @@ __global__ void __launch_bounds__(256) moments_kernel(const double *__restrict__
         for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = partial_merge(r, sh[w]);
         partials[blockIdx.x] = r;
     }
+    (void)target;
 }
 
 __global__ void __launch_bounds__(32) moments_final_kernel(const MomentsPartial *__restrict__ partials, int n_partials,
-                                                           double *__restrict__ out) {
+                                                           double target, double *__restrict__ out) {
     // one warp: lane l merges partials l, l+32, ... in order, then the warp tree (fixed order => deterministic)
     const int lane = threadIdx.x;
     MomentsPartial p;
     p.m = moments_empty();
-    p.sq_target = p.sum = p.n_nan = p.n_pinf = p.n_ninf = 0.0;
-    p.vmin = bits_to_double(0x7ff0000000000000ULL);
-    p.vmax = bits_to_double(0xfff0000000000000ULL);
+    p.sum = p.n_nan = p.n_pinf = p.n_ninf = 0.0;
     for (int i = lane; i < n_partials; i += 32) p = partial_merge(p, partials[i]);
     p = partial_warp_reduce(p);
     if (lane == 0) {
+        const double dt = p.m.mean - target;
         out[0] = p.m.n;
         out[1] = p.n_nan;
         out[2] = p.n_pinf;
@@ -198,10 +187,10 @@ __global__ void __launch_bounds__(32) moments_final_kernel(const MomentsPartial 
         out[5] = p.m.m2;
         out[6] = p.m.m3;
         out[7] = p.m.m4;
-        out[8] = p.sq_target;
+        out[8] = p.m.n > 0.0 ? fma(p.m.n * dt, dt, p.m.m2) : 0.0;  // sum (x - target)^2
         out[9] = p.sum;
-        out[10] = p.vmin;
-        out[11] = p.vmax;
+        out[10] = 0.0;  // reserved
+        out[11] = 0.0;
     }
 }
 
@@ -246,30 +235,36 @@ __global__ void __launch_bounds__(512) select_hist_kernel(const double *__restri
     __syncthreads();
     const int shift = 64 - SEL_BITS * (pass + 1);  // digit position of this pass
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i0 = tid - (threadIdx.x & 31); i0 < n; i0 += nthr) {  // warp-uniform trip count
-        const int64_t i = i0 + (threadIdx.x & 31);
-        int slot = -1;
-        if (i < n) {
-            const uint64_t key = select_key(__ldg(&x[i]), omit);
-            const unsigned digit = (unsigned)(key >> shift) & (SEL_BINS - 1);
-            if (pass == 0) {
-                slot = (int)digit;
-            } else {
-                const uint64_t pre = key >> (shift + SEL_BITS);
-                int lo = 0, hi = n_uniq - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (sh_uniq[mid] < pre)
-                        lo = mid + 1;
-                    else
-                        hi = mid;
+    for (int64_t i0 = tid - (threadIdx.x & 31); i0 < n; i0 += 2 * nthr) {  // warp-uniform trip count, 2 loads in flight
+        const int64_t ia = i0 + (threadIdx.x & 31), ib = ia + nthr;
+        const double xa = ia < n ? __ldg(&x[ia]) : 0.0, xb = ib < n ? __ldg(&x[ib]) : 0.0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int64_t i = h ? ib : ia;
+            int slot = -1;
+            if (i < n) {
+                const uint64_t key = select_key(h ? xb : xa, omit);
+                const unsigned digit = (unsigned)(key >> shift) & (SEL_BINS - 1);
+                if (pass == 0) {
+                    slot = (int)digit;
+                } else {
+                    const uint64_t pre = key >> (shift + SEL_BITS);
+                    int lo = 0, hi = n_uniq - 1;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (sh_uniq[mid] < pre)
+                            lo = mid + 1;
+                        else
+                            hi = mid;
+                    }
+                    if (sh_uniq[lo] == pre) slot = lo * SEL_BINS + (int)digit;
                 }
-                if (sh_uniq[lo] == pre) slot = lo * SEL_BINS + (int)digit;
             }
+            // warp-aggregated shared-memory atomics: one add per distinct bin per warp; later passes mostly skip
+            if (__ballot_sync(0xffffffffu, slot >= 0) == 0u) continue;
+            const unsigned peers = __match_any_sync(0xffffffffu, slot);
+            if (slot >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh_hist[slot], __popc(peers));
         }
-        // warp-aggregated shared-memory atomics: one add per distinct bin per warp
-        const unsigned peers = __match_any_sync(0xffffffffu, slot);
-        if (slot >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh_hist[slot], __popc(peers));
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n_uniq * SEL_BINS; i += blockDim.x) {
@@ -588,19 +583,20 @@ __device__ __forceinline__ double lsm_intrinsic(double s, double K, int is_put) 
     return is_put ? fmax(K - s, 0.0) : fmax(s - K, 0.0);
 }
 
+// cf[i] holds the cash flow DISCOUNTED TO TIME 0: intrinsic(exercise step) * exp(-r*dt*exercise step).  The
+// regression target of step t is then cf[i]*exp(+r*dt*t) -- one scalar per step instead of one exp per path.
 __global__ void __launch_bounds__(LSM_THREADS) lsm_init_kernel(const double *__restrict__ s_T, int64_t n_paths,
-                                                               int32_t n_steps, double K, int is_put,
+                                                               int32_t n_steps, double K, int is_put, double disc_T,
                                                                int32_t *__restrict__ ex, double *__restrict__ cf) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_paths; i += (int64_t)gridDim.x * blockDim.x) {
         ex[i] = n_steps;
-        cf[i] = lsm_intrinsic(s_T[i], K, is_put);
+        cf[i] = lsm_intrinsic(s_T[i], K, is_put) * disc_T;
     }
 }
 
-// sweep 1 of step t: sums of the normal equations over in-the-money paths
+// sweep 1 of step t: sums of the normal equations over in-the-money paths (16 B per path: S_t and cf)
 __global__ void __launch_bounds__(LSM_THREADS) lsm_reduce_kernel(const double *__restrict__ s_t, int64_t n_paths,
-                                                                 int32_t t, double K, double rdt, int is_put,
-                                                                 const int32_t *__restrict__ ex,
+                                                                 double K, double grow_t, int is_put,
                                                                  const double *__restrict__ cf,
                                                                  double *__restrict__ partials) {
     double a[8];
@@ -609,8 +605,9 @@ __global__ void __launch_bounds__(LSM_THREADS) lsm_reduce_kernel(const double *_
     const double invK = 1.0 / K;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_paths; i += (int64_t)gridDim.x * blockDim.x) {
         const double s = __ldg(&s_t[i]);
+        const double c = __ldg(&cf[i]);
         if (lsm_intrinsic(s, K, is_put) > 0.0) {
-            const double y = cf[i] * exp(-rdt * (double)(ex[i] - t));
+            const double y = c * grow_t;
             const double u = (s - K) * invK, u2 = u * u;
             a[0] += 1.0;
             a[1] += u;
@@ -720,7 +717,8 @@ __global__ void lsm_solve_kernel(LsmState *st) {
 
 // sweep 2 of step t: exercise where intrinsic > fitted continuation
 __global__ void __launch_bounds__(LSM_THREADS) lsm_apply_kernel(const double *__restrict__ s_t, int64_t n_paths, int32_t t,
-                                                                double K, int is_put, const LsmState *__restrict__ st,
+                                                                double K, int is_put, double disc_t,
+                                                                const LsmState *__restrict__ st,
                                                                 int32_t *__restrict__ ex, double *__restrict__ cf) {
     if (!st->have_fit) return;
     const double c0 = st->coef[0], c1 = st->coef[1], c2 = st->coef[2], invK = 1.0 / K;
@@ -732,19 +730,18 @@ __global__ void __launch_bounds__(LSM_THREADS) lsm_apply_kernel(const double *__
             const double fitted = fma(fma(c2, u, c1), u, c0);
             if (intr > fitted) {
                 ex[i] = t;
-                cf[i] = intr;
+                cf[i] = intr * disc_t;
             }
         }
     }
 }
 
 // discounted cash flows: per-block partial sums (column 0 of partials)
-__global__ void __launch_bounds__(LSM_THREADS) lsm_price_kernel(int64_t n_paths, double rdt, const int32_t *__restrict__ ex,
-                                                                const double *__restrict__ cf,
+__global__ void __launch_bounds__(LSM_THREADS) lsm_price_kernel(int64_t n_paths, const double *__restrict__ cf,
                                                                 double *__restrict__ partials) {
     double a = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_paths; i += (int64_t)gridDim.x * blockDim.x)
-        a += cf[i] * exp(-rdt * (double)ex[i]);
+        a += cf[i];
     __shared__ double sh[LSM_THREADS / 32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -871,7 +868,7 @@ int mcf_moments(const double *d_x, int64_t n, double target, double *d_out, void
     const int blocks = grid_cap(n, 256 * 8, MCF_SM_COUNT * 8);
     moments_kernel<<<blocks, 256, 0, cs>>>(d_x, n, target, (MomentsPartial *)d_workspace);
     MCF_CUDA_OK(cudaGetLastError());
-    moments_final_kernel<<<1, 32, 0, cs>>>((const MomentsPartial *)d_workspace, blocks, d_out);
+    moments_final_kernel<<<1, 32, 0, cs>>>((const MomentsPartial *)d_workspace, blocks, target, d_out);
     MCF_CUDA_OK(cudaGetLastError());
     return MCF_OK;
 }
@@ -1013,15 +1010,15 @@ int64_t mcf_lsm_workspace_bytes(int64_t n_paths) {
 }
 int64_t mcf_lsm_sums_offset(void) { return 0; }
 
-int mcf_lsm_begin(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K, int32_t is_put, void *d_workspace,
-                  int64_t workspace_bytes, void *cuda_stream) {
+int mcf_lsm_begin(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K, double r, double dt,
+                  int32_t is_put, void *d_workspace, int64_t workspace_bytes, void *cuda_stream) {
     if (!d_paths_tm || n_paths <= 0 || n_steps < 1 || n_steps > 0x7fffffff || !d_workspace) return MCF_ERR_BAD_ARG;
     const LsmGeom g = lsm_geom(n_paths);
     if (workspace_bytes < g.total) return MCF_ERR_WORKSPACE_TOO_SMALL;
     char *ws = (char *)d_workspace;
     lsm_init_kernel<<<g.n_blocks, LSM_THREADS, 0, (cudaStream_t)cuda_stream>>>(
-        d_paths_tm + (size_t)n_steps * (size_t)n_paths, n_paths, (int32_t)n_steps, K, is_put, (int32_t *)(ws + g.off_ex),
-        (double *)(ws + g.off_cf));
+        d_paths_tm + (size_t)n_steps * (size_t)n_paths, n_paths, (int32_t)n_steps, K, is_put,
+        exp(-r * dt * (double)n_steps), (int32_t *)(ws + g.off_ex), (double *)(ws + g.off_cf));
     MCF_CUDA_OK(cudaGetLastError());
     return MCF_OK;
 }
@@ -1033,9 +1030,9 @@ int mcf_lsm_reduce(const double *d_paths_tm, int64_t n_paths, int64_t t, double 
     const LsmGeom g = lsm_geom(n_paths);
     char *ws = (char *)d_workspace;
     cudaStream_t cs = (cudaStream_t)cuda_stream;
-    lsm_reduce_kernel<<<g.n_blocks, LSM_THREADS, 0, cs>>>(d_paths_tm + (size_t)t * (size_t)n_paths, n_paths, (int32_t)t, K,
-                                                          r * dt, is_put, (const int32_t *)(ws + g.off_ex),
-                                                          (const double *)(ws + g.off_cf), (double *)(ws + g.off_partials));
+    lsm_reduce_kernel<<<g.n_blocks, LSM_THREADS, 0, cs>>>(d_paths_tm + (size_t)t * (size_t)n_paths, n_paths, K,
+                                                          exp(r * dt * (double)t), is_put, (const double *)(ws + g.off_cf),
+                                                          (double *)(ws + g.off_partials));
     MCF_CUDA_OK(cudaGetLastError());
     lsm_sum_partials_kernel<<<1, 256, 0, cs>>>((const double *)(ws + g.off_partials), g.n_blocks,
                                                (LsmState *)(ws + g.off_state));
@@ -1043,8 +1040,8 @@ int mcf_lsm_reduce(const double *d_paths_tm, int64_t n_paths, int64_t t, double 
     return MCF_OK;
 }
 
-int mcf_lsm_apply(const double *d_paths_tm, int64_t n_paths, int64_t t, double K, int32_t is_put, void *d_workspace,
-                  void *cuda_stream) {
+int mcf_lsm_apply(const double *d_paths_tm, int64_t n_paths, int64_t t, double K, double r, double dt, int32_t is_put,
+                  void *d_workspace, void *cuda_stream) {
     if (!d_paths_tm || n_paths <= 0 || t < 0 || !d_workspace) return MCF_ERR_BAD_ARG;
     const LsmGeom g = lsm_geom(n_paths);
     char *ws = (char *)d_workspace;
@@ -1052,7 +1049,8 @@ int mcf_lsm_apply(const double *d_paths_tm, int64_t n_paths, int64_t t, double K
     lsm_solve_kernel<<<1, 32, 0, cs>>>((LsmState *)(ws + g.off_state));
     MCF_CUDA_OK(cudaGetLastError());
     lsm_apply_kernel<<<g.n_blocks, LSM_THREADS, 0, cs>>>(d_paths_tm + (size_t)t * (size_t)n_paths, n_paths, (int32_t)t, K,
-                                                         is_put, (const LsmState *)(ws + g.off_state),
+                                                         is_put, exp(-r * dt * (double)t),
+                                                         (const LsmState *)(ws + g.off_state),
                                                          (int32_t *)(ws + g.off_ex), (double *)(ws + g.off_cf));
     MCF_CUDA_OK(cudaGetLastError());
     return MCF_OK;
@@ -1065,8 +1063,10 @@ int mcf_lsm_finish(int64_t n_paths, double r, double dt, void *d_workspace, doub
     const LsmGeom g = lsm_geom(n_paths);
     char *ws = (char *)d_workspace;
     cudaStream_t cs = (cudaStream_t)cuda_stream;
-    lsm_price_kernel<<<g.n_blocks, LSM_THREADS, 0, cs>>>(n_paths, r * dt, (const int32_t *)(ws + g.off_ex),
-                                                         (const double *)(ws + g.off_cf), (double *)(ws + g.off_partials));
+    lsm_price_kernel<<<g.n_blocks, LSM_THREADS, 0, cs>>>(n_paths, (const double *)(ws + g.off_cf),
+                                                         (double *)(ws + g.off_partials));
+    (void)r;
+    (void)dt;
     MCF_CUDA_OK(cudaGetLastError());
     lsm_sum_partials_kernel<<<1, 256, 0, cs>>>((const double *)(ws + g.off_partials), g.n_blocks,
                                                (LsmState *)(ws + g.off_state));
@@ -1080,12 +1080,12 @@ int mcf_lsm_finish(int64_t n_paths, double r, double dt, void *d_workspace, doub
 
 int mcf_lsm(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K, double r, double dt, int32_t is_put,
             void *d_workspace, int64_t workspace_bytes, double *d_price, int32_t *d_exercise_times, void *cuda_stream) {
-    int rc = mcf_lsm_begin(d_paths_tm, n_paths, n_steps, K, is_put, d_workspace, workspace_bytes, cuda_stream);
+    int rc = mcf_lsm_begin(d_paths_tm, n_paths, n_steps, K, r, dt, is_put, d_workspace, workspace_bytes, cuda_stream);
     if (rc) return rc;
     for (int64_t t = n_steps - 1; t >= 1; t--) {
         rc = mcf_lsm_reduce(d_paths_tm, n_paths, t, K, r, dt, is_put, d_workspace, cuda_stream);
         if (rc) return rc;
-        rc = mcf_lsm_apply(d_paths_tm, n_paths, t, K, is_put, d_workspace, cuda_stream);
+        rc = mcf_lsm_apply(d_paths_tm, n_paths, t, K, r, dt, is_put, d_workspace, cuda_stream);
         if (rc) return rc;
     }
     return mcf_lsm_finish(n_paths, r, dt, d_workspace, NULL, d_price, d_exercise_times, cuda_stream);

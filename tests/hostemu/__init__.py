@@ -56,22 +56,47 @@ def pi_hits(layout, n_points, antithetic=False):
     return hits
 
 
+class Plan:
+    """Host-emulated plan: replication starts, stream ends and the emit masks the replay reads."""
+
+    def __init__(self, rc, sim_start, stream_end, regen, emit, entry, cps):
+        self.rc, self.sim_start, self.stream_end, self.regen = rc, sim_start, stream_end, regen
+        self.emit, self.entry, self.cps = emit, entry, cps
+
+    def __iter__(self):  # (rc, sim_start, stream_end, regenerated) -- the tuple older tests unpack
+        return iter((self.rc, self.sim_start, self.stream_end, self.regen))
+
+
 def normal_plan(layout, nps, slack=0.03, iters=3):
     sim_start = np.full(layout.n_total, np.iinfo(np.uint64).max, dtype=np.uint64)
     stream_end = np.zeros(layout.n_streams, dtype=np.uint64)
     regen = C.c_int64(0)
+    cps = C.c_int64(0)
+    lib().emu_plan_chunks.restype = C.c_int64
+    n_chunks = lib().emu_plan_chunks(layout.n_streams, C.c_int64(layout.max_sims), C.c_int64(nps), C.c_double(slack),
+                                     C.byref(cps))
+    emit = np.zeros(n_chunks, dtype=np.uint64)
+    entry = np.zeros(n_chunks, dtype=np.uint8)
     rc = lib().emu_normal_plan(C.c_uint32(layout.kind), _vp(layout.records), layout.n_streams,
                                C.c_int64(layout.max_sims), C.c_int64(nps), C.c_double(slack), iters, _vp(sim_start),
-                               _vp(stream_end), C.byref(regen))
-    return rc, sim_start, stream_end, regen.value
+                               _vp(stream_end), C.byref(regen), _vp(emit), _vp(entry))
+    return Plan(rc, sim_start, stream_end, regen.value, emit, entry, cps.value)
 
 
-def gbm_terminal(layout, n_steps, sim_start, specs):
+def gbm_terminal(layout, n_steps, plan, specs, masked=True):
+    """``plan``: a Plan (mask-driven replay, what the kernels do) or a bare sim_start array (state machine)."""
     out = np.empty((len(specs), layout.n_total))
     arr = specs_array(specs)
-    rc = lib().emu_gbm_terminal(C.c_uint32(layout.kind), _vp(layout.records), layout.n_streams,
-                                C.c_int64(layout.n_total), C.c_int64(n_steps), C.c_int64(layout.hint), _vp(sim_start),
-                                arr, len(specs), _vp(out))
+    if isinstance(plan, Plan) and masked:
+        rc = lib().emu_gbm_terminal(C.c_uint32(layout.kind), _vp(layout.records), layout.n_streams,
+                                    C.c_int64(layout.n_total), C.c_int64(n_steps), C.c_int64(layout.hint),
+                                    _vp(plan.sim_start), arr, len(specs), _vp(out), _vp(plan.emit), _vp(plan.entry),
+                                    C.c_int64(plan.cps), _vp(plan.stream_end))
+    else:
+        starts = plan.sim_start if isinstance(plan, Plan) else plan
+        rc = lib().emu_gbm_terminal(C.c_uint32(layout.kind), _vp(layout.records), layout.n_streams,
+                                    C.c_int64(layout.n_total), C.c_int64(n_steps), C.c_int64(layout.hint), _vp(starts),
+                                    arr, len(specs), _vp(out), None, None, C.c_int64(0), None)
     assert rc == 0, rc
     return out
 

@@ -76,7 +76,8 @@ static void pi_impl(const mcf_stream *streams, int n_streams, int64_t n_total, i
 
 template <int KIND>
 static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims, int64_t nps, double slack, int iters,
-                     uint64_t *sim_start, uint64_t *stream_end, int64_t *n_regenerated) {
+                     uint64_t *sim_start, uint64_t *stream_end, int64_t *n_regenerated, uint64_t *em_out,
+                     uint8_t *ent_out) {
     const ZigTables t = host_tables();
     const PlanGeom g = plan_geom(n_streams, max_sims, nps, slack);
     std::vector<uint64_t> sm(g.n_chunks), em(g.n_chunks), tsum(g.n_tiles), tpre(g.n_tiles);
@@ -162,27 +163,45 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
             E += popc64(em[id] & m);
         }
     }
+    if (em_out)
+        for (int64_t id = 0; id < g.n_chunks; id++) {
+            em_out[id] = em[id];
+            ent_out[id] = ent[id];
+        }
     return status;
 }
 
 template <int KIND>
 static int terminal_impl(const mcf_stream *streams, int n_streams, int64_t n_total, int64_t n_steps, int64_t hint,
-                         const uint64_t *sim_start, const mcf_gbm_spec *specs, int n_specs, double *out) {
+                         const uint64_t *sim_start, const mcf_gbm_spec *specs, int n_specs, double *out,
+                         const uint64_t *em, const uint8_t *ent, int64_t cps, const uint64_t *stream_end) {
     const ZigTables t = host_tables();
+    PlanView pv;
+    pv.emit = em;
+    pv.entry = ent;
+    pv.cps = cps;
     SpecPack pack;
     pack.n = n_specs;
     for (int s = 0; s < n_specs; s++)
         if (derive_spec(specs[s], n_steps, &pack.g[s])) return MCF_ERR_BAD_ARG;
     for (int64_t i = 0; i < n_total; i++) {
-        const mcf_stream st = streams[stream_of(streams, n_streams, i, hint)];
+        const int64_t si = stream_of(streams, n_streams, i, hint);
+        const mcf_stream st = streams[si];
         Cursor<KIND> cur;
         cur.init(st, sim_start[i]);
-        if (n_specs == 1) {
+        if (!em) {  // state-machine replay (no masks)
+            if (n_specs != 1) return MCF_ERR_BAD_ARG;
             out[i] = run_terminal(cur, t, n_steps, pack.g[0]);
             continue;
         }
+        const uint64_t start = sim_start[i];
+        const uint64_t end = (i + 1 == st.first_sim + st.n_sims) ? stream_end[si] : sim_start[i + 1];
+        if (n_specs == 1) {
+            out[i] = terminal_value([&](auto f) { replay_emits(cur, st, pv, si, start, end, t.wi, t.ki[0], f); }, pack.g[0]);
+            continue;
+        }
         double zsum = 0.0;
-        for (int64_t k = 0; k < n_steps; k++) zsum = xadd(zsum, zig_normal(cur, t));
+        replay_emits(cur, st, pv, si, start, end, t.wi, t.ki[0], [&](double z) { zsum = xadd(zsum, z); });
         for (int s = 0; s < n_specs; s++) {
             const GbmDerived &g = pack.g[s];
             const double acc = xadd(xmul((double)n_steps, g.a), xmul(g.b, zsum));
@@ -240,20 +259,30 @@ void emu_pi_hits(uint32_t kind, const mcf_stream *streams, int n_streams, int64_
         pi_impl<MCF_GEN_PHILOX>(streams, n_streams, n_total, n_points, antithetic, hint, hits);
 }
 
+int64_t emu_plan_chunks(int n_streams, int64_t max_sims, int64_t nps, double slack, int64_t *cps) {
+    const PlanGeom g = plan_geom(n_streams, max_sims, nps, slack);
+    *cps = g.cps;
+    return g.n_chunks;
+}
+
 int emu_normal_plan(uint32_t kind, const mcf_stream *streams, int n_streams, int64_t max_sims, int64_t nps,
-                    double slack, int iters, uint64_t *sim_start, uint64_t *stream_end, int64_t *n_regenerated) {
+                    double slack, int iters, uint64_t *sim_start, uint64_t *stream_end, int64_t *n_regenerated,
+                    uint64_t *em_out, uint8_t *ent_out) {
     if (kind == MCF_GEN_PCG64)
         return plan_impl<MCF_GEN_PCG64>(streams, n_streams, max_sims, nps, slack, iters, sim_start, stream_end,
-                                        n_regenerated);
+                                        n_regenerated, em_out, ent_out);
     return plan_impl<MCF_GEN_PHILOX>(streams, n_streams, max_sims, nps, slack, iters, sim_start, stream_end,
-                                     n_regenerated);
+                                     n_regenerated, em_out, ent_out);
 }
 
 int emu_gbm_terminal(uint32_t kind, const mcf_stream *streams, int n_streams, int64_t n_total, int64_t n_steps,
-                     int64_t hint, const uint64_t *sim_start, const mcf_gbm_spec *specs, int n_specs, double *out) {
+                     int64_t hint, const uint64_t *sim_start, const mcf_gbm_spec *specs, int n_specs, double *out,
+                     const uint64_t *em, const uint8_t *ent, int64_t cps, const uint64_t *stream_end) {
     if (kind == MCF_GEN_PCG64)
-        return terminal_impl<MCF_GEN_PCG64>(streams, n_streams, n_total, n_steps, hint, sim_start, specs, n_specs, out);
-    return terminal_impl<MCF_GEN_PHILOX>(streams, n_streams, n_total, n_steps, hint, sim_start, specs, n_specs, out);
+        return terminal_impl<MCF_GEN_PCG64>(streams, n_streams, n_total, n_steps, hint, sim_start, specs, n_specs, out,
+                                            em, ent, cps, stream_end);
+    return terminal_impl<MCF_GEN_PHILOX>(streams, n_streams, n_total, n_steps, hint, sim_start, specs, n_specs, out, em,
+                                         ent, cps, stream_end);
 }
 
 void emu_gbm_paths(uint32_t kind, const mcf_stream *streams, int n_streams, int64_t n_total, int64_t n_steps,

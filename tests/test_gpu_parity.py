@@ -187,7 +187,6 @@ def test_moments_vs_numpy_scipy(sd, n):
     np.testing.assert_allclose(m.mean, x.mean(), rtol=1e-14)
     np.testing.assert_allclose(m.total, x.sum(), rtol=1e-13)
     np.testing.assert_allclose(m.sq_target, ((x - 4.5) ** 2).sum(), rtol=1e-13)
-    assert m.vmin == x.min() and m.vmax == x.max()
     if n > 1:
         np.testing.assert_allclose(np.sqrt(m.m2 / (n - 1)), x.std(ddof=1), rtol=1e-13)
     if n > 3:

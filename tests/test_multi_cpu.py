@@ -21,7 +21,7 @@ def _summary_of(a):
 
     m = a.mean() if a.size else 0.0
     return MomentSummary(a.size, 0, 0, 0, m, ((a - m) ** 2).sum(), ((a - m) ** 3).sum(), ((a - m) ** 4).sum(),
-                         ((a - 2.0) ** 2).sum(), a.sum(), a.min() if a.size else np.inf, a.max() if a.size else -np.inf)
+                         ((a - 2.0) ** 2).sum(), a.sum())
 
 
 def _worker(rank, world, port, q):
@@ -56,7 +56,7 @@ def _worker(rank, world, port, q):
         dist.all_gather(parts, part)
         merged = merge_summaries(MomentSummary.from_array(p.numpy()) for p in parts)
         whole = _summary_of(x)
-        for f in ("n", "mean", "m2", "m3", "m4", "sq_target", "total", "vmin", "vmax"):
+        for f in ("n", "mean", "m2", "m3", "m4", "sq_target", "total"):
             np.testing.assert_allclose(getattr(merged, f), getattr(whole, f), rtol=1e-11)
 
         # (4) radix-select combine: summed per-rank digit histograms select the global order statistic
