@@ -15,7 +15,7 @@ struct PlanGeom {
     int64_t tps;        // tiles per stream
     int64_t n_chunks;   // n_streams * cps
     int64_t n_tiles;
-    int64_t off_start, off_emit, off_exit, off_gen, off_entry, off_tsum, off_tpre, off_send, total;
+    int64_t off_start, off_emit, off_exit, off_gen, off_entry, off_tsum, off_tpre, off_send, off_zsum, total;
 };
 
 // Device-resident description of a finished plan (at byte MCF_LAYOUT_OFFSET of the workspace): lets the replay
@@ -23,7 +23,7 @@ struct PlanGeom {
 #define MCF_LAYOUT_OFFSET 64
 #define MCF_LAYOUT_MAGIC 0x6d63665f706c616eLL
 struct PlanLayout {
-    int64_t magic, cps, off_emit, off_entry, off_send, n_streams;
+    int64_t magic, cps, off_emit, off_entry, off_send, off_zsum, n_streams;
 };
 
 static inline PlanGeom plan_geom(int32_t n_streams, int64_t max_sims, int64_t nps, double slack) {
@@ -53,6 +53,9 @@ static inline PlanGeom plan_geom(int32_t n_streams, int64_t max_sims, int64_t np
     o = (o + 255) / 256 * 256;
     g.off_send = o;
     o += (int64_t)n_streams * 8;
+    o = (o + 255) / 256 * 256;
+    g.off_zsum = o;
+    o += g.n_chunks * 8;
     g.total = (o + 255) / 256 * 256;
     return g;
 }
@@ -60,6 +63,7 @@ static inline PlanGeom plan_geom(int32_t n_streams, int64_t max_sims, int64_t np
 #define MCF_MAX_SPECS 8
 struct SpecPack {
     int n;
+    int affine;  // every set is affine in sum(Z): terminal values come from chunk sums + the two partial chunks
     mcf::GbmDerived g[MCF_MAX_SPECS];
 };
 

@@ -107,7 +107,7 @@ template <int KIND, int RUN>
 __global__ void __launch_bounds__(256) plan_scan_kernel(const mcf_stream *__restrict__ streams, int64_t cps,
                                                         int64_t n_runs, uint64_t *__restrict__ startmask,
                                                         uint64_t *__restrict__ emitmask, uint8_t *__restrict__ exit_,
-                                                        uint8_t *__restrict__ gen, int *hdr) {
+                                                        uint8_t *__restrict__ gen, double *__restrict__ zsum, int *hdr) {
     __shared__ ZigShared sh;
     const ZigTables t = load_zig_tables(sh);
     const int64_t run = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(256) plan_scan_kernel(const mcf_stream *__rest
         emitmask[id] = ci.emitmask;
         exit_[id] = (uint8_t)ci.exit;
         gen[id] = (uint8_t)ci.gen_entry;
+        zsum[id] = ci.zsum;
         if (ci.exit == MCF_EXIT_OVERFLOW) atomicExch(&hdr[0], MCF_ERR_NOT_CONVERGED);
         entry = ci.exit;
     }
@@ -138,14 +139,17 @@ __global__ void __launch_bounds__(256) plan_resolve_kernel(const mcf_stream *__r
                                                            int64_t n_chunks, uint64_t *__restrict__ startmask,
                                                            uint64_t *__restrict__ emitmask, uint8_t *exit_,
                                                            uint8_t *__restrict__ gen, uint8_t *__restrict__ entry_true,
-                                                           int *hdr, int iter) {
+                                                           double *__restrict__ zsum, int *hdr, int iter) {
     __shared__ ZigShared sh;
     const ZigTables t = load_zig_tables(sh);
     const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n_chunks) return;
     const int64_t si = id / cps, c = id - si * cps;
     const uint32_t e = c == 0 ? 0u : (uint32_t)((volatile uint8_t *)exit_)[id - 1];
-    if (!chunk_valid_for_entry(startmask[id], gen[id], e)) {
+    // Re-walk whenever the true entry differs from the one the chunk was generated with.  (The masks alone would
+    // stay usable when `e` happens to be an attempt start of the speculative walk -- chains coincide from there --
+    // but the stored chunk sum must not contain the attempts the speculative walk started before `e`.)
+    if (e != (uint32_t)gen[id]) {
         const mcf_stream st = streams[si];
         Cursor<KIND> cur;
         cur.init(st, (uint64_t)c * MCF_CHUNK + e);
@@ -153,6 +157,7 @@ __global__ void __launch_bounds__(256) plan_resolve_kernel(const mcf_stream *__r
         startmask[id] = ci.startmask;
         emitmask[id] = ci.emitmask;
         gen[id] = (uint8_t)ci.gen_entry;
+        zsum[id] = ci.zsum;
         if (ci.exit != exit_[id]) {
             ((volatile uint8_t *)exit_)[id] = (uint8_t)ci.exit;
             atomicExch(&hdr[1 + iter], 1);
@@ -316,6 +321,7 @@ __device__ __forceinline__ ReplaySetup replay_setup(const mcf_stream *__restrict
     r.st = streams[r.si];
     r.pv.emit = reinterpret_cast<const uint64_t *>(plan_ws + lay->off_emit);
     r.pv.entry = reinterpret_cast<const uint8_t *>(plan_ws + lay->off_entry);
+    r.pv.zsum = reinterpret_cast<const double *>(plan_ws + lay->off_zsum);
     r.pv.cps = lay->cps;
     r.start = sim_start[i];
     const bool last = (i + 1 == r.st.first_sim + r.st.n_sims);
@@ -336,15 +342,14 @@ __global__ void __launch_bounds__(256, 3) gbm_terminal_kernel(const mcf_stream *
     if (i >= n_total) return;
     const ReplaySetup rs = replay_setup(streams, n_streams, hint, sim_start, plan_ws, i);
     Cursor<KIND> cur;
-    if (specs.n == 1) {
+    if (!specs.affine) {  // path-dependent body (one parameter set): every normal, in order
         out[i] = terminal_value([&](auto f) { replay_emits(cur, rs.st, rs.pv, rs.si, rs.start, rs.end, wi, ki0, f); },
                                 specs.g[0]);
         return;
     }
-    // several parameter sets on common random numbers (Greeks): the terminal log-price is affine
-    // in sum(Z), so one pass over the normals serves every set (all sets are affine-sum modes).
-    double zsum = 0.0;
-    replay_emits(cur, rs.st, rs.pv, rs.si, rs.start, rs.end, wi, ki0, [&](double z) { zsum = xadd(zsum, z); });
+    // Terminal log-price is affine in sum(Z): n*a + b*sum(Z).  One pass serves every parameter set (Greeks on common
+    // random numbers), and whole chunks of the stream contribute through the sums the planning pass stored.
+    const double zsum = replay_zsum(cur, rs.st, rs.pv, rs.si, rs.start, rs.end, wi, ki0);
     for (int s = 0; s < specs.n; s++) {
         const GbmDerived &g = specs.g[s];
         const double acc = xadd(xmul(n_steps_f, g.a), xmul(g.b, zsum));
@@ -445,21 +450,23 @@ static int normal_plan_impl(const mcf_stream *d_streams, const PlanGeom &g, int6
     uint64_t *sm = (uint64_t *)(ws + g.off_start), *em = (uint64_t *)(ws + g.off_emit);
     uint64_t *tsum = (uint64_t *)(ws + g.off_tsum), *tpre = (uint64_t *)(ws + g.off_tpre);
     uint8_t *ex = (uint8_t *)(ws + g.off_exit), *gen = (uint8_t *)(ws + g.off_gen), *ent = (uint8_t *)(ws + g.off_entry);
+    double *zs = (double *)(ws + g.off_zsum);
     PlanLayout layout;
     layout.magic = MCF_LAYOUT_MAGIC;
     layout.cps = g.cps;
     layout.off_emit = g.off_emit;
     layout.off_entry = g.off_entry;
     layout.off_send = g.off_send;
+    layout.off_zsum = g.off_zsum;
     layout.n_streams = g.n_chunks / g.cps;
     plan_init_kernel<<<1, 32, 0, cs>>>(hdr, iters, layout);
     constexpr int RUN = KIND == MCF_GEN_PCG64 ? 8 : 1;  // PCG64 pays an O(log n) jump per thread
     const int64_t n_runs = g.n_chunks / RUN;
-    plan_scan_kernel<KIND, RUN><<<grid_for(n_runs, 256), 256, 0, cs>>>(d_streams, g.cps, n_runs, sm, em, ex, gen, hdr);
+    plan_scan_kernel<KIND, RUN><<<grid_for(n_runs, 256), 256, 0, cs>>>(d_streams, g.cps, n_runs, sm, em, ex, gen, zs, hdr);
     MCF_CUDA_OK(cudaGetLastError());
     for (int it = 0; it < iters; it++) {
         plan_resolve_kernel<KIND><<<grid_for(g.n_chunks, 256), 256, 0, cs>>>(d_streams, g.cps, g.n_chunks, sm, em, ex,
-                                                                             gen, ent, hdr, it);
+                                                                             gen, ent, zs, hdr, it);
         MCF_CUDA_OK(cudaGetLastError());
     }
     plan_tile_count_kernel<<<(unsigned)g.n_tiles, 256, 0, cs>>>(em, ent, tsum);
@@ -557,12 +564,14 @@ int mcf_gbm_terminal(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_s
         return MCF_ERR_BAD_ARG;
     SpecPack pack;
     pack.n = n_specs;
+    pack.affine = 1;
     for (int s = 0; s < n_specs; s++) {
         int rc = derive_spec(h_specs[s], n_steps, &pack.g[s]);
         if (rc) return rc;
         const int m = h_specs[s].mode;
-        if (n_specs > 1 && (m == MCF_BS_AMER_CALL || m == MCF_BS_AMER_PUT || m == MCF_PORTFOLIO_LOG1P))
-            return MCF_ERR_BAD_ARG;  // path-dependent bodies take one parameter set per launch
+        const bool path_dependent = (m == MCF_BS_AMER_CALL || m == MCF_BS_AMER_PUT || m == MCF_PORTFOLIO_LOG1P);
+        if (path_dependent) pack.affine = 0;
+        if (n_specs > 1 && path_dependent) return MCF_ERR_BAD_ARG;  // path-dependent bodies take one set per launch
     }
     cudaStream_t cs = (cudaStream_t)cuda_stream;
     if (gen_kind == MCF_GEN_PCG64)

@@ -59,9 +59,9 @@ def pi_hits(layout, n_points, antithetic=False):
 class Plan:
     """Host-emulated plan: replication starts, stream ends and the emit masks the replay reads."""
 
-    def __init__(self, rc, sim_start, stream_end, regen, emit, entry, cps):
+    def __init__(self, rc, sim_start, stream_end, regen, emit, entry, zsum, cps):
         self.rc, self.sim_start, self.stream_end, self.regen = rc, sim_start, stream_end, regen
-        self.emit, self.entry, self.cps = emit, entry, cps
+        self.emit, self.entry, self.zsum, self.cps = emit, entry, zsum, cps
 
     def __iter__(self):  # (rc, sim_start, stream_end, regenerated) -- the tuple older tests unpack
         return iter((self.rc, self.sim_start, self.stream_end, self.regen))
@@ -77,10 +77,11 @@ def normal_plan(layout, nps, slack=0.03, iters=3):
                                      C.byref(cps))
     emit = np.zeros(n_chunks, dtype=np.uint64)
     entry = np.zeros(n_chunks, dtype=np.uint8)
+    zsum = np.zeros(n_chunks, dtype=np.float64)
     rc = lib().emu_normal_plan(C.c_uint32(layout.kind), _vp(layout.records), layout.n_streams,
                                C.c_int64(layout.max_sims), C.c_int64(nps), C.c_double(slack), iters, _vp(sim_start),
-                               _vp(stream_end), C.byref(regen), _vp(emit), _vp(entry))
-    return Plan(rc, sim_start, stream_end, regen.value, emit, entry, cps.value)
+                               _vp(stream_end), C.byref(regen), _vp(emit), _vp(entry), _vp(zsum))
+    return Plan(rc, sim_start, stream_end, regen.value, emit, entry, zsum, cps.value)
 
 
 def gbm_terminal(layout, n_steps, plan, specs, masked=True):
@@ -91,12 +92,12 @@ def gbm_terminal(layout, n_steps, plan, specs, masked=True):
         rc = lib().emu_gbm_terminal(C.c_uint32(layout.kind), _vp(layout.records), layout.n_streams,
                                     C.c_int64(layout.n_total), C.c_int64(n_steps), C.c_int64(layout.hint),
                                     _vp(plan.sim_start), arr, len(specs), _vp(out), _vp(plan.emit), _vp(plan.entry),
-                                    C.c_int64(plan.cps), _vp(plan.stream_end))
+                                    _vp(plan.zsum), C.c_int64(plan.cps), _vp(plan.stream_end))
     else:
         starts = plan.sim_start if isinstance(plan, Plan) else plan
         rc = lib().emu_gbm_terminal(C.c_uint32(layout.kind), _vp(layout.records), layout.n_streams,
                                     C.c_int64(layout.n_total), C.c_int64(n_steps), C.c_int64(layout.hint), _vp(starts),
-                                    arr, len(specs), _vp(out), None, None, C.c_int64(0), None)
+                                    arr, len(specs), _vp(out), None, None, None, C.c_int64(0), None)
     assert rc == 0, rc
     return out
 

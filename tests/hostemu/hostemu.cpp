@@ -77,11 +77,12 @@ static void pi_impl(const mcf_stream *streams, int n_streams, int64_t n_total, i
 template <int KIND>
 static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims, int64_t nps, double slack, int iters,
                      uint64_t *sim_start, uint64_t *stream_end, int64_t *n_regenerated, uint64_t *em_out,
-                     uint8_t *ent_out) {
+                     uint8_t *ent_out, double *zs_out) {
     const ZigTables t = host_tables();
     const PlanGeom g = plan_geom(n_streams, max_sims, nps, slack);
     std::vector<uint64_t> sm(g.n_chunks), em(g.n_chunks), tsum(g.n_tiles), tpre(g.n_tiles);
     std::vector<uint8_t> ex(g.n_chunks), gen(g.n_chunks), ent(g.n_chunks);
+    std::vector<double> zs(g.n_chunks);
     int status = 0;
     constexpr int RUN = KIND == MCF_GEN_PCG64 ? 8 : 1;
     // scan
@@ -97,6 +98,7 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
             em[id] = ci.emitmask;
             ex[id] = (uint8_t)ci.exit;
             gen[id] = (uint8_t)ci.gen_entry;
+            zs[id] = ci.zsum;
             if (ci.exit == MCF_EXIT_OVERFLOW) status = MCF_ERR_NOT_CONVERGED;
             entry = ci.exit;
         }
@@ -111,7 +113,7 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
         for (int64_t id = 0; id < g.n_chunks; id++) {
             const int64_t si = id / g.cps, c = id - si * g.cps;
             const uint32_t e = c == 0 ? 0u : ex_snapshot[id - 1];
-            if (!chunk_valid_for_entry(sm[id], gen[id], e)) {
+            if (e != (uint32_t)gen[id]) {  // same rule as plan_resolve_kernel
                 regen++;
                 Cursor<KIND> cur;
                 cur.init(streams[si], (uint64_t)c * MCF_CHUNK + e);
@@ -119,6 +121,7 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
                 sm[id] = ci.startmask;
                 em[id] = ci.emitmask;
                 gen[id] = (uint8_t)ci.gen_entry;
+                zs[id] = ci.zsum;
                 if (ci.exit != ex[id]) {
                     ex[id] = (uint8_t)ci.exit;
                     changed_last = 1;
@@ -167,6 +170,7 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
         for (int64_t id = 0; id < g.n_chunks; id++) {
             em_out[id] = em[id];
             ent_out[id] = ent[id];
+            zs_out[id] = zs[id];
         }
     return status;
 }
@@ -174,12 +178,19 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
 template <int KIND>
 static int terminal_impl(const mcf_stream *streams, int n_streams, int64_t n_total, int64_t n_steps, int64_t hint,
                          const uint64_t *sim_start, const mcf_gbm_spec *specs, int n_specs, double *out,
-                         const uint64_t *em, const uint8_t *ent, int64_t cps, const uint64_t *stream_end) {
+                         const uint64_t *em, const uint8_t *ent, const double *zs, int64_t cps,
+                         const uint64_t *stream_end) {
     const ZigTables t = host_tables();
     PlanView pv;
     pv.emit = em;
     pv.entry = ent;
+    pv.zsum = zs;
     pv.cps = cps;
+    bool affine = true;
+    for (int s = 0; s < n_specs; s++) {
+        const int m = specs[s].mode;
+        if (m == MCF_BS_AMER_CALL || m == MCF_BS_AMER_PUT || m == MCF_PORTFOLIO_LOG1P) affine = false;
+    }
     SpecPack pack;
     pack.n = n_specs;
     for (int s = 0; s < n_specs; s++)
@@ -196,12 +207,12 @@ static int terminal_impl(const mcf_stream *streams, int n_streams, int64_t n_tot
         }
         const uint64_t start = sim_start[i];
         const uint64_t end = (i + 1 == st.first_sim + st.n_sims) ? stream_end[si] : sim_start[i + 1];
-        if (n_specs == 1) {
+        if (!affine) {
+            if (n_specs != 1) return MCF_ERR_BAD_ARG;
             out[i] = terminal_value([&](auto f) { replay_emits(cur, st, pv, si, start, end, t.wi, t.ki[0], f); }, pack.g[0]);
             continue;
         }
-        double zsum = 0.0;
-        replay_emits(cur, st, pv, si, start, end, t.wi, t.ki[0], [&](double z) { zsum = xadd(zsum, z); });
+        const double zsum = replay_zsum(cur, st, pv, si, start, end, t.wi, t.ki[0]);
         for (int s = 0; s < n_specs; s++) {
             const GbmDerived &g = pack.g[s];
             const double acc = xadd(xmul((double)n_steps, g.a), xmul(g.b, zsum));
@@ -267,22 +278,23 @@ int64_t emu_plan_chunks(int n_streams, int64_t max_sims, int64_t nps, double sla
 
 int emu_normal_plan(uint32_t kind, const mcf_stream *streams, int n_streams, int64_t max_sims, int64_t nps,
                     double slack, int iters, uint64_t *sim_start, uint64_t *stream_end, int64_t *n_regenerated,
-                    uint64_t *em_out, uint8_t *ent_out) {
+                    uint64_t *em_out, uint8_t *ent_out, double *zs_out) {
     if (kind == MCF_GEN_PCG64)
         return plan_impl<MCF_GEN_PCG64>(streams, n_streams, max_sims, nps, slack, iters, sim_start, stream_end,
-                                        n_regenerated, em_out, ent_out);
+                                        n_regenerated, em_out, ent_out, zs_out);
     return plan_impl<MCF_GEN_PHILOX>(streams, n_streams, max_sims, nps, slack, iters, sim_start, stream_end,
-                                     n_regenerated, em_out, ent_out);
+                                     n_regenerated, em_out, ent_out, zs_out);
 }
 
 int emu_gbm_terminal(uint32_t kind, const mcf_stream *streams, int n_streams, int64_t n_total, int64_t n_steps,
                      int64_t hint, const uint64_t *sim_start, const mcf_gbm_spec *specs, int n_specs, double *out,
-                     const uint64_t *em, const uint8_t *ent, int64_t cps, const uint64_t *stream_end) {
+                     const uint64_t *em, const uint8_t *ent, const double *zs, int64_t cps,
+                     const uint64_t *stream_end) {
     if (kind == MCF_GEN_PCG64)
         return terminal_impl<MCF_GEN_PCG64>(streams, n_streams, n_total, n_steps, hint, sim_start, specs, n_specs, out,
-                                            em, ent, cps, stream_end);
+                                            em, ent, zs, cps, stream_end);
     return terminal_impl<MCF_GEN_PHILOX>(streams, n_streams, n_total, n_steps, hint, sim_start, specs, n_specs, out, em,
-                                         ent, cps, stream_end);
+                                         ent, zs, cps, stream_end);
 }
 
 void emu_gbm_paths(uint32_t kind, const mcf_stream *streams, int n_streams, int64_t n_total, int64_t n_steps,

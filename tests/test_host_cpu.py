@@ -220,7 +220,11 @@ def test_hostemu_terminal_values_match_reference_golden(emu, golden):
         assert plan.rc == 0
         masked = emu.gbm_terminal(lay, steps, plan, [(mode, p)])[0]  # what the kernels do: replay from the emit masks
         np.testing.assert_allclose(masked, a[key], rtol=1e-12, atol=1e-11)
-        assert np.array_equal(masked, emu.gbm_terminal(lay, steps, plan, [(mode, p)], masked=False)[0])  # == state machine
+        fsm = emu.gbm_terminal(lay, steps, plan, [(mode, p)], masked=False)[0]  # state machine, strictly sequential sums
+        if mode in (N.BS_AMER_PUT, N.BS_AMER_CALL, N.PORTFOLIO_LOG1P):
+            assert np.array_equal(masked, fsm)  # path-dependent bodies: same normals, same order, same bits
+        else:  # affine bodies: chunk sums + partial chunks => different (deterministic) summation order
+            np.testing.assert_allclose(masked, fsm, rtol=1e-12, atol=1e-11)
     # Greeks-style launch: several parameter sets from one replay of the normals
     lay = S.parallel_layout(np.random.SeedSequence(11), 20_000, 4)
     plan = emu.normal_plan(lay, 64)
@@ -249,3 +253,23 @@ def test_hostemu_ziggurat_with_certified_wedge_bounds_is_numpy_bit_for_bit(emu):
         probe.bit_generator.state = before
         S.consume_draws(probe, int(end))
         assert probe.bit_generator.random_raw(4).tolist() == gen.bit_generator.random_raw(4).tolist()
+
+
+@pytest.mark.parametrize("steps", [1, 7, 63, 64, 65, 100, 252, 1000])
+def test_hostemu_chunk_sum_replay_equals_sequential_replay(emu, steps):
+    """Affine bodies take whole chunks from the sums stored by the planning pass: same normals, different
+    (deterministic) summation order.  Checked against the strictly sequential state-machine replay for
+    replications shorter than / equal to / longer than a chunk, on both generators."""
+    from mcframework_b200 import _native as N, _streams as S
+
+    n = max(50, 30_000 // steps)
+    for lay in (S.sequential_layout(np.random.default_rng(steps), n),
+                S.parallel_layout(np.random.SeedSequence(steps), max(20_000, n), 3) if steps <= 100 else
+                S.parallel_layout(np.random.SeedSequence(steps), 20_000, 64)):
+        if lay.n_total * steps > 3_000_000:
+            continue
+        plan = emu.normal_plan(lay, steps)
+        assert plan.rc == 0
+        got = emu.gbm_terminal(lay, steps, plan, [(N.NORMAL_SUM, [])])[0]
+        want = emu.gbm_terminal(lay, steps, plan, [(N.NORMAL_SUM, [])], masked=False)[0]
+        np.testing.assert_allclose(got, want, rtol=0, atol=5e-13 * max(1.0, np.sqrt(steps)))
