@@ -15,11 +15,13 @@ struct PlanGeom {
     int64_t tps;        // tiles per stream
     int64_t n_chunks;   // n_streams * cps
     int64_t n_tiles;
-    int64_t off_start, off_emit, off_exit, off_gen, off_entry, off_tsum, off_tpre, off_send, off_zsum, total;
+    int64_t off_start, off_emit, off_exit, off_gen, off_entry, off_tsum, off_tpre, off_send, off_zsum, off_queue, q_cap,
+        total;
 };
 
 // Device-resident description of a finished plan (at byte MCF_LAYOUT_OFFSET of the workspace): lets the replay
 // kernels find the emit masks without the host having to remember the geometry.
+#define MCF_QCOUNT_OFFSET 128  // int counters[16] inside the first 256 bytes of the workspace, one per fix-up iteration
 #define MCF_LAYOUT_OFFSET 64
 #define MCF_LAYOUT_MAGIC 0x6d63665f706c616eLL
 struct PlanLayout {
@@ -56,6 +58,10 @@ static inline PlanGeom plan_geom(int32_t n_streams, int64_t max_sims, int64_t np
     o = (o + 255) / 256 * 256;
     g.off_zsum = o;
     o += g.n_chunks * 8;
+    o = (o + 255) / 256 * 256;
+    g.q_cap = g.n_chunks / 8 + 4096;  // chunks whose entry differs from the speculative one: ~2 % expected
+    g.off_queue = o;
+    o += g.q_cap * 8;
     g.total = (o + 255) / 256 * 256;
     return g;
 }

@@ -94,7 +94,10 @@ __global__ void pi_finalize_kernel(const unsigned long long *__restrict__ hits, 
 
 // ========================================================================== planning pass
 __global__ void plan_init_kernel(int *hdr, int iters, PlanLayout layout) {
-    if (threadIdx.x < MCF_HDR_WORDS) hdr[threadIdx.x] = 0;
+    if (threadIdx.x < MCF_HDR_WORDS) {
+        hdr[threadIdx.x] = 0;
+        hdr[MCF_QCOUNT_OFFSET / 4 + threadIdx.x] = 0;  // per-iteration work-queue counters
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         hdr[MCF_HDR_WORDS - 1] = iters;
@@ -133,38 +136,62 @@ __global__ void __launch_bounds__(256) plan_scan_kernel(const mcf_stream *__rest
     }
 }
 
-// fix chunk entries: a chunk's true entry offset is its predecessor's exit
-template <int KIND>
-__global__ void __launch_bounds__(256) plan_resolve_kernel(const mcf_stream *__restrict__ streams, int64_t cps,
-                                                           int64_t n_chunks, uint64_t *__restrict__ startmask,
-                                                           uint64_t *__restrict__ emitmask, uint8_t *exit_,
-                                                           uint8_t *__restrict__ gen, uint8_t *__restrict__ entry_true,
-                                                           double *__restrict__ zsum, int *hdr, int iter) {
-    __shared__ ZigShared sh;
-    const ZigTables t = load_zig_tables(sh);
+// Fix chunk entries: a chunk's true entry offset is its predecessor's exit.  Two kernels per iteration so that the
+// (rare, 2 %) re-walks run DENSELY: with one thread per chunk, half of all warps would drag a 64-draw re-walk along
+// for one or two lanes.
+//   plan_entries_kernel : entry_true[id] = exit[id-1]; chunks generated with another entry go to a work queue
+//   plan_rescan_kernel  : one thread per queued chunk re-walks it from its true entry
+__global__ void __launch_bounds__(256) plan_entries_kernel(int64_t cps, int64_t n_chunks, const uint8_t *__restrict__ exit_,
+                                                           const uint8_t *__restrict__ gen,
+                                                           uint8_t *__restrict__ entry_true, int64_t *__restrict__ queue,
+                                                           int64_t q_cap, int *hdr, int iter) {
     const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n_chunks) return;
-    const int64_t si = id / cps, c = id - si * cps;
-    const uint32_t e = c == 0 ? 0u : (uint32_t)((volatile uint8_t *)exit_)[id - 1];
+    const int64_t c = id % cps;
+    const uint32_t e = c == 0 ? 0u : (uint32_t)exit_[id - 1];
+    entry_true[id] = (uint8_t)e;
     // Re-walk whenever the true entry differs from the one the chunk was generated with.  (The masks alone would
     // stay usable when `e` happens to be an attempt start of the speculative walk -- chains coincide from there --
     // but the stored chunk sum must not contain the attempts the speculative walk started before `e`.)
     if (e != (uint32_t)gen[id]) {
+        int *qcount = reinterpret_cast<int *>(reinterpret_cast<char *>(hdr) + MCF_QCOUNT_OFFSET) + iter;
+        const int k = atomicAdd(qcount, 1);
+        if (k < q_cap)
+            queue[k] = id;
+        else
+            atomicExch(&hdr[0], MCF_ERR_NOT_CONVERGED);  // queue overflow: the caller re-plans with more iterations/slack
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) plan_rescan_kernel(const mcf_stream *__restrict__ streams, int64_t cps,
+                                                          const int64_t *__restrict__ queue, int64_t q_cap,
+                                                          uint64_t *__restrict__ startmask, uint64_t *__restrict__ emitmask,
+                                                          uint8_t *__restrict__ exit_, uint8_t *__restrict__ gen,
+                                                          const uint8_t *__restrict__ entry_true,
+                                                          double *__restrict__ zsum, int *hdr, int iter) {
+    __shared__ ZigShared sh;
+    const ZigTables t = load_zig_tables(sh);
+    int count = *(reinterpret_cast<const int *>(reinterpret_cast<const char *>(hdr) + MCF_QCOUNT_OFFSET) + iter);
+    if (count > q_cap) count = (int)q_cap;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t id = queue[k];
+        const int64_t si = id / cps, c = id - si * cps;
+        const uint32_t e = entry_true[id];
         const mcf_stream st = streams[si];
         Cursor<KIND> cur;
         cur.init(st, (uint64_t)c * MCF_CHUNK + e);
-        ChunkInfo ci = scan_chunk(cur, (uint64_t)c * MCF_CHUNK, e, t);
+        const ChunkInfo ci = scan_chunk(cur, (uint64_t)c * MCF_CHUNK, e, t);
         startmask[id] = ci.startmask;
         emitmask[id] = ci.emitmask;
         gen[id] = (uint8_t)ci.gen_entry;
         zsum[id] = ci.zsum;
-        if (ci.exit != exit_[id]) {
-            ((volatile uint8_t *)exit_)[id] = (uint8_t)ci.exit;
+        if (ci.exit != (uint32_t)exit_[id]) {
+            exit_[id] = (uint8_t)ci.exit;
             atomicExch(&hdr[1 + iter], 1);
         }
         if (ci.exit == MCF_EXIT_OVERFLOW) atomicExch(&hdr[0], MCF_ERR_NOT_CONVERGED);
     }
-    entry_true[id] = (uint8_t)e;
 }
 
 __device__ __forceinline__ uint32_t block_reduce_sum(uint32_t v, uint32_t *sh) {
@@ -464,9 +491,15 @@ static int normal_plan_impl(const mcf_stream *d_streams, const PlanGeom &g, int6
     const int64_t n_runs = g.n_chunks / RUN;
     plan_scan_kernel<KIND, RUN><<<grid_for(n_runs, 256), 256, 0, cs>>>(d_streams, g.cps, n_runs, sm, em, ex, gen, zs, hdr);
     MCF_CUDA_OK(cudaGetLastError());
+    int64_t *queue = (int64_t *)(ws + g.off_queue);
     for (int it = 0; it < iters; it++) {
-        plan_resolve_kernel<KIND><<<grid_for(g.n_chunks, 256), 256, 0, cs>>>(d_streams, g.cps, g.n_chunks, sm, em, ex,
-                                                                             gen, ent, zs, hdr, it);
+        plan_entries_kernel<<<grid_for(g.n_chunks, 256), 256, 0, cs>>>(g.cps, g.n_chunks, ex, gen, ent, queue, g.q_cap, hdr,
+                                                                       it);
+        MCF_CUDA_OK(cudaGetLastError());
+        // the first iteration carries ~2 % of the chunks, later ones almost nothing: size the grids accordingly
+        const int64_t expect = it == 0 ? g.q_cap : g.q_cap / 64 + 256;
+        plan_rescan_kernel<KIND><<<grid_for(expect, 256), 256, 0, cs>>>(d_streams, g.cps, queue, g.q_cap, sm, em, ex, gen,
+                                                                        ent, zs, hdr, it);
         MCF_CUDA_OK(cudaGetLastError());
     }
     plan_tile_count_kernel<<<(unsigned)g.n_tiles, 256, 0, cs>>>(em, ent, tsum);
