@@ -486,12 +486,16 @@ MCF_HD int64_t pi_count_hits(Cur &cur, int64_t npts) {
 //   gen_entry       : offset the masks were generated from (0 = speculative)
 // ---------------------------------------------------------------------------------------
 #define MCF_CHUNK 64
+#define MCF_SUBS 4       // sub-chunks per chunk (for the stored partial sums)
+#define MCF_SUB_SHIFT 4  // log2(draws per sub-chunk)
 #define MCF_EXIT_OVERFLOW 255
 
 struct ChunkInfo {
     uint64_t startmask, emitmask;
     uint32_t exit, gen_entry;
-    double zsum;  // sum (in stream order) of the normals emitted by the attempts that start in this chunk
+    // zsub[k]: sum (in stream order) of the normals emitted by the attempts that START in draws [16k, 16k+16) of
+    // the chunk.  Replays of sum-only bodies read these instead of regenerating the draws.
+    double zsub[MCF_SUBS];
 };
 
 // cursor must be positioned at chunk_base + entry
@@ -501,7 +505,7 @@ MCF_HD ChunkInfo scan_chunk(Cur &cur, uint64_t chunk_base, uint32_t entry, const
     ci.startmask = 0;
     ci.emitmask = 0;
     ci.gen_entry = entry;
-    ci.zsum = 0.0;
+    double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
     const uint64_t end = chunk_base + MCF_CHUNK;
     if (cur.pos < end) {
         ZigFsm s;
@@ -516,12 +520,20 @@ MCF_HD ChunkInfo scan_chunk(Cur &cur, uint64_t chunk_base, uint32_t entry, const
             double x;
             if (zig_feed(s, r, t, x)) {
                 ci.emitmask |= 1ULL << js;
-                ci.zsum = xadd(ci.zsum, x);
+                const unsigned sub = js >> MCF_SUB_SHIFT;  // predicated adds: the sums stay in registers
+                if (sub == 0) z0 = xadd(z0, x);
+                if (sub == 1) z1 = xadd(z1, x);
+                if (sub == 2) z2 = xadd(z2, x);
+                if (sub == 3) z3 = xadd(z3, x);
             }
             j++;
             return !(s.state == 0 && j >= MCF_CHUNK);  // go on inside the chunk, or until the straddling attempt ends
         });
     }
+    ci.zsub[0] = z0;
+    ci.zsub[1] = z1;
+    ci.zsub[2] = z2;
+    ci.zsub[3] = z3;
     const uint64_t over = cur.pos - end;
     ci.exit = over >= MCF_EXIT_OVERFLOW ? MCF_EXIT_OVERFLOW : (uint32_t)over;
     return ci;
@@ -564,7 +576,7 @@ MCF_HD void locate_in_chunk(uint64_t chunk_base, uint64_t eff_start, uint64_t ef
 struct PlanView {
     const uint64_t *emit;  // [n_streams * cps]
     const uint8_t *entry;  // [n_streams * cps] true entry offset of every chunk
-    const double *zsum;    // [n_streams * cps] sum of the normals of the attempts starting in the chunk (>= entry)
+    const double *zsum;    // [n_streams * cps * MCF_SUBS] sums of the normals of the attempts starting in each sub-chunk
     int64_t cps;           // chunks per stream
 };
 
@@ -649,27 +661,27 @@ MCF_HD void replay_emits(Cursor<MCF_GEN_PHILOX> &cur, const mcf_stream &st, cons
     }
 }
 
-// Sum of the normals of the attempts starting in [start, end): whole chunks come from the sums the planning
-// pass stored, only the two partial chunks at the ends are regenerated (a quarter of the draws for 252 steps,
-// 2.5 % for 2520).  Summation order: head partial, chunk sums in order, tail partial (deterministic).
+// Sum of the normals of the attempts starting in [start, end): whole 16-draw sub-chunks come from the sums the
+// planning pass stored, only the two partial sub-chunks at the ends are regenerated (about 6 % of the draws for
+// 252 steps, 0.6 % for 2520).  Summation order: head partial, stored sums in order, tail partial (deterministic).
 template <int KIND>
 MCF_HD double replay_zsum(Cursor<KIND> &cur, const mcf_stream &st, const PlanView &pv, int64_t si, uint64_t start,
                           uint64_t end, const double *wi, uint64_t ki0) {
     double acc = 0.0;
     if (end <= start) return acc;
-    const uint64_t c0 = start >> 6, c1 = (end - 1) >> 6;
+    const uint64_t s0 = start >> MCF_SUB_SHIFT, s1 = (end - 1) >> MCF_SUB_SHIFT;
     auto add = [&](double z) { acc = xadd(acc, z); };
-    if (c0 == c1) {
+    if (s0 == s1) {
         replay_emits(cur, st, pv, si, start, end, wi, ki0, add);
         return acc;
     }
-    const int64_t row = si * pv.cps;
-    if (start == (c0 << 6) + (uint64_t)pv.entry[row + (int64_t)c0])
-        acc = pv.zsum[row + (int64_t)c0];  // the replication starts with the chunk's first attempt
+    const double *sums = pv.zsum + si * pv.cps * MCF_SUBS;
+    if ((start & ((1ULL << MCF_SUB_SHIFT) - 1ULL)) == 0)
+        acc = sums[s0];  // aligned start: nothing of this sub-chunk belongs to the previous replication
     else
-        replay_emits(cur, st, pv, si, start, (c0 + 1) << 6, wi, ki0, add);
-    for (uint64_t c = c0 + 1; c < c1; c++) acc = xadd(acc, pv.zsum[row + (int64_t)c]);
-    replay_emits(cur, st, pv, si, c1 << 6, end, wi, ki0, add);
+        replay_emits(cur, st, pv, si, start, (s0 + 1) << MCF_SUB_SHIFT, wi, ki0, add);
+    for (uint64_t k = s0 + 1; k < s1; k++) acc = xadd(acc, sums[k]);
+    replay_emits(cur, st, pv, si, s1 << MCF_SUB_SHIFT, end, wi, ki0, add);
     return acc;
 }
 

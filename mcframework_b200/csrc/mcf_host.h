@@ -57,7 +57,7 @@ static inline PlanGeom plan_geom(int32_t n_streams, int64_t max_sims, int64_t np
     o += (int64_t)n_streams * 8;
     o = (o + 255) / 256 * 256;
     g.off_zsum = o;
-    o += g.n_chunks * 8;
+    o += g.n_chunks * 8 * MCF_SUBS;
     o = (o + 255) / 256 * 256;
     g.q_cap = g.n_chunks / 8 + 4096;  // chunks whose entry differs from the speculative one: ~2 % expected
     g.off_queue = o;

@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(256) plan_scan_kernel(const mcf_stream *__rest
         emitmask[id] = ci.emitmask;
         exit_[id] = (uint8_t)ci.exit;
         gen[id] = (uint8_t)ci.gen_entry;
-        zsum[id] = ci.zsum;
+        reinterpret_cast<double2 *>(zsum)[id * 2] = make_double2(ci.zsub[0], ci.zsub[1]);
+        reinterpret_cast<double2 *>(zsum)[id * 2 + 1] = make_double2(ci.zsub[2], ci.zsub[3]);
         if (ci.exit == MCF_EXIT_OVERFLOW) atomicExch(&hdr[0], MCF_ERR_NOT_CONVERGED);
         entry = ci.exit;
     }
@@ -185,7 +186,8 @@ __global__ void __launch_bounds__(256) plan_rescan_kernel(const mcf_stream *__re
         startmask[id] = ci.startmask;
         emitmask[id] = ci.emitmask;
         gen[id] = (uint8_t)ci.gen_entry;
-        zsum[id] = ci.zsum;
+        reinterpret_cast<double2 *>(zsum)[id * 2] = make_double2(ci.zsub[0], ci.zsub[1]);
+        reinterpret_cast<double2 *>(zsum)[id * 2 + 1] = make_double2(ci.zsub[2], ci.zsub[3]);
         if (ci.exit != (uint32_t)exit_[id]) {
             exit_[id] = (uint8_t)ci.exit;
             atomicExch(&hdr[1 + iter], 1);

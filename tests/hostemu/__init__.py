@@ -77,7 +77,7 @@ def normal_plan(layout, nps, slack=0.03, iters=3):
                                      C.byref(cps))
     emit = np.zeros(n_chunks, dtype=np.uint64)
     entry = np.zeros(n_chunks, dtype=np.uint8)
-    zsum = np.zeros(n_chunks, dtype=np.float64)
+    zsum = np.zeros(n_chunks * 4, dtype=np.float64)  # MCF_SUBS sums per chunk
     rc = lib().emu_normal_plan(C.c_uint32(layout.kind), _vp(layout.records), layout.n_streams,
                                C.c_int64(layout.max_sims), C.c_int64(nps), C.c_double(slack), iters, _vp(sim_start),
                                _vp(stream_end), C.byref(regen), _vp(emit), _vp(entry), _vp(zsum))

@@ -82,7 +82,7 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
     const PlanGeom g = plan_geom(n_streams, max_sims, nps, slack);
     std::vector<uint64_t> sm(g.n_chunks), em(g.n_chunks), tsum(g.n_tiles), tpre(g.n_tiles);
     std::vector<uint8_t> ex(g.n_chunks), gen(g.n_chunks), ent(g.n_chunks);
-    std::vector<double> zs(g.n_chunks);
+    std::vector<double> zs(g.n_chunks * MCF_SUBS);
     int status = 0;
     constexpr int RUN = KIND == MCF_GEN_PCG64 ? 8 : 1;
     // scan
@@ -98,7 +98,7 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
             em[id] = ci.emitmask;
             ex[id] = (uint8_t)ci.exit;
             gen[id] = (uint8_t)ci.gen_entry;
-            zs[id] = ci.zsum;
+            for (int q = 0; q < MCF_SUBS; q++) zs[id * MCF_SUBS + q] = ci.zsub[q];
             if (ci.exit == MCF_EXIT_OVERFLOW) status = MCF_ERR_NOT_CONVERGED;
             entry = ci.exit;
         }
@@ -121,7 +121,7 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
                 sm[id] = ci.startmask;
                 em[id] = ci.emitmask;
                 gen[id] = (uint8_t)ci.gen_entry;
-                zs[id] = ci.zsum;
+                for (int q = 0; q < MCF_SUBS; q++) zs[id * MCF_SUBS + q] = ci.zsub[q];
                 if (ci.exit != ex[id]) {
                     ex[id] = (uint8_t)ci.exit;
                     changed_last = 1;
@@ -170,7 +170,7 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
         for (int64_t id = 0; id < g.n_chunks; id++) {
             em_out[id] = em[id];
             ent_out[id] = ent[id];
-            zs_out[id] = zs[id];
+            for (int q = 0; q < MCF_SUBS; q++) zs_out[id * MCF_SUBS + q] = zs[id * MCF_SUBS + q];
         }
     return status;
 }
