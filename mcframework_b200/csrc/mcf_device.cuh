@@ -493,47 +493,46 @@ MCF_HD int64_t pi_count_hits(Cur &cur, int64_t npts) {
 struct ChunkInfo {
     uint64_t startmask, emitmask;
     uint32_t exit, gen_entry;
-    // zsub[k]: sum (in stream order) of the normals emitted by the attempts that START in draws [16k, 16k+16) of
-    // the chunk.  Replays of sum-only bodies read these instead of regenerating the draws.
-    double zsub[MCF_SUBS];
 };
 
-// cursor must be positioned at chunk_base + entry
+// cursor must be positioned at chunk_base + entry; zsub_out[MCF_SUBS] receives the sub-chunk sums
 template <class Cur>
-MCF_HD ChunkInfo scan_chunk(Cur &cur, uint64_t chunk_base, uint32_t entry, const ZigTables &t) {
+MCF_HD ChunkInfo scan_chunk(Cur &cur, uint64_t chunk_base, uint32_t entry, const ZigTables &t, double *zsub_out) {
     ChunkInfo ci;
     ci.startmask = 0;
     ci.emitmask = 0;
     ci.gen_entry = entry;
-    double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
+    for (int k = 0; k < MCF_SUBS; k++) zsub_out[k] = 0.0;
     const uint64_t end = chunk_base + MCF_CHUNK;
     if (cur.pos < end) {
         ZigFsm s;
         zig_reset(s);
         unsigned j = (unsigned)(cur.pos - chunk_base);  // offset of the next draw inside the chunk (may pass 64)
         unsigned js = 0;                                // offset where the attempt in progress started
+        // Attempt starts are monotone and an attempt emits before the next one starts, so one running sum that is
+        // flushed whenever a start enters a new sub-chunk yields the per-sub-chunk sums in stream order.
+        unsigned cursub = j >> MCF_SUB_SHIFT;
+        double zc = 0.0;
         consume_draws(cur, [&](uint64_t r) {
             if (s.state == 0) {
                 js = j;
                 ci.startmask |= 1ULL << js;
+                if (js < MCF_CHUNK && (js >> MCF_SUB_SHIFT) != cursub) {
+                    zsub_out[cursub] = zc;
+                    cursub = js >> MCF_SUB_SHIFT;
+                    zc = 0.0;
+                }
             }
             double x;
             if (zig_feed(s, r, t, x)) {
                 ci.emitmask |= 1ULL << js;
-                const unsigned sub = js >> MCF_SUB_SHIFT;  // predicated adds: the sums stay in registers
-                if (sub == 0) z0 = xadd(z0, x);
-                if (sub == 1) z1 = xadd(z1, x);
-                if (sub == 2) z2 = xadd(z2, x);
-                if (sub == 3) z3 = xadd(z3, x);
+                zc = xadd(zc, x);
             }
             j++;
             return !(s.state == 0 && j >= MCF_CHUNK);  // go on inside the chunk, or until the straddling attempt ends
         });
+        if (cursub < MCF_SUBS) zsub_out[cursub] = zc;
     }
-    ci.zsub[0] = z0;
-    ci.zsub[1] = z1;
-    ci.zsub[2] = z2;
-    ci.zsub[3] = z3;
     const uint64_t over = cur.pos - end;
     ci.exit = over >= MCF_EXIT_OVERFLOW ? MCF_EXIT_OVERFLOW : (uint32_t)over;
     return ci;

@@ -107,7 +107,7 @@ __global__ void plan_init_kernel(int *hdr, int iters, PlanLayout layout) {
 
 // one thread scans RUN consecutive chunks of one stream, carrying the ziggurat chain through
 template <int KIND, int RUN>
-__global__ void __launch_bounds__(256) plan_scan_kernel(const mcf_stream *__restrict__ streams, int64_t cps,
+__global__ void __launch_bounds__(256, 3) plan_scan_kernel(const mcf_stream *__restrict__ streams, int64_t cps,
                                                         int64_t n_runs, uint64_t *__restrict__ startmask,
                                                         uint64_t *__restrict__ emitmask, uint8_t *__restrict__ exit_,
                                                         uint8_t *__restrict__ gen, double *__restrict__ zsum, int *hdr) {
@@ -125,13 +125,11 @@ __global__ void __launch_bounds__(256) plan_scan_kernel(const mcf_stream *__rest
 #pragma unroll 1
     for (int c = 0; c < RUN; c++) {
         const int64_t id = si * cps + c0 + c;
-        ChunkInfo ci = scan_chunk(cur, (uint64_t)(c0 + c) * MCF_CHUNK, entry, t);
+        ChunkInfo ci = scan_chunk(cur, (uint64_t)(c0 + c) * MCF_CHUNK, entry, t, zsum + id * MCF_SUBS);
         startmask[id] = ci.startmask;
         emitmask[id] = ci.emitmask;
         exit_[id] = (uint8_t)ci.exit;
         gen[id] = (uint8_t)ci.gen_entry;
-        reinterpret_cast<double2 *>(zsum)[id * 2] = make_double2(ci.zsub[0], ci.zsub[1]);
-        reinterpret_cast<double2 *>(zsum)[id * 2 + 1] = make_double2(ci.zsub[2], ci.zsub[3]);
         if (ci.exit == MCF_EXIT_OVERFLOW) atomicExch(&hdr[0], MCF_ERR_NOT_CONVERGED);
         entry = ci.exit;
     }
@@ -182,12 +180,10 @@ __global__ void __launch_bounds__(256) plan_rescan_kernel(const mcf_stream *__re
         const mcf_stream st = streams[si];
         Cursor<KIND> cur;
         cur.init(st, (uint64_t)c * MCF_CHUNK + e);
-        const ChunkInfo ci = scan_chunk(cur, (uint64_t)c * MCF_CHUNK, e, t);
+        const ChunkInfo ci = scan_chunk(cur, (uint64_t)c * MCF_CHUNK, e, t, zsum + id * MCF_SUBS);
         startmask[id] = ci.startmask;
         emitmask[id] = ci.emitmask;
         gen[id] = (uint8_t)ci.gen_entry;
-        reinterpret_cast<double2 *>(zsum)[id * 2] = make_double2(ci.zsub[0], ci.zsub[1]);
-        reinterpret_cast<double2 *>(zsum)[id * 2 + 1] = make_double2(ci.zsub[2], ci.zsub[3]);
         if (ci.exit != (uint32_t)exit_[id]) {
             exit_[id] = (uint8_t)ci.exit;
             atomicExch(&hdr[1 + iter], 1);

@@ -93,12 +93,11 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
         uint32_t entry = 0;
         for (int c = 0; c < RUN; c++) {
             const int64_t id = si * g.cps + c0 + c;
-            ChunkInfo ci = scan_chunk(cur, (uint64_t)(c0 + c) * MCF_CHUNK, entry, t);
+            ChunkInfo ci = scan_chunk(cur, (uint64_t)(c0 + c) * MCF_CHUNK, entry, t, &zs[id * MCF_SUBS]);
             sm[id] = ci.startmask;
             em[id] = ci.emitmask;
             ex[id] = (uint8_t)ci.exit;
             gen[id] = (uint8_t)ci.gen_entry;
-            for (int q = 0; q < MCF_SUBS; q++) zs[id * MCF_SUBS + q] = ci.zsub[q];
             if (ci.exit == MCF_EXIT_OVERFLOW) status = MCF_ERR_NOT_CONVERGED;
             entry = ci.exit;
         }
@@ -117,11 +116,10 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
                 regen++;
                 Cursor<KIND> cur;
                 cur.init(streams[si], (uint64_t)c * MCF_CHUNK + e);
-                ChunkInfo ci = scan_chunk(cur, (uint64_t)c * MCF_CHUNK, e, t);
+                ChunkInfo ci = scan_chunk(cur, (uint64_t)c * MCF_CHUNK, e, t, &zs[id * MCF_SUBS]);
                 sm[id] = ci.startmask;
                 em[id] = ci.emitmask;
                 gen[id] = (uint8_t)ci.gen_entry;
-                for (int q = 0; q < MCF_SUBS; q++) zs[id * MCF_SUBS + q] = ci.zsub[q];
                 if (ci.exit != ex[id]) {
                     ex[id] = (uint8_t)ci.exit;
                     changed_last = 1;
