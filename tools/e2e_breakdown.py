@@ -33,8 +33,41 @@ def step():
     return t1 - t0, t2 - t1, res.execution_time
 
 
+for _ in range(3):
+    before = torch.cuda.memory_stats()
+    out = step()
+    after = torch.cuda.memory_stats()
+    print("run_simulation %.3f s (execution_time %.3f), calculate_greeks %.3f s" % tuple(out[i] for i in (0, 2, 1)),
+          "| cudaMalloc calls:", after.get("num_device_alloc", 0) - before.get("num_device_alloc", 0), "cudaFree:",
+          after.get("num_device_free", 0) - before.get("num_device_free", 0), "segments:",
+          after.get("segment.all.allocated", 0) - before.get("segment.all.allocated", 0), "retries:",
+          after.get("num_alloc_retries", 0) - before.get("num_alloc_retries", 0),
+          "reserved GB: %.1f" % (after.get("reserved_bytes.all.current", 0) / 1e9))
+
+# device-level pieces with explicit syncs
+from mcframework_b200 import _device as D, _native as N, _streams as S
+import numpy as np
+
+lay = S.parallel_layout(np.random.SeedSequence(42), n, 8)
+dl = D.DeviceLayout.of(lay)
+
+
+def timed(label, fn):
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    r = fn()
+    torch.cuda.synchronize()
+    print("  %-28s %.1f ms" % (label, (time.perf_counter() - t) * 1e3))
+    return r
+
+
 for _ in range(2):
-    print("run_simulation %.3f s (execution_time %.3f), calculate_greeks %.3f s" % tuple(step()[i] for i in (0, 2, 1)))
+    plan = timed("normal_plan", lambda: D.normal_plan(dl, 252))
+    one = timed("gbm_terminal x1", lambda: D.gbm_terminal(dl, 252, plan, [(N.BS_EURO_CALL, [100.0, 100.0, 1.0, 0.05, 0.2])]))
+    eight = timed("gbm_terminal x8", lambda: D.gbm_terminal(dl, 252, plan, [(N.BS_EURO_CALL, [100.0 + k, 100.0, 1.0, 0.05, 0.2]) for k in range(8)]))
+    host = timed("D2H 800 MB (pinned)", lambda: torch.empty(one.shape, dtype=torch.float64, pin_memory=True).copy_(one))
+    host2 = timed("D2H 800 MB (.cpu())", lambda: one.cpu())
+    del plan, one, eight, host, host2
 pr = cProfile.Profile()
 pr.enable()
 step()
