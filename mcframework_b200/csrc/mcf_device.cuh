@@ -489,6 +489,7 @@ MCF_HD int64_t pi_count_hits(Cur &cur, int64_t npts) {
 #define MCF_SUBS 4       // sub-chunks per chunk (for the stored partial sums)
 #define MCF_SUB_SHIFT 4  // log2(draws per sub-chunk)
 #define MCF_EXIT_OVERFLOW 255
+#define MCF_GEN_ENTRY_INVALID 254  // "generated with no usable entry": forces the general re-walk
 
 struct ChunkInfo {
     uint64_t startmask, emitmask;
@@ -535,6 +536,118 @@ MCF_HD ChunkInfo scan_chunk(Cur &cur, uint64_t chunk_base, uint32_t entry, const
     }
     const uint64_t over = cur.pos - end;
     ci.exit = over >= MCF_EXIT_OVERFLOW ? MCF_EXIT_OVERFLOW : (uint32_t)over;
+    return ci;
+}
+
+// ---------------------------------------------------------------------------------------
+// Fast speculative walk of one chunk of a block-aligned Philox stream (entry offset 0).
+//
+// Same result as scan_chunk(cur, chunk_base, 0, ...), organised for SIMT:
+//   * one Philox block per loop trip for every lane, plus one block of look-ahead, so the draws an attempt may need
+//     (its own, the wedge uniform, the first tail pair) are always in registers;
+//   * the chain is a skip counter: a fast attempt takes 1 draw, a wedge attempt 2, a tail attempt 3 (first pair
+//     accepted); nothing else decides where the next attempt starts;
+//   * wedge acceptance only decides the EMIT bit, so the tests are parked (two slots) and evaluated once per
+//     16-draw sub-chunk instead of once per draw (a warp meets a wedge in 38 % of its draws);
+//   * whatever does not fit -- a tail whose first pair is rejected, a third wedge inside one sub-chunk -- marks the
+//     chunk invalid (`*valid = false`); the caller queues it for the dense, fully general re-walk.
+// Normals of wedge-accepted attempts are added to their sub-chunk sum after its fast ones (deterministic order).
+// ---------------------------------------------------------------------------------------
+MCF_HD ChunkInfo scan_chunk_fast(Cursor<MCF_GEN_PHILOX> &cur, uint64_t chunk_base, const ZigTables &t, double *zsub_out,
+                                 bool *valid) {
+    ChunkInfo ci;
+    ci.gen_entry = 0;
+    uint64_t sm = 0, em = 0;
+    bool ok = true;
+    unsigned skip = 0;
+    const uint64_t blk0 = (cur.q - cur.pos + chunk_base) >> 2;  // q - pos = buffer offset of the stream (multiple of 4)
+    cur.load_block(blk0);
+    uint64_t w0 = cur.v0, w1 = cur.v1, w2 = cur.v2, w3 = cur.v3, w4, w5, w6, w7;
+#pragma unroll 1
+    for (unsigned sub = 0; sub < MCF_SUBS; sub++) {
+        double zc = 0.0;
+        uint64_t ea0 = 0, eb0 = 0, ea1 = 0, eb1 = 0;  // parked wedge tests: (start draw, uniform draw)
+        unsigned ej0 = 0, ej1 = 0, nev = 0;
+#pragma unroll 1
+        for (unsigned bb = 0; bb < 4; bb++) {
+            const unsigned b = sub * 4 + bb;
+            cur.load_block(blk0 + b + 1);
+            w4 = cur.v0;
+            w5 = cur.v1;
+            w6 = cur.v2;
+            w7 = cur.v3;
+            unsigned snib = 0, enib = 0;
+#define MCF_FAST_DRAW(J, WA, WB, WC)                                                                   \
+    if (skip > 0) {                                                                                    \
+        skip--;                                                                                        \
+    } else {                                                                                           \
+        snib |= 1u << (J);                                                                             \
+        const unsigned idx = (unsigned)((WA)&0xffULL);                                                 \
+        const uint64_t rabs = ((WA) >> 9) & 0x000fffffffffffffULL;                                     \
+        if (rabs < t.ki[idx]) {                                                                        \
+            enib |= 1u << (J);                                                                         \
+            const double v = xmul(u52_to_double(rabs), t.wi[idx]);                                     \
+            zc = xadd(zc, (((WA) >> 8) & 1ULL) ? -v : v);                                              \
+        } else if (idx != 0) {                                                                         \
+            skip = 1;                                                                                  \
+            if (nev == 0) {                                                                            \
+                ea0 = (WA);                                                                            \
+                eb0 = (WB);                                                                            \
+                ej0 = b * 4 + (J);                                                                     \
+            } else if (nev == 1) {                                                                     \
+                ea1 = (WA);                                                                            \
+                eb1 = (WB);                                                                            \
+                ej1 = b * 4 + (J);                                                                     \
+            } else {                                                                                   \
+                ok = false;                                                                            \
+            }                                                                                          \
+            nev++;                                                                                     \
+        } else {                                                                                       \
+            skip = 2;                                                                                  \
+            const double xx = xmul(-MCF_ZIG_INV_R, log1p(-u64_to_unit_double(WB)));                    \
+            const double yy = -log1p(-u64_to_unit_double(WC));                                         \
+            if (xadd(yy, yy) > xmul(xx, xx)) {                                                         \
+                enib |= 1u << (J);                                                                     \
+                const double m = xadd(MCF_ZIG_R, xx);                                                  \
+                zc = xadd(zc, ((rabs >> 8) & 1ULL) ? -m : m);                                          \
+            } else {                                                                                   \
+                ok = false; /* longer tail: general re-walk */                                         \
+            }                                                                                          \
+        }                                                                                              \
+    }
+            MCF_FAST_DRAW(0, w0, w1, w2)
+            MCF_FAST_DRAW(1, w1, w2, w3)
+            MCF_FAST_DRAW(2, w2, w3, w4)
+            MCF_FAST_DRAW(3, w3, w4, w5)
+#undef MCF_FAST_DRAW
+            sm |= (uint64_t)snib << (4 * b);
+            em |= (uint64_t)enib << (4 * b);
+            w0 = w4;
+            w1 = w5;
+            w2 = w6;
+            w3 = w7;
+        }
+        // parked wedge tests of this sub-chunk (same arithmetic and decision as zig_feed, state 1)
+        for (unsigned e = 0; e < (nev < 2u ? nev : 2u); e++) {
+            const uint64_t a = e ? ea1 : ea0, u = e ? eb1 : eb0;
+            const unsigned js = e ? ej1 : ej0;
+            ZigFsm f;
+            zig_reset(f);
+            double x;
+            zig_feed(f, a, t, x);              // state 0 -> 1 (wedge): stores idx, rabs, x
+            if (zig_feed(f, u, t, x)) {        // acceptance test
+                em |= 1ULL << js;
+                zc = xadd(zc, x);
+            }
+        }
+        zsub_out[sub] = zc;
+    }
+    ci.startmask = sm;
+    ci.emitmask = em;
+    ci.exit = skip;
+    *valid = ok;
+    cur.pos = chunk_base + MCF_CHUNK + skip;
+    cur.q = (blk0 << 2) + MCF_CHUNK + skip;
     return ci;
 }
 

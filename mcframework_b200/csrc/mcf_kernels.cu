@@ -122,6 +122,19 @@ __global__ void __launch_bounds__(256, 3) plan_scan_kernel(const mcf_stream *__r
     Cursor<KIND> cur;
     cur.init(st, (uint64_t)c0 * MCF_CHUNK);
     uint32_t entry = 0;
+    if (KIND == MCF_GEN_PHILOX && RUN == 1 && (st.buf_pos & 3u) == 0) {
+        // block-aligned Philox stream (every stream of a parallel run): SIMT-friendly walk; chunks it cannot finish
+        // are tagged with an impossible generation entry so that the fix-up pass queues them for the general walk
+        const int64_t id = si * cps + c0;
+        bool valid;
+        ChunkInfo ci = scan_chunk_fast(*reinterpret_cast<Cursor<MCF_GEN_PHILOX> *>(&cur), (uint64_t)c0 * MCF_CHUNK, t,
+                                       zsum + id * MCF_SUBS, &valid);
+        startmask[id] = ci.startmask;
+        emitmask[id] = ci.emitmask;
+        exit_[id] = (uint8_t)ci.exit;
+        gen[id] = valid ? (uint8_t)0 : (uint8_t)MCF_GEN_ENTRY_INVALID;
+        return;
+    }
 #pragma unroll 1
     for (int c = 0; c < RUN; c++) {
         const int64_t id = si * cps + c0 + c;

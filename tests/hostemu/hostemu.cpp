@@ -84,6 +84,7 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
     std::vector<uint8_t> ex(g.n_chunks), gen(g.n_chunks), ent(g.n_chunks);
     std::vector<double> zs(g.n_chunks * MCF_SUBS);
     int status = 0;
+    int64_t n_fast_invalid = 0;
     constexpr int RUN = KIND == MCF_GEN_PCG64 ? 8 : 1;
     // scan
     for (int64_t run = 0; run < g.n_chunks / RUN; run++) {
@@ -91,6 +92,18 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
         Cursor<KIND> cur;
         cur.init(streams[si], (uint64_t)c0 * MCF_CHUNK);
         uint32_t entry = 0;
+        if (KIND == MCF_GEN_PHILOX && RUN == 1 && (streams[si].buf_pos & 3u) == 0) {  // as plan_scan_kernel
+            const int64_t id = si * g.cps + c0;
+            bool valid;
+            ChunkInfo ci = scan_chunk_fast(*reinterpret_cast<Cursor<MCF_GEN_PHILOX> *>(&cur), (uint64_t)c0 * MCF_CHUNK, t,
+                                           &zs[id * MCF_SUBS], &valid);
+            sm[id] = ci.startmask;
+            em[id] = ci.emitmask;
+            ex[id] = (uint8_t)ci.exit;
+            gen[id] = valid ? (uint8_t)0 : (uint8_t)MCF_GEN_ENTRY_INVALID;
+            n_fast_invalid += valid ? 0 : 1;
+            continue;
+        }
         for (int c = 0; c < RUN; c++) {
             const int64_t id = si * g.cps + c0 + c;
             ChunkInfo ci = scan_chunk(cur, (uint64_t)(c0 + c) * MCF_CHUNK, entry, t, &zs[id * MCF_SUBS]);

@@ -273,3 +273,24 @@ def test_hostemu_chunk_sum_replay_equals_sequential_replay(emu, steps):
         got = emu.gbm_terminal(lay, steps, plan, [(N.NORMAL_SUM, [])])[0]
         want = emu.gbm_terminal(lay, steps, plan, [(N.NORMAL_SUM, [])], masked=False)[0]
         np.testing.assert_allclose(got, want, rtol=0, atol=5e-13 * max(1.0, np.sqrt(steps)))
+
+
+def test_hostemu_fast_philox_scan_positions_match_oracle(emu):
+    """Block-aligned Philox streams take the SIMT-friendly chunk walk (parked wedge tests, skip-counter chain,
+    invalid chunks re-walked through the queue): replication starts and stream ends must still be exact."""
+    from mcframework_b200 import _streams as S
+    from oracle import c_oracle as co
+
+    for seed, n, workers, steps in ((11, 40_000, 4, 64), (5, 20_000, 8, 252), (9, 20_011, 2, 17)):
+        lay = S.parallel_layout(np.random.SeedSequence(seed), n, workers)
+        plan = emu.normal_plan(lay, steps)
+        assert plan.rc == 0
+        for k in (0, lay.n_streams // 2, lay.n_streams - 1):
+            rec = lay.records[k]
+            g, want = co.Gen.philox_from_key(rec["s"][:2]), []
+            for _ in range(int(rec["n_sims"])):
+                want.append(g.consumed)
+                g.standard_normal(steps)
+            f = int(rec["first_sim"])
+            assert np.array_equal(plan.sim_start[f:f + len(want)], np.array(want, dtype=np.uint64))
+            assert int(plan.stream_end[k]) == g.consumed
