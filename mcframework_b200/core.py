@@ -251,10 +251,18 @@ class MonteCarloSimulation(ABC):
         return out
 
     # ------------------------------------------------------------------ replication loop
-    def _finish_device_run(self, values_dev, group=None) -> np.ndarray:
-        """Device results -> (a) DeviceSample kept for the statistics, (b) the host ndarray of the result."""
+    @staticmethod
+    def _to_host(t) -> np.ndarray:
+        """Device vector -> fresh host ndarray.  Large vectors go through pinned memory (PyTorch's caching host
+        allocator recycles the buffer once the previous result is released): ~50 GB/s instead of ~2 GB/s pageable."""
         import torch
 
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=t.numel() >= (1 << 20))
+        host.copy_(t, non_blocking=False)
+        return host.numpy()
+
+    def _finish_device_run(self, values_dev, group=None) -> np.ndarray:
+        """Device results -> (a) DeviceSample kept for the statistics, (b) the host ndarray of the result."""
         if group is not None:
             from . import _multi
 
@@ -263,14 +271,12 @@ class MonteCarloSimulation(ABC):
             local = values_dev
             if getattr(self, "gather_mode", "all") == "root":
                 full = _multi.gather_results_to_root(local, group)
-                host = (full if full is not None else local).cpu().numpy()
+                host = self._to_host(full if full is not None else local)
             else:
-                host = _multi.gather_results(local, group).cpu().numpy()
+                host = self._to_host(_multi.gather_results(local, group))
             self._device_sample = DeviceSample(local, host, group)
         else:
-            host = torch.empty(values_dev.shape, dtype=torch.float64, pin_memory=values_dev.numel() >= (1 << 20))
-            host.copy_(values_dev, non_blocking=False)
-            host = host.numpy()
+            host = self._to_host(values_dev)
             self._device_sample = DeviceSample(values_dev, host, None)
         return host
 
