@@ -283,12 +283,12 @@ def b200_arm(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    draws_per_gpu = P * N_STEPS * 1.0157  # ziggurat consumes ~1.57% extra 64-bit draws
+    draws_per_gpu = P * N_STEPS * 1.022  # the ziggurat consumes ~2.2 % extra 64-bit draws (measured: 257.55 per 252)
     n_chunks = draws_per_gpu * 1.03 / 64
     alg_bytes = {  # algorithmic HBM bytes per launch group (DESIGN.md "bytes per unit")
-        "plan": n_chunks * (8 + 8 + 1 + 1) + P * 8,          # masks/exit/entry written once + sim_start
-        "replay1": P * (8 + 8),                               # read sim_start, write payoff
-        "replay8": P * (8 + 8 * 8),
+        "plan": n_chunks * (8 + 8 + 1 + 1 + 1 + 32) + P * 8,  # masks, exit, gen, entry, 4 sub-chunk sums + sim_start
+        "replay1": P * (8 + 8) + n_chunks * 32,               # sim_start, payoff, the stored sub-chunk sums read once
+        "replay8": P * (8 + 8 * 8) + n_chunks * 32,
         "moments": 8 * P * 8,
     }
     inst = {}
