@@ -103,9 +103,12 @@ int mcf_pi_hits(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_stream
  * no acceptance tests are repeated, only emitted draws are converted.  Path state stays in registers. */
 int64_t mcf_normal_plan_workspace_bytes(int32_t n_streams, int64_t max_sims_per_stream, int64_t normals_per_sim,
                                         double slack);
-int mcf_normal_plan(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total,
-                    int64_t max_sims_per_stream, int64_t normals_per_sim, double slack, int32_t resolve_iters, void *d_workspace,
-                    int64_t workspace_bytes, uint64_t *d_sim_start /* [n_total] */,
+/* h_streams: optional HOST copy of the same records (may be NULL).  With it, block-aligned Philox streams are walked
+ * by one launch per stream whose round keys are launch constants (no key-schedule instructions). */
+int mcf_normal_plan(uint32_t gen_kind, const mcf_stream *d_streams, const mcf_stream *h_streams, int32_t n_streams,
+                    int64_t n_total, int64_t max_sims_per_stream, int64_t normals_per_sim, double slack,
+                    int32_t resolve_iters, void *d_workspace, int64_t workspace_bytes,
+                    uint64_t *d_sim_start /* [n_total] */,
                     uint64_t *d_stream_end /* [n_streams] draws consumed per stream; may be NULL */, void *cuda_stream);
 /* 0 if the last plan in this workspace was valid, else MCF_ERR_WINDOW_TOO_SMALL / MCF_ERR_NOT_CONVERGED.
  * Synchronises the stream (reads one word back). */

@@ -86,11 +86,13 @@ def normal_plan(dl: DeviceLayout, normals_per_sim: int, slack: float = 0.03, res
         if nbytes < 0:
             N.check("mcf_normal_plan_workspace_bytes", int(nbytes))
         ws = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda")
-        rc = lib.mcf_normal_plan(lay.kind, _ptr(dl.records), lay.n_streams, lay.n_total, lay.max_sims,
+        host_records = np.ascontiguousarray(lay.records)
+        rc = lib.mcf_normal_plan(lay.kind, _ptr(dl.records), host_records.ctypes.data_as(C.c_void_p), lay.n_streams,
+                                 lay.n_total, lay.max_sims,
                                  int(normals_per_sim), float(slack), int(resolve_iters), _ptr(ws), int(nbytes),
                                  _ptr(sim_start), _ptr(stream_end), _stream_ptr())
         N.check("mcf_normal_plan", rc)
-        LAUNCHES["plan"] += 5 + resolve_iters
+        LAUNCHES["plan"] += 4 + 2 * resolve_iters + (lay.n_streams if lay.kind == 1 and lay.n_streams <= 1024 else 1)
         status = lib.mcf_workspace_status(_ptr(ws), _stream_ptr())
         if status == N.OK:
             return NormalPlan(sim_start, stream_end, int(normals_per_sim), ws)

@@ -186,6 +186,50 @@ MCF_HD void philox4x64_10(uint64_t c0, uint64_t c1, uint64_t c2, uint64_t c3, ui
     out[3] = c3;
 }
 
+// The same block function with the ten round keys precomputed (k + r*W): when the key is a launch constant (one
+// launch per stream, keys in the kernel-parameter constant bank) the key schedule costs no instruction at all.
+struct PhiloxKeys {
+    uint64_t rk[20];          // rk[2r], rk[2r+1]: keys of round r
+    uint64_t b0, b1, b2, b3;  // base counter of the stream
+    uint64_t off;             // buffer offset of the stream (buf_pos; multiple of 4 for the fast paths)
+};
+MCF_HD PhiloxKeys philox_keys_of(const mcf_stream &s) {
+    PhiloxKeys K;
+    uint64_t k0 = s.s[0], k1 = s.s[1];
+    for (int r = 0; r < 10; r++) {
+        K.rk[2 * r] = k0;
+        K.rk[2 * r + 1] = k1;
+        k0 += MCF_PHILOX_W0;
+        k1 += MCF_PHILOX_W1;
+    }
+    K.b0 = s.s[2];
+    K.b1 = s.s[3];
+    K.b2 = s.s[4];
+    K.b3 = s.s[5];
+    K.off = (uint64_t)s.buf_pos;
+    return K;
+}
+MCF_HD void philox_block_keys(const PhiloxKeys &K, uint64_t blk, uint64_t &o0, uint64_t &o1, uint64_t &o2, uint64_t &o3) {
+    uint64_t c0 = K.b0 + blk;
+    const uint64_t carry = c0 < K.b0 ? 1ULL : 0ULL;
+    uint64_t c1 = K.b1 + carry;
+    uint64_t c2 = K.b2 + ((carry && c1 == 0) ? 1ULL : 0ULL);
+    uint64_t c3 = K.b3;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t hi0 = mulhi64(MCF_PHILOX_M0, c0), lo0 = MCF_PHILOX_M0 * c0;
+        const uint64_t hi1 = mulhi64(MCF_PHILOX_M1, c2), lo1 = MCF_PHILOX_M1 * c2;
+        c0 = hi1 ^ c1 ^ K.rk[2 * r];
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ K.rk[2 * r + 1];
+        c3 = lo0;
+    }
+    o0 = c0;
+    o1 = c1;
+    o2 = c2;
+    o3 = c3;
+}
+
 // ---------------------------------------------------------------------------------------
 // Cursors: random access into a reference stream.  `pos` counts 64-bit draws from the
 // state captured in the mcf_stream record (pos 0 = the next value NumPy would return).
@@ -318,10 +362,15 @@ MCF_HD void consume_draws(Cursor<MCF_GEN_PHILOX> &cur, F f) {
 // ---------------------------------------------------------------------------------------
 // Ziggurat
 // ---------------------------------------------------------------------------------------
+struct ZigKW {  // ki and wi of one layer side by side: one 16-byte shared-memory load per draw in the fast walk
+    uint64_t ki;
+    double wi;
+};
 struct ZigTables {
     const uint64_t *ki;
     const double *wi;
     const double *fi;
+    const ZigKW *kw;
 };
 #define MCF_ZIG_R 3.6541528853610088
 #define MCF_ZIG_INV_R 0.27366123732975828
@@ -553,29 +602,25 @@ MCF_HD ChunkInfo scan_chunk(Cur &cur, uint64_t chunk_base, uint32_t entry, const
 //     chunk invalid (`*valid = false`); the caller queues it for the dense, fully general re-walk.
 // Normals of wedge-accepted attempts are added to their sub-chunk sum after its fast ones (deterministic order).
 // ---------------------------------------------------------------------------------------
-MCF_HD ChunkInfo scan_chunk_fast(Cursor<MCF_GEN_PHILOX> &cur, uint64_t chunk_base, const ZigTables &t, double *zsub_out,
-                                 bool *valid) {
+// `load(blk, a, b, c, d)` yields the four draws of Philox block `blk` (relative to the stream's base counter);
+// `blk0` is the block holding the chunk's first draw.  Returns the chunk description; `*valid` as explained above.
+template <class Load>
+MCF_HD ChunkInfo scan_chunk_fast(Load load, uint64_t blk0, const ZigTables &t, double *zsub_out, bool *valid) {
     ChunkInfo ci;
     ci.gen_entry = 0;
     uint64_t sm = 0, em = 0;
     bool ok = true;
     unsigned skip = 0;
-    const uint64_t blk0 = (cur.q - cur.pos + chunk_base) >> 2;  // q - pos = buffer offset of the stream (multiple of 4)
-    cur.load_block(blk0);
-    uint64_t w0 = cur.v0, w1 = cur.v1, w2 = cur.v2, w3 = cur.v3, w4, w5, w6, w7;
+    uint64_t w0, w1, w2, w3, w4, w5, w6, w7;
+    load(blk0, w0, w1, w2, w3);
 #pragma unroll 1
     for (unsigned sub = 0; sub < MCF_SUBS; sub++) {
         double zc = 0.0;
         uint64_t ea0 = 0, eb0 = 0, ea1 = 0, eb1 = 0;  // parked wedge tests: (start draw, uniform draw)
         unsigned ej0 = 0, ej1 = 0, nev = 0;
 #pragma unroll 1
-        for (unsigned bb = 0; bb < 4; bb++) {
-            const unsigned b = sub * 4 + bb;
-            cur.load_block(blk0 + b + 1);
-            w4 = cur.v0;
-            w5 = cur.v1;
-            w6 = cur.v2;
-            w7 = cur.v3;
+        for (unsigned half = 0; half < 2; half++) {
+            unsigned b = sub * 4 + half * 2;
             unsigned snib = 0, enib = 0;
 #define MCF_FAST_DRAW(J, WA, WB, WC)                                                                   \
     if (skip > 0) {                                                                                    \
@@ -584,20 +629,21 @@ MCF_HD ChunkInfo scan_chunk_fast(Cursor<MCF_GEN_PHILOX> &cur, uint64_t chunk_bas
         snib |= 1u << (J);                                                                             \
         const unsigned idx = (unsigned)((WA)&0xffULL);                                                 \
         const uint64_t rabs = ((WA) >> 9) & 0x000fffffffffffffULL;                                     \
-        if (rabs < t.ki[idx]) {                                                                        \
+        const ZigKW kw = t.kw[idx];                                                                    \
+        if (rabs < kw.ki) {                                                                            \
             enib |= 1u << (J);                                                                         \
-            const double v = xmul(u52_to_double(rabs), t.wi[idx]);                                     \
+            const double v = xmul(u52_to_double(rabs), kw.wi);                                         \
             zc = xadd(zc, (((WA) >> 8) & 1ULL) ? -v : v);                                              \
         } else if (idx != 0) {                                                                         \
             skip = 1;                                                                                  \
             if (nev == 0) {                                                                            \
                 ea0 = (WA);                                                                            \
                 eb0 = (WB);                                                                            \
-                ej0 = b * 4 + (J);                                                                     \
+                ej0 = b * 4 + ((J)&3);                                                                 \
             } else if (nev == 1) {                                                                     \
                 ea1 = (WA);                                                                            \
                 eb1 = (WB);                                                                            \
-                ej1 = b * 4 + (J);                                                                     \
+                ej1 = b * 4 + ((J)&3);                                                                 \
             } else {                                                                                   \
                 ok = false;                                                                            \
             }                                                                                          \
@@ -615,17 +661,21 @@ MCF_HD ChunkInfo scan_chunk_fast(Cursor<MCF_GEN_PHILOX> &cur, uint64_t chunk_bas
             }                                                                                          \
         }                                                                                              \
     }
+            // block b lives in w0..w3 (look-ahead w4, w5); block b+1 in w4..w7 (look-ahead w0, w1 of block b+2)
+            load(blk0 + b + 1, w4, w5, w6, w7);
             MCF_FAST_DRAW(0, w0, w1, w2)
             MCF_FAST_DRAW(1, w1, w2, w3)
             MCF_FAST_DRAW(2, w2, w3, w4)
             MCF_FAST_DRAW(3, w3, w4, w5)
+            b++;
+            load(blk0 + b + 1, w0, w1, w2, w3);
+            MCF_FAST_DRAW(4, w4, w5, w6)
+            MCF_FAST_DRAW(5, w5, w6, w7)
+            MCF_FAST_DRAW(6, w6, w7, w0)
+            MCF_FAST_DRAW(7, w7, w0, w1)
 #undef MCF_FAST_DRAW
-            sm |= (uint64_t)snib << (4 * b);
-            em |= (uint64_t)enib << (4 * b);
-            w0 = w4;
-            w1 = w5;
-            w2 = w6;
-            w3 = w7;
+            sm |= (uint64_t)snib << (4 * (b - 1));
+            em |= (uint64_t)enib << (4 * (b - 1));
         }
         // parked wedge tests of this sub-chunk (same arithmetic and decision as zig_feed, state 1)
         for (unsigned e = 0; e < (nev < 2u ? nev : 2u); e++) {
@@ -634,8 +684,8 @@ MCF_HD ChunkInfo scan_chunk_fast(Cursor<MCF_GEN_PHILOX> &cur, uint64_t chunk_bas
             ZigFsm f;
             zig_reset(f);
             double x;
-            zig_feed(f, a, t, x);              // state 0 -> 1 (wedge): stores idx, rabs, x
-            if (zig_feed(f, u, t, x)) {        // acceptance test
+            zig_feed(f, a, t, x);        // state 0 -> 1 (wedge): stores idx, rabs, x
+            if (zig_feed(f, u, t, x)) {  // acceptance test
                 em |= 1ULL << js;
                 zc = xadd(zc, x);
             }
@@ -646,8 +696,6 @@ MCF_HD ChunkInfo scan_chunk_fast(Cursor<MCF_GEN_PHILOX> &cur, uint64_t chunk_bas
     ci.emitmask = em;
     ci.exit = skip;
     *valid = ok;
-    cur.pos = chunk_base + MCF_CHUNK + skip;
-    cur.q = (blk0 << 2) + MCF_CHUNK + skip;
     return ci;
 }
 

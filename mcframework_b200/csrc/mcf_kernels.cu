@@ -26,6 +26,7 @@ struct ZigShared {
     uint64_t ki[256];
     double wi[256];
     double fi[256];
+    ZigKW kw[256];
 };
 
 __device__ __forceinline__ ZigTables load_zig_tables(ZigShared &sh) {
@@ -33,12 +34,15 @@ __device__ __forceinline__ ZigTables load_zig_tables(ZigShared &sh) {
         sh.ki[i] = g_zig_ki[i];
         sh.wi[i] = __longlong_as_double((long long)g_zig_wi[i]);
         sh.fi[i] = __longlong_as_double((long long)g_zig_fi[i]);
+        sh.kw[i].ki = g_zig_ki[i];
+        sh.kw[i].wi = __longlong_as_double((long long)g_zig_wi[i]);
     }
     __syncthreads();
     ZigTables t;
     t.ki = sh.ki;
     t.wi = sh.wi;
     t.fi = sh.fi;
+    t.kw = sh.kw;
     return t;
 }
 
@@ -127,8 +131,17 @@ __global__ void __launch_bounds__(256, 3) plan_scan_kernel(const mcf_stream *__r
         // are tagged with an impossible generation entry so that the fix-up pass queues them for the general walk
         const int64_t id = si * cps + c0;
         bool valid;
-        ChunkInfo ci = scan_chunk_fast(*reinterpret_cast<Cursor<MCF_GEN_PHILOX> *>(&cur), (uint64_t)c0 * MCF_CHUNK, t,
-                                       zsum + id * MCF_SUBS, &valid);
+        Cursor<MCF_GEN_PHILOX> &pc = *reinterpret_cast<Cursor<MCF_GEN_PHILOX> *>(&cur);
+        const uint64_t blk0 = ((uint64_t)st.buf_pos + (uint64_t)c0 * MCF_CHUNK) >> 2;
+        ChunkInfo ci = scan_chunk_fast(
+            [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
+                pc.load_block(blk);
+                a = pc.v0;
+                b = pc.v1;
+                c = pc.v2;
+                d = pc.v3;
+            },
+            blk0, t, zsum + id * MCF_SUBS, &valid);
         startmask[id] = ci.startmask;
         emitmask[id] = ci.emitmask;
         exit_[id] = (uint8_t)ci.exit;
@@ -146,6 +159,30 @@ __global__ void __launch_bounds__(256, 3) plan_scan_kernel(const mcf_stream *__r
         if (ci.exit == MCF_EXIT_OVERFLOW) atomicExch(&hdr[0], MCF_ERR_NOT_CONVERGED);
         entry = ci.exit;
     }
+}
+
+// One launch per stream: the stream's ten Philox round keys and base counter are kernel parameters, i.e. operands
+// in the constant bank -- the key schedule costs no instruction and no register.
+__global__ void __launch_bounds__(256, 3) plan_scan_philox_stream_kernel(const __grid_constant__ PhiloxKeys K, int64_t row0,
+                                                                         int64_t cps, uint64_t *__restrict__ startmask,
+                                                                         uint64_t *__restrict__ emitmask,
+                                                                         uint8_t *__restrict__ exit_,
+                                                                         uint8_t *__restrict__ gen,
+                                                                         double *__restrict__ zsum) {
+    __shared__ ZigShared sh;
+    const ZigTables t = load_zig_tables(sh);
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cps) return;
+    const int64_t id = row0 + c;
+    bool valid;
+    const uint64_t blk0 = (K.off + (uint64_t)c * MCF_CHUNK) >> 2;
+    const ChunkInfo ci = scan_chunk_fast(
+        [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &cc, uint64_t &d) { philox_block_keys(K, blk, a, b, cc, d); },
+        blk0, t, zsum + id * MCF_SUBS, &valid);
+    startmask[id] = ci.startmask;
+    emitmask[id] = ci.emitmask;
+    exit_[id] = (uint8_t)ci.exit;
+    gen[id] = valid ? (uint8_t)0 : (uint8_t)MCF_GEN_ENTRY_INVALID;
 }
 
 // Fix chunk entries: a chunk's true entry offset is its predecessor's exit.  Two kernels per iteration so that the
@@ -482,8 +519,8 @@ static int g_last_cuda_error = 0;
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 template <int KIND>
-static int normal_plan_impl(const mcf_stream *d_streams, const PlanGeom &g, int64_t nps, int32_t iters, char *ws,
-                            uint64_t *d_sim_start, uint64_t *d_stream_end, cudaStream_t cs) {
+static int normal_plan_impl(const mcf_stream *d_streams, const mcf_stream *h_streams, const PlanGeom &g, int64_t nps,
+                            int32_t iters, char *ws, uint64_t *d_sim_start, uint64_t *d_stream_end, cudaStream_t cs) {
     int *hdr = (int *)ws;
     uint64_t *sm = (uint64_t *)(ws + g.off_start), *em = (uint64_t *)(ws + g.off_emit);
     uint64_t *tsum = (uint64_t *)(ws + g.off_tsum), *tpre = (uint64_t *)(ws + g.off_tpre);
@@ -500,7 +537,18 @@ static int normal_plan_impl(const mcf_stream *d_streams, const PlanGeom &g, int6
     plan_init_kernel<<<1, 32, 0, cs>>>(hdr, iters, layout);
     constexpr int RUN = KIND == MCF_GEN_PCG64 ? 8 : 1;  // PCG64 pays an O(log n) jump per thread
     const int64_t n_runs = g.n_chunks / RUN;
-    plan_scan_kernel<KIND, RUN><<<grid_for(n_runs, 256), 256, 0, cs>>>(d_streams, g.cps, n_runs, sm, em, ex, gen, zs, hdr);
+    const int64_t n_streams = g.n_chunks / g.cps;
+    bool per_stream = KIND == MCF_GEN_PHILOX && h_streams != nullptr && n_streams <= 1024;
+    for (int64_t si = 0; per_stream && si < n_streams; si++) per_stream = (h_streams[si].buf_pos & 3u) == 0;
+    if (per_stream) {
+        for (int64_t si = 0; si < n_streams; si++) {
+            const PhiloxKeys K = philox_keys_of(h_streams[si]);
+            plan_scan_philox_stream_kernel<<<grid_for(g.cps, 256), 256, 0, cs>>>(K, si * g.cps, g.cps, sm, em, ex, gen, zs);
+        }
+    } else {
+        plan_scan_kernel<KIND, RUN><<<grid_for(n_runs, 256), 256, 0, cs>>>(d_streams, g.cps, n_runs, sm, em, ex, gen, zs,
+                                                                          hdr);
+    }
     MCF_CUDA_OK(cudaGetLastError());
     int64_t *queue = (int64_t *)(ws + g.off_queue);
     for (int it = 0; it < iters; it++) {
@@ -567,10 +615,10 @@ int64_t mcf_normal_plan_workspace_bytes(int32_t n_streams, int64_t max_sims_per_
     return plan_geom(n_streams, max_sims_per_stream, normals_per_sim, slack).total;
 }
 
-int mcf_normal_plan(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total,
-                      int64_t max_sims_per_stream, int64_t normals_per_sim, double slack, int32_t resolve_iters,
-                      void *d_workspace, int64_t workspace_bytes, uint64_t *d_sim_start, uint64_t *d_stream_end,
-                      void *cuda_stream) {
+int mcf_normal_plan(uint32_t gen_kind, const mcf_stream *d_streams, const mcf_stream *h_streams, int32_t n_streams,
+                      int64_t n_total, int64_t max_sims_per_stream, int64_t normals_per_sim, double slack,
+                      int32_t resolve_iters, void *d_workspace, int64_t workspace_bytes, uint64_t *d_sim_start,
+                      uint64_t *d_stream_end, void *cuda_stream) {
     if (!d_streams || n_streams <= 0 || n_total <= 0 || max_sims_per_stream <= 0 || normals_per_sim <= 0 ||
         !d_workspace || !d_sim_start || resolve_iters < 1 || resolve_iters > MCF_HDR_WORDS - 3)
         return MCF_ERR_BAD_ARG;
@@ -578,9 +626,9 @@ int mcf_normal_plan(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_st
     if (workspace_bytes < g.total) return MCF_ERR_WORKSPACE_TOO_SMALL;
     cudaStream_t cs = (cudaStream_t)cuda_stream;
     if (gen_kind == MCF_GEN_PCG64)
-        return normal_plan_impl<MCF_GEN_PCG64>(d_streams, g, normals_per_sim, resolve_iters, (char *)d_workspace,
+        return normal_plan_impl<MCF_GEN_PCG64>(d_streams, h_streams, g, normals_per_sim, resolve_iters, (char *)d_workspace,
                                                d_sim_start, d_stream_end, cs);
-    return normal_plan_impl<MCF_GEN_PHILOX>(d_streams, g, normals_per_sim, resolve_iters, (char *)d_workspace,
+    return normal_plan_impl<MCF_GEN_PHILOX>(d_streams, h_streams, g, normals_per_sim, resolve_iters, (char *)d_workspace,
                                             d_sim_start, d_stream_end, cs);
 }
 

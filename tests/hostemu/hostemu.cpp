@@ -20,12 +20,15 @@ static const unsigned long long h_fi[256] = {MCF_ZIG_FI_BITS_LIST};
 static ZigTables host_tables() {
     static double wi[256], fi[256];
     static uint64_t ki[256];
+    static ZigKW kw[256];
     static bool init = false;
     if (!init) {
         for (int i = 0; i < 256; i++) {
             ki[i] = h_ki[i];
             wi[i] = bits_to_double(h_wi[i]);
             fi[i] = bits_to_double(h_fi[i]);
+            kw[i].ki = ki[i];
+            kw[i].wi = wi[i];
         }
         init = true;
     }
@@ -33,6 +36,7 @@ static ZigTables host_tables() {
     t.ki = ki;
     t.wi = wi;
     t.fi = fi;
+    t.kw = kw;
     return t;
 }
 
@@ -95,8 +99,11 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
         if (KIND == MCF_GEN_PHILOX && RUN == 1 && (streams[si].buf_pos & 3u) == 0) {  // as plan_scan_kernel
             const int64_t id = si * g.cps + c0;
             bool valid;
-            ChunkInfo ci = scan_chunk_fast(*reinterpret_cast<Cursor<MCF_GEN_PHILOX> *>(&cur), (uint64_t)c0 * MCF_CHUNK, t,
-                                           &zs[id * MCF_SUBS], &valid);
+            const PhiloxKeys K = philox_keys_of(streams[si]);  // as plan_scan_philox_stream_kernel
+            const uint64_t blk0 = (K.off + (uint64_t)c0 * MCF_CHUNK) >> 2;
+            ChunkInfo ci = scan_chunk_fast(
+                [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &cc, uint64_t &d) { philox_block_keys(K, blk, a, b, cc, d); },
+                blk0, t, &zs[id * MCF_SUBS], &valid);
             sm[id] = ci.startmask;
             em[id] = ci.emitmask;
             ex[id] = (uint8_t)ci.exit;
