@@ -36,33 +36,24 @@ static inline PlanGeom plan_geom(int32_t n_streams, int64_t max_sims, int64_t np
     g.tps = g.cps / MCF_TILE;
     g.n_chunks = (int64_t)n_streams * g.cps;
     g.n_tiles = (int64_t)n_streams * g.tps;
-    int64_t o = MCF_HDR_WORDS * 4;
-    o = (o + 255) / 256 * 256;
-    g.off_start = o;
-    o += g.n_chunks * 8;
-    g.off_emit = o;
-    o += g.n_chunks * 8;
-    g.off_tsum = o;
-    o += g.n_tiles * 8;
-    g.off_tpre = o;
-    o += g.n_tiles * 8;
-    g.off_exit = o;
-    o += g.n_chunks;
-    g.off_gen = o;
-    o += g.n_chunks;
-    g.off_entry = o;
-    o += g.n_chunks;
-    o = (o + 255) / 256 * 256;
-    g.off_send = o;
-    o += (int64_t)n_streams * 8;
-    o = (o + 255) / 256 * 256;
-    g.off_zsum = o;
-    o += g.n_chunks * 8 * MCF_SUBS;
-    o = (o + 255) / 256 * 256;
     g.q_cap = g.n_chunks / 8 + 4096;  // chunks whose entry differs from the speculative one: ~2 % expected
-    g.off_queue = o;
-    o += g.q_cap * 8;
-    g.total = (o + 255) / 256 * 256;
+    int64_t o = 256;                  // header: status words, PlanLayout, queue counters
+    auto region = [&o](int64_t bytes) {  // every region starts 256-byte aligned (vector loads/stores on the byte arrays)
+        const int64_t at = o;
+        o = (o + bytes + 255) / 256 * 256;
+        return at;
+    };
+    g.off_start = region(g.n_chunks * 8);
+    g.off_emit = region(g.n_chunks * 8);
+    g.off_tsum = region(g.n_tiles * 8);
+    g.off_tpre = region(g.n_tiles * 8);
+    g.off_exit = region(g.n_chunks);
+    g.off_gen = region(g.n_chunks);
+    g.off_entry = region(g.n_chunks);
+    g.off_send = region((int64_t)n_streams * 8);
+    g.off_zsum = region(g.n_chunks * 8 * MCF_SUBS);
+    g.off_queue = region(2 * g.q_cap * 8);  // two queues, used alternately by the fix-up rounds
+    g.total = o;
     return g;
 }
 

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256, 3) plan_scan_kernel(const mcf_stream *__r
 
 // One launch per stream: the stream's ten Philox round keys and base counter are kernel parameters, i.e. operands
 // in the constant bank -- the key schedule costs no instruction and no register.
-__global__ void __launch_bounds__(256, 3) plan_scan_philox_stream_kernel(const __grid_constant__ PhiloxKeys K, int64_t row0,
+__global__ void __launch_bounds__(256, 4) plan_scan_philox_stream_kernel(const __grid_constant__ PhiloxKeys K, int64_t row0,
                                                                          int64_t cps, uint64_t *__restrict__ startmask,
                                                                          uint64_t *__restrict__ emitmask,
                                                                          uint8_t *__restrict__ exit_,
@@ -190,25 +190,63 @@ __global__ void __launch_bounds__(256, 3) plan_scan_philox_stream_kernel(const _
 // for one or two lanes.
 //   plan_entries_kernel : entry_true[id] = exit[id-1]; chunks generated with another entry go to a work queue
 //   plan_rescan_kernel  : one thread per queued chunk re-walks it from its true entry
+__device__ __forceinline__ void plan_enqueue(int64_t id, int64_t *__restrict__ queue, int64_t q_cap, int *hdr, int iter) {
+    int *qcount = reinterpret_cast<int *>(reinterpret_cast<char *>(hdr) + MCF_QCOUNT_OFFSET) + iter;
+    const int k = atomicAdd(qcount, 1);
+    if (k < q_cap)
+        queue[k] = id;
+    else
+        atomicExch(&hdr[0], MCF_ERR_NOT_CONVERGED);  // queue overflow: the caller re-plans with more iterations/slack
+}
+
+// First round: every chunk.  16 chunks per thread through 16-byte loads/stores of the byte arrays
+// (cps is a multiple of 1024, so a group of 16 never straddles two streams).
 __global__ void __launch_bounds__(256) plan_entries_kernel(int64_t cps, int64_t n_chunks, const uint8_t *__restrict__ exit_,
                                                            const uint8_t *__restrict__ gen,
                                                            uint8_t *__restrict__ entry_true, int64_t *__restrict__ queue,
-                                                           int64_t q_cap, int *hdr, int iter) {
-    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= n_chunks) return;
-    const int64_t c = id % cps;
-    const uint32_t e = c == 0 ? 0u : (uint32_t)exit_[id - 1];
-    entry_true[id] = (uint8_t)e;
-    // Re-walk whenever the true entry differs from the one the chunk was generated with.  (The masks alone would
-    // stay usable when `e` happens to be an attempt start of the speculative walk -- chains coincide from there --
-    // but the stored chunk sum must not contain the attempts the speculative walk started before `e`.)
-    if (e != (uint32_t)gen[id]) {
-        int *qcount = reinterpret_cast<int *>(reinterpret_cast<char *>(hdr) + MCF_QCOUNT_OFFSET) + iter;
-        const int k = atomicAdd(qcount, 1);
-        if (k < q_cap)
-            queue[k] = id;
-        else
-            atomicExch(&hdr[0], MCF_ERR_NOT_CONVERGED);  // queue overflow: the caller re-plans with more iterations/slack
+                                                           int64_t q_cap, int *hdr) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t id0 = g * 16;
+    if (id0 >= n_chunks) return;
+    const uint4 ex4 = *reinterpret_cast<const uint4 *>(exit_ + id0);
+    const uint4 gn4 = *reinterpret_cast<const uint4 *>(gen + id0);
+    const uint8_t prev = (id0 % cps) == 0 ? (uint8_t)0 : exit_[id0 - 1];
+    const uint32_t exw[4] = {ex4.x, ex4.y, ex4.z, ex4.w}, gnw[4] = {gn4.x, gn4.y, gn4.z, gn4.w};
+    uint32_t enw[4];
+    uint32_t carry = prev;  // exit of the chunk before the current one
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        // entry bytes of this word = exit bytes shifted by one chunk
+        enw[w] = (exw[w] << 8) | carry;
+        carry = exw[w] >> 24;
+        uint32_t diff = enw[w] ^ gnw[w];
+        // Re-walk whenever the true entry differs from the one the chunk was generated with.  (The masks alone would
+        // stay usable when the entry happens to be an attempt start of the speculative walk -- chains coincide from
+        // there -- but the stored sums must not contain the attempts the speculative walk started before it.)
+        while (diff) {
+            const int byte = (__ffs(diff) - 1) >> 3;
+            plan_enqueue(id0 + w * 4 + byte, queue, q_cap, hdr, 0);
+            diff &= ~(0xFFu << (byte * 8));
+        }
+    }
+    *reinterpret_cast<uint4 *>(entry_true + id0) = make_uint4(enw[0], enw[1], enw[2], enw[3]);
+}
+
+// Later rounds: only the successors of the chunks re-walked in the previous round can have a new entry.
+__global__ void __launch_bounds__(256) plan_entries_from_queue_kernel(int64_t cps, const uint8_t *__restrict__ exit_,
+                                                                      const uint8_t *__restrict__ gen,
+                                                                      uint8_t *__restrict__ entry_true,
+                                                                      const int64_t *__restrict__ prev_queue,
+                                                                      int64_t *__restrict__ queue, int64_t q_cap, int *hdr,
+                                                                      int iter) {
+    int count = *(reinterpret_cast<const int *>(reinterpret_cast<const char *>(hdr) + MCF_QCOUNT_OFFSET) + iter - 1);
+    if (count > q_cap) count = (int)q_cap;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t id = prev_queue[k] + 1;
+        if (id % cps == 0) continue;  // the re-walked chunk was the last of its stream
+        const uint8_t e = exit_[id - 1];
+        entry_true[id] = e;
+        if (e != gen[id]) plan_enqueue(id, queue, q_cap, hdr, iter);
     }
 }
 
@@ -550,13 +588,19 @@ static int normal_plan_impl(const mcf_stream *d_streams, const mcf_stream *h_str
                                                                           hdr);
     }
     MCF_CUDA_OK(cudaGetLastError());
-    int64_t *queue = (int64_t *)(ws + g.off_queue);
+    // two work queues, used alternately: round k reads the chunks re-walked in round k-1
+    int64_t *queues[2] = {(int64_t *)(ws + g.off_queue), (int64_t *)(ws + g.off_queue) + g.q_cap};
     for (int it = 0; it < iters; it++) {
-        plan_entries_kernel<<<grid_for(g.n_chunks, 256), 256, 0, cs>>>(g.cps, g.n_chunks, ex, gen, ent, queue, g.q_cap, hdr,
-                                                                       it);
-        MCF_CUDA_OK(cudaGetLastError());
-        // the first iteration carries ~2 % of the chunks, later ones almost nothing: size the grids accordingly
+        int64_t *queue = queues[it & 1];
+        // the first round carries ~2 % of the chunks, later ones almost nothing: size the grids accordingly
         const int64_t expect = it == 0 ? g.q_cap : g.q_cap / 64 + 256;
+        if (it == 0)
+            plan_entries_kernel<<<grid_for(g.n_chunks / 16, 256), 256, 0, cs>>>(g.cps, g.n_chunks, ex, gen, ent, queue,
+                                                                                g.q_cap, hdr);
+        else
+            plan_entries_from_queue_kernel<<<grid_for(expect, 256), 256, 0, cs>>>(g.cps, ex, gen, ent, queues[(it - 1) & 1],
+                                                                                  queue, g.q_cap, hdr, it);
+        MCF_CUDA_OK(cudaGetLastError());
         plan_rescan_kernel<KIND><<<grid_for(expect, 256), 256, 0, cs>>>(d_streams, g.cps, queue, g.q_cap, sm, em, ex, gen,
                                                                         ent, zs, hdr, it);
         MCF_CUDA_OK(cudaGetLastError());
