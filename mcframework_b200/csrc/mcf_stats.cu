@@ -112,7 +112,7 @@ __device__ __forceinline__ void mom_add(MomAcc &a, double x) {
     a.s4 = fma(d2, d2, a.s4);
 }
 
-__global__ void __launch_bounds__(256, 4) moments_kernel(const double *__restrict__ x, int64_t n, double target,
+__global__ void __launch_bounds__(256, 3) moments_kernel(const double *__restrict__ x, int64_t n, double target,
                                                          MomentsPartial *__restrict__ partials) {
     MomAcc a;
     a.s1 = a.s2 = a.s3 = a.s4 = 0.0;
@@ -127,17 +127,15 @@ __global__ void __launch_bounds__(256, 4) moments_kernel(const double *__restric
         const double2 *x2 = reinterpret_cast<const double2 *>(x);
         const int64_t n2 = n >> 1;
         int64_t i = tid;
-        for (; i + 3 * nthr < n2; i += 4 * nthr) {  // 4 independent 16 B loads in flight
-            const double2 v0 = __ldg(&x2[i]), v1 = __ldg(&x2[i + nthr]), v2 = __ldg(&x2[i + 2 * nthr]),
-                          v3 = __ldg(&x2[i + 3 * nthr]);
-            mom_add(a, v0.x);
-            mom_add(a, v0.y);
-            mom_add(a, v1.x);
-            mom_add(a, v1.y);
-            mom_add(a, v2.x);
-            mom_add(a, v2.y);
-            mom_add(a, v3.x);
-            mom_add(a, v3.y);
+        for (; i + 7 * nthr < n2; i += 8 * nthr) {  // 8 independent 16 B loads in flight per thread
+            double2 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = __ldg(&x2[i + k * nthr]);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                mom_add(a, v[k].x);
+                mom_add(a, v[k].y);
+            }
         }
         for (; i < n2; i += nthr) {
             const double2 v = __ldg(&x2[i]);
@@ -224,46 +222,68 @@ __global__ void select_init_kernel(SelectState *st, unsigned long long *hist, Se
     if (threadIdx.x == 0) *st = init;
 }
 
+__device__ __forceinline__ int select_slot(double v, int omit, int pass, int shift, int n_uniq,
+                                           const uint64_t *__restrict__ sh_uniq, const unsigned *__restrict__ sh_bloom) {
+    const uint64_t key = select_key(v, omit);
+    if (pass == 0) return (int)(key >> 56);
+    const uint64_t pre = key >> (shift + SEL_BITS);
+    // cheap reject: the last decided digit of the element must be the last digit of SOME tracked prefix
+    const unsigned last = (unsigned)pre & (SEL_BINS - 1);
+    if (!((sh_bloom[last >> 5] >> (last & 31)) & 1u)) return -1;
+    int lo = 0, hi = n_uniq - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sh_uniq[mid] < pre)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    if (sh_uniq[lo] != pre) return -1;
+    return lo * SEL_BINS + (int)((unsigned)(key >> shift) & (SEL_BINS - 1));
+}
+
 __global__ void __launch_bounds__(512) select_hist_kernel(const double *__restrict__ x, int64_t n, int omit,
                                                           const SelectState *__restrict__ st,
                                                           unsigned long long *__restrict__ hist) {
     __shared__ unsigned int sh_hist[MCF_SELECT_MAX_RANKS * SEL_BINS];
     __shared__ uint64_t sh_uniq[MCF_SELECT_MAX_RANKS];
+    __shared__ unsigned sh_bloom[SEL_BINS / 32];
     const int n_uniq = st->n_uniq, pass = st->pass;
     for (int i = threadIdx.x; i < n_uniq * SEL_BINS; i += blockDim.x) sh_hist[i] = 0u;
-    if (threadIdx.x < n_uniq) sh_uniq[threadIdx.x] = st->uniq[threadIdx.x];
+    if (threadIdx.x < SEL_BINS / 32) sh_bloom[threadIdx.x] = 0u;
+    __syncthreads();
+    if (threadIdx.x < n_uniq) {
+        const uint64_t u = st->uniq[threadIdx.x];
+        sh_uniq[threadIdx.x] = u;
+        atomicOr(&sh_bloom[((unsigned)u & (SEL_BINS - 1)) >> 5], 1u << ((unsigned)u & 31u));
+    }
     __syncthreads();
     const int shift = 64 - SEL_BITS * (pass + 1);  // digit position of this pass
+    const int lane = threadIdx.x & 31;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i0 = tid - (threadIdx.x & 31); i0 < n; i0 += 2 * nthr) {  // warp-uniform trip count, 2 loads in flight
-        const int64_t ia = i0 + (threadIdx.x & 31), ib = ia + nthr;
-        const double xa = ia < n ? __ldg(&x[ia]) : 0.0, xb = ib < n ? __ldg(&x[ib]) : 0.0;
+    constexpr int UNROLL = 4;
+    for (int64_t i0 = tid - lane; i0 < n; i0 += UNROLL * nthr) {  // warp-uniform trip count, UNROLL loads in flight
+        double v[UNROLL];
+        int slot[UNROLL];
+        bool any = false;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int64_t i = h ? ib : ia;
-            int slot = -1;
-            if (i < n) {
-                const uint64_t key = select_key(h ? xb : xa, omit);
-                const unsigned digit = (unsigned)(key >> shift) & (SEL_BINS - 1);
-                if (pass == 0) {
-                    slot = (int)digit;
-                } else {
-                    const uint64_t pre = key >> (shift + SEL_BITS);
-                    int lo = 0, hi = n_uniq - 1;
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if (sh_uniq[mid] < pre)
-                            lo = mid + 1;
-                        else
-                            hi = mid;
-                    }
-                    if (sh_uniq[lo] == pre) slot = lo * SEL_BINS + (int)digit;
-                }
-            }
-            // warp-aggregated shared-memory atomics: one add per distinct bin per warp; later passes mostly skip
-            if (__ballot_sync(0xffffffffu, slot >= 0) == 0u) continue;
-            const unsigned peers = __match_any_sync(0xffffffffu, slot);
-            if (slot >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh_hist[slot], __popc(peers));
+        for (int k = 0; k < UNROLL; k++) {
+            const int64_t i = i0 + lane + k * nthr;
+            v[k] = i < n ? __ldg(&x[i]) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) {
+            const int64_t i = i0 + lane + k * nthr;
+            slot[k] = i < n ? select_slot(v[k], omit, pass, shift, n_uniq, sh_uniq, sh_bloom) : -1;
+            any |= slot[k] >= 0;
+        }
+        if (__ballot_sync(0xffffffffu, any) == 0u) continue;  // later passes: nothing of interest in 128 elements
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) {
+            // warp-aggregated shared-memory atomics: one add per distinct bin per warp
+            if (__ballot_sync(0xffffffffu, slot[k] >= 0) == 0u) continue;
+            const unsigned peers = __match_any_sync(0xffffffffu, slot[k]);
+            if (slot[k] >= 0 && (int)(__ffs(peers) - 1) == lane) atomicAdd(&sh_hist[slot[k]], __popc(peers));
         }
     }
     __syncthreads();
