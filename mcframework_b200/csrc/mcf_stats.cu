@@ -166,16 +166,22 @@ __global__ void __launch_bounds__(256, 3) moments_kernel(const double *__restric
     (void)target;
 }
 
-__global__ void __launch_bounds__(32) moments_final_kernel(const MomentsPartial *__restrict__ partials, int n_partials,
-                                                           double target, double *__restrict__ out) {
-    // one warp: lane l merges partials l, l+32, ... in order, then the warp tree (fixed order => deterministic)
-    const int lane = threadIdx.x;
+__global__ void __launch_bounds__(256) moments_final_kernel(const MomentsPartial *__restrict__ partials, int n_partials,
+                                                            double target, double *__restrict__ out) {
+    // thread t merges partials t, t+256, ... in order, then the warp trees, then warp 0 merges the 8 warp results:
+    // a fixed order, so the result is deterministic
     MomentsPartial p;
     p.m = moments_empty();
     p.sum = p.n_nan = p.n_pinf = p.n_ninf = 0.0;
-    for (int i = lane; i < n_partials; i += 32) p = partial_merge(p, partials[i]);
+    for (int i = threadIdx.x; i < n_partials; i += blockDim.x) p = partial_merge(p, partials[i]);
     p = partial_warp_reduce(p);
-    if (lane == 0) {
+    __shared__ MomentsPartial sh[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sh[wid] = p;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        p = sh[0];
+        for (int w = 1; w < 8; w++) p = partial_merge(p, sh[w]);
         const double dt = p.m.mean - target;
         out[0] = p.m.n;
         out[1] = p.n_nan;
@@ -294,22 +300,44 @@ __global__ void __launch_bounds__(512) select_hist_kernel(const double *__restri
 }
 
 // one CTA: every rank walks the histogram of its prefix, picks its digit, then prefixes are re-uniqued
-__global__ void select_choose_kernel(SelectState *st, unsigned long long *hist) {
+__global__ void __launch_bounds__(1024) select_choose_kernel(SelectState *st, unsigned long long *hist) {
     __shared__ SelectState s;
     if (threadIdx.x == 0) s = *st;
     __syncthreads();
-    if (threadIdx.x < s.k) {
-        const int r = threadIdx.x;
+    const int n_rows = s.n_uniq;
+    // one warp per rank: 8 coalesced 32-bin loads + shuffle scans instead of 256 dependent global loads
+    const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
+    if (r < s.k) {
         const unsigned long long *h = hist + (size_t)s.uniq_of[r] * SEL_BINS;
         int64_t rem = s.rank[r];
-        int d = 0;
-        for (; d < SEL_BINS - 1; d++) {
-            const int64_t c = (int64_t)h[d];
-            if (rem < c) break;
-            rem -= c;
+        int d = SEL_BINS - 1;
+        bool found = false;
+        for (int c0 = 0; c0 < SEL_BINS && !found; c0 += 32) {
+            const int64_t c = (int64_t)h[c0 + lane];
+            int64_t incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, rem < incl);
+            if (hit) {
+                const int first = __ffs(hit) - 1;
+                const int64_t before = __shfl_sync(0xffffffffu, incl - c, first);
+                d = c0 + first;
+                rem -= before;
+                found = true;
+            } else {
+                rem -= __shfl_sync(0xffffffffu, incl, 31);
+            }
         }
-        s.rank[r] = rem;
-        s.prefix[r] = (s.prefix[r] << SEL_BITS) | (uint64_t)d;
+        if (!found) {  // rank beyond the counted elements (cannot happen for valid ranks): clamp to the last bin
+            d = SEL_BINS - 1;
+        }
+        if (lane == 0) {
+            s.rank[r] = rem;
+            s.prefix[r] = (s.prefix[r] << SEL_BITS) | (uint64_t)d;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -340,7 +368,7 @@ __global__ void select_choose_kernel(SelectState *st, unsigned long long *hist) 
         *st = s;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < MCF_SELECT_MAX_RANKS * SEL_BINS; i += blockDim.x) hist[i] = 0ULL;
+    for (int i = threadIdx.x; i < n_rows * SEL_BINS; i += blockDim.x) hist[i] = 0ULL;  // only the rows that were used
 }
 
 __global__ void select_finish_kernel(const SelectState *st, double *out) {
@@ -888,7 +916,7 @@ int mcf_moments(const double *d_x, int64_t n, double target, double *d_out, void
     const int blocks = grid_cap(n, 256 * 8, MCF_SM_COUNT * 8);
     moments_kernel<<<blocks, 256, 0, cs>>>(d_x, n, target, (MomentsPartial *)d_workspace);
     MCF_CUDA_OK(cudaGetLastError());
-    moments_final_kernel<<<1, 32, 0, cs>>>((const MomentsPartial *)d_workspace, blocks, target, d_out);
+    moments_final_kernel<<<1, 256, 0, cs>>>((const MomentsPartial *)d_workspace, blocks, target, d_out);
     MCF_CUDA_OK(cudaGetLastError());
     return MCF_OK;
 }
@@ -933,7 +961,7 @@ int mcf_select_choose(void *d_workspace, void *cuda_stream) {
     if (!d_workspace) return MCF_ERR_BAD_ARG;
     const SelectGeom g = select_geom();
     char *ws = (char *)d_workspace;
-    select_choose_kernel<<<1, 256, 0, (cudaStream_t)cuda_stream>>>((SelectState *)(ws + g.off_state),
+    select_choose_kernel<<<1, 1024, 0, (cudaStream_t)cuda_stream>>>((SelectState *)(ws + g.off_state),
                                                                    (unsigned long long *)(ws + g.off_hist));
     MCF_CUDA_OK(cudaGetLastError());
     return MCF_OK;
