@@ -699,12 +699,6 @@ MCF_HD ChunkInfo scan_chunk_fast(Load load, uint64_t blk0, const ZigTables &t, d
     return ci;
 }
 
-// Is a chunk generated from `gen_entry` valid for true entry offset `e`?
-MCF_HD bool chunk_valid_for_entry(uint64_t startmask, uint32_t gen_entry, uint32_t e) {
-    if (e == gen_entry) return true;
-    return e < MCF_CHUNK && ((startmask >> e) & 1ULL);
-}
-
 // For a chunk whose emissions have stream-local ordinals [E, E+count): find every replication
 // boundary inside.  Replication m (m >= 1) starts right after the attempt that emitted normal
 // number m*nps-1.  `visit(m, position)` is called for m in [1, n_sims]; m == n_sims marks the

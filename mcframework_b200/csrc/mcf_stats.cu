@@ -1056,7 +1056,6 @@ int64_t mcf_lsm_workspace_bytes(int64_t n_paths) {
     if (n_paths <= 0) return MCF_ERR_BAD_ARG;
     return lsm_geom(n_paths).total;
 }
-int64_t mcf_lsm_sums_offset(void) { return 0; }
 
 int mcf_lsm_begin(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K, double r, double dt,
                   int32_t is_put, void *d_workspace, int64_t workspace_bytes, void *cuda_stream) {

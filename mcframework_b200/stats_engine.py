@@ -495,23 +495,14 @@ def ci_mean_bootstrap(x, ctx: StatsContext) -> dict[str, float | str] | None:
     data = v.data()
     means = SD.bootstrap_means(data, int(ctx.n_bootstrap), gen, group=v.sample.group)
     lo_q, hi_q = ctx.q_bound()
-    if ctx.bootstrap == "percentile" or v.size < 3:
-        nan_means = v.tainted  # a NaN/inf population poisons the resample means
-        low, high = SD.percentiles(means, [lo_q, hi_q], has_nan=False) if not nan_means else _host_pct(means, [lo_q, hi_q])
-        return _CIResult(ctx.confidence, "bootstrap-percentile", low, high).as_dict()
-    if v.tainted:
-        low, high = _host_pct(means, [lo_q, hi_q])
-        return _CIResult(ctx.confidence, "bootstrap-bca", low, high).as_dict()
+    # a population with NaN/inf under "propagate" poisons the resample means: NumPy's percentile then returns NaN
+    poisoned = bool(v.tainted and SD.moments(means).n_nan > 0)
+    if ctx.bootstrap == "percentile" or v.size < 3 or v.tainted:
+        label = "bootstrap-percentile" if (ctx.bootstrap == "percentile" or v.size < 3) else "bootstrap-bca"
+        low, high = SD.percentiles(means, [lo_q, hi_q], has_nan=poisoned)
+        return _CIResult(ctx.confidence, label, low, high).as_dict()
     low, high = _compute_bca_interval(v, means, ctx.confidence)
     return _CIResult(ctx.confidence, "bootstrap-bca", low, high).as_dict()
-
-
-def _host_pct(means_dev, qs):
-    # non-finite resample means (population contained NaN/inf under "propagate"): census + NumPy's NaN rule
-    from . import _stats_device as SD
-
-    s = SD.moments(means_dev)
-    return SD.percentiles(means_dev, qs, has_nan=s.n_nan > 0)
 
 
 @_device_metric
