@@ -204,6 +204,8 @@ int mcf_select(const double *d_x, int64_t n, int32_t omit_nonfinite, const int64
  * Multi-GPU: shard the slot range, all-gather the per-rank totals to get each rank's ordinal_base,
  * all-reduce d_sums.  d_sums must be zeroed by the caller; mcf_bootstrap_finalize divides by n.
  * Needs 2 <= n < 2^32 (NumPy's 32-bit path; n == 1 consumes no randomness). */
+/* device-wide hint for L2's DRAM fetch size on a miss (32/64/128 bytes); the bootstrap's random gathers want 32 */
+int mcf_set_l2_fetch_granularity(int32_t bytes);
 int64_t mcf_bootstrap_workspace_bytes(int64_t n_slots, int32_t chunk_slots);
 int mcf_bootstrap_count(uint32_t gen_kind, const mcf_stream *d_stream, int64_t n, uint64_t slot_lo, uint64_t slot_hi,
                         int32_t chunk_slots, void *d_workspace, int64_t workspace_bytes, uint64_t *d_total,

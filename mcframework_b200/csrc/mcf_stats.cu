@@ -552,7 +552,9 @@ __global__ void __launch_bounds__(BOOT_THREADS) boot_accumulate_kernel(
                 if (s < s1) ok[j] = slot_accept(rule, w.get(s), idx[j]);
             }
 #pragma unroll
-            for (int j = 0; j < 8; j++) v[j] = ok[j] ? __ldg(&x[idx[j]]) : 0.0;
+            // ld.global.cg: random 8-byte gathers must not drag whole 128-byte lines through L1 (measured: 113 B of DRAM
+            // traffic per gather with ld.global.nc) -- L2-only caching requests single 32-byte sectors
+            for (int j = 0; j < 8; j++) v[j] = ok[j] ? __ldcg(&x[idx[j]]) : 0.0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 if (ok[j] && !done) {
@@ -987,6 +989,12 @@ int mcf_select(const double *d_x, int64_t n, int32_t omit_nonfinite, const int64
         if (rc) return rc;
     }
     return mcf_select_finish(d_workspace, d_out, cuda_stream);
+}
+
+// Device-wide hint: how many bytes L2 fetches from DRAM on a miss (32, 64 or 128).  Random gathers want 32.
+int mcf_set_l2_fetch_granularity(int32_t bytes) {
+    MCF_CUDA_OK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+    return MCF_OK;
 }
 
 int64_t mcf_bootstrap_workspace_bytes(int64_t n_slots, int32_t chunk_slots) {
