@@ -215,6 +215,23 @@ int mcf_bootstrap_accumulate(uint32_t gen_kind, const mcf_stream *d_stream, cons
                              uint64_t ordinal_base, const void *d_workspace, int64_t workspace_bytes, double *d_sums,
                              uint64_t *d_end_slot, void *cuda_stream);
 int mcf_bootstrap_finalize(double *d_sums, int64_t n_resamples, int64_t n, void *cuda_stream);
+/* Binned variant of mcf_bootstrap_accumulate for populations larger than L2 (a random 8-byte gather from HBM moves a
+ * 128-byte line; from an L2-resident region it is 3-4x faster): the accepted indices of `resamples_per_batch`
+ * resamples are first appended (4 bytes each) to per-(resample, 2^region_shift-element region of x) queues, then
+ * summed region by region.  Same index stream, bit for bit; only the order of a resample's additions differs.
+ * h_block_base: host copy of the per-CTA ordinal prefix of the count pass (mcf_bootstrap_blocks entries, filled by
+ * mcf_bootstrap_block_base).  region_shift 0 = automatic (64 MB regions, at most 16).  Needs 256*chunk_slots <= n,
+ * chunk_slots % 8 == 0.  Synchronises the stream (reads the queue-overflow flag). */
+int64_t mcf_bootstrap_blocks(int64_t n_slots, int32_t chunk_slots);
+int mcf_bootstrap_block_base(const void *d_workspace, int64_t n_slots, int32_t chunk_slots, uint64_t *h_block_base,
+                             void *cuda_stream);
+int64_t mcf_bootstrap_binned_workspace_bytes(int64_t n, int32_t resamples_per_batch, int32_t region_shift);
+int mcf_bootstrap_accumulate_binned(uint32_t gen_kind, const mcf_stream *d_stream, const double *d_x, int64_t n,
+                                    int64_t n_resamples, uint64_t slot_lo, uint64_t slot_hi, int32_t chunk_slots,
+                                    uint64_t ordinal_base, const void *d_workspace, int64_t workspace_bytes,
+                                    const uint64_t *h_block_base, int32_t resamples_per_batch, int32_t region_shift,
+                                    void *d_bin_workspace, int64_t bin_workspace_bytes, double *d_sums,
+                                    uint64_t *d_end_slot, void *cuda_stream);
 /* *d_count = #{i : d_x[i] < value}  (BCa bias correction z0, stats_engine.py:1075-1078) */
 int mcf_count_less(const double *d_x, int64_t n, double value, int64_t *d_count, void *cuda_stream);
 /* nan_policy="omit" (_clean, stats_engine.py:734-742): d_out[0..*d_count) = finite values of d_x, order kept. */

@@ -209,8 +209,13 @@ def rejection_probability(n: int) -> float:
     return float(((1 << 32) % n) / float(1 << 32))
 
 
+#: populations above this many elements use the binned (L2-resident regions) gather path
+BINNED_MIN_N = 12_000_000
+
+
 def bootstrap_means(x, n_resamples: int, gen: np.random.Generator, group=None, advance: bool = True,
-                    chunk_slots: int | None = None):
+                    chunk_slots: int | None = None, binned: bool | None = None, region_shift: int = 0,
+                    resamples_per_batch: int = 16):
     """``x[rng.integers(0, n, size=(B, n))].mean(axis=1)`` (stats_engine.py:1039-1041) without the index
     matrix: float64[B] device tensor.  ``gen`` is advanced exactly as NumPy would have advanced it.
 
@@ -261,10 +266,29 @@ def bootstrap_means(x, n_resamples: int, gen: np.random.Generator, group=None, a
     else:
         raise N.NativeError("mcf_bootstrap_count", N.ERR_WINDOW_TOO_SMALL, "slot window too small after retries")
     base = sum(totals[:rank])
-    rc = lib.mcf_bootstrap_accumulate(kind, _ptr(d_rec), _ptr(x), n, B, lo, hi, cs, base, _ptr(ws), nbytes, _ptr(sums),
-                                      _ptr(end_slot), _stream_ptr())
-    N.check("mcf_bootstrap_accumulate", rc)
-    LAUNCHES["stats"] += 2
+    if binned is None:
+        binned = n >= BINNED_MIN_N
+    if binned and 256 * cs > n:
+        binned = False  # a CTA must not span more than two resamples
+    if binned:
+        nb = int(lib.mcf_bootstrap_blocks(nslots, cs))
+        h_bb = np.empty(nb, dtype=np.uint64)
+        N.check("mcf_bootstrap_block_base", lib.mcf_bootstrap_block_base(_ptr(ws), nslots, cs, h_bb.ctypes.data_as(C.c_void_p), _stream_ptr()))
+        bbytes = int(lib.mcf_bootstrap_binned_workspace_bytes(n, int(resamples_per_batch), int(region_shift)))
+        if bbytes < 0:
+            N.check("mcf_bootstrap_binned_workspace_bytes", bbytes)
+        bws = torch.empty(bbytes, dtype=torch.uint8, device=x.device)
+        rc = lib.mcf_bootstrap_accumulate_binned(kind, _ptr(d_rec), _ptr(x), n, B, lo, hi, cs, base, _ptr(ws), nbytes,
+                                                 h_bb.ctypes.data_as(C.c_void_p), int(resamples_per_batch), int(region_shift),
+                                                 _ptr(bws), bbytes, _ptr(sums), _ptr(end_slot), _stream_ptr())
+        N.check("mcf_bootstrap_accumulate_binned", rc)
+        LAUNCHES["stats"] += 2
+        del bws
+    else:
+        rc = lib.mcf_bootstrap_accumulate(kind, _ptr(d_rec), _ptr(x), n, B, lo, hi, cs, base, _ptr(ws), nbytes, _ptr(sums),
+                                          _ptr(end_slot), _stream_ptr())
+        N.check("mcf_bootstrap_accumulate", rc)
+        LAUNCHES["stats"] += 2
     if group is not None:
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(end_slot, op=dist.ReduceOp.MAX, group=group)

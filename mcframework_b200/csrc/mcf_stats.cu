@@ -594,6 +594,169 @@ __global__ void __launch_bounds__(BOOT_THREADS) boot_accumulate_kernel(
     }
 }
 
+// ----------------------------------------------------------------------------- binned bootstrap (large populations)
+// A random 8-byte gather from an HBM-resident vector moves a whole 128-byte line (measured: 113 B of DRAM traffic
+// per gather, 5.8e10 gathers/s = the HBM limit at that granularity), while the same gather from an L2-resident
+// table runs at 1.7e11/s.  For populations larger than L2 the work is therefore split:
+//   boot_bin_kernel    : regenerate the slots of a batch of resamples and append every accepted index to the queue
+//                        of (its resample, its 2^shift-element REGION of x) -- 4 bytes written per index, through
+//                        per-CTA shared-memory staging (one global atomic per queue per flush, coalesced stores);
+//   boot_gather_kernel : region by region (so that the region's part of x stays in L2 while all queues that point
+//                        into it are streamed once), sum x[region + local index] per (resample, region) queue.
+// The index stream is unchanged (bit-exact); only the order in which a resample's terms are added differs.
+#define BIN_MAX_REGIONS 16
+#define BIN_STAGE_CAP 704   // entries per staging buffer; flushed every BIN_FLUSH_EVERY groups of 8 slots per thread
+#define BIN_FLUSH_EVERY 3   // 3 * 2048 entries per CTA over >= 12 regions: 512 +- 22 per buffer
+
+struct BinParams {
+    uint32_t n;               // population size
+    uint32_t region_shift;    // region = idx >> region_shift
+    uint32_t n_regions;       // <= BIN_MAX_REGIONS
+    uint32_t n_res_window;    // resamples that can receive entries in this batch (queues per region)
+    uint64_t b_first;         // first resample of the batch window
+    uint64_t cap;             // entries per queue
+    uint64_t n_resamples;     // B
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(BOOT_THREADS) boot_bin_kernel(const mcf_stream *__restrict__ stream, BinParams bp,
+                                                                uint64_t slot_lo, uint64_t slot_hi, int chunk_slots,
+                                                                int64_t n_chunks, int64_t block0, uint64_t ordinal_base,
+                                                                const uint32_t *__restrict__ counts,
+                                                                const unsigned long long *__restrict__ block_base,
+                                                                uint32_t *__restrict__ queues,
+                                                                unsigned int *__restrict__ tails,
+                                                                unsigned long long *__restrict__ end_slot, int *overflow) {
+    __shared__ uint32_t warp_tot[BOOT_THREADS / 32];
+    // staging for the CTA's FIRST resample only; the few CTAs that straddle a resample boundary append the entries of
+    // the second one directly (1 CTA in n / (256 * chunk_slots))
+    __shared__ uint32_t sh_stage[BIN_MAX_REGIONS][BIN_STAGE_CAP];
+    __shared__ unsigned int sh_cnt[BIN_MAX_REGIONS], sh_n[BIN_MAX_REGIONS], sh_base[BIN_MAX_REGIONS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t blk = block0 + blockIdx.x;
+    const int64_t chunk = blk * BOOT_THREADS + threadIdx.x;
+    const uint32_t R = bp.n_regions;
+    if (threadIdx.x < BIN_MAX_REGIONS) sh_cnt[threadIdx.x] = 0;
+    // block-exclusive scan of the per-chunk accepted counts (as in boot_accumulate_kernel)
+    const uint32_t cnt = counts[chunk];
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int w2 = 0; w2 < wid; w2++) wbase += warp_tot[w2];
+    const uint64_t blk_ord = ordinal_base + block_base[blk];  // first ordinal of this CTA's slots
+    uint64_t ord = blk_ord + wbase + (incl - cnt);
+    const uint64_t total_needed = bp.n_resamples * (uint64_t)bp.n;
+    const uint64_t b_blk = blk_ord / bp.n;  // the CTA's slots (256 * chunk_slots <= n) touch resamples b_blk, b_blk + 1
+
+    const SlotRule rule = slot_rule(bp.n);
+    const mcf_stream st = *stream;
+    const uint64_t s0 = slot_lo + (uint64_t)chunk * (uint64_t)chunk_slots;
+    uint64_t s1 = s0 + (uint64_t)chunk_slots;
+    if (s1 > slot_hi) s1 = slot_hi;
+    const bool live = chunk < n_chunks && s0 < slot_hi;
+    uint64_t b = live ? ord / bp.n : 0, next_boundary = (b + 1) * (uint64_t)bp.n;
+    SlotWalker<KIND> w;
+    if (live) w.init(st, s0);
+    bool done = !live || ord >= total_needed;
+    const uint32_t mask = (1u << bp.region_shift) - 1u;
+    const int groups = chunk_slots / 8;
+    for (int g = 0; g < groups; g++) {  // uniform trip count: the flushes below are CTA-wide
+        const uint64_t sb = s0 + (uint64_t)g * 8;
+        if (!done && sb < s1) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint64_t s = sb + j;
+                uint32_t idx;
+                if (s < s1 && !done && slot_accept(rule, w.get(s), idx)) {
+                    if (ord == next_boundary) {
+                        b++;
+                        next_boundary += bp.n;
+                    }
+                    const unsigned q = idx >> bp.region_shift;
+                    const unsigned pos = b == b_blk ? atomicAdd(&sh_cnt[q], 1u) : 0xFFFFFFFFu;
+                    if (pos < BIN_STAGE_CAP) {
+                        sh_stage[q][pos] = idx & mask;
+                    } else {  // second resample of a straddling CTA, or staging full: append directly
+                        const uint64_t gq = (b - bp.b_first) * R + (idx >> bp.region_shift);
+                        const unsigned gp = atomicAdd(&tails[gq], 1u);
+                        if (gp < bp.cap)
+                            queues[gq * bp.cap + gp] = idx & mask;
+                        else
+                            atomicExch(overflow, 1);
+                    }
+                    ord++;
+                    if (ord == total_needed) {
+                        *end_slot = s + 1;  // slots consumed by the whole (B, n) draw
+                        done = true;
+                    }
+                }
+            }
+        }
+        if ((g % BIN_FLUSH_EVERY) == BIN_FLUSH_EVERY - 1 || g == groups - 1) {
+            __syncthreads();
+            if (threadIdx.x < R) {
+                unsigned c = sh_cnt[threadIdx.x];
+                if (c > BIN_STAGE_CAP) c = BIN_STAGE_CAP;
+                const uint64_t gq = (b_blk - bp.b_first) * R + threadIdx.x;
+                sh_n[threadIdx.x] = c;
+                sh_base[threadIdx.x] = c ? atomicAdd(&tails[gq], c) : 0u;
+                sh_cnt[threadIdx.x] = 0;
+            }
+            __syncthreads();
+            for (unsigned q = wid; q < R; q += BOOT_THREADS / 32) {
+                const unsigned c = sh_n[q], base = sh_base[q];
+                const uint64_t gq = (b_blk - bp.b_first) * R + q;
+                if (c && (uint64_t)base + c > bp.cap) atomicExch(overflow, 1);
+                for (unsigned j = lane; j < c; j += 32)
+                    if ((uint64_t)base + j < bp.cap) queues[gq * bp.cap + base + j] = sh_stage[q][j];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// grid (G, n_res_window): one (resample, region) queue per blockIdx.y, `region` fixed per launch
+__global__ void __launch_bounds__(256) boot_gather_kernel(const double *__restrict__ x, BinParams bp, uint32_t region,
+                                                          const uint32_t *__restrict__ queues,
+                                                          const unsigned int *__restrict__ tails,
+                                                          double *__restrict__ sums) {
+    const uint64_t gq = (uint64_t)blockIdx.y * bp.n_regions + region;
+    uint64_t cnt = tails[gq];
+    if (cnt > bp.cap) cnt = bp.cap;
+    const uint32_t *seg = queues + gq * bp.cap;
+    const double *xr = x + ((uint64_t)region << bp.region_shift);
+    double acc = 0.0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 7 * stride < cnt; i += 8 * stride) {  // 8 independent gathers in flight
+        uint32_t e[8];
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) e[k] = __ldcs(&seg[i + k * stride]);  // streamed once: evict-first
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = __ldcg(&xr[e[k]]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc += v[k];
+    }
+    for (; i < cnt; i += stride) acc += __ldcg(&xr[__ldcs(&seg[i])]);
+    __shared__ double sh[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w2 = 0; w2 < 8; w2++) t += sh[w2];
+        if (cnt) atomicAdd(&sums[bp.b_first + blockIdx.y], t);
+    }
+}
+
 __global__ void boot_finalize_kernel(double *__restrict__ sums, int64_t B, double n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B) sums[i] = __ddiv_rn(sums[i], n);
@@ -1050,6 +1213,113 @@ int mcf_bootstrap_accumulate(uint32_t gen_kind, const mcf_stream *d_stream, cons
             counts, bbase, d_sums, (unsigned long long *)d_end_slot);
     MCF_CUDA_OK(cudaGetLastError());
     return MCF_OK;
+}
+
+// Binned variant of mcf_bootstrap_accumulate for populations that do not fit L2 (see boot_bin_kernel).
+// h_block_base: HOST copy of the per-CTA ordinal prefix (mcf_bootstrap_block_base copies it out after the count pass).
+// region_shift: log2(elements per region), 0 = choose (2^23 elements = 64 MB, at most 16 regions).
+int64_t mcf_bootstrap_blocks(int64_t n_slots, int32_t chunk_slots) {
+    if (n_slots <= 0 || chunk_slots < 8) return MCF_ERR_BAD_ARG;
+    return boot_geom(n_slots, chunk_slots).n_blocks;
+}
+
+int mcf_bootstrap_block_base(const void *d_workspace, int64_t n_slots, int32_t chunk_slots, uint64_t *h_block_base,
+                             void *cuda_stream) {
+    if (!d_workspace || !h_block_base || n_slots <= 0 || chunk_slots < 8) return MCF_ERR_BAD_ARG;
+    const BootGeom g = boot_geom(n_slots, chunk_slots);
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    MCF_CUDA_OK(cudaMemcpyAsync(h_block_base, (const char *)d_workspace + g.off_bbase, (size_t)g.n_blocks * 8,
+                                cudaMemcpyDeviceToHost, cs));
+    MCF_CUDA_OK(cudaStreamSynchronize(cs));
+    return MCF_OK;
+}
+
+static inline uint32_t bin_region_shift(int64_t n, int32_t requested) {
+    if (requested > 0) return (uint32_t)requested;
+    uint32_t s = 23;
+    while (((n + (1LL << s) - 1) >> s) > BIN_MAX_REGIONS) s++;
+    return s;
+}
+
+int64_t mcf_bootstrap_binned_workspace_bytes(int64_t n, int32_t resamples_per_batch, int32_t region_shift) {
+    if (n < 2 || resamples_per_batch < 1) return MCF_ERR_BAD_ARG;
+    const uint32_t sh = bin_region_shift(n, region_shift);
+    const int64_t R = (n + (1LL << sh) - 1) >> sh;
+    if (R > BIN_MAX_REGIONS) return MCF_ERR_BAD_ARG;
+    const int64_t region_len = 1LL << sh;
+    const int64_t cap = region_len + 8 * (int64_t)sqrt((double)region_len) + 4096;
+    const int64_t window = resamples_per_batch + 2;
+    return align256(window * R * cap * 4) + align256(window * R * 4) + 256;
+}
+
+int mcf_bootstrap_accumulate_binned(uint32_t gen_kind, const mcf_stream *d_stream, const double *d_x, int64_t n,
+                                    int64_t n_resamples, uint64_t slot_lo, uint64_t slot_hi, int32_t chunk_slots,
+                                    uint64_t ordinal_base, const void *d_workspace, int64_t workspace_bytes,
+                                    const uint64_t *h_block_base, int32_t resamples_per_batch, int32_t region_shift,
+                                    void *d_bin_workspace, int64_t bin_workspace_bytes, double *d_sums,
+                                    uint64_t *d_end_slot, void *cuda_stream) {
+    if (!d_stream || !d_x || n < 2 || n > 0xFFFFFFFFLL || n_resamples <= 0 || slot_hi <= slot_lo || chunk_slots < 8 ||
+        (chunk_slots % 8) || !d_workspace || !h_block_base || resamples_per_batch < 1 || !d_bin_workspace || !d_sums ||
+        !d_end_slot || (int64_t)BOOT_THREADS * chunk_slots > n)
+        return MCF_ERR_BAD_ARG;
+    const BootGeom g = boot_geom((int64_t)(slot_hi - slot_lo), chunk_slots);
+    if (workspace_bytes < g.total) return MCF_ERR_WORKSPACE_TOO_SMALL;
+    if (bin_workspace_bytes < mcf_bootstrap_binned_workspace_bytes(n, resamples_per_batch, region_shift))
+        return MCF_ERR_WORKSPACE_TOO_SMALL;
+    const uint32_t sh = bin_region_shift(n, region_shift);
+    const int64_t R = (n + (1LL << sh) - 1) >> sh;
+    const int64_t region_len = 1LL << sh;
+    const int64_t cap = region_len + 8 * (int64_t)sqrt((double)region_len) + 4096;
+    const int64_t window = resamples_per_batch + 2;
+    char *bws = (char *)d_bin_workspace;
+    uint32_t *queues = (uint32_t *)bws;
+    unsigned int *tails = (unsigned int *)(bws + align256(window * R * cap * 4));
+    int *overflow = (int *)(bws + align256(window * R * cap * 4) + align256(window * R * 4));
+    const char *ws = (const char *)d_workspace;
+    const uint32_t *counts = (const uint32_t *)(ws + g.off_counts);
+    const unsigned long long *bbase = (const unsigned long long *)(ws + g.off_bbase);
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    MCF_CUDA_OK(cudaMemsetAsync(overflow, 0, 4, cs));
+    const uint64_t total_needed = (uint64_t)n_resamples * (uint64_t)n;
+    // batches = runs of CTAs whose slots start inside `resamples_per_batch` consecutive resamples
+    int64_t blk = 0;
+    while (blk < g.n_blocks) {
+        const uint64_t ord0 = ordinal_base + h_block_base[blk];
+        if (ord0 >= total_needed) break;
+        const uint64_t b_first = ord0 / (uint64_t)n;
+        int64_t end = blk + 1;
+        while (end < g.n_blocks && (ordinal_base + h_block_base[end]) / (uint64_t)n < b_first + (uint64_t)resamples_per_batch &&
+               ordinal_base + h_block_base[end] < total_needed)
+            end++;
+        BinParams bp;
+        bp.n = (uint32_t)n;
+        bp.region_shift = sh;
+        bp.n_regions = (uint32_t)R;
+        bp.n_res_window = (uint32_t)window;
+        bp.b_first = b_first;
+        bp.cap = (uint64_t)cap;
+        bp.n_resamples = (uint64_t)n_resamples;
+        MCF_CUDA_OK(cudaMemsetAsync(tails, 0, (size_t)(window * R * 4), cs));
+        if (gen_kind == MCF_GEN_PCG64)
+            boot_bin_kernel<MCF_GEN_PCG64><<<(unsigned)(end - blk), BOOT_THREADS, 0, cs>>>(
+                d_stream, bp, slot_lo, slot_hi, chunk_slots, g.n_chunks, blk, ordinal_base, counts, bbase, queues, tails,
+                (unsigned long long *)d_end_slot, overflow);
+        else
+            boot_bin_kernel<MCF_GEN_PHILOX><<<(unsigned)(end - blk), BOOT_THREADS, 0, cs>>>(
+                d_stream, bp, slot_lo, slot_hi, chunk_slots, g.n_chunks, blk, ordinal_base, counts, bbase, queues, tails,
+                (unsigned long long *)d_end_slot, overflow);
+        MCF_CUDA_OK(cudaGetLastError());
+        for (uint32_t r = 0; r < (uint32_t)R; r++) {
+            dim3 grid(64, (unsigned)window);
+            boot_gather_kernel<<<grid, 256, 0, cs>>>(d_x, bp, r, queues, tails, d_sums);
+        }
+        MCF_CUDA_OK(cudaGetLastError());
+        blk = end;
+    }
+    int h_over = 0;
+    MCF_CUDA_OK(cudaMemcpyAsync(&h_over, overflow, 4, cudaMemcpyDeviceToHost, cs));
+    MCF_CUDA_OK(cudaStreamSynchronize(cs));
+    return h_over ? MCF_ERR_WINDOW_TOO_SMALL : MCF_OK;
 }
 
 int mcf_bootstrap_finalize(double *d_sums, int64_t n_resamples, int64_t n, void *cuda_stream) {

@@ -320,3 +320,18 @@ def test_path_slices_are_strided_paths(dev):
     term = D.gbm_terminal(dl, 48, plan, [(N.PORTFOLIO_GBM, [1e4, 0.07, 0.2])])[0].cpu().numpy()
     assert np.all(pf[0] == 1e4)
     np.testing.assert_allclose(pf[1], term, rtol=FP_RTOL)  # strictly sequential sum vs chunk sums
+
+
+@pytest.mark.parametrize("n,B,shift,cs", [(50_000, 40, 12, 64), (120_000, 25, 13, 256), (3_000_000, 6, 18, 1024)])
+def test_bootstrap_binned_path_is_the_same_index_stream(sd, n, B, shift, cs):
+    """The binned gather (queues per resample and per region of x, regions summed one after the other) draws the
+    very same indices: integer-valued data give exact sums, the generator ends in NumPy's state."""
+    xi = np.random.default_rng(2).integers(0, 1 << 20, n).astype(float)
+    g_ref, g_dev, g_dev2 = (np.random.default_rng(5) for _ in range(3))
+    want = np.stack([xi[g_ref.integers(0, n, size=n)].sum() for _ in range(B)])
+    got = sd.bootstrap_means(_dev_tensor(xi), B, g_dev, binned=True, region_shift=shift, chunk_slots=cs,
+                             resamples_per_batch=7).cpu().numpy() * n
+    assert np.array_equal(np.rint(got), want)
+    assert g_dev.bit_generator.state == g_ref.bit_generator.state
+    plain = sd.bootstrap_means(_dev_tensor(xi), B, g_dev2, binned=False, chunk_slots=cs).cpu().numpy() * n
+    assert np.array_equal(np.rint(plain), want)
