@@ -215,12 +215,16 @@ BINNED_MIN_N = 12_000_000
 
 def bootstrap_means(x, n_resamples: int, gen: np.random.Generator, group=None, advance: bool = True,
                     chunk_slots: int | None = None, binned: bool | None = None, region_shift: int = 0,
-                    resamples_per_batch: int = 16):
+                    resamples_per_batch: int = 32):
     """``x[rng.integers(0, n, size=(B, n))].mean(axis=1)`` (stats_engine.py:1039-1041) without the index
     matrix: float64[B] device tensor.  ``gen`` is advanced exactly as NumPy would have advanced it.
 
     With ``group`` the slot range of the stream is sharded across ranks (every rank holds all of ``x``);
-    two small collectives combine the result (all-gather of accepted counts, all-reduce of B sums)."""
+    two small collectives combine the result (all-gather of accepted counts, all-reduce of B sums).
+
+    Populations larger than L2 (``binned``; default from ``BINNED_MIN_N``) first queue the indices per (resample,
+    64 MB region of ``x``) and then sum region by region: a random gather from an L2-resident region is 3-4x faster
+    than one from HBM, where every 8-byte gather moves a 128-byte line."""
     torch = _torch()
     lib = N.lib()
     n, B = int(x.numel()), int(n_resamples)
