@@ -207,29 +207,57 @@ __global__ void __launch_bounds__(256) plan_entries_kernel(int64_t cps, int64_t 
                                                            int64_t q_cap, int *hdr) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t id0 = g * 16;
-    if (id0 >= n_chunks) return;
-    const uint4 ex4 = *reinterpret_cast<const uint4 *>(exit_ + id0);
-    const uint4 gn4 = *reinterpret_cast<const uint4 *>(gen + id0);
-    const uint8_t prev = (id0 % cps) == 0 ? (uint8_t)0 : exit_[id0 - 1];
-    const uint32_t exw[4] = {ex4.x, ex4.y, ex4.z, ex4.w}, gnw[4] = {gn4.x, gn4.y, gn4.z, gn4.w};
-    uint32_t enw[4];
-    uint32_t carry = prev;  // exit of the chunk before the current one
+    const bool live = id0 < n_chunks;
+    uint32_t diffw[4] = {0u, 0u, 0u, 0u};
+    int mine = 0;
+    if (live) {
+        const uint4 ex4 = *reinterpret_cast<const uint4 *>(exit_ + id0);
+        const uint4 gn4 = *reinterpret_cast<const uint4 *>(gen + id0);
+        const uint8_t prev = (id0 % cps) == 0 ? (uint8_t)0 : exit_[id0 - 1];
+        const uint32_t exw[4] = {ex4.x, ex4.y, ex4.z, ex4.w}, gnw[4] = {gn4.x, gn4.y, gn4.z, gn4.w};
+        uint32_t enw[4];
+        uint32_t carry = prev;  // exit of the chunk before the current one
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            enw[w] = (exw[w] << 8) | carry;  // entry bytes of this word = exit bytes shifted by one chunk
+            carry = exw[w] >> 24;
+            // Re-walk whenever the true entry differs from the one the chunk was generated with.  (The masks alone
+            // would stay usable when the entry happens to be an attempt start of the speculative walk -- chains
+            // coincide from there -- but the stored sums must not contain the attempts started before it.)
+            const uint32_t d = enw[w] ^ gnw[w];
+            // one flag bit per differing byte (bit 8*k)
+            diffw[w] = ((d | (d >> 1) | (d >> 2) | (d >> 3) | (d >> 4) | (d >> 5) | (d >> 6) | (d >> 7)) & 0x01010101u);
+            mine += __popc(diffw[w]);
+        }
+        *reinterpret_cast<uint4 *>(entry_true + id0) = make_uint4(enw[0], enw[1], enw[2], enw[3]);
+    }
+    // one atomic per warp: exclusive scan of the per-thread counts
+    const int lane = threadIdx.x & 31;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    int base = 0;
+    if (lane == 31) base = atomicAdd(reinterpret_cast<int *>(reinterpret_cast<char *>(hdr) + MCF_QCOUNT_OFFSET), total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    int k = base + incl - mine;
 #pragma unroll
     for (int w = 0; w < 4; w++) {
-        // entry bytes of this word = exit bytes shifted by one chunk
-        enw[w] = (exw[w] << 8) | carry;
-        carry = exw[w] >> 24;
-        uint32_t diff = enw[w] ^ gnw[w];
-        // Re-walk whenever the true entry differs from the one the chunk was generated with.  (The masks alone would
-        // stay usable when the entry happens to be an attempt start of the speculative walk -- chains coincide from
-        // there -- but the stored sums must not contain the attempts the speculative walk started before it.)
-        while (diff) {
-            const int byte = (__ffs(diff) - 1) >> 3;
-            plan_enqueue(id0 + w * 4 + byte, queue, q_cap, hdr, 0);
-            diff &= ~(0xFFu << (byte * 8));
+        uint32_t d = diffw[w];
+        while (d) {
+            const int byte = (__ffs(d) - 1) >> 3;
+            if (k < q_cap)
+                queue[k] = id0 + w * 4 + byte;
+            else
+                atomicExch(&hdr[0], MCF_ERR_NOT_CONVERGED);  // queue overflow: the caller re-plans
+            k++;
+            d &= d - 1;
         }
     }
-    *reinterpret_cast<uint4 *>(entry_true + id0) = make_uint4(enw[0], enw[1], enw[2], enw[3]);
 }
 
 // Later rounds: only the successors of the chunks re-walked in the previous round can have a new entry.

@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--paths", type=float, default=1e7)
     ap.add_argument("--steps", type=int, default=252)
     ap.add_argument("--cmd", default="python bench.py")
+    ap.add_argument("--streams", type=int, default=64, help="plan scan = one launch per stream; captured launches are scaled")
     a = ap.parse_args()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out_dir = os.path.join(root, "profiles")
@@ -77,17 +78,30 @@ def main():
             kernels.append(rec)
         units_total = a.paths * a.steps
         inst = {"source": f"profiles/{a.tag}_kernels.json (ncu --set full, {a.cmd} --paths {a.paths:g})", "paths": a.paths, "steps": a.steps}
+        # the plan scan is one launch per stream: merge each run of consecutive launches of the same kernel
+        runs = []
         for rec in kernels:
-            name = rec["kernel"]
-            wi = rec.get("smsp__inst_executed.sum")
-            traffic = rec.get("dram__bytes_read.sum", 0) + rec.get("dram__bytes_write.sum", 0)
-            if wi and "plan_scan" in name:
-                inst["plan_warp_inst_per_path_step"] = wi / units_total
-                inst["plan_dram_bytes_per_path_step"] = traffic / units_total
+            if runs and runs[-1]["kernel"] == rec["kernel"] and "plan_scan" in rec["kernel"]:
+                run = runs[-1]
+                run["launches"] += 1
+                for k in ("gpu__time_duration.sum", "smsp__inst_executed.sum", "dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    run[k] = run.get(k, 0) + rec.get(k, 0)
+            else:
+                runs.append(dict(rec, launches=1))
+        for run in runs:
+            name = run["kernel"]
+            wi = run.get("smsp__inst_executed.sum")
+            traffic = run.get("dram__bytes_read.sum", 0) + run.get("dram__bytes_write.sum", 0)
+            if wi and "plan_scan" in name and "plan_warp_inst_per_path_step" not in inst:
+                # `launches` of the a.streams equally sized per-stream launches were captured
+                frac = run["launches"] / a.streams if "philox_stream" in name else 1.0
+                inst["plan_warp_inst_per_path_step"] = wi / (units_total * frac)
+                inst["plan_dram_bytes_per_path_step"] = traffic / (units_total * frac)
+                inst["plan_scan_launches_captured"] = run["launches"]
             if wi and "gbm_terminal" in name:
-                key = "replay8" if rec.get("dram__bytes_write.sum", 0) > 3 * a.paths * 8 else "replay1"
-                inst[key + "_warp_inst_per_path_step"] = wi / units_total
-                inst[key + "_dram_bytes_per_path_step"] = traffic / units_total
+                key = "replay8" if run.get("dram__bytes_write.sum", 0) > 3 * a.paths * 8 else "replay1"
+                inst.setdefault(key + "_warp_inst_per_path_step", wi / units_total)
+                inst.setdefault(key + "_dram_bytes_per_path_step", traffic / units_total)
         json.dump(kernels, open(os.path.join(out_dir, f"{a.tag}_kernels.json"), "w"), indent=1)
         json.dump(inst, open(os.path.join(out_dir, "inst_per_unit.json"), "w"), indent=1)
         print(json.dumps(inst, indent=1))
