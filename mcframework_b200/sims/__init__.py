@@ -1,17 +1,19 @@
-"""Built-in simulations (same exports as the reference's ``mcframework/sims/__init__.py:5-23``)."""
+"""Built-in simulations; the same public names as the reference's ``mcframework/sims/__init__.py:5-23``."""
 from __future__ import annotations
 
-from .black_scholes import (BlackScholesPathSimulation, BlackScholesSimulation, _american_exercise_lsm,
-                            _european_payoff, _simulate_gbm_path)
-from .pi import PiEstimationSimulation
-from .portfolio import PortfolioSimulation
+from . import black_scholes as _bs
+from . import pi as _pi
+from . import portfolio as _pf
 
-__all__ = [
-    "PiEstimationSimulation",
-    "PortfolioSimulation",
-    "BlackScholesSimulation",
-    "BlackScholesPathSimulation",
-    "_european_payoff",
-    "_simulate_gbm_path",
-    "_american_exercise_lsm",
-]
+PiEstimationSimulation = _pi.PiEstimationSimulation
+PortfolioSimulation = _pf.PortfolioSimulation
+BlackScholesSimulation = _bs.BlackScholesSimulation
+BlackScholesPathSimulation = _bs.BlackScholesPathSimulation
+# module-level helpers the reference also exports (leading underscore kept for drop-in imports)
+_european_payoff = _bs._european_payoff
+_simulate_gbm_path = _bs._simulate_gbm_path
+_american_exercise_lsm = _bs._american_exercise_lsm
+
+__all__ = sorted(
+    ["PiEstimationSimulation", "PortfolioSimulation", "BlackScholesSimulation", "BlackScholesPathSimulation",
+     "_european_payoff", "_simulate_gbm_path", "_american_exercise_lsm"], key=lambda s: (s.startswith("_"), s))
