@@ -107,3 +107,29 @@ def test_unreseeded_runs_continue_streams(m):
     for n, par in ((300, False), (20_000, True), (150, False), (20_000, True)):
         got = bs.run(n, parallel=par, n_workers=4, n_steps=11, compute_stats=False).results
         np.testing.assert_allclose(got, port.run(n, parallel=par, n_workers=4, n_steps=11), rtol=RTOL, atol=ATOL)
+
+
+def test_percentile_merging_and_metadata(m):
+    """User percentiles merged over the engine defaults (core.py:452-484 of the reference), with and without stats."""
+    sim = m.PiEstimationSimulation()
+    sim.set_seed(3)
+    r = sim.run(2000, n_points=200, percentiles=[10, 90, 50])
+    assert set(r.percentiles) == {5, 25, 50, 75, 95, 10, 90}
+    for p, v in r.percentiles.items():
+        assert v == np.percentile(r.results, p)
+    assert r.metadata["requested_percentiles"] == [10, 90, 50] and r.metadata["engine_defaults_used"] is True
+    sim.set_seed(3)
+    r2 = sim.run(2000, n_points=200, percentiles=[10, 90], compute_stats=False)
+    assert set(r2.percentiles) == {10, 90} and r2.stats == {} and r2.metadata["engine_defaults_used"] is False
+    assert np.array_equal(r.results, r2.results)
+    sim.set_seed(3)
+    r3 = sim.run(2000, n_points=200, compute_stats=False)
+    assert r3.percentiles == {} and r3.mean == pytest.approx(r.results.mean(), rel=1e-14)
+    fw = m.MonteCarloFramework()
+    fw.register_simulation(sim, "pi")
+    fw.results["pi"] = r
+    assert fw.compare_results(["pi"], "p90") == {"pi": r.percentiles[90]}
+    with pytest.raises(ValueError, match="Percentile 25 not computed"):
+        fw.compare_results(["pi"], "p25")  # engine default, but not among the REQUESTED ones
+    text = r.result_to_string()
+    assert "Results for simulation 'Pi Estimation':" in text and "Number of simulations: 2000" in text
