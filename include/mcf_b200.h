@@ -87,8 +87,11 @@ int mcf_last_cuda_error(void);    /* cudaError_t behind the last MCF_ERR_CUDA */
  * (sims/pi.py:69-82; core.py:593-594,661-662).
  * d_hits[i]  : points with x*x+y*y<=1 of replication i (bit-exact integer)
  * d_out[i]   : 4.0*hits/n_points (what single_simulation returns); may be NULL */
-int mcf_pi_hits(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total, int64_t n_points,
-                int32_t antithetic, int64_t sims_per_stream_hint, int64_t *d_hits, double *d_out, void *cuda_stream);
+/* h_streams: optional HOST copy of the records (may be NULL); with it block-aligned Philox streams get one launch per
+ * stream with launch-constant round keys. */
+int mcf_pi_hits(uint32_t gen_kind, const mcf_stream *d_streams, const mcf_stream *h_streams, int32_t n_streams,
+                int64_t n_total, int64_t n_points, int32_t antithetic, int64_t sims_per_stream_hint, int64_t *d_hits,
+                double *d_out, void *cuda_stream);
 
 /* ---- (2) normal-consuming replications -------------------------------------------------
  * Step A, mcf_normal_plan: locate, for every replication, the position in its reference

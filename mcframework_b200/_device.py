@@ -56,10 +56,11 @@ def pi_hits(dl: DeviceLayout, n_points: int, antithetic: bool = False):
     lay = dl.layout
     hits = torch.empty(lay.n_total, dtype=torch.int64, device="cuda")
     out = torch.empty(lay.n_total, dtype=torch.float64, device="cuda")
-    rc = N.lib().mcf_pi_hits(lay.kind, _ptr(dl.records), lay.n_streams, lay.n_total, int(n_points), int(bool(antithetic)),
-                             lay.hint, _ptr(hits), _ptr(out), _stream_ptr())
+    host_records = np.ascontiguousarray(lay.records)
+    rc = N.lib().mcf_pi_hits(lay.kind, _ptr(dl.records), host_records.ctypes.data_as(C.c_void_p), lay.n_streams, lay.n_total,
+                             int(n_points), int(bool(antithetic)), lay.hint, _ptr(hits), _ptr(out), _stream_ptr())
     N.check("mcf_pi_hits", rc)
-    LAUNCHES["pi"] += 2
+    LAUNCHES["pi"] += 1 + (lay.n_streams if lay.kind == 1 and lay.n_streams <= 1024 else 1)
     return hits, out
 
 

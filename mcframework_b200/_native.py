@@ -46,7 +46,7 @@ SIGNATURES = {
     "mcf_abi_version": (C.c_int, []),
     "mcf_build_info": (C.c_char_p, []),
     "mcf_last_cuda_error": (C.c_int, []),
-    "mcf_pi_hits": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i32, _i64, _vp, _vp, _vp]),
+    "mcf_pi_hits": (C.c_int, [_u32, _vp, _vp, _i32, _i64, _i64, _i32, _i64, _vp, _vp, _vp]),
     "mcf_normal_plan_workspace_bytes": (_i64, [_i32, _i64, _i64, _f64]),
     "mcf_normal_plan": (C.c_int, [_u32, _vp, _vp, _i32, _i64, _i64, _i64, _f64, _i32, _vp, _i64, _vp, _vp, _vp]),
     "mcf_workspace_status": (C.c_int, [_vp, _vp]),

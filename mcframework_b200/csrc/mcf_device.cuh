@@ -527,6 +527,34 @@ MCF_HD int64_t pi_count_hits(Cur &cur, int64_t npts) {
     return hits;
 }
 
+// Block form for block-aligned Philox streams whose lanes start on block boundaries: two points per Philox block,
+// no per-draw bookkeeping.  One coordinate costs 2 exact integer->double conversions and 2 FMAs:
+//   x = -1 + 2*((v >> 11) * 2^-53) = fma(k, 2^-52, -1) with k = v >> 11 exact in a double (one rounding, the same one).
+MCF_HD double pi_coord(uint64_t v) {
+    const uint64_t k = v >> 11;  // < 2^53
+    const double kd = fma(u52_to_double(k >> 32), 4294967296.0, u52_to_double(k & 0xFFFFFFFFULL));  // exact
+    return fma(kd, 1.0 / 4503599627370496.0, -1.0);
+}
+MCF_HD int pi_inside(uint64_t vx, uint64_t vy) {
+    const double x = pi_coord(vx), y = pi_coord(vy);
+    return (xadd(xmul(x, x), xmul(y, y)) <= 1.0) ? 1 : 0;
+}
+// hits among `npts` points whose first draw is the first draw of block `blk0`
+template <class Load>
+MCF_HD int64_t pi_count_hits_blocks(Load load, uint64_t blk0, int64_t npts) {
+    int64_t hits = 0;
+    uint64_t blk = blk0, a, b, c, d;
+    for (; npts >= 2; npts -= 2, blk++) {
+        load(blk, a, b, c, d);
+        hits += pi_inside(a, b) + pi_inside(c, d);
+    }
+    if (npts > 0) {
+        load(blk, a, b, c, d);
+        hits += pi_inside(a, b);
+    }
+    return hits;
+}
+
 // ---------------------------------------------------------------------------------------
 // Planning pass over a stream window.  A chunk is 64 consecutive draw positions.
 //   startmask bit j : a ziggurat attempt starts at chunk_base + j

@@ -90,6 +90,37 @@ __global__ void __launch_bounds__(256) pi_kernel(const mcf_stream *__restrict__ 
     }
 }
 
+// One launch per block-aligned Philox stream (round keys = launch constants), lanes on Philox block boundaries:
+// requires draws_per_sim % 4 == 0 (ppt is even by construction).
+__global__ void __launch_bounds__(256) pi_philox_stream_kernel(const __grid_constant__ PhiloxKeys K, int64_t first_sim,
+                                                               int64_t n_sims, int64_t m, int64_t draws_per_sim, int64_t ppt,
+                                                               int64_t parts, int weight, int extra_point,
+                                                               unsigned long long *__restrict__ hits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_units = n_sims * parts;
+    auto load = [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) { philox_block_keys(K, blk, a, b, c, d); };
+    for (int64_t unit = warp0; unit < n_units; unit += n_warps) {
+        const int64_t sim = unit / parts, part = unit - sim * parts;
+        const uint64_t base = K.off + (uint64_t)sim * (uint64_t)draws_per_sim;  // multiple of 4
+        const int64_t p0 = (part * 32 + lane) * ppt;
+        int64_t cnt = m - p0;
+        cnt = cnt < 0 ? 0 : (cnt > ppt ? ppt : cnt);
+        int64_t h = 0;
+        if (cnt > 0) h = pi_count_hits_blocks(load, (base + 2ULL * (uint64_t)p0) >> 2, cnt) * weight;
+        if (extra_point && part == 0 && lane == 0) {  // odd n_points with antithetic pairs (sims/pi.py:79-80)
+            const uint64_t q = base + 2ULL * (uint64_t)m;  // even; the point is (v0, v1) or (v2, v3) of its block
+            uint64_t a, b, c, d;
+            load(q >> 2, a, b, c, d);
+            h += (q & 2ULL) ? pi_inside(c, d) : pi_inside(a, b);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+        if (lane == 0) atomicAdd(&hits[first_sim + sim], (unsigned long long)h);
+    }
+}
+
 __global__ void pi_finalize_kernel(const unsigned long long *__restrict__ hits, int64_t n_total, double n_points,
                                    double *__restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -653,8 +684,9 @@ const char *mcf_build_info(void) {
 
 int mcf_last_cuda_error(void) { return g_last_cuda_error; }
 
-int mcf_pi_hits(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total, int64_t n_points,
-                  int32_t antithetic, int64_t sims_per_stream_hint, int64_t *d_hits, double *d_out, void *cuda_stream) {
+int mcf_pi_hits(uint32_t gen_kind, const mcf_stream *d_streams, const mcf_stream *h_streams, int32_t n_streams,
+                  int64_t n_total, int64_t n_points, int32_t antithetic, int64_t sims_per_stream_hint, int64_t *d_hits,
+                  double *d_out, void *cuda_stream) {
     if (!d_streams || n_streams <= 0 || n_total <= 0 || n_points <= 0 || !d_hits) return MCF_ERR_BAD_ARG;
     cudaStream_t cs = (cudaStream_t)cuda_stream;
     const PiGeom pg = pi_geom(n_points, antithetic);
@@ -663,7 +695,19 @@ int mcf_pi_hits(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_stream
     int64_t blocks = (n_units + 7) / 8;  // 8 warps per CTA
     const int64_t max_blocks = 148LL * 8 * 64;
     if (blocks > max_blocks) blocks = max_blocks;
-    if (gen_kind == MCF_GEN_PCG64)
+    bool per_stream = gen_kind == MCF_GEN_PHILOX && h_streams != nullptr && n_streams <= 1024 && (pg.draws_per_sim % 4) == 0;
+    for (int si = 0; per_stream && si < n_streams; si++) per_stream = (h_streams[si].buf_pos & 3u) == 0;
+    if (per_stream) {
+        for (int si = 0; si < n_streams; si++) {
+            const PhiloxKeys K = philox_keys_of(h_streams[si]);
+            int64_t b = (h_streams[si].n_sims * pg.parts + 7) / 8;
+            if (b > max_blocks) b = max_blocks;
+            if (b < 1) continue;
+            pi_philox_stream_kernel<<<(unsigned)b, 256, 0, cs>>>(K, h_streams[si].first_sim, h_streams[si].n_sims, pg.m,
+                                                                 pg.draws_per_sim, pg.ppt, pg.parts, pg.weight, pg.extra,
+                                                                 (unsigned long long *)d_hits);
+        }
+    } else if (gen_kind == MCF_GEN_PCG64)
         pi_kernel<MCF_GEN_PCG64><<<(unsigned)blocks, 256, 0, cs>>>(
             d_streams, n_streams, n_total, pg.m, pg.draws_per_sim, pg.ppt, pg.parts, pg.weight, pg.extra,
             sims_per_stream_hint, (unsigned long long *)d_hits);

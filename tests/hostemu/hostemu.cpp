@@ -58,6 +58,26 @@ static void pi_impl(const mcf_stream *streams, int n_streams, int64_t n_total, i
         const int64_t sim = unit / pg.parts, part = unit - sim * pg.parts;
         const mcf_stream st = streams[stream_of(streams, n_streams, sim, hint)];
         const uint64_t base = (uint64_t)(sim - st.first_sim) * (uint64_t)pg.draws_per_sim;
+        if (KIND == MCF_GEN_PHILOX && (st.buf_pos & 3u) == 0 && (pg.draws_per_sim % 4) == 0) {  // as pi_philox_stream_kernel
+            const PhiloxKeys K = philox_keys_of(st);
+            auto load = [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) { philox_block_keys(K, blk, a, b, c, d); };
+            const uint64_t qbase = K.off + base;
+            for (int lane = 0; lane < 32; lane++) {
+                const int64_t p0 = (part * 32 + lane) * pg.ppt;
+                int64_t cnt = pg.m - p0;
+                cnt = cnt < 0 ? 0 : (cnt > pg.ppt ? pg.ppt : cnt);
+                int64_t h = 0;
+                if (cnt > 0) h = pi_count_hits_blocks(load, (qbase + 2ULL * (uint64_t)p0) >> 2, cnt) * pg.weight;
+                if (pg.extra && part == 0 && lane == 0) {
+                    const uint64_t q = qbase + 2ULL * (uint64_t)pg.m;
+                    uint64_t a, b, c, d;
+                    load(q >> 2, a, b, c, d);
+                    h += (q & 2ULL) ? pi_inside(c, d) : pi_inside(a, b);
+                }
+                hits[sim] += h;
+            }
+            continue;
+        }
         for (int lane = 0; lane < 32; lane++) {
             const int64_t p0 = (part * 32 + lane) * pg.ppt;
             int64_t cnt = pg.m - p0;
