@@ -509,13 +509,19 @@ MCF_HD int find_stream(const mcf_stream *streams, int n_streams, int64_t sim) {
 // ---------------------------------------------------------------------------------------
 // Pi: hits among `npts` consecutive points starting at the cursor (sims/pi.py:71-72)
 // ---------------------------------------------------------------------------------------
+// x = -1 + 2*((v >> 11) * 2^-53) = fma(k, 2^-52, -1) with k = v >> 11 exact in a double (one rounding, the same one)
+MCF_HD double pi_coord(uint64_t v) {
+    const uint64_t k = v >> 11;  // < 2^53
+    const double kd = fma(u52_to_double(k >> 32), 4294967296.0, u52_to_double(k & 0xFFFFFFFFULL));  // exact
+    return fma(kd, 1.0 / 4503599627370496.0, -1.0);
+}
 template <class Cur>
 MCF_HD int64_t pi_count_hits(Cur &cur, int64_t npts) {
     if (npts <= 0) return 0;
     int64_t hits = 0, left = 2 * npts;
     double x = 0.0;
     consume_draws(cur, [&](uint64_t r) {
-        const double c = xadd(-1.0, xmul(2.0, u64_to_unit_double(r)));
+        const double c = pi_coord(r);  // == -1 + 2*next_double, one rounding either way
         if (left & 1) {  // second coordinate of the point
             hits += (xadd(xmul(x, x), xmul(c, c)) <= 1.0) ? 1 : 0;
         } else {
@@ -530,11 +536,6 @@ MCF_HD int64_t pi_count_hits(Cur &cur, int64_t npts) {
 // Block form for block-aligned Philox streams whose lanes start on block boundaries: two points per Philox block,
 // no per-draw bookkeeping.  One coordinate costs 2 exact integer->double conversions and 2 FMAs:
 //   x = -1 + 2*((v >> 11) * 2^-53) = fma(k, 2^-52, -1) with k = v >> 11 exact in a double (one rounding, the same one).
-MCF_HD double pi_coord(uint64_t v) {
-    const uint64_t k = v >> 11;  // < 2^53
-    const double kd = fma(u52_to_double(k >> 32), 4294967296.0, u52_to_double(k & 0xFFFFFFFFULL));  // exact
-    return fma(kd, 1.0 / 4503599627370496.0, -1.0);
-}
 MCF_HD int pi_inside(uint64_t vx, uint64_t vy) {
     const double x = pi_coord(vx), y = pi_coord(vy);
     return (xadd(xmul(x, x), xmul(y, y)) <= 1.0) ? 1 : 0;
