@@ -404,7 +404,7 @@ struct SlotWalker {
     Cursor<KIND> cur;
     uint64_t v;
     uint32_t has, uinteger;
-    bool have_v;
+    bool have_v, aligned;
     __device__ __forceinline__ void init(const mcf_stream &st, uint64_t s0) {
         has = st.has_uint32 ? 1u : 0u;
         uinteger = st.uinteger;
@@ -412,6 +412,21 @@ struct SlotWalker {
         cur.init(st, t0 >> 1);
         have_v = false;
         v = 0;
+        aligned = has == 0 && (s0 & 1ULL) == 0;  // chunk lengths are multiples of 8: every group starts on a draw
+    }
+    // the 8 slots [sb, sb+8) -- four whole draws when the walker is aligned (no per-slot parity bookkeeping)
+    __device__ __forceinline__ void get8(uint64_t sb, uint32_t u[8]) {
+        if (aligned) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint64_t d = cur.next64();
+                u[2 * k] = (uint32_t)d;
+                u[2 * k + 1] = (uint32_t)(d >> 32);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) u[j] = get(sb + j);
+        }
     }
     __device__ __forceinline__ uint32_t get(uint64_t s) {
         if (has && s == 0) return uinteger;
@@ -442,9 +457,14 @@ __global__ void __launch_bounds__(BOOT_THREADS) boot_count_kernel(const mcf_stre
             const mcf_stream st = *stream;
             SlotWalker<KIND> w;
             w.init(st, s0);
-            for (uint64_t s = s0; s < s1; s++) {
-                uint32_t idx;
-                cnt += slot_accept(rule, w.get(s), idx) ? 1u : 0u;
+            for (uint64_t sb = s0; sb < s1; sb += 8) {
+                uint32_t u[8];
+                w.get8(sb, u);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    uint32_t idx;
+                    cnt += (sb + j < s1 && slot_accept(rule, u[j], idx)) ? 1u : 0u;
+                }
             }
         }
     }
@@ -541,15 +561,14 @@ __global__ void __launch_bounds__(BOOT_THREADS) boot_accumulate_kernel(
         w.init(st, s0);
         bool done = false;
         for (uint64_t sb = s0; sb < s1 && !done; sb += 8) {
-            uint32_t idx[8];
+            uint32_t idx[8], u[8];
             bool ok[8];
             double v[8];
+            w.get8(sb, u);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const uint64_t s = sb + j;
-                ok[j] = false;
                 idx[j] = 0;
-                if (s < s1) ok[j] = slot_accept(rule, w.get(s), idx[j]);
+                ok[j] = slot_accept(rule, u[j], idx[j]) && (sb + j < s1);
             }
 #pragma unroll
             // ld.global.cg: random 8-byte gathers must not drag whole 128-byte lines through L1 (measured: 113 B of DRAM
@@ -669,11 +688,13 @@ __global__ void __launch_bounds__(BOOT_THREADS) boot_bin_kernel(const mcf_stream
     for (int g = 0; g < groups; g++) {  // uniform trip count: the flushes below are CTA-wide
         const uint64_t sb = s0 + (uint64_t)g * 8;
         if (!done && sb < s1) {
+            uint32_t u[8];
+            w.get8(sb, u);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const uint64_t s = sb + j;
                 uint32_t idx;
-                if (s < s1 && !done && slot_accept(rule, w.get(s), idx)) {
+                if (s < s1 && !done && slot_accept(rule, u[j], idx)) {
                     if (ord == next_boundary) {
                         b++;
                         next_boundary += bp.n;
