@@ -192,6 +192,13 @@ struct PhiloxKeys {
     uint64_t rk[20];          // rk[2r], rk[2r+1]: keys of round r
     uint64_t b0, b1, b2, b3;  // base counter of the stream
     uint64_t off;             // buffer offset of the stream (buf_pos; multiple of 4 for the fast paths)
+    // Rounds 0 and 1 with the constant halves folded (see philox_block_folded): three of the four counter words of a
+    // stream never change, so one of the two multiplications of round 0 and of round 1 has launch-constant operands.
+    uint64_t f0_c2x;  // b3 ^ rk[1]:                              round-0 c2' = mulhi(M0, c0) ^ f0_c2x
+    uint64_t f1_c0x;  // M1*b2 ^ rk[2]:                           round-1 c0'' = mulhi(M1, c2') ^ f1_c0x
+    uint64_t f1_c2x;  // mulhi(M0, A0) ^ rk[3]:                   round-1 c2'' = c3' ^ f1_c2x
+    uint64_t f1_c3;   // M0 * A0,  A0 = mulhi(M1, b2) ^ b1 ^ rk[0]: round-1 c3''
+    uint32_t fold_ok;  // b0 + block never carries into b1 for any block this stream can reach
 };
 MCF_HD PhiloxKeys philox_keys_of(const mcf_stream &s) {
     PhiloxKeys K;
@@ -207,6 +214,12 @@ MCF_HD PhiloxKeys philox_keys_of(const mcf_stream &s) {
     K.b2 = s.s[4];
     K.b3 = s.s[5];
     K.off = (uint64_t)s.buf_pos;
+    const uint64_t A0 = mulhi64(MCF_PHILOX_M1, K.b2) ^ K.b1 ^ K.rk[0];
+    K.f0_c2x = K.b3 ^ K.rk[1];
+    K.f1_c0x = (MCF_PHILOX_M1 * K.b2) ^ K.rk[2];
+    K.f1_c2x = mulhi64(MCF_PHILOX_M0, A0) ^ K.rk[3];
+    K.f1_c3 = MCF_PHILOX_M0 * A0;
+    K.fold_ok = K.b0 < (1ULL << 62) ? 1u : 0u;  // block indices stay far below 2^62
     return K;
 }
 MCF_HD void philox_block_keys(const PhiloxKeys &K, uint64_t blk, uint64_t &o0, uint64_t &o1, uint64_t &o2, uint64_t &o3) {
@@ -217,6 +230,30 @@ MCF_HD void philox_block_keys(const PhiloxKeys &K, uint64_t blk, uint64_t &o0, u
     uint64_t c3 = K.b3;
 #pragma unroll
     for (int r = 0; r < 10; r++) {
+        const uint64_t hi0 = mulhi64(MCF_PHILOX_M0, c0), lo0 = MCF_PHILOX_M0 * c0;
+        const uint64_t hi1 = mulhi64(MCF_PHILOX_M1, c2), lo1 = MCF_PHILOX_M1 * c2;
+        c0 = hi1 ^ c1 ^ K.rk[2 * r];
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ K.rk[2 * r + 1];
+        c3 = lo0;
+    }
+    o0 = c0;
+    o1 = c1;
+    o2 = c2;
+    o3 = c3;
+}
+
+// Block `blk` of a stream whose low counter word never carries (K.fold_ok): 18 wide multiplications instead of 20.
+//   round 0: (x, b1, b2, b3)      -> (A0,              M1*b2,      mulhi(M0,x) ^ b3 ^ rk1, M0*x)     A0 constant
+//   round 1: (A0, M1*b2, c2, c3)  -> (mulhi(M1,c2) ^ M1*b2 ^ rk2, M1*c2, mulhi(M0,A0) ^ c3 ^ rk3, M0*A0)
+MCF_HD void philox_block_folded(const PhiloxKeys &K, uint64_t blk, uint64_t &o0, uint64_t &o1, uint64_t &o2, uint64_t &o3) {
+    const uint64_t x = K.b0 + blk;
+    uint64_t c2 = mulhi64(MCF_PHILOX_M0, x) ^ K.f0_c2x, c3 = MCF_PHILOX_M0 * x;  // round 0
+    uint64_t c0 = mulhi64(MCF_PHILOX_M1, c2) ^ K.f1_c0x, c1 = MCF_PHILOX_M1 * c2;  // round 1
+    c2 = c3 ^ K.f1_c2x;
+    c3 = K.f1_c3;
+#pragma unroll
+    for (int r = 2; r < 10; r++) {
         const uint64_t hi0 = mulhi64(MCF_PHILOX_M0, c0), lo0 = MCF_PHILOX_M0 * c0;
         const uint64_t hi1 = mulhi64(MCF_PHILOX_M1, c2), lo1 = MCF_PHILOX_M1 * c2;
         c0 = hi1 ^ c1 ^ K.rk[2 * r];
@@ -362,7 +399,7 @@ MCF_HD void consume_draws(Cursor<MCF_GEN_PHILOX> &cur, F f) {
 // ---------------------------------------------------------------------------------------
 // Ziggurat
 // ---------------------------------------------------------------------------------------
-struct ZigKW {  // ki and wi of one layer side by side: one 16-byte shared-memory load per draw in the fast walk
+struct ZigKW {  // ki and wi side by side: one 16-byte shared-memory load per draw in the fast walk
     uint64_t ki;
     double wi;
 };
@@ -370,8 +407,15 @@ struct ZigTables {
     const uint64_t *ki;
     const double *wi;
     const double *fi;
-    const ZigKW *kw;
+    // 512 entries indexed by the low 9 bits of a draw (layer, sign): {ki[layer] | 2^52-exponent bits, sign ? -wi : wi}.
+    // `rabs < ki` becomes a compare of the biased words and the signed normal is one add and one multiply.
+    const ZigKW *kws;
 };
+#define MCF_U52_BIAS 0x4330000000000000ULL
+MCF_HD void zig_fill_kws(ZigKW *kws, unsigned e, uint64_t ki, double wi) {
+    kws[e].ki = ki | MCF_U52_BIAS;
+    kws[e].wi = (e & 0x100u) ? -wi : wi;
+}
 #define MCF_ZIG_R 3.6541528853610088
 #define MCF_ZIG_INV_R 0.27366123732975828
 
@@ -618,112 +662,150 @@ MCF_HD ChunkInfo scan_chunk(Cur &cur, uint64_t chunk_base, uint32_t entry, const
 }
 
 // ---------------------------------------------------------------------------------------
-// Fast speculative walk of one chunk of a block-aligned Philox stream (entry offset 0).
-//
-// Same result as scan_chunk(cur, chunk_base, 0, ...), organised for SIMT:
-//   * one Philox block per loop trip for every lane, plus one block of look-ahead, so the draws an attempt may need
-//     (its own, the wedge uniform, the first tail pair) are always in registers;
-//   * the chain is a skip counter: a fast attempt takes 1 draw, a wedge attempt 2, a tail attempt 3 (first pair
-//     accepted); nothing else decides where the next attempt starts;
-//   * wedge acceptance only decides the EMIT bit, so the tests are parked (two slots) and evaluated once per
-//     16-draw sub-chunk instead of once per draw (a warp meets a wedge in 38 % of its draws);
-//   * whatever does not fit -- a tail whose first pair is rejected, a third wedge inside one sub-chunk -- marks the
-//     chunk invalid (`*valid = false`); the caller queues it for the dense, fully general re-walk.
-// Normals of wedge-accepted attempts are added to their sub-chunk sum after its fast ones (deterministic order).
-// ---------------------------------------------------------------------------------------
+// Speculative walk of one chunk of a block-aligned Philox stream (entry offset 0), branch-light form.
+// Same result as scan_chunk(cur, chunk_base, 0, ...) up to the summation order of the sub-chunk sums.
 // `load(blk, a, b, c, d)` yields the four draws of Philox block `blk` (relative to the stream's base counter);
-// `blk0` is the block holding the chunk's first draw.  Returns the chunk description; `*valid` as explained above.
+// `blk0` is the block holding the chunk's first draw; one block of look-ahead is always loaded.
+//
+// Phase 1 touches every draw once and has no dependence between draws: the draw is converted as if an attempt
+// started there (one 16-byte table load, one 64-bit compare, DADD + DMUL), its value is added to the sub-chunk sum
+// when it is "fast-looking" (rabs < ki), and a draw that is not (1.57 %) is parked in a per-thread slot together
+// with its two successors.  Phase 2 resolves the chain from the parked draws alone, in order:
+//   * a parked draw that an earlier attempt consumed is not a start -- drop it;
+//   * otherwise it starts a wedge attempt (consumes the next draw) or a tail attempt (the next two); the draws it
+//     consumes stop being starts, and where they were fast-looking their value leaves the sum again;
+//   * the acceptance test decides its emit bit and adds its normal.
+// Fast-looking draws that nobody consumed are exactly the fast attempts, so
+//     startmask = ~consumed,  emitmask = (fast-looking & ~consumed) | accepted.
+// More parked draws than slots (6e-4 of the chunks) or a tail whose first pair is rejected mark the chunk invalid
+// for the general re-walk, as before.  The sums differ from scan_chunk's by summation order only (deterministic).
+// ---------------------------------------------------------------------------------------
+#define MCF_PARK_CAP 5
+struct ParkSlots {  // slot k of this thread: a[k * stride], b[k * stride], c[k * stride]
+    uint64_t *a, *b, *c;
+    unsigned stride;
+};
+MCF_HD double zig_fast_value(uint64_t w, const ZigTables &t) {  // signed value of a fast-looking draw
+    const uint64_t dbits = ((w >> 9) & 0x000fffffffffffffULL) | MCF_U52_BIAS;
+    return xmul(xadd(bits_to_double(dbits), -4503599627370496.0), t.kws[(unsigned)w & 0x1ffu].wi);
+}
+
 template <class Load>
-MCF_HD ChunkInfo scan_chunk_fast(Load load, uint64_t blk0, const ZigTables &t, double *zsub_out, bool *valid) {
-    ChunkInfo ci;
-    ci.gen_entry = 0;
-    uint64_t sm = 0, em = 0;
-    bool ok = true;
-    unsigned skip = 0;
-    uint64_t w0, w1, w2, w3, w4, w5, w6, w7;
+MCF_HD ChunkInfo scan_chunk_fast2(Load load, uint64_t blk0, const ZigTables &t, const ParkSlots &park, double *zsub_out,
+                                  bool *valid) {
+    uint64_t F = 0;   // fast-looking draws
+    unsigned np = 0;  // parked draws
+    double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
+    uint64_t w0, w1, w2, w3, n0, n1, n2, n3;
     load(blk0, w0, w1, w2, w3);
+#define MCF_FAST2_DRAW(J, WA, WB, WC)                                                             \
+    {                                                                                             \
+        const uint64_t dbits = (((WA) >> 9) & 0x000fffffffffffffULL) | MCF_U52_BIAS;              \
+        const ZigKW kw = t.kws[(unsigned)(WA)&0x1ffu];                                            \
+        const double v = xmul(xadd(bits_to_double(dbits), -4503599627370496.0), kw.wi);           \
+        if (dbits < kw.ki) {                                                                      \
+            f16 |= 1u << (J);                                                                     \
+            zc = xadd(zc, v);                                                                     \
+        } else {                                                                                  \
+            if (np < MCF_PARK_CAP) {                                                              \
+                park.a[np * park.stride] = (WA);                                                  \
+                park.b[np * park.stride] = (WB);                                                  \
+                park.c[np * park.stride] = (WC);                                                  \
+            }                                                                                     \
+            np++;                                                                                 \
+        }                                                                                         \
+    }
 #pragma unroll 1
     for (unsigned sub = 0; sub < MCF_SUBS; sub++) {
         double zc = 0.0;
-        uint64_t ea0 = 0, eb0 = 0, ea1 = 0, eb1 = 0;  // parked wedge tests: (start draw, uniform draw)
-        unsigned ej0 = 0, ej1 = 0, nev = 0;
-#pragma unroll 1
-        for (unsigned half = 0; half < 2; half++) {
-            unsigned b = sub * 4 + half * 2;
-            unsigned snib = 0, enib = 0;
-#define MCF_FAST_DRAW(J, WA, WB, WC)                                                                   \
-    if (skip > 0) {                                                                                    \
-        skip--;                                                                                        \
-    } else {                                                                                           \
-        snib |= 1u << (J);                                                                             \
-        const unsigned idx = (unsigned)((WA)&0xffULL);                                                 \
-        const uint64_t rabs = ((WA) >> 9) & 0x000fffffffffffffULL;                                     \
-        const ZigKW kw = t.kw[idx];                                                                    \
-        if (rabs < kw.ki) {                                                                            \
-            enib |= 1u << (J);                                                                         \
-            const double v = xmul(u52_to_double(rabs), kw.wi);                                         \
-            zc = xadd(zc, (((WA) >> 8) & 1ULL) ? -v : v);                                              \
-        } else if (idx != 0) {                                                                         \
-            skip = 1;                                                                                  \
-            if (nev == 0) {                                                                            \
-                ea0 = (WA);                                                                            \
-                eb0 = (WB);                                                                            \
-                ej0 = b * 4 + ((J)&3);                                                                 \
-            } else if (nev == 1) {                                                                     \
-                ea1 = (WA);                                                                            \
-                eb1 = (WB);                                                                            \
-                ej1 = b * 4 + ((J)&3);                                                                 \
-            } else {                                                                                   \
-                ok = false;                                                                            \
-            }                                                                                          \
-            nev++;                                                                                     \
-        } else {                                                                                       \
-            skip = 2;                                                                                  \
-            const double xx = xmul(-MCF_ZIG_INV_R, log1p(-u64_to_unit_double(WB)));                    \
-            const double yy = -log1p(-u64_to_unit_double(WC));                                         \
-            if (xadd(yy, yy) > xmul(xx, xx)) {                                                         \
-                enib |= 1u << (J);                                                                     \
-                const double m = xadd(MCF_ZIG_R, xx);                                                  \
-                zc = xadd(zc, ((rabs >> 8) & 1ULL) ? -m : m);                                          \
-            } else {                                                                                   \
-                ok = false; /* longer tail: general re-walk */                                         \
-            }                                                                                          \
-        }                                                                                              \
+        unsigned f16 = 0;
+        const uint64_t b = blk0 + sub * 4;
+        // blocks b, b+2 live in w0..w3, blocks b+1, b+3 in n0..n3; the block after the current one is always loaded
+        load(b + 1, n0, n1, n2, n3);
+        MCF_FAST2_DRAW(0, w0, w1, w2)
+        MCF_FAST2_DRAW(1, w1, w2, w3)
+        MCF_FAST2_DRAW(2, w2, w3, n0)
+        MCF_FAST2_DRAW(3, w3, n0, n1)
+        load(b + 2, w0, w1, w2, w3);
+        MCF_FAST2_DRAW(4, n0, n1, n2)
+        MCF_FAST2_DRAW(5, n1, n2, n3)
+        MCF_FAST2_DRAW(6, n2, n3, w0)
+        MCF_FAST2_DRAW(7, n3, w0, w1)
+        load(b + 3, n0, n1, n2, n3);
+        MCF_FAST2_DRAW(8, w0, w1, w2)
+        MCF_FAST2_DRAW(9, w1, w2, w3)
+        MCF_FAST2_DRAW(10, w2, w3, n0)
+        MCF_FAST2_DRAW(11, w3, n0, n1)
+        load(b + 4, w0, w1, w2, w3);
+        MCF_FAST2_DRAW(12, n0, n1, n2)
+        MCF_FAST2_DRAW(13, n1, n2, n3)
+        MCF_FAST2_DRAW(14, n2, n3, w0)
+        MCF_FAST2_DRAW(15, n3, w0, w1)
+        F |= (uint64_t)f16 << (16 * sub);
+        z0 = z1;
+        z1 = z2;
+        z2 = z3;
+        z3 = zc;
     }
-            // block b lives in w0..w3 (look-ahead w4, w5); block b+1 in w4..w7 (look-ahead w0, w1 of block b+2)
-            load(blk0 + b + 1, w4, w5, w6, w7);
-            MCF_FAST_DRAW(0, w0, w1, w2)
-            MCF_FAST_DRAW(1, w1, w2, w3)
-            MCF_FAST_DRAW(2, w2, w3, w4)
-            MCF_FAST_DRAW(3, w3, w4, w5)
-            b++;
-            load(blk0 + b + 1, w0, w1, w2, w3);
-            MCF_FAST_DRAW(4, w4, w5, w6)
-            MCF_FAST_DRAW(5, w5, w6, w7)
-            MCF_FAST_DRAW(6, w6, w7, w0)
-            MCF_FAST_DRAW(7, w7, w0, w1)
-#undef MCF_FAST_DRAW
-            sm |= (uint64_t)snib << (4 * (b - 1));
-            em |= (uint64_t)enib << (4 * (b - 1));
-        }
-        // parked wedge tests of this sub-chunk (same arithmetic and decision as zig_feed, state 1)
-        for (unsigned e = 0; e < (nev < 2u ? nev : 2u); e++) {
-            const uint64_t a = e ? ea1 : ea0, u = e ? eb1 : eb0;
-            const unsigned js = e ? ej1 : ej0;
+#undef MCF_FAST2_DRAW
+    // phase 2: the chain, from the parked draws
+    bool ok = np <= MCF_PARK_CAP;
+    uint64_t S = ~0ULL, A = 0, N = ~F;
+    unsigned exitv = 0, k = 0;
+    auto add_to_sub = [&](unsigned sub, double x) {
+        z0 = sub == 0 ? xadd(z0, x) : z0;
+        z1 = sub == 1 ? xadd(z1, x) : z1;
+        z2 = sub == 2 ? xadd(z2, x) : z2;
+        z3 = sub == 3 ? xadd(z3, x) : z3;
+    };
+    while (N != 0 && k < MCF_PARK_CAP) {
+        const unsigned j = (unsigned)ctz64(N);
+        N &= N - 1;
+        const uint64_t a = park.a[k * park.stride], u = park.b[k * park.stride], u2 = park.c[k * park.stride];
+        k++;
+        if (!((S >> j) & 1ULL)) continue;  // consumed by an earlier attempt
+        unsigned len;
+        bool acc;
+        double x;
+        if ((a & 0xffULL) != 0) {  // wedge: same arithmetic and decision as zig_feed, state 1
+            len = 1;
             ZigFsm f;
             zig_reset(f);
-            double x;
-            zig_feed(f, a, t, x);        // state 0 -> 1 (wedge): stores idx, rabs, x
-            if (zig_feed(f, u, t, x)) {  // acceptance test
-                em |= 1ULL << js;
-                zc = xadd(zc, x);
-            }
+            zig_feed(f, a, t, x);
+            acc = zig_feed(f, u, t, x);
+        } else {  // tail, first pair
+            len = 2;
+            const uint64_t rabs = (a >> 9) & 0x000fffffffffffffULL;
+            const double xx = xmul(-MCF_ZIG_INV_R, log1p(-u64_to_unit_double(u)));
+            const double yy = -log1p(-u64_to_unit_double(u2));
+            acc = xadd(yy, yy) > xmul(xx, xx);
+            const double m = xadd(MCF_ZIG_R, xx);
+            x = ((rabs >> 8) & 1ULL) ? -m : m;
+            if (!acc) ok = false;  // longer tail: general re-walk
         }
-        zsub_out[sub] = zc;
+        if (acc) {
+            A |= 1ULL << j;
+            add_to_sub(j >> MCF_SUB_SHIFT, x);
+        }
+        for (unsigned q = 1; q <= len; q++) {
+            const unsigned f = j + q;
+            if (f >= MCF_CHUNK) {
+                exitv++;
+                continue;
+            }
+            S &= ~(1ULL << f);
+            if ((F >> f) & 1ULL) add_to_sub(f >> MCF_SUB_SHIFT, -zig_fast_value(q == 1 ? u : u2, t));
+        }
     }
-    ci.startmask = sm;
-    ci.emitmask = em;
-    ci.exit = skip;
+    zsub_out[0] = z0;
+    zsub_out[1] = z1;
+    zsub_out[2] = z2;
+    zsub_out[3] = z3;
+    ChunkInfo ci;
+    ci.gen_entry = 0;
+    ci.startmask = S;
+    ci.emitmask = (S & F) | A;
+    ci.exit = exitv;
     *valid = ok;
     return ci;
 }

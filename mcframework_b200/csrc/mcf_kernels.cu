@@ -26,7 +26,12 @@ struct ZigShared {
     uint64_t ki[256];
     double wi[256];
     double fi[256];
-    ZigKW kw[256];
+};
+// the speculative scan adds the (layer, sign)-indexed table and the per-thread parking slots (256 threads per CTA)
+struct ScanShared {
+    ZigShared z;
+    ZigKW kws[512];
+    uint64_t park[3 * MCF_PARK_CAP * 256];
 };
 
 __device__ __forceinline__ ZigTables load_zig_tables(ZigShared &sh) {
@@ -34,15 +39,25 @@ __device__ __forceinline__ ZigTables load_zig_tables(ZigShared &sh) {
         sh.ki[i] = g_zig_ki[i];
         sh.wi[i] = __longlong_as_double((long long)g_zig_wi[i]);
         sh.fi[i] = __longlong_as_double((long long)g_zig_fi[i]);
-        sh.kw[i].ki = g_zig_ki[i];
-        sh.kw[i].wi = __longlong_as_double((long long)g_zig_wi[i]);
     }
     __syncthreads();
     ZigTables t;
     t.ki = sh.ki;
     t.wi = sh.wi;
     t.fi = sh.fi;
-    t.kw = sh.kw;
+    t.kws = nullptr;
+    return t;
+}
+
+__device__ __forceinline__ ZigTables load_scan_tables(ScanShared &sh, ParkSlots &park) {
+    for (int e = threadIdx.x; e < 512; e += blockDim.x)
+        zig_fill_kws(sh.kws, (unsigned)e, g_zig_ki[e & 255], __longlong_as_double((long long)g_zig_wi[e & 255]));
+    ZigTables t = load_zig_tables(sh.z);
+    t.kws = sh.kws;
+    park.a = sh.park + threadIdx.x;
+    park.b = park.a + MCF_PARK_CAP * 256;
+    park.c = park.b + MCF_PARK_CAP * 256;
+    park.stride = 256;
     return t;
 }
 
@@ -146,8 +161,9 @@ __global__ void __launch_bounds__(256, 3) plan_scan_kernel(const mcf_stream *__r
                                                         int64_t n_runs, uint64_t *__restrict__ startmask,
                                                         uint64_t *__restrict__ emitmask, uint8_t *__restrict__ exit_,
                                                         uint8_t *__restrict__ gen, double *__restrict__ zsum, int *hdr) {
-    __shared__ ZigShared sh;
-    const ZigTables t = load_zig_tables(sh);
+    __shared__ ScanShared sh;
+    ParkSlots park;
+    const ZigTables t = load_scan_tables(sh, park);
     const int64_t run = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (run >= n_runs) return;
     const int64_t runs_per_stream = cps / RUN;
@@ -164,7 +180,7 @@ __global__ void __launch_bounds__(256, 3) plan_scan_kernel(const mcf_stream *__r
         bool valid;
         Cursor<MCF_GEN_PHILOX> &pc = *reinterpret_cast<Cursor<MCF_GEN_PHILOX> *>(&cur);
         const uint64_t blk0 = ((uint64_t)st.buf_pos + (uint64_t)c0 * MCF_CHUNK) >> 2;
-        ChunkInfo ci = scan_chunk_fast(
+        ChunkInfo ci = scan_chunk_fast2(
             [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
                 pc.load_block(blk);
                 a = pc.v0;
@@ -172,7 +188,7 @@ __global__ void __launch_bounds__(256, 3) plan_scan_kernel(const mcf_stream *__r
                 c = pc.v2;
                 d = pc.v3;
             },
-            blk0, t, zsum + id * MCF_SUBS, &valid);
+            blk0, t, park, zsum + id * MCF_SUBS, &valid);
         startmask[id] = ci.startmask;
         emitmask[id] = ci.emitmask;
         exit_[id] = (uint8_t)ci.exit;
@@ -200,16 +216,17 @@ __global__ void __launch_bounds__(256, 4) plan_scan_philox_stream_kernel(const _
                                                                          uint8_t *__restrict__ exit_,
                                                                          uint8_t *__restrict__ gen,
                                                                          double *__restrict__ zsum) {
-    __shared__ ZigShared sh;
-    const ZigTables t = load_zig_tables(sh);
+    __shared__ ScanShared sh;
+    ParkSlots park;
+    const ZigTables t = load_scan_tables(sh, park);
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cps) return;
     const int64_t id = row0 + c;
     bool valid;
     const uint64_t blk0 = (K.off + (uint64_t)c * MCF_CHUNK) >> 2;
-    const ChunkInfo ci = scan_chunk_fast(
-        [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &cc, uint64_t &d) { philox_block_keys(K, blk, a, b, cc, d); },
-        blk0, t, zsum + id * MCF_SUBS, &valid);
+    const ChunkInfo ci = scan_chunk_fast2(
+        [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &cc, uint64_t &d) { philox_block_folded(K, blk, a, b, cc, d); },
+        blk0, t, park, zsum + id * MCF_SUBS, &valid);
     startmask[id] = ci.startmask;
     emitmask[id] = ci.emitmask;
     exit_[id] = (uint8_t)ci.exit;
@@ -636,7 +653,8 @@ static int normal_plan_impl(const mcf_stream *d_streams, const mcf_stream *h_str
     const int64_t n_runs = g.n_chunks / RUN;
     const int64_t n_streams = g.n_chunks / g.cps;
     bool per_stream = KIND == MCF_GEN_PHILOX && h_streams != nullptr && n_streams <= 1024;
-    for (int64_t si = 0; per_stream && si < n_streams; si++) per_stream = (h_streams[si].buf_pos & 3u) == 0;
+    for (int64_t si = 0; per_stream && si < n_streams; si++)
+        per_stream = (h_streams[si].buf_pos & 3u) == 0 && h_streams[si].s[2] < (1ULL << 62);  // aligned, foldable counter
     if (per_stream) {
         for (int64_t si = 0; si < n_streams; si++) {
             const PhiloxKeys K = philox_keys_of(h_streams[si]);
