@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MCF_ABI_VERSION 1
+#define MCF_ABI_VERSION 2
 
 enum {
     MCF_OK = 0,
@@ -119,9 +119,12 @@ int mcf_workspace_status(const void *d_workspace, void *cuda_stream);
 
 /* d_out[k*n_total + i] = value of replication i under specs[k] (common random numbers).
  * replaces BlackScholesSimulation / BlackScholesPathSimulation / PortfolioSimulation
- * .single_simulation under the replication loop. */
-int mcf_gbm_terminal(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total,
-                     int64_t n_steps, int64_t sims_per_stream_hint, const uint64_t *d_sim_start,
+ * .single_simulation under the replication loop.
+ * h_streams: optional HOST copy of the stream records (may be NULL).  With it, affine bodies (European payoffs,
+ * portfolio GBM, path terminal) on block-aligned Philox streams run one launch per stream and regenerate at most two
+ * Philox blocks per replication (the shorter side of the replication boundary; the rest comes from the stored sums). */
+int mcf_gbm_terminal(uint32_t gen_kind, const mcf_stream *d_streams, const mcf_stream *h_streams, int32_t n_streams,
+                     int64_t n_total, int64_t n_steps, int64_t sims_per_stream_hint, const uint64_t *d_sim_start,
                      const void *d_plan_workspace, const mcf_gbm_spec *h_specs, int32_t n_specs, double *d_out,
                      void *cuda_stream);
 

@@ -121,11 +121,12 @@ def gbm_terminal(dl: DeviceLayout, n_steps: int, plan: NormalPlan, specs):
     torch = _torch()
     lay = dl.layout
     out = torch.empty((len(specs), lay.n_total), dtype=torch.float64, device="cuda")
-    rc = N.lib().mcf_gbm_terminal(lay.kind, _ptr(dl.records), lay.n_streams, lay.n_total, int(n_steps), lay.hint,
-                                  _ptr(plan.sim_start), _ptr(plan.workspace), _spec_array(specs), len(specs), _ptr(out),
-                                  _stream_ptr())
+    host_records = np.ascontiguousarray(lay.records)
+    rc = N.lib().mcf_gbm_terminal(lay.kind, _ptr(dl.records), host_records.ctypes.data_as(C.c_void_p), lay.n_streams,
+                                  lay.n_total, int(n_steps), lay.hint, _ptr(plan.sim_start), _ptr(plan.workspace),
+                                  _spec_array(specs), len(specs), _ptr(out), _stream_ptr())
     N.check("mcf_gbm_terminal", rc)
-    LAUNCHES["gbm"] += 1
+    LAUNCHES["gbm"] += 1  # one launch per stream for affine bodies on aligned Philox streams; counted as one here
     return out
 
 

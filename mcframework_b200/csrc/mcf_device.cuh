@@ -865,14 +865,88 @@ MCF_HD double zig_tail_value(const mcf_stream &st, uint64_t p, uint64_t rabs) {
     }
 }
 
-template <int KIND>
-MCF_HD double zig_value_of_start(const mcf_stream &st, uint64_t p, uint64_t r, const double *wi, uint64_t ki0) {
+// `tail(p, rabs)` yields the normal of the tail attempt whose first draw sits at position p (3e-4 of the emits)
+template <class Tail>
+MCF_HD double zig_value_of_start_t(Tail tail, uint64_t p, uint64_t r, const double *wi, uint64_t ki0) {
     const unsigned idx = (unsigned)(r & 0xffULL);
     const unsigned sign = (unsigned)((r >> 8) & 1ULL);
     const uint64_t rabs = (r >> 9) & 0x000fffffffffffffULL;
-    if (idx == 0 && rabs >= ki0) return zig_tail_value<KIND>(st, p, rabs);  // 3e-4 of the emits
+    if (idx == 0 && rabs >= ki0) return tail(p, rabs);
     const double v = xmul(u52_to_double(rabs), wi[idx]);
     return sign ? -v : v;
+}
+template <int KIND>
+MCF_HD double zig_value_of_start(const mcf_stream &st, uint64_t p, uint64_t r, const double *wi, uint64_t ki0) {
+    return zig_value_of_start_t([&](uint64_t pp, uint64_t rabs) { return zig_tail_value<KIND>(st, pp, rabs); }, p, r, wi,
+                                ki0);
+}
+
+// Block-aligned Philox streams (off % 4 == 0): f(z) for every normal emitted by attempts starting in [start, end), whole
+// blocks of four draws, every lane generating its block in the same loop trip.  `load(blk, a, b, c, d)` yields block
+// `blk` counted from the stream's base counter.
+template <class Load, class Tail, class F>
+MCF_HD void replay_emits_blocks(Load load, Tail tail, const PlanView &pv, int64_t si, uint64_t off, uint64_t start,
+                                uint64_t end, const double *wi, uint64_t ki0, F f) {
+    if (end <= start) return;
+    const uint64_t b_first = (start + off) >> 2, b_last = (end - 1 + off) >> 2;
+    uint64_t chunk = ~0ULL, word = 0;
+    for (uint64_t blk = b_first; blk <= b_last; blk++) {
+        const uint64_t p0 = (blk << 2) - off;  // stream position of the block's first draw (may precede `start`)
+        const uint64_t c = (p0 + 3) >> 6;      // blocks never straddle chunks when off % 4 == 0 (p0 % 4 == 0)
+        if (c != chunk) {
+            chunk = c;
+            word = plan_emit_word(pv, si, c);
+        }
+        unsigned nib = (unsigned)(word >> (p0 & 63ULL)) & 0xFu;
+        if (blk == b_first) nib &= (0xFu << (unsigned)(start - p0)) & 0xFu;
+        if (blk == b_last) nib &= 0xFu >> (unsigned)(p0 + 4 - end);
+        uint64_t v0, v1, v2, v3;
+        load(blk, v0, v1, v2, v3);
+        if (nib & 1u) f(zig_value_of_start_t(tail, p0, v0, wi, ki0));
+        if (nib & 2u) f(zig_value_of_start_t(tail, p0 + 1, v1, wi, ki0));
+        if (nib & 4u) f(zig_value_of_start_t(tail, p0 + 2, v2, wi, ki0));
+        if (nib & 8u) f(zig_value_of_start_t(tail, p0 + 3, v3, wi, ki0));
+    }
+}
+
+// A replication boundary at stream position p cuts its 16-draw sub-chunk in two.  Only the SHORTER side is regenerated
+// (at most two Philox blocks); the other side is the stored sub-chunk sum minus it.  `before` belongs to the
+// replication that ends at p, `after` to the one that starts there.
+struct BoundarySums {
+    double before, after;
+};
+template <class Load, class Tail>
+MCF_HD BoundarySums boundary_sums(Load load, Tail tail, const PlanView &pv, int64_t si, uint64_t off, uint64_t p,
+                                  const double *wi, uint64_t ki0) {
+    const uint64_t s = p >> MCF_SUB_SHIFT, o = p & ((1ULL << MCF_SUB_SHIFT) - 1ULL);
+    const double S = pv.zsum[si * pv.cps * MCF_SUBS + (int64_t)s];
+    BoundarySums r;
+    if (o == 0) {
+        r.before = 0.0;
+        r.after = S;
+        return r;
+    }
+    double acc = 0.0;
+    auto add = [&](double z) { acc = xadd(acc, z); };
+    if (o <= 8) {
+        replay_emits_blocks(load, tail, pv, si, off, s << MCF_SUB_SHIFT, p, wi, ki0, add);
+        r.before = acc;
+        r.after = xsub(S, acc);
+    } else {
+        replay_emits_blocks(load, tail, pv, si, off, p, (s + 1) << MCF_SUB_SHIFT, wi, ki0, add);
+        r.before = xsub(S, acc);
+        r.after = acc;
+    }
+    return r;
+}
+// sum of the normals of the replication [start, end) given the two boundary cuts (requires end - start >= 16):
+// after(start), the whole sub-chunks in between in order, before(end)
+MCF_HD double zsum_from_boundaries(const PlanView &pv, int64_t si, uint64_t start, uint64_t end, double after_start,
+                                   double before_end) {
+    const double *sums = pv.zsum + si * pv.cps * MCF_SUBS;
+    double acc = after_start;
+    for (uint64_t k = (start >> MCF_SUB_SHIFT) + 1; k < (end >> MCF_SUB_SHIFT); k++) acc = xadd(acc, sums[k]);
+    return xadd(acc, before_end);
 }
 
 // f(z) for every normal emitted by attempts starting in [start, end) of stream `si`, in stream order
@@ -906,24 +980,16 @@ MCF_HD void replay_emits(Cursor<MCF_GEN_PHILOX> &cur, const mcf_stream &st, cons
         }
         return;
     }
-    const uint64_t b_first = (start + off) >> 2, b_last = (end - 1 + off) >> 2;
-    uint64_t chunk = ~0ULL, word = 0;
-    for (uint64_t blk = b_first; blk <= b_last; blk++) {
-        const uint64_t p0 = (blk << 2) - off;  // stream position of the block's first draw (may precede `start`)
-        const uint64_t c = (p0 + 3) >> 6;      // blocks never straddle chunks when off % 4 == 0 (p0 % 4 == 0)
-        if (c != chunk) {
-            chunk = c;
-            word = plan_emit_word(pv, si, c);
-        }
-        unsigned nib = (unsigned)(word >> (p0 & 63ULL)) & 0xFu;
-        if (blk == b_first) nib &= (0xFu << (unsigned)(start - p0)) & 0xFu;
-        if (blk == b_last) nib &= 0xFu >> (unsigned)(p0 + 4 - end);
-        cur.load_block(blk);
-        if (nib & 1u) f(zig_value_of_start<MCF_GEN_PHILOX>(st, p0, cur.v0, wi, ki0));
-        if (nib & 2u) f(zig_value_of_start<MCF_GEN_PHILOX>(st, p0 + 1, cur.v1, wi, ki0));
-        if (nib & 4u) f(zig_value_of_start<MCF_GEN_PHILOX>(st, p0 + 2, cur.v2, wi, ki0));
-        if (nib & 8u) f(zig_value_of_start<MCF_GEN_PHILOX>(st, p0 + 3, cur.v3, wi, ki0));
-    }
+    replay_emits_blocks(
+        [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
+            cur.load_block(blk);
+            a = cur.v0;
+            b = cur.v1;
+            c = cur.v2;
+            d = cur.v3;
+        },
+        [&](uint64_t p, uint64_t rabs) { return zig_tail_value<MCF_GEN_PHILOX>(st, p, rabs); }, pv, si, off, start, end,
+        wi, ki0, f);
 }
 
 // Sum of the normals of the attempts starting in [start, end): whole 16-draw sub-chunks come from the sums the

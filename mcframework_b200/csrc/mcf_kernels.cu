@@ -558,6 +558,65 @@ __global__ void __launch_bounds__(256, 3) gbm_terminal_kernel(const mcf_stream *
     }
 }
 
+// Affine bodies on block-aligned Philox streams, one launch per stream (round keys and base counter in the constant
+// bank, rounds 0/1 folded): every thread regenerates only the shorter side of the boundary at the END of its
+// replication (at most two Philox blocks) and takes the other side of the boundary at its START from its neighbour.
+__global__ void __launch_bounds__(256, 4)
+    gbm_terminal_affine_stream_kernel(const __grid_constant__ PhiloxKeys K, const mcf_stream *__restrict__ streams, int64_t si,
+                                      int64_t first_sim, int64_t n_sims, int64_t n_total,
+                                      const uint64_t *__restrict__ sim_start, const char *__restrict__ plan_ws,
+                                      const __grid_constant__ SpecPack specs, double n_steps_f, double *__restrict__ out) {
+    __shared__ WiShared sh;
+    __shared__ double sh_after[8];
+    const double *wi = load_wi_table(sh);
+    const uint64_t ki0 = g_zig_ki[0];
+    const PlanLayout *lay = reinterpret_cast<const PlanLayout *>(plan_ws + MCF_LAYOUT_OFFSET);
+    PlanView pv;
+    pv.emit = reinterpret_cast<const uint64_t *>(plan_ws + lay->off_emit);
+    pv.entry = reinterpret_cast<const uint8_t *>(plan_ws + lay->off_entry);
+    pv.zsum = reinterpret_cast<const double *>(plan_ws + lay->off_zsum);
+    pv.cps = lay->cps;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = j < n_sims;
+    const int64_t i = first_sim + j;
+    auto load = [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) { philox_block_folded(K, blk, a, b, c, d); };
+    auto tail = [&](uint64_t p, uint64_t rabs) { return zig_tail_value<MCF_GEN_PHILOX>(streams[si], p, rabs); };
+    uint64_t start = 0, end = 0;
+    BoundarySums be;
+    be.before = 0.0;
+    be.after = 0.0;
+    if (active) {
+        start = sim_start[i];
+        end = (j + 1 == n_sims) ? reinterpret_cast<const uint64_t *>(plan_ws + lay->off_send)[si] : sim_start[i + 1];
+        be = boundary_sums(load, tail, pv, si, K.off, end, wi, ki0);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double h = __shfl_up_sync(0xffffffffu, be.after, 1);
+    if (lane == 31) sh_after[warp] = be.after;
+    __syncthreads();
+    if (lane == 0 && warp > 0) h = sh_after[warp - 1];
+    if (!active) return;
+    if (threadIdx.x == 0 || j == 0) h = boundary_sums(load, tail, pv, si, K.off, start, wi, ki0).after;
+    const double zsum = zsum_from_boundaries(pv, si, start, end, h, be.before);
+    for (int s = 0; s < specs.n; s++) {
+        const GbmDerived &g = specs.g[s];
+        const double acc = xadd(xmul(n_steps_f, g.a), xmul(g.b, zsum));
+        double v;
+        if (g.mode == MCF_NORMAL_SUM) {
+            v = zsum;
+        } else if (g.mode == MCF_PATH_TERMINAL) {
+            v = exp(xadd(g.logs0, acc));
+        } else {
+            const double stv = xmul(g.s0, exp(acc));
+            if (g.mode == MCF_PORTFOLIO_GBM)
+                v = stv;
+            else
+                v = xmul(g.mode == MCF_BS_EURO_CALL ? fmax(xsub(stv, g.K), 0.0) : fmax(xsub(g.K, stv), 0.0), g.disc);
+        }
+        out[(int64_t)s * n_total + i] = v;
+    }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256, 3) gbm_paths_kernel(const mcf_stream *__restrict__ streams, int n_streams,
                                                            int64_t n_total, int64_t n_steps, int64_t hint,
@@ -782,9 +841,10 @@ int mcf_workspace_status(const void *d_workspace, void *cuda_stream) {
 
 extern "C" {
 
-int mcf_gbm_terminal(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total, int64_t n_steps,
-                       int64_t sims_per_stream_hint, const uint64_t *d_sim_start, const void *d_plan_workspace,
-                       const mcf_gbm_spec *h_specs, int32_t n_specs, double *d_out, void *cuda_stream) {
+int mcf_gbm_terminal(uint32_t gen_kind, const mcf_stream *d_streams, const mcf_stream *h_streams, int32_t n_streams,
+                     int64_t n_total, int64_t n_steps, int64_t sims_per_stream_hint, const uint64_t *d_sim_start,
+                     const void *d_plan_workspace, const mcf_gbm_spec *h_specs, int32_t n_specs, double *d_out,
+                     void *cuda_stream) {
     if (!d_streams || n_streams <= 0 || n_total <= 0 || n_steps <= 0 || !d_sim_start || !d_plan_workspace || !h_specs ||
         n_specs < 1 || n_specs > MCF_MAX_SPECS || !d_out)
         return MCF_ERR_BAD_ARG;
@@ -800,6 +860,22 @@ int mcf_gbm_terminal(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_s
         if (n_specs > 1 && path_dependent) return MCF_ERR_BAD_ARG;  // path-dependent bodies take one set per launch
     }
     cudaStream_t cs = (cudaStream_t)cuda_stream;
+    // affine bodies of at least one sub-chunk per replication on aligned, foldable Philox streams: boundary form
+    bool per_stream = gen_kind == MCF_GEN_PHILOX && pack.affine && n_steps >= (1 << MCF_SUB_SHIFT) && h_streams != nullptr &&
+                      n_streams <= 1024;
+    for (int si = 0; per_stream && si < n_streams; si++)
+        per_stream = (h_streams[si].buf_pos & 3u) == 0 && h_streams[si].s[2] < (1ULL << 62);
+    if (per_stream) {
+        for (int si = 0; si < n_streams; si++) {
+            if (h_streams[si].n_sims <= 0) continue;
+            const PhiloxKeys K = philox_keys_of(h_streams[si]);
+            gbm_terminal_affine_stream_kernel<<<grid_for(h_streams[si].n_sims, 256), 256, 0, cs>>>(
+                K, d_streams, si, h_streams[si].first_sim, h_streams[si].n_sims, n_total, d_sim_start,
+                (const char *)d_plan_workspace, pack, (double)n_steps, d_out);
+        }
+        MCF_CUDA_OK(cudaGetLastError());
+        return MCF_OK;
+    }
     if (gen_kind == MCF_GEN_PCG64)
         gbm_terminal_kernel<MCF_GEN_PCG64><<<grid_for(n_total, 256), 256, 0, cs>>>(
             d_streams, n_streams, n_total, sims_per_stream_hint, d_sim_start, (const char *)d_plan_workspace, pack,

@@ -273,7 +273,19 @@ static int terminal_impl(const mcf_stream *streams, int n_streams, int64_t n_tot
             out[i] = terminal_value([&](auto f) { replay_emits(cur, st, pv, si, start, end, t.wi, t.ki[0], f); }, pack.g[0]);
             continue;
         }
-        const double zsum = replay_zsum(cur, st, pv, si, start, end, t.wi, t.ki[0]);
+        double zsum;
+        if (KIND == MCF_GEN_PHILOX && (st.buf_pos & 3u) == 0 && st.s[2] < (1ULL << 62) && n_steps >= (1 << MCF_SUB_SHIFT)) {
+            // as gbm_terminal_affine_stream_kernel: the boundary at the end is cut by this replication, the one at the
+            // start by its predecessor (same function, same arithmetic)
+            const PhiloxKeys K = philox_keys_of(st);
+            auto load = [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) { philox_block_folded(K, blk, a, b, c, d); };
+            auto tail = [&](uint64_t p, uint64_t rabs) { return zig_tail_value<MCF_GEN_PHILOX>(st, p, rabs); };
+            const BoundarySums be = boundary_sums(load, tail, pv, si, K.off, end, t.wi, t.ki[0]);
+            const BoundarySums bs = boundary_sums(load, tail, pv, si, K.off, start, t.wi, t.ki[0]);
+            zsum = zsum_from_boundaries(pv, si, start, end, bs.after, be.before);
+        } else {
+            zsum = replay_zsum(cur, st, pv, si, start, end, t.wi, t.ki[0]);
+        }
         for (int s = 0; s < n_specs; s++) {
             const GbmDerived &g = pack.g[s];
             const double acc = xadd(xmul((double)n_steps, g.a), xmul(g.b, zsum));
