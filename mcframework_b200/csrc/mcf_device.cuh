@@ -703,7 +703,7 @@ MCF_HD ChunkInfo scan_chunk_fast2(Load load, uint64_t blk0, const ZigTables &t, 
         const uint64_t dbits = (((WA) >> 9) & 0x000fffffffffffffULL) | MCF_U52_BIAS;              \
         const ZigKW kw = t.kws[(unsigned)(WA)&0x1ffu];                                            \
         const double v = xmul(xadd(bits_to_double(dbits), -4503599627370496.0), kw.wi);           \
-        if (dbits < kw.ki) {                                                                      \
+        if (bits_to_double(dbits) < bits_to_double(kw.ki)) {                                      \
             f16 |= 1u << (J);                                                                     \
             zc = xadd(zc, v);                                                                     \
         } else {                                                                                  \

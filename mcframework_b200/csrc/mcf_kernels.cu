@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) pi_philox_stream_kernel(const __grid_cons
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n_units = n_sims * parts;
-    auto load = [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) { philox_block_keys(K, blk, a, b, c, d); };
+    auto load = [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) { philox_block_folded(K, blk, a, b, c, d); };
     for (int64_t unit = warp0; unit < n_units; unit += n_warps) {
         const int64_t sim = unit / parts, part = unit - sim * parts;
         const uint64_t base = K.off + (uint64_t)sim * (uint64_t)draws_per_sim;  // multiple of 4
@@ -773,7 +773,8 @@ int mcf_pi_hits(uint32_t gen_kind, const mcf_stream *d_streams, const mcf_stream
     const int64_t max_blocks = 148LL * 8 * 64;
     if (blocks > max_blocks) blocks = max_blocks;
     bool per_stream = gen_kind == MCF_GEN_PHILOX && h_streams != nullptr && n_streams <= 1024 && (pg.draws_per_sim % 4) == 0;
-    for (int si = 0; per_stream && si < n_streams; si++) per_stream = (h_streams[si].buf_pos & 3u) == 0;
+    for (int si = 0; per_stream && si < n_streams; si++)
+        per_stream = (h_streams[si].buf_pos & 3u) == 0 && h_streams[si].s[2] < (1ULL << 62);  // aligned, foldable counter
     if (per_stream) {
         for (int si = 0; si < n_streams; si++) {
             const PhiloxKeys K = philox_keys_of(h_streams[si]);

@@ -623,9 +623,9 @@ __global__ void __launch_bounds__(BOOT_THREADS) boot_accumulate_kernel(
 //   boot_gather_kernel : region by region (so that the region's part of x stays in L2 while all queues that point
 //                        into it are streamed once), sum x[region + local index] per (resample, region) queue.
 // The index stream is unchanged (bit-exact); only the order in which a resample's terms are added differs.
-#define BIN_MAX_REGIONS 16
-#define BIN_STAGE_CAP 704   // entries per staging buffer; flushed every BIN_FLUSH_EVERY groups of 8 slots per thread
-#define BIN_FLUSH_EVERY 3   // 3 * 2048 entries per CTA over >= 12 regions: 512 +- 22 per buffer
+#define BIN_MAX_REGIONS 32
+#define BIN_STAGE_CAP 352   // entries per staging buffer; flushed every BIN_FLUSH_EVERY groups of 8 slots per thread
+#define BIN_FLUSH_EVERY 3   // 3 * 2048 entries per CTA over >= 24 regions: 256 +- 16 per buffer
 
 struct BinParams {
     uint32_t n;               // population size
@@ -685,7 +685,74 @@ __global__ void __launch_bounds__(BOOT_THREADS) boot_bin_kernel(const mcf_stream
     bool done = !live || ord >= total_needed;
     const uint32_t mask = (1u << bp.region_shift) - 1u;
     const int groups = chunk_slots / 8;
-    for (int g = 0; g < groups; g++) {  // uniform trip count: the flushes below are CTA-wide
+    const uint64_t q_row = (b_blk - bp.b_first) * R;  // queues of the CTA's first resample
+
+    // CTA-wide flush of the staging buffers: one global atomic per region, coalesced stores
+    auto flush = [&]() {
+        __syncthreads();
+        if (threadIdx.x < R) {
+            unsigned c = sh_cnt[threadIdx.x];
+            if (c > BIN_STAGE_CAP) c = BIN_STAGE_CAP;
+            sh_n[threadIdx.x] = c;
+            sh_base[threadIdx.x] = c ? atomicAdd(&tails[q_row + threadIdx.x], c) : 0u;
+            sh_cnt[threadIdx.x] = 0;
+        }
+        __syncthreads();
+        for (unsigned q = wid; q < R; q += BOOT_THREADS / 32) {
+            const unsigned c = sh_n[q], base = sh_base[q];
+            const uint64_t gq = q_row + q;
+            if (c && (uint64_t)base + c > bp.cap) atomicExch(overflow, 1);
+            for (unsigned j = lane; j < c; j += 32)
+                if ((uint64_t)base + j < bp.cap) queues[gq * bp.cap + base + j] = sh_stage[q][j];
+        }
+        __syncthreads();
+    };
+    auto append_direct = [&](uint64_t bb, uint32_t idx) {  // staging full, or the second resample of a straddling CTA
+        const uint64_t gq = (bb - bp.b_first) * R + (idx >> bp.region_shift);
+        const unsigned gp = atomicAdd(&tails[gq], 1u);
+        if (gp < bp.cap)
+            queues[gq * bp.cap + gp] = idx & mask;
+        else
+            atomicExch(overflow, 1);
+    };
+
+    // Nearly every CTA lies inside ONE resample, before the end of the (B, n) draw, with all its slots in range:
+    // no ordinal bookkeeping in the loop, just accept -> stage.
+    uint64_t cta_total = 0;
+    for (int w2 = 0; w2 < BOOT_THREADS / 32; w2++) cta_total += warp_tot[w2];
+    const uint64_t cta_end = blk_ord + cta_total;
+    const bool simple = cta_end <= (b_blk + 1) * (uint64_t)bp.n && cta_end < total_needed &&
+                        (blk + 1) * BOOT_THREADS <= n_chunks &&
+                        slot_lo + (uint64_t)(blk + 1) * BOOT_THREADS * (uint64_t)chunk_slots <= slot_hi;
+    if (simple) {
+        // 32-bit shared-window addresses, computed once (the generic-pointer form recomputes them per slot)
+        unsigned cnt_addr = (unsigned)__cvta_generic_to_shared(sh_cnt);
+        unsigned stage_addr = (unsigned)__cvta_generic_to_shared(&sh_stage[0][0]);
+        unsigned shift = bp.region_shift, lowmask = mask;
+        asm volatile("" : "+r"(cnt_addr), "+r"(stage_addr), "+r"(shift), "+r"(lowmask));  // keep them in registers
+        for (int g = 0; g < groups; g++) {
+            uint32_t u[8];
+            w.get8(s0 + (uint64_t)g * 8, u);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t idx;
+                if (slot_accept(rule, u[j], idx)) {
+                    const unsigned q = idx >> shift;
+                    unsigned pos;
+                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(cnt_addr + q * 4u) : "memory");
+                    if (pos < BIN_STAGE_CAP)
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(stage_addr + q * (BIN_STAGE_CAP * 4u) + pos * 4u),
+                                     "r"(idx & lowmask)
+                                     : "memory");
+                    else
+                        append_direct(b_blk, idx);
+                }
+            }
+            if ((g % BIN_FLUSH_EVERY) == BIN_FLUSH_EVERY - 1 || g == groups - 1) flush();
+        }
+        return;
+    }
+    for (int g = 0; g < groups; g++) {  // uniform trip count: the flushes are CTA-wide
         const uint64_t sb = s0 + (uint64_t)g * 8;
         if (!done && sb < s1) {
             uint32_t u[8];
@@ -701,16 +768,10 @@ __global__ void __launch_bounds__(BOOT_THREADS) boot_bin_kernel(const mcf_stream
                     }
                     const unsigned q = idx >> bp.region_shift;
                     const unsigned pos = b == b_blk ? atomicAdd(&sh_cnt[q], 1u) : 0xFFFFFFFFu;
-                    if (pos < BIN_STAGE_CAP) {
+                    if (pos < BIN_STAGE_CAP)
                         sh_stage[q][pos] = idx & mask;
-                    } else {  // second resample of a straddling CTA, or staging full: append directly
-                        const uint64_t gq = (b - bp.b_first) * R + (idx >> bp.region_shift);
-                        const unsigned gp = atomicAdd(&tails[gq], 1u);
-                        if (gp < bp.cap)
-                            queues[gq * bp.cap + gp] = idx & mask;
-                        else
-                            atomicExch(overflow, 1);
-                    }
+                    else
+                        append_direct(b, idx);
                     ord++;
                     if (ord == total_needed) {
                         *end_slot = s + 1;  // slots consumed by the whole (B, n) draw
@@ -719,26 +780,7 @@ __global__ void __launch_bounds__(BOOT_THREADS) boot_bin_kernel(const mcf_stream
                 }
             }
         }
-        if ((g % BIN_FLUSH_EVERY) == BIN_FLUSH_EVERY - 1 || g == groups - 1) {
-            __syncthreads();
-            if (threadIdx.x < R) {
-                unsigned c = sh_cnt[threadIdx.x];
-                if (c > BIN_STAGE_CAP) c = BIN_STAGE_CAP;
-                const uint64_t gq = (b_blk - bp.b_first) * R + threadIdx.x;
-                sh_n[threadIdx.x] = c;
-                sh_base[threadIdx.x] = c ? atomicAdd(&tails[gq], c) : 0u;
-                sh_cnt[threadIdx.x] = 0;
-            }
-            __syncthreads();
-            for (unsigned q = wid; q < R; q += BOOT_THREADS / 32) {
-                const unsigned c = sh_n[q], base = sh_base[q];
-                const uint64_t gq = (b_blk - bp.b_first) * R + q;
-                if (c && (uint64_t)base + c > bp.cap) atomicExch(overflow, 1);
-                for (unsigned j = lane; j < c; j += 32)
-                    if ((uint64_t)base + j < bp.cap) queues[gq * bp.cap + base + j] = sh_stage[q][j];
-            }
-            __syncthreads();
-        }
+        if ((g % BIN_FLUSH_EVERY) == BIN_FLUSH_EVERY - 1 || g == groups - 1) flush();
     }
 }
 
@@ -755,15 +797,15 @@ __global__ void __launch_bounds__(256) boot_gather_kernel(const double *__restri
     double acc = 0.0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 7 * stride < cnt; i += 8 * stride) {  // 8 independent gathers in flight
-        uint32_t e[8];
-        double v[8];
+    for (; i + 15 * stride < cnt; i += 16 * stride) {  // 16 independent gathers in flight: the kernel is L2-latency bound
+        uint32_t e[16];
+        double v[16];
 #pragma unroll
-        for (int k = 0; k < 8; k++) e[k] = __ldcs(&seg[i + k * stride]);  // streamed once: evict-first
+        for (int k = 0; k < 16; k++) e[k] = __ldcs(&seg[i + k * stride]);  // streamed once: evict-first
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = __ldcg(&xr[e[k]]);
+        for (int k = 0; k < 16; k++) v[k] = __ldcg(&xr[e[k]]);
 #pragma unroll
-        for (int k = 0; k < 8; k++) acc += v[k];
+        for (int k = 0; k < 16; k++) acc += v[k];
     }
     for (; i < cnt; i += stride) acc += __ldcg(&xr[__ldcs(&seg[i])]);
     __shared__ double sh[8];
@@ -793,7 +835,7 @@ struct LsmState {
 };
 
 struct LsmGeom {
-    int64_t off_state, off_partials, off_ex, off_cf, total;
+    int64_t off_state, off_counter, off_partials, off_ex, off_cf, total;
     int n_blocks;
 };
 #define LSM_THREADS 256
@@ -802,7 +844,9 @@ static inline LsmGeom lsm_geom(int64_t n_paths) {
     g.n_blocks = grid_cap(n_paths, LSM_THREADS * 4, MCF_SM_COUNT * 8);
     int64_t o = 0;
     g.off_state = o;
-    o = align256(o + (int64_t)sizeof(LsmState));
+    o = align256(o + 2 * (int64_t)sizeof(LsmState));  // fused path: coefficients double-buffered by step parity
+    g.off_counter = o;
+    o = align256(o + 8);
     g.off_partials = o;
     o = align256(o + (int64_t)g.n_blocks * 8 * 8);
     g.off_ex = o;
@@ -884,30 +928,38 @@ __global__ void __launch_bounds__(256) lsm_sum_partials_kernel(const double *__r
 // symmetric 3x3 eigen-decomposition (cyclic Jacobi) -> pseudo-inverse solve with lstsq's rcond=eps*max(M,N) spirit
 __device__ void lsm_solve3(const double G[3][3], const double rhs[3], double n_rows, double coef[3]) {
     double A[3][3], V[3][3];
+#pragma unroll
     for (int i = 0; i < 3; i++)
+#pragma unroll
         for (int j = 0; j < 3; j++) {
             A[i][j] = G[i][j];
             V[i][j] = i == j ? 1.0 : 0.0;
         }
     for (int sweep = 0; sweep < 30; sweep++) {
+        // converged when the off-diagonal mass is far below one ulp of the diagonal (further rotations are no-ops)
         const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
-        if (off == 0.0) break;
+        if (off <= 1e-22 * (fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]))) break;
+#pragma unroll
         for (int p = 0; p < 2; p++)
+#pragma unroll
             for (int q = p + 1; q < 3; q++) {
                 if (A[p][q] == 0.0) continue;
                 const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
                 const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                 const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
+#pragma unroll
                 for (int k = 0; k < 3; k++) {
                     const double akp = A[k][p], akq = A[k][q];
                     A[k][p] = c * akp - s * akq;
                     A[k][q] = s * akp + c * akq;
                 }
+#pragma unroll
                 for (int k = 0; k < 3; k++) {
                     const double apk = A[p][k], aqk = A[q][k];
                     A[p][k] = c * apk - s * aqk;
                     A[q][k] = s * apk + c * aqk;
                 }
+#pragma unroll
                 for (int k = 0; k < 3; k++) {
                     const double vkp = V[k][p], vkq = V[k][q];
                     V[k][p] = c * vkp - s * vkq;
@@ -920,17 +972,23 @@ __device__ void lsm_solve3(const double G[3][3], const double rhs[3], double n_r
     const double rc = 2.220446049250313e-16 * fmax(n_rows, 3.0);
     const double cutoff = lmax * rc * rc;
     coef[0] = coef[1] = coef[2] = 0.0;
+#pragma unroll
     for (int e = 0; e < 3; e++) {
         const double lam = A[e][e];
         if (lam > cutoff && lam > 0.0) {
             const double proj = (V[0][e] * rhs[0] + V[1][e] * rhs[1] + V[2][e] * rhs[2]) / lam;
+#pragma unroll
             for (int i = 0; i < 3; i++) coef[i] += V[i][e] * proj;
         }
     }
 }
 
+__device__ void lsm_solve_state(LsmState *st);
 __global__ void lsm_solve_kernel(LsmState *st) {
     if (threadIdx.x != 0) return;
+    lsm_solve_state(st);
+}
+__device__ void lsm_solve_state(LsmState *st) {
     const double *s = st->sums;
     if (s[0] <= 0.0) {
         st->have_fit = 0;
@@ -966,6 +1024,108 @@ __global__ void __launch_bounds__(LSM_THREADS) lsm_apply_kernel(const double *__
                 ex[i] = t;
                 cf[i] = intr * disc_t;
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- fused single-GPU backward induction
+// One launch per step t: every path applies the exercise decision of step t (coefficients fitted by the previous
+// launch) and, with its updated cash flow, contributes to the normal equations of step t-1.  The CTA that finishes
+// last adds the per-CTA partial sums in a fixed order (deterministic) and solves the 3x3 system for step t-1, so the
+// serial part costs no launch.  Per path and step: S_t and S_{t-1} (8 B each), cf read (8 B), cf written only where
+// the option is exercised.  t == n_steps is the initialisation (cf = discounted terminal intrinsic, no decision);
+// t == 1 accumulates the price sum instead of regression sums.
+__global__ void __launch_bounds__(LSM_THREADS, 4)
+    lsm_fused_step_kernel(const double *__restrict__ s_t, const double *__restrict__ s_prev, int64_t n_paths, int32_t t,
+                          int32_t n_steps, double K, int is_put, double disc_t, double grow_prev,
+                          const LsmState *__restrict__ st_cur, LsmState *__restrict__ st_next,
+                          int32_t *__restrict__ ex, double *__restrict__ cf, double *__restrict__ partials,
+                          unsigned int *__restrict__ counter, double *__restrict__ price_out) {
+    const bool init = t == n_steps, last_step = t == 1;
+    const bool have_fit = !init && st_cur->have_fit;
+    const double c0 = have_fit ? st_cur->coef[0] : 0.0, c1 = have_fit ? st_cur->coef[1] : 0.0,
+                 c2 = have_fit ? st_cur->coef[2] : 0.0;
+    const double invK = 1.0 / K;
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    auto one = [&](int64_t i, double s, double c, double sp) {
+        const double intr = lsm_intrinsic(s, K, is_put);
+        if (init) {
+            c = intr * disc_t;
+            cf[i] = c;
+            if (ex) ex[i] = t;
+        } else if (have_fit && intr > 0.0) {
+            const double u = (s - K) * invK;
+            const double fitted = fma(fma(c2, u, c1), u, c0);
+            if (intr > fitted) {
+                c = intr * disc_t;
+                cf[i] = c;
+                if (ex) ex[i] = t;
+            }
+        }
+        if (last_step) {
+            a[0] += c;
+        } else if (lsm_intrinsic(sp, K, is_put) > 0.0) {
+            const double y = c * grow_prev;
+            const double u = (sp - K) * invK, u2 = u * u;
+            a[0] += 1.0;
+            a[1] += u;
+            a[2] += u2;
+            a[3] = fma(u2, u, a[3]);
+            a[4] = fma(u2, u2, a[4]);
+            a[5] += y;
+            a[6] = fma(u, y, a[6]);
+            a[7] = fma(u2, y, a[7]);
+        }
+    };
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < n_paths; i += 2 * stride) {  // two paths per trip: six independent loads in flight
+        const double s0 = __ldcs(&s_t[i]), s1 = __ldcs(&s_t[i + stride]);
+        const double p0 = last_step ? 0.0 : __ldg(&s_prev[i]), p1 = last_step ? 0.0 : __ldg(&s_prev[i + stride]);
+        const double k0 = init ? 0.0 : cf[i], k1 = init ? 0.0 : cf[i + stride];
+        one(i, s0, k0, p0);
+        one(i + stride, s1, k1, p1);
+    }
+    if (i < n_paths) one(i, __ldcs(&s_t[i]), init ? 0.0 : cf[i], last_step ? 0.0 : __ldg(&s_prev[i]));
+
+    __shared__ double sh[LSM_THREADS / 32][8];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        double v = a[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[wid][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double v = 0.0;
+        for (int w2 = 0; w2 < LSM_THREADS / 32; w2++) v += sh[w2][threadIdx.x];
+        partials[(size_t)blockIdx.x * 8 + threadIdx.x] = v;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    {  // 8 warps, warp k sums column k in a fixed order (as lsm_sum_partials_kernel)
+        double v = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(&partials[(size_t)b * 8 + wid]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) st_next->sums[wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *counter = 0;
+        if (last_step) {
+            if (price_out) *price_out = st_next->sums[0] / (double)n_paths;
+        } else {
+            lsm_solve_state(st_next);
         }
     }
 }
@@ -1238,7 +1398,7 @@ int mcf_bootstrap_accumulate(uint32_t gen_kind, const mcf_stream *d_stream, cons
 
 // Binned variant of mcf_bootstrap_accumulate for populations that do not fit L2 (see boot_bin_kernel).
 // h_block_base: HOST copy of the per-CTA ordinal prefix (mcf_bootstrap_block_base copies it out after the count pass).
-// region_shift: log2(elements per region), 0 = choose (2^23 elements = 64 MB, at most 16 regions).
+// region_shift: log2(elements per region), 0 = choose (2^22 elements = 32 MB -- half of one L2 partition --, at most 32 regions).
 int64_t mcf_bootstrap_blocks(int64_t n_slots, int32_t chunk_slots) {
     if (n_slots <= 0 || chunk_slots < 8) return MCF_ERR_BAD_ARG;
     return boot_geom(n_slots, chunk_slots).n_blocks;
@@ -1257,7 +1417,7 @@ int mcf_bootstrap_block_base(const void *d_workspace, int64_t n_slots, int32_t c
 
 static inline uint32_t bin_region_shift(int64_t n, int32_t requested) {
     if (requested > 0) return (uint32_t)requested;
-    uint32_t s = 23;
+    uint32_t s = 22;
     while (((n + (1LL << s) - 1) >> s) > BIN_MAX_REGIONS) s++;
     return s;
 }
@@ -1426,15 +1586,26 @@ int mcf_lsm_finish(int64_t n_paths, double r, double dt, void *d_workspace, doub
 
 int mcf_lsm(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K, double r, double dt, int32_t is_put,
             void *d_workspace, int64_t workspace_bytes, double *d_price, int32_t *d_exercise_times, void *cuda_stream) {
-    int rc = mcf_lsm_begin(d_paths_tm, n_paths, n_steps, K, r, dt, is_put, d_workspace, workspace_bytes, cuda_stream);
-    if (rc) return rc;
-    for (int64_t t = n_steps - 1; t >= 1; t--) {
-        rc = mcf_lsm_reduce(d_paths_tm, n_paths, t, K, r, dt, is_put, d_workspace, cuda_stream);
-        if (rc) return rc;
-        rc = mcf_lsm_apply(d_paths_tm, n_paths, t, K, r, dt, is_put, d_workspace, cuda_stream);
-        if (rc) return rc;
+    if (!d_paths_tm || n_paths <= 0 || n_steps < 1 || n_steps > 0x7fffffff || !d_workspace) return MCF_ERR_BAD_ARG;
+    const LsmGeom g = lsm_geom(n_paths);
+    if (workspace_bytes < g.total) return MCF_ERR_WORKSPACE_TOO_SMALL;
+    char *ws = (char *)d_workspace;
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    LsmState *st = (LsmState *)(ws + g.off_state);
+    unsigned int *counter = (unsigned int *)(ws + g.off_counter);
+    double *cf = (double *)(ws + g.off_cf), *partials = (double *)(ws + g.off_partials);
+    MCF_CUDA_OK(cudaMemsetAsync(ws + g.off_state, 0, (size_t)(g.off_partials - g.off_state), cs));
+    const int grid = g.n_blocks;
+    // t = n_steps: initialise cash flows and fit step n_steps-1; t = n_steps-1 .. 1: decide step t, fit step t-1
+    for (int64_t t = n_steps; t >= 1; t--) {
+        const double *s_t = d_paths_tm + (size_t)t * (size_t)n_paths;
+        lsm_fused_step_kernel<<<grid, LSM_THREADS, 0, cs>>>(
+            s_t, s_t - n_paths, n_paths, (int32_t)t, (int32_t)n_steps, K, is_put, exp(-r * dt * (double)t),
+            exp(r * dt * (double)(t - 1)), st + (t & 1), st + ((t - 1) & 1), d_exercise_times, cf, partials, counter,
+            d_price);
     }
-    return mcf_lsm_finish(n_paths, r, dt, d_workspace, NULL, d_price, d_exercise_times, cuda_stream);
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
 }
 
 int mcf_transpose(const double *d_in, int64_t n_rows, int64_t n_cols, double *d_out, void *cuda_stream) {
