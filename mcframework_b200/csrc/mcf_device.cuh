@@ -690,12 +690,20 @@ MCF_HD double zig_fast_value(uint64_t w, const ZigTables &t) {  // signed value 
     return xmul(xadd(bits_to_double(dbits), -4503599627370496.0), t.kws[(unsigned)w & 0x1ffu].wi);
 }
 
-template <class Load>
+//
+// Entry patch.  `entry_of(exit)` is called once, with the chunk's speculative exit, and returns the exit of the
+// PREVIOUS chunk of the stream where the caller can know it cheaply (the neighbouring lane's; 0 otherwise).  A
+// non-zero entry e (1 or 2 draws consumed by the previous chunk's last attempt) whose skipped draws were plain fast
+// attempts leaves the chain untouched from e on: their values leave the first sub-chunk sum, their start bits are
+// cleared, and the chunk is recorded as generated with entry e -- no re-walk (97 % of the chunks that would be
+// re-walked).  Anything else marks the chunk invalid for the general walk.
+template <class Load, class EntryOf>
 MCF_HD ChunkInfo scan_chunk_fast2(Load load, uint64_t blk0, const ZigTables &t, const ParkSlots &park, double *zsub_out,
-                                  bool *valid) {
+                                  bool *valid, EntryOf entry_of) {
     uint64_t F = 0;   // fast-looking draws
     unsigned np = 0;  // parked draws
     double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
+    double vk0 = 0.0, vk1 = 0.0;  // values of the chunk's first two draws (entry patch)
     uint64_t w0, w1, w2, w3, n0, n1, n2, n3;
     load(blk0, w0, w1, w2, w3);
 #define MCF_FAST2_DRAW(J, WA, WB, WC)                                                             \
@@ -703,6 +711,8 @@ MCF_HD ChunkInfo scan_chunk_fast2(Load load, uint64_t blk0, const ZigTables &t, 
         const uint64_t dbits = (((WA) >> 9) & 0x000fffffffffffffULL) | MCF_U52_BIAS;              \
         const ZigKW kw = t.kws[(unsigned)(WA)&0x1ffu];                                            \
         const double v = xmul(xadd(bits_to_double(dbits), -4503599627370496.0), kw.wi);           \
+        if ((J) == 0 && sub == 0) vk0 = v;                                                        \
+        if ((J) == 1 && sub == 0) vk1 = v;                                                        \
         if (bits_to_double(dbits) < bits_to_double(kw.ki)) {                                      \
             f16 |= 1u << (J);                                                                     \
             zc = xadd(zc, v);                                                                     \
@@ -797,12 +807,25 @@ MCF_HD ChunkInfo scan_chunk_fast2(Load load, uint64_t blk0, const ZigTables &t, 
             if ((F >> f) & 1ULL) add_to_sub(f >> MCF_SUB_SHIFT, -zig_fast_value(q == 1 ? u : u2, t));
         }
     }
+    const unsigned e = entry_of(exitv);
+    unsigned gen_entry = 0;
+    if (e != 0) {
+        const uint64_t low = (1ULL << (e & 63u)) - 1ULL;
+        if (ok && e <= 2 && (F & S & low) == low) {
+            z0 = xsub(z0, vk0);
+            if (e == 2) z0 = xsub(z0, vk1);
+            S &= ~low;
+            gen_entry = e;
+        } else {
+            ok = false;
+        }
+    }
     zsub_out[0] = z0;
     zsub_out[1] = z1;
     zsub_out[2] = z2;
     zsub_out[3] = z3;
     ChunkInfo ci;
-    ci.gen_entry = 0;
+    ci.gen_entry = gen_entry;
     ci.startmask = S;
     ci.emitmask = (S & F) | A;
     ci.exit = exitv;

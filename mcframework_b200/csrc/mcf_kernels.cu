@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256, 3) plan_scan_kernel(const mcf_stream *__r
                 c = pc.v2;
                 d = pc.v3;
             },
-            blk0, t, park, zsum + id * MCF_SUBS, &valid);
+            blk0, t, park, zsum + id * MCF_SUBS, &valid, [](unsigned) { return 0u; });
         startmask[id] = ci.startmask;
         emitmask[id] = ci.emitmask;
         exit_[id] = (uint8_t)ci.exit;
@@ -219,18 +219,22 @@ __global__ void __launch_bounds__(256, 4) plan_scan_philox_stream_kernel(const _
     __shared__ ScanShared sh;
     ParkSlots park;
     const ZigTables t = load_scan_tables(sh, park);
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // cps is a multiple of 1024: whole warps are live
     if (c >= cps) return;
     const int64_t id = row0 + c;
     bool valid;
     const uint64_t blk0 = (K.off + (uint64_t)c * MCF_CHUNK) >> 2;
     const ChunkInfo ci = scan_chunk_fast2(
         [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &cc, uint64_t &d) { philox_block_folded(K, blk, a, b, cc, d); },
-        blk0, t, park, zsum + id * MCF_SUBS, &valid);
+        blk0, t, park, zsum + id * MCF_SUBS, &valid, [&](unsigned exit_spec) {
+            // the previous chunk of the stream is the neighbouring lane's; lane 0 cannot know it (entry 0, fixed up later)
+            const unsigned prev = __shfl_up_sync(0xffffffffu, exit_spec, 1);
+            return (threadIdx.x & 31) == 0 ? 0u : prev;
+        });
     startmask[id] = ci.startmask;
     emitmask[id] = ci.emitmask;
     exit_[id] = (uint8_t)ci.exit;
-    gen[id] = valid ? (uint8_t)0 : (uint8_t)MCF_GEN_ENTRY_INVALID;
+    gen[id] = valid ? (uint8_t)ci.gen_entry : (uint8_t)MCF_GEN_ENTRY_INVALID;
 }
 
 // Fix chunk entries: a chunk's true entry offset is its predecessor's exit.  Two kernels per iteration so that the

@@ -123,3 +123,10 @@ def normals(record, pos, n):
     lib().emu_normals(C.c_uint32(int(record["kind"][0])), _vp(record), C.c_uint64(pos), C.c_int64(n), _vp(out),
                       C.byref(end))
     return out, end.value
+
+
+def philox_folded(record, blk0, n_blocks):
+    """4*n_blocks raw draws from block ``blk0`` (relative to the record's counter) via philox_block_folded."""
+    out = np.empty(4 * n_blocks, dtype=np.uint64)
+    rc = lib().emu_philox_folded(_vp(record), C.c_uint64(blk0), C.c_int64(n_blocks), _vp(out))
+    return rc, out

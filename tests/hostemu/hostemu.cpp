@@ -108,6 +108,7 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
     std::vector<double> zs(g.n_chunks * MCF_SUBS);
     int status = 0;
     int64_t n_fast_invalid = 0, n_fast_mismatch = 0;
+    unsigned prev_exit_spec = 0;
     constexpr int RUN = KIND == MCF_GEN_PCG64 ? 8 : 1;
     // scan
     for (int64_t run = 0; run < g.n_chunks / RUN; run++) {
@@ -133,13 +134,20 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
                     else
                         philox_block_keys(K, blk, a, b, cc, d);
                 },
-                blk0, t, park, &zs[id * MCF_SUBS], &valid);
-            if (valid) {  // the speculative walk must agree with the general one from entry 0
+                blk0, t, park, &zs[id * MCF_SUBS], &valid, [&](unsigned exit_spec) {
+                    // as plan_scan_philox_stream_kernel: the neighbouring lane's speculative exit, none for lane 0
+                    const unsigned e = (c0 & 31) == 0 ? 0u : prev_exit_spec;
+                    prev_exit_spec = exit_spec;
+                    return e;
+                });
+            if (valid) {  // the speculative walk must agree with the general one from the same entry
                 double zref[MCF_SUBS];
                 Cursor<KIND> c2;
-                c2.init(streams[si], (uint64_t)c0 * MCF_CHUNK);
-                const ChunkInfo cr = scan_chunk(c2, (uint64_t)c0 * MCF_CHUNK, 0u, t, zref);
-                bool same = cr.startmask == ci.startmask && cr.emitmask == ci.emitmask && cr.exit == ci.exit;
+                c2.init(streams[si], (uint64_t)c0 * MCF_CHUNK + ci.gen_entry);
+                const ChunkInfo cr = scan_chunk(c2, (uint64_t)c0 * MCF_CHUNK, ci.gen_entry, t, zref);
+                const uint64_t m = mask_from(ci.gen_entry);
+                bool same = (cr.startmask & m) == (ci.startmask & m) && (cr.emitmask & m) == (ci.emitmask & m) &&
+                            cr.exit == ci.exit;
                 for (int q = 0; q < MCF_SUBS; q++) {
                     const double d = zref[q] - zs[id * MCF_SUBS + q];
                     same = same && (d < 1e-13 && d > -1e-13);
@@ -149,7 +157,7 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
             sm[id] = ci.startmask;
             em[id] = ci.emitmask;
             ex[id] = (uint8_t)ci.exit;
-            gen[id] = valid ? (uint8_t)0 : (uint8_t)MCF_GEN_ENTRY_INVALID;
+            gen[id] = valid ? (uint8_t)ci.gen_entry : (uint8_t)MCF_GEN_ENTRY_INVALID;
             n_fast_invalid += valid ? 0 : 1;
             continue;
         }
@@ -341,6 +349,15 @@ void emu_pi_hits(uint32_t kind, const mcf_stream *streams, int n_streams, int64_
         pi_impl<MCF_GEN_PCG64>(streams, n_streams, n_total, n_points, antithetic, hint, hits);
     else
         pi_impl<MCF_GEN_PHILOX>(streams, n_streams, n_total, n_points, antithetic, hint, hits);
+}
+
+// raw draws of a block-aligned Philox stream through the folded block function (4*n_blocks values from block blk0)
+int emu_philox_folded(const mcf_stream *st, uint64_t blk0, int64_t n_blocks, uint64_t *out) {
+    const PhiloxKeys K = philox_keys_of(*st);
+    if (!K.fold_ok) return -1;
+    for (int64_t b = 0; b < n_blocks; b++)
+        philox_block_folded(K, blk0 + (uint64_t)b, out[4 * b], out[4 * b + 1], out[4 * b + 2], out[4 * b + 3]);
+    return 0;
 }
 
 int64_t emu_plan_chunks(int n_streams, int64_t max_sims, int64_t nps, double slack, int64_t *cps) {

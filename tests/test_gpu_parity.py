@@ -163,6 +163,26 @@ def test_large_run_sum_of_normals_matches_oracle_blockwise(dev):
     assert abs(sums.mean()) < 5 * np.sqrt(252 / sums.size)
 
 
+@pytest.mark.parametrize("steps", [15, 16, 17, 31, 32, 33, 47, 100])
+def test_boundary_replay_sums_match_oracle_normals(dev, steps):
+    """Affine bodies on aligned Philox streams regenerate only the shorter side of every replication boundary and take
+    the rest from the stored sub-chunk sums (>= 16 steps; below that the direct replay runs): per-replication sums of
+    NumPy's normals, for step counts around the 16-draw sub-chunk size and ragged stream lengths."""
+    from oracle import c_oracle as co
+    D, N, S = dev
+    lay = S.parallel_layout(np.random.SeedSequence(700 + steps), 20_003, 5)
+    dl = D.DeviceLayout.of(lay)
+    plan = D.normal_plan(dl, steps)
+    sums = D.gbm_terminal(dl, steps, plan, [(N.NORMAL_SUM, []), (N.BS_EURO_PUT, BS)]).cpu().numpy()
+    for k in (0, lay.n_streams // 2, lay.n_streams - 1):
+        rec = lay.records[k]
+        n, f = int(rec["n_sims"]), int(rec["first_sim"])
+        z = co.Gen.philox_from_key(rec["s"][:2]).standard_normal(n * steps).reshape(n, steps)
+        np.testing.assert_allclose(sums[0, f:f + n], z.sum(axis=1), rtol=0, atol=1e-12 * max(1.0, steps ** 0.5))
+    single = D.gbm_terminal(dl, steps, plan, [(N.BS_EURO_PUT, BS)])[0].cpu().numpy()
+    assert np.array_equal(single, sums[1])  # deterministic: same launch shape or not, same bits
+
+
 # ======================================================================= StatsEngine kernels
 STAT_RTOL = 1e-11  # device one-pass sums vs NumPy's pairwise sums / SciPy's two-pass moments
 

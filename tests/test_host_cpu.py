@@ -255,7 +255,7 @@ def test_hostemu_ziggurat_with_certified_wedge_bounds_is_numpy_bit_for_bit(emu):
         assert probe.bit_generator.random_raw(4).tolist() == gen.bit_generator.random_raw(4).tolist()
 
 
-@pytest.mark.parametrize("steps", [1, 7, 63, 64, 65, 100, 252, 1000])
+@pytest.mark.parametrize("steps", [1, 7, 15, 16, 17, 31, 32, 33, 63, 64, 65, 100, 252, 1000])
 def test_hostemu_chunk_sum_replay_equals_sequential_replay(emu, steps):
     """Affine bodies take whole chunks from the sums stored by the planning pass: same normals, different
     (deterministic) summation order.  Checked against the strictly sequential state-machine replay for
@@ -294,3 +294,25 @@ def test_hostemu_fast_philox_scan_positions_match_oracle(emu):
             f = int(rec["first_sim"])
             assert np.array_equal(plan.sim_start[f:f + len(want)], np.array(want, dtype=np.uint64))
             assert int(plan.stream_end[k]) == g.consumed
+
+
+def test_hostemu_folded_philox_blocks_equal_numpy_raw_draws(emu):
+    """Rounds 0 and 1 with their launch-constant halves folded (18 wide multiplications instead of 20) give NumPy's
+    Philox4x64-10 output bit for bit -- fresh streams, spawned keys, and a generator advanced far into its stream."""
+    from mcframework_b200 import _streams as S
+
+    gens = [np.random.Generator(np.random.Philox(5)), np.random.Generator(np.random.Philox(np.random.SeedSequence(42).spawn(3)[2])),
+            np.random.Generator(np.random.Philox(key=np.array([2**64 - 1, 12345], dtype=np.uint64))),
+            np.random.Generator(np.random.Philox(9).advance(2**70 + 12345))]
+    for g in gens:
+        _, rec = S.generator_record(g)
+        assert int(rec["buf_pos"][0]) % 4 == 0
+        b0 = int(rec["buf_pos"][0]) // 4  # NumPy increments the counter before each block: a fresh buffer starts at block 1
+        rc, got = emu.philox_folded(rec, b0, 64)
+        assert rc == 0
+        assert np.array_equal(got, g.bit_generator.random_raw(256))
+        rc, got = emu.philox_folded(rec, b0 + (1 << 40), 8)  # far ahead: compare with NumPy's own jump
+        bg = type(g.bit_generator)()
+        bg.state = g.bit_generator.state
+        bg.advance((1 << 40) - 64)  # the generator above already consumed 64 blocks
+        assert rc == 0 and np.array_equal(got, bg.random_raw(32))
