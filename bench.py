@@ -175,7 +175,7 @@ def b200_arm(args):
 
     greek_sets = [(N.BS_EURO_CALL, p) for p in bump_sets()]
     dl = D.DeviceLayout.of(layout())  # stream records resident in HBM before the timed region
-    phases = {"plan": [], "replay1": [], "replay8": [], "moments": []}
+    phases = {"plan": [], "replay1": [], "replay8": [], "moments": [], "draws": 0}
 
     def ev():
         e = torch.cuda.Event(enable_timing=True)
@@ -197,6 +197,7 @@ def b200_arm(args):
         marks.append(ev())
         if record:
             torch.cuda.synchronize()
+            phases["draws"] = plan.stream_end  # 64-bit draws the replications consume (exact); summed after the timing
             d = [marks[i].elapsed_time(marks[i + 1]) for i in range(5)]
             phases["plan"] += [d[0], d[2]]
             phases["replay1"].append(d[1])
@@ -272,6 +273,9 @@ def b200_arm(args):
               "delta_e2e": greeks["delta"], "results_len": int(res.results.size)}
 
     # ---- roofline of the dominant kernel group (measured live, CUDA events on the launch stream)
+    draws = int(phases.pop("draws").sum().item())
+    if os.environ.get("MCF_BENCH_DEBUG"):
+        print({k: [round(x, 2) for x in v] for k, v in phases.items()}, file=sys.stderr)
     mean_ms = {k: (sum(v) / len(v) if v else 0.0) for k, v in phases.items()}
     per_step_ms = {"plan": 2 * mean_ms["plan"], "replay1": mean_ms["replay1"], "replay8": mean_ms["replay8"], "moments": mean_ms["moments"]}
     dominant = max(per_step_ms, key=per_step_ms.get)
@@ -283,7 +287,7 @@ def b200_arm(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    draws_per_gpu = P * N_STEPS * 1.022  # the ziggurat consumes ~2.2 % extra 64-bit draws (measured: 257.55 per 252)
+    draws_per_gpu = float(draws) if draws else P * N_STEPS * 1.0157  # the ziggurat consumes 1.57 % extra 64-bit draws
     n_chunks = draws_per_gpu * 1.03 / 64
     alg_bytes = {  # algorithmic HBM bytes per launch group (DESIGN.md "bytes per unit")
         "plan": n_chunks * (8 + 8 + 1 + 1 + 1 + 32) + P * 8,  # masks, exit, gen, entry, 4 sub-chunk sums + sim_start
@@ -291,28 +295,37 @@ def b200_arm(args):
         "replay8": P * (8 + 8 * 8) + n_chunks * 32,
         "moments": 8 * P * 8,
     }
-    inst = {}
+    # The planning pass is bound by the integer-multiply pipe: Philox4x64-10 is 18 64x64->128 multiplications per block
+    # of 4 draws (20 minus the two with launch-constant operands) = 72 IMAD.WIDE.U32 per block and thread, and the
+    # measured issue rate of that instruction (tools/probe_pipes.cu on this GPU model, profiles/r1_probe_pipes.json) is
+    # ~0.30 per clock per SM sub-partition.  ALGORITHMIC work = blocks that hold draws the replications consume (the
+    # look-ahead block per chunk, the 3 % window slack and the re-walks are overhead, not work).
+    ri = {}
     try:
-        with open(os.path.join(ROOT, "profiles", "inst_per_unit.json")) as f:
-            inst = json.load(f)
+        with open(os.path.join(ROOT, "profiles", "r1_roofline_inputs.json")) as f:
+            ri = json.load(f)
     except OSError:
         pass
     dom_ms = mean_ms["plan"] if dominant == "plan" else per_step_ms[dominant]
     sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
-    issue_peak = 148 * 4 * sm_mhz * 1e6  # warp-instructions/s: 4 schedulers per SM, 1 issue/clk each
-    roof = {"kernel": dominant, "bound": "issue" if dominant != "moments" else "hbm"}
+    roof = {"kernel": dominant, "bound": "imad" if dominant != "moments" else "hbm"}
     hbm_ach = alg_bytes[dominant] / (dom_ms / 1e3) / 1e9 if dom_ms else None
     if roof["bound"] == "hbm":
         roof.update({"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "traffic": None,
                      "peak_source": peak_src})
     else:
-        wi = inst.get(dominant + "_warp_inst_per_path_step")
-        ach = (wi * P * N_STEPS / (dom_ms / 1e3)) if (wi and dom_ms) else None
-        tr = inst.get(dominant + "_dram_bytes_per_path_step")
-        roof.update({"achieved": ach / 1e9 if ach else None, "peak": issue_peak / 1e9, "unit": "Gwarp-inst/s",
-                     "frac": (ach / issue_peak) if ach else None, "traffic": tr * P * N_STEPS if tr else None,
-                     "peak_source": f"148 SM x 4 schedulers x {sm_mhz:.0f} MHz (median SM clock under load)",
-                     "inst_source": inst.get("source"),
+        wide_peak = float(ri.get("imad_wide_warp_inst_per_s", 3.4755e11)) * (sm_mhz / float(ri.get("probe_sm_mhz", 1965.0)))
+        blocks = draws / 4.0 if dominant == "plan" else P * 2.0  # replay: at most two blocks per replication boundary
+        ach = blocks * 72.0 / 32.0 / (dom_ms / 1e3) if dom_ms else None
+        roof.update({"achieved": ach / 1e9 if ach else None, "peak": wide_peak / 1e9, "unit": "Gwarp-IMAD.WIDE/s",
+                     "frac": (ach / wide_peak) if ach else None,
+                     "traffic": ri.get(dominant + "_dram_bytes_per_launch_1e7_paths"),
+                     "algorithmic_work": "Philox blocks holding consumed draws x 72 IMAD.WIDE.U32 per block and thread",
+                     "peak_source": "measured IMAD.WIDE.U32 issue rate (tools/probe_pipes.cu, profiles/r1_probe_pipes.json), "
+                                    f"scaled to {sm_mhz:.0f} MHz",
+                     "ncu_pipe_busy": ri.get(dominant + "_fmaheavy_busy_frac"),
+                     "ncu_issue_active": ri.get(dominant + "_issue_active_frac"),
+                     "ncu_source": ri.get("source"),
                      "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak if hbm_ach else None,
                              "algorithmic_bytes_per_launch": alg_bytes[dominant], "peak_source": peak_src,
                              "note": "register-resident kernel: HBM is not the binding resource"}})

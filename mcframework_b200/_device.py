@@ -126,7 +126,9 @@ def gbm_terminal(dl: DeviceLayout, n_steps: int, plan: NormalPlan, specs):
                                   lay.n_total, int(n_steps), lay.hint, _ptr(plan.sim_start), _ptr(plan.workspace),
                                   _spec_array(specs), len(specs), _ptr(out), _stream_ptr())
     N.check("mcf_gbm_terminal", rc)
-    LAUNCHES["gbm"] += 1  # one launch per stream for affine bodies on aligned Philox streams; counted as one here
+    affine = all(int(m) not in (N.BS_AMER_CALL, N.BS_AMER_PUT, N.PORTFOLIO_LOG1P) for m, _ in specs)
+    per_stream = lay.kind == 1 and lay.n_streams <= 1024 and affine and int(n_steps) >= 16
+    LAUNCHES["gbm"] += lay.n_streams if per_stream else 1  # boundary-form replay: one launch per stream
     return out
 
 

@@ -331,7 +331,7 @@ def lsm_price(paths_tm, K: float, r: float, dt: float, is_put: bool, group=None,
         rc = lib.mcf_lsm(_ptr(paths_tm), n_paths, n_steps, float(K), float(r), float(dt), int(bool(is_put)), _ptr(ws),
                          nbytes, _ptr(price), _ptr(ex) if ex is not None else None, sp)
         N.check("mcf_lsm", rc)
-        LAUNCHES["lsm"] += 1 + 4 * max(0, n_steps - 1) + 3
+        LAUNCHES["lsm"] += n_steps  # fused apply+reduce step kernel, one launch per step (the last CTA solves)
         return (price, ex) if return_exercise else price
     import torch.distributed as dist
 

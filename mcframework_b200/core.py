@@ -58,6 +58,56 @@ def make_blocks(n: int, block_size: int = 10_000) -> list[tuple[int, int]]:
     return [(lo, min(lo + block_size, n)) for lo in range(0, n, block_size)] if n > 0 else []
 
 
+class DeviceResults:
+    """Result vector left in HBM (opt-in: ``sim.keep_results_on_device = True``).
+
+    The reference hands back a host ndarray (``core.py:137-147``); between the two halves of the hot path --
+    replications and statistics -- that is an 800 MB device-to-host copy nobody reads when only the summary is used.
+    This object stands in for the ndarray: ``.device`` is the float64 CUDA tensor, and anything that needs host
+    values (``np.asarray``, indexing, iteration, ``.numpy()``) materialises the host copy ONCE, on first use.
+    """
+
+    __array_priority__ = 100
+
+    def __init__(self, dev):
+        self._dev = dev
+        self._host = None
+
+    @property
+    def device(self):
+        return self._dev
+
+    def numpy(self) -> np.ndarray:
+        if self._host is None:
+            self._host = MonteCarloSimulation._to_host(self._dev)
+        return self._host
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    @property
+    def materialised(self) -> bool:
+        return self._host is not None
+
+    size = property(lambda self: int(self._dev.numel()))
+    shape = property(lambda self: (int(self._dev.numel()),))
+    ndim = 1
+    dtype = np.dtype(np.float64)
+
+    def __len__(self) -> int:
+        return int(self._dev.numel())
+
+    def __getitem__(self, key):
+        return self.numpy()[key]
+
+    def __iter__(self):
+        return iter(self.numpy())
+
+    def __repr__(self) -> str:
+        return f"DeviceResults(n={len(self)}, materialised={self.materialised})"
+
+
 @dataclass
 class SimulationResult:
     """Outcome of one run (:137-238).  ``results`` is a host float64 ndarray owned by this object."""
@@ -275,6 +325,9 @@ class MonteCarloSimulation(ABC):
             else:
                 host = self._to_host(_multi.gather_results(local, group))
             self._device_sample = DeviceSample(local, host, group)
+        elif getattr(self, "keep_results_on_device", False):
+            host = DeviceResults(values_dev)  # lazy host copy; the statistics read the device tensor
+            self._device_sample = DeviceSample(values_dev, host, None)
         else:
             host = self._to_host(values_dev)
             self._device_sample = DeviceSample(values_dev, host, None)

@@ -932,9 +932,48 @@ MCF_HD void replay_emits_blocks(Load load, Tail tail, const PlanView &pv, int64_
     }
 }
 
+// Sum of the normals emitted by attempts starting in [start, end) -- the same additions in the same order as
+// replay_emits_blocks with an accumulating f, but branch-free per draw (converted always, added under the emit bit):
+// lanes of a warp sit at different offsets inside their blocks, and four data-dependent branches per block would
+// serialise them.  Only the tail (3e-4 of the emits) branches.
+template <class Load, class Tail>
+MCF_HD double sum_emits_blocks(Load load, Tail tail, const PlanView &pv, int64_t si, uint64_t off, uint64_t start,
+                               uint64_t end, const double *wi, uint64_t ki0) {
+    double acc = 0.0;
+    if (end <= start) return acc;
+    const uint64_t b_first = (start + off) >> 2, b_last = (end - 1 + off) >> 2;
+    uint64_t chunk = ~0ULL, word = 0;
+    for (uint64_t blk = b_first; blk <= b_last; blk++) {
+        const uint64_t p0 = (blk << 2) - off;
+        const uint64_t c = (p0 + 3) >> 6;
+        if (c != chunk) {
+            chunk = c;
+            word = plan_emit_word(pv, si, c);
+        }
+        unsigned nib = (unsigned)(word >> (p0 & 63ULL)) & 0xFu;
+        if (blk == b_first) nib &= (0xFu << (unsigned)(start - p0)) & 0xFu;
+        if (blk == b_last) nib &= 0xFu >> (unsigned)(p0 + 4 - end);
+        uint64_t v[4];
+        load(blk, v[0], v[1], v[2], v[3]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint64_t r = v[k];
+            const unsigned idx = (unsigned)(r & 0xffULL);
+            const uint64_t rabs = (r >> 9) & 0x000fffffffffffffULL;
+            const double m = xmul(u52_to_double(rabs), wi[idx]);
+            double z = ((r >> 8) & 1ULL) ? -m : m;
+            const bool on = (nib >> k) & 1u;
+            if (on && idx == 0 && rabs >= ki0) z = tail(p0 + (uint64_t)k, rabs);
+            acc = on ? xadd(acc, z) : acc;
+        }
+    }
+    return acc;
+}
+
 // A replication boundary at stream position p cuts its 16-draw sub-chunk in two.  Only the SHORTER side is regenerated
-// (at most two Philox blocks); the other side is the stored sub-chunk sum minus it.  `before` belongs to the
-// replication that ends at p, `after` to the one that starts there.
+// (at most two Philox blocks, one loop for both cases so that a warp does not run it twice); the other side is the
+// stored sub-chunk sum minus it.  `before` belongs to the replication that ends at p, `after` to the one that starts
+// there.  An aligned boundary (offset 0) regenerates nothing: before = 0, after = the whole sum.
 struct BoundarySums {
     double before, after;
 };
@@ -943,23 +982,13 @@ MCF_HD BoundarySums boundary_sums(Load load, Tail tail, const PlanView &pv, int6
                                   const double *wi, uint64_t ki0) {
     const uint64_t s = p >> MCF_SUB_SHIFT, o = p & ((1ULL << MCF_SUB_SHIFT) - 1ULL);
     const double S = pv.zsum[si * pv.cps * MCF_SUBS + (int64_t)s];
+    const bool head = o <= 8;  // regenerate [sub-chunk start, p), else [p, sub-chunk end)
+    const double part = sum_emits_blocks(load, tail, pv, si, off, head ? (s << MCF_SUB_SHIFT) : p,
+                                         head ? p : ((s + 1) << MCF_SUB_SHIFT), wi, ki0);
+    const double rest = xsub(S, part);
     BoundarySums r;
-    if (o == 0) {
-        r.before = 0.0;
-        r.after = S;
-        return r;
-    }
-    double acc = 0.0;
-    auto add = [&](double z) { acc = xadd(acc, z); };
-    if (o <= 8) {
-        replay_emits_blocks(load, tail, pv, si, off, s << MCF_SUB_SHIFT, p, wi, ki0, add);
-        r.before = acc;
-        r.after = xsub(S, acc);
-    } else {
-        replay_emits_blocks(load, tail, pv, si, off, p, (s + 1) << MCF_SUB_SHIFT, wi, ki0, add);
-        r.before = xsub(S, acc);
-        r.after = acc;
-    }
+    r.before = head ? part : rest;
+    r.after = head ? rest : part;
     return r;
 }
 // sum of the normals of the replication [start, end) given the two boundary cuts (requires end - start >= 16):

@@ -122,6 +122,32 @@ def test_black_scholes_runs(m, golden):
         bs.run(10, exercise_type="bermudan")
 
 
+def test_results_can_stay_on_the_device_until_somebody_reads_them(m, golden):
+    """SURVEY 8(f).2: opt-in device-resident results.  Statistics, percentiles and compare_results need no host copy;
+    the ndarray appears (once) when the caller touches it, and equals the one an ordinary run returns."""
+    from mcframework_b200.core import DeviceResults
+
+    _, a = golden
+    bs = m.BlackScholesSimulation()
+    fw = m.MonteCarloFramework()
+    fw.register_simulation(bs)
+    bs.set_seed(11)
+    plain = fw.run_simulation(bs.name, 20_000, parallel=True, n_workers=4, n_steps=64, percentiles=(10, 90))
+    bs.keep_results_on_device = True
+    bs.set_seed(11)
+    lazy = fw.run_simulation(bs.name, 20_000, parallel=True, n_workers=4, n_steps=64, percentiles=(10, 90))
+    assert isinstance(lazy.results, DeviceResults) and not lazy.results.materialised
+    assert lazy.results.device.is_cuda and len(lazy.results) == 20_000 and lazy.results.size == 20_000
+    assert (lazy.mean, lazy.std, lazy.percentiles) == (plain.mean, plain.std, plain.percentiles)
+    assert lazy.stats["ci_mean"] == plain.stats["ci_mean"]
+    assert fw.compare_results([bs.name], "p90")[bs.name] == plain.percentiles[90]
+    assert not lazy.results.materialised  # nothing above needed the host copy
+    assert np.array_equal(np.asarray(lazy.results), plain.results) and lazy.results.materialised
+    assert lazy.results[3] == plain.results[3] and float(np.mean(lazy.results)) == float(np.mean(plain.results))
+    np.testing.assert_allclose(np.asarray(lazy.results), a["G4_bs_call_par"], rtol=RES_RTOL, atol=PAY_ATOL)
+    bs.keep_results_on_device = False
+
+
 def test_greeks(m, golden):
     j, _ = golden
     bs = m.BlackScholesSimulation()

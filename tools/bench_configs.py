@@ -101,7 +101,7 @@ def cfg_lsm(scale):
     del plan
     tl, price = timed(lambda: SD.lsm_price(paths, 100.0, 0.05, 1.0 / steps, True), reps=1)
     pbytes = paths.numel() * 8
-    alg = (steps - 1) * n * (2 * 8 + 2 * 12) + n * 8  # two sweeps per step: S_t (8 B) + state (12 B) each
+    alg = steps * n * 24  # fused step kernel: S_t (decision) + S_{t-1} (regression) + discounted cash flow, 8 B each
     return {"paths": n, "steps": steps, "plan_s": tp, "paths_s": tg, "paths_store_GBps": pbytes / tg / 1e9, "lsm_s": tl,
             "lsm_path_steps_per_s": n * steps / tl, "lsm_algorithmic_GBps": alg / tl / 1e9,
             "lsm_frac_of_hbm_peak": alg / tl / 1e9 / PEAK_HBM, "american_put_price": float(price.cpu()[0])}
