@@ -68,7 +68,9 @@ enum {
     MCF_PATH_TERMINAL = 4,   /* p={S0,r,sigma,T}     sims/black_scholes.py:399-401 */
     MCF_PORTFOLIO_GBM = 5,   /* p={V0,mu,sigma}      sims/portfolio.py:79-82 */
     MCF_PORTFOLIO_LOG1P = 6, /* p={V0,mu,sigma}      sims/portfolio.py:83-84 */
-    MCF_NORMAL_SUM = 7       /* sum of the n_steps standard normals (building block / tests) */
+    MCF_NORMAL_SUM = 7,      /* sum of the n_steps standard normals (building block / tests) */
+    MCF_NORMAL_LOC_SCALE = 8 /* p={loc,scale}: n_steps*loc + scale*sum(z); n_steps = 1 is rng.normal(loc, scale) bit for bit
+                                (declared draw programs of user simulations, tests/conftest.py:9-14 of the reference) */
 };
 
 typedef struct mcf_gbm_spec {
@@ -144,6 +146,18 @@ int mcf_gbm_slices(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_str
                    int64_t sims_per_stream_hint, const uint64_t *d_sim_start, const void *d_plan_workspace,
                    const mcf_gbm_spec *h_spec, int64_t slice_stride, int32_t time_major, double *d_out,
                    void *cuda_stream);
+
+/* ---- (2b) declared integer draw programs ------------------------------------------------
+ * A user simulation whose hook is `rng.integers(low, high, size=k)` followed by a reduction (the reference's dice
+ * fixture core.py:22-25, the coin-flip streak of docs/source/getting-started.md:139-183) can declare that instead of
+ * being looped in Python.  Replication i of a stream reads the 32-bit slots [i*k, (i+1)*k) (NumPy's buffered
+ * next_uint32: low half, then high half of each 64-bit draw) through the 32-bit Lemire rule.  op 0: sum of the values;
+ * op 1: longest run of values equal to `match`.  A rejected slot (probability < 2^-32*(high-low) per draw) would shift
+ * every later slot: the kernel raises *d_rejected and the caller falls back to the reference's own loop.
+ * Requires 2 <= high-low < 2^32. */
+int mcf_draw_integers(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total,
+                      int64_t sims_per_stream_hint, int64_t low, int64_t high, int32_t size, int32_t op, int64_t match,
+                      double *d_out, int32_t *d_rejected, void *cuda_stream);
 
 /* ---- (3) Longstaff-Schwartz backward induction ------------------------------------------
  * replaces _american_exercise_lsm (sims/black_scholes.py:109-193).  `d_paths_tm` is TIME-MAJOR:

@@ -132,6 +132,20 @@ def gbm_terminal(dl: DeviceLayout, n_steps: int, plan: NormalPlan, specs):
     return out
 
 
+def draw_integers(dl: DeviceLayout, low: int, high: int, size: int, op: int, match: int = 0):
+    """Per replication ``rng.integers(low, high, size=size)`` reduced on the device (op 0: sum, op 1: longest run of
+    ``match``).  Returns (float64[n] results, rejected flag tensor int32[1])."""
+    torch = _torch()
+    lay = dl.layout
+    out = torch.empty(lay.n_total, dtype=torch.float64, device="cuda")
+    rejected = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rc = N.lib().mcf_draw_integers(lay.kind, _ptr(dl.records), lay.n_streams, lay.n_total, lay.hint, int(low), int(high),
+                                   int(size), int(op), int(match), _ptr(out), _ptr(rejected), _stream_ptr())
+    N.check("mcf_draw_integers", rc)
+    LAUNCHES["pi"] += 1
+    return out, rejected
+
+
 def gbm_paths(dl: DeviceLayout, n_steps: int, plan: NormalPlan, S0: float, r: float, sigma: float, T: float,
               time_major: bool = False):
     torch = _torch()

@@ -22,7 +22,7 @@ _ERR_NAMES = {
 }
 
 # replication bodies (enum in include/mcf_b200.h)
-BS_EURO_CALL, BS_EURO_PUT, BS_AMER_CALL, BS_AMER_PUT, PATH_TERMINAL, PORTFOLIO_GBM, PORTFOLIO_LOG1P, NORMAL_SUM = range(8)
+BS_EURO_CALL, BS_EURO_PUT, BS_AMER_CALL, BS_AMER_PUT, PATH_TERMINAL, PORTFOLIO_GBM, PORTFOLIO_LOG1P, NORMAL_SUM, NORMAL_LOC_SCALE = range(9)
 
 
 class DeviceUnavailableError(RuntimeError):
@@ -50,6 +50,7 @@ SIGNATURES = {
     "mcf_normal_plan_workspace_bytes": (_i64, [_i32, _i64, _i64, _f64]),
     "mcf_normal_plan": (C.c_int, [_u32, _vp, _vp, _i32, _i64, _i64, _i64, _f64, _i32, _vp, _i64, _vp, _vp, _vp]),
     "mcf_workspace_status": (C.c_int, [_vp, _vp]),
+    "mcf_draw_integers": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _i64, _vp, _vp, _vp]),
     "mcf_gbm_terminal": (C.c_int, [_u32, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, C.POINTER(GbmSpec), _i32, _vp, _vp]),
     "mcf_gbm_paths": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i64, _vp, _vp, C.POINTER(_f64), _i32, _vp, _vp]),
     "mcf_gbm_slices": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i64, _vp, _vp, C.POINTER(GbmSpec), _i64, _i32, _vp, _vp]),

@@ -16,15 +16,25 @@ from . import _native as N
 from . import _streams as S
 
 
+class HostLoopRequired(RuntimeError):
+    """The declared program met a case only the reference's own loop reproduces (a rejected Lemire slot)."""
+
+
 @dataclass
 class ReplicationProgram:
-    kind: str  # "pi" | "normals"
+    kind: str  # "pi" | "normals" | "integers"
     # pi
     n_points: int = 0
     antithetic: bool = False
     # normals
     n_steps: int = 0
     specs: list = field(default_factory=list)  # [(mode, params)], common random numbers when > 1
+    # integers
+    low: int = 0
+    high: int = 0
+    size: int = 0
+    op: int = 0      # 0: sum of the values, 1: longest run of `match`
+    match: int = 0
 
     def execute(self, dl: D.DeviceLayout):
         """-> (float64[n] device tensor of results, int64[n_streams] device tensor of draws per stream | fixed int)"""
@@ -33,9 +43,25 @@ class ReplicationProgram:
             m = self.n_points // 2 if self.antithetic else self.n_points
             per_sim = 2 * m + (2 if (self.antithetic and 2 * m < self.n_points) else 0)
             return out, per_sim
+        if self.kind == "integers":
+            out, rejected = D.draw_integers(dl, self.low, self.high, self.size, self.op, self.match)
+            if int(rejected.item()):
+                raise HostLoopRequired("a Lemire slot was rejected: later slots shift, run the hook's own loop")
+            return out, SlotCount(self.size)
         plan = D.normal_plan(dl, self.n_steps)
         out = D.gbm_terminal(dl, self.n_steps, plan, self.specs)
         return (out[0] if len(self.specs) == 1 else out), plan.stream_end
+
+
+class SlotCount(int):
+    """32-bit slots (not 64-bit draws) one replication consumes: the generator keeps half a draw buffered."""
+
+
+def integers_program(low: int, high: int, size: int, op: int = 0, match: int = 0) -> ReplicationProgram:
+    low, high, size = int(low), int(high), int(size)
+    if size <= 0 or not (2 <= high - low < (1 << 32)):
+        raise ValueError("integers program needs size >= 1 and 2 <= high - low < 2**32")
+    return ReplicationProgram("integers", low=low, high=high, size=size, op=int(op), match=int(match))
 
 
 def pi_program(n_points: int, antithetic: bool) -> ReplicationProgram:
@@ -56,6 +82,11 @@ def run_sequential(prog: ReplicationProgram, rng: np.random.Generator, n: int):
     """One PCG64 stream, replications back to back.  Returns (device results, draws consumed)."""
     dl = D.DeviceLayout.of(S.sequential_layout(rng, n))
     values, used = prog.execute(dl)
+    if isinstance(used, SlotCount):  # buffered 32-bit slots: leave the generator (and its half-draw buffer) as NumPy would
+        from ._stats_device import _advance_generator
+
+        _advance_generator(rng, int(used) * n)
+        return values, 0
     draws = used * n if isinstance(used, int) else int(used.cpu().numpy()[0])
     return values, draws
 
@@ -71,8 +102,22 @@ def run_blocks(prog: ReplicationProgram, blocks, children, n: int, group=None):
         import torch
 
         return torch.empty(0, dtype=torch.float64, device="cuda")
-    values, _ = prog.execute(D.DeviceLayout.of(lay))
+    try:
+        values, _ = prog.execute(D.DeviceLayout.of(lay))
+        failed = False
+    except HostLoopRequired:
+        values, failed = None, True
+    if group is not None:  # every rank takes the same path
+        import torch
+        import torch.distributed as dist
+
+        flag = torch.tensor([1 if failed else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        failed = bool(int(flag.item()))
+    if failed:
+        raise HostLoopRequired("a rank met a rejected Lemire slot")
     return values
 
 
-__all__ = ["ReplicationProgram", "pi_program", "normals_program", "run_sequential", "run_blocks", "N"]
+__all__ = ["ReplicationProgram", "HostLoopRequired", "SlotCount", "pi_program", "normals_program", "integers_program",
+           "run_sequential", "run_blocks", "N"]

@@ -190,7 +190,15 @@ class MonteCarloSimulation(ABC):
         means "arbitrary Python hook" (looped on the host as user plugin code)."""
         return None
 
+    def draw_program(self, **simulation_kwargs):
+        """Optional declaration (``mcframework_b200.programs``) of what ``single_simulation`` draws and computes;
+        ``None`` (default) means the hook is arbitrary Python."""
+        return None
+
     def _program_for(self, simulation_kwargs):
+        declared = self.draw_program(**simulation_kwargs)
+        if declared is not None:
+            return declared
         prog = self._replication_program(**simulation_kwargs)
         if prog is None:
             return None
@@ -341,15 +349,20 @@ class MonteCarloSimulation(ABC):
         if prog is not None and isinstance(getattr(self.rng, "bit_generator", None), np.random.PCG64):
             from . import _programs
 
-            values, draws = _programs.run_sequential(prog, self.rng, n_simulations)
-            self.rng.bit_generator.advance(int(draws))  # leave the stream where the reference would
-            results = self._finish_device_run(values)
-            if progress_callback:
-                for done in range(step, n_simulations + 1, step):
-                    progress_callback(done, n_simulations)
-                if n_simulations % step:
-                    progress_callback(n_simulations, n_simulations)
-            return results
+            try:
+                values, draws = _programs.run_sequential(prog, self.rng, n_simulations)
+            except _programs.HostLoopRequired:
+                values = None  # the generator was not advanced: loop the hook below, exactly like the reference
+            if values is not None:
+                if draws:  # (advance() also clears NumPy's buffered half draw: integer programs advance themselves)
+                    self.rng.bit_generator.advance(int(draws))  # leave the stream where the reference would
+                results = self._finish_device_run(values)
+                if progress_callback:
+                    for done in range(step, n_simulations + 1, step):
+                        progress_callback(done, n_simulations)
+                    if n_simulations % step:
+                        progress_callback(n_simulations, n_simulations)
+                return results
         results = np.empty(n_simulations, dtype=float)
         for i in range(n_simulations):
             results[i] = float(self.single_simulation(**simulation_kwargs))
@@ -440,7 +453,11 @@ class MonteCarloSimulation(ABC):
             from . import _programs
 
             group = self._shard_group()
-            values = _programs.run_blocks(prog, blocks, children, n_simulations, group)
+            try:
+                values = _programs.run_blocks(prog, blocks, children, n_simulations, group)
+            except _programs.HostLoopRequired:
+                values = None  # spawned children are untouched: loop the hook over the same blocks below
+        if prog is not None and values is not None:
             results = self._finish_device_run(values, group)
             if progress_callback:
                 done = 0

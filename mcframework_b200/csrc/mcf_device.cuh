@@ -677,10 +677,10 @@ MCF_HD ChunkInfo scan_chunk(Cur &cur, uint64_t chunk_base, uint32_t entry, const
 //   * the acceptance test decides its emit bit and adds its normal.
 // Fast-looking draws that nobody consumed are exactly the fast attempts, so
 //     startmask = ~consumed,  emitmask = (fast-looking & ~consumed) | accepted.
-// More parked draws than slots (6e-4 of the chunks) or a tail whose first pair is rejected mark the chunk invalid
+// More parked draws than slots (4e-3 of the chunks) or a tail whose first pair is rejected mark the chunk invalid
 // for the general re-walk, as before.  The sums differ from scan_chunk's by summation order only (deterministic).
 // ---------------------------------------------------------------------------------------
-#define MCF_PARK_CAP 5
+#define MCF_PARK_CAP 4
 struct ParkSlots {  // slot k of this thread: a[k * stride], b[k * stride], c[k * stride]
     uint64_t *a, *b, *c;
     unsigned stride;
@@ -697,15 +697,21 @@ MCF_HD double zig_fast_value(uint64_t w, const ZigTables &t) {  // signed value 
 // attempts leaves the chain untouched from e on: their values leave the first sub-chunk sum, their start bits are
 // cleared, and the chunk is recorded as generated with entry e -- no re-walk (97 % of the chunks that would be
 // re-walked).  Anything else marks the chunk invalid for the general walk.
-template <class Load, class EntryOf>
+//
+// Look-ahead.  The last two draws of a chunk may need the first two draws of the NEXT chunk (wedge uniform, tail pair).
+// `share_first(w0, w1)` is called once with the chunk's own first two draws and `lookahead(a, b)` must later return
+// the next chunk's: on the device the neighbouring thread's (through shared memory), so the 17th Philox block per
+// chunk is generated by one thread per CTA only; the host build simply generates it.
+template <class Load, class EntryOf, class ShareFirst, class LookAhead>
 MCF_HD ChunkInfo scan_chunk_fast2(Load load, uint64_t blk0, const ZigTables &t, const ParkSlots &park, double *zsub_out,
-                                  bool *valid, EntryOf entry_of) {
+                                  bool *valid, EntryOf entry_of, ShareFirst share_first, LookAhead lookahead) {
     uint64_t F = 0;   // fast-looking draws
     unsigned np = 0;  // parked draws
     double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
     double vk0 = 0.0, vk1 = 0.0;  // values of the chunk's first two draws (entry patch)
     uint64_t w0, w1, w2, w3, n0, n1, n2, n3;
     load(blk0, w0, w1, w2, w3);
+    share_first(w0, w1);
 #define MCF_FAST2_DRAW(J, WA, WB, WC)                                                             \
     {                                                                                             \
         const uint64_t dbits = (((WA) >> 9) & 0x000fffffffffffffULL) | MCF_U52_BIAS;              \
@@ -746,7 +752,10 @@ MCF_HD ChunkInfo scan_chunk_fast2(Load load, uint64_t blk0, const ZigTables &t, 
         MCF_FAST2_DRAW(9, w1, w2, w3)
         MCF_FAST2_DRAW(10, w2, w3, n0)
         MCF_FAST2_DRAW(11, w3, n0, n1)
-        load(b + 4, w0, w1, w2, w3);
+        if (sub + 1 < MCF_SUBS)
+            load(b + 4, w0, w1, w2, w3);
+        else
+            lookahead(w0, w1);  // first two draws of the next chunk
         MCF_FAST2_DRAW(12, n0, n1, n2)
         MCF_FAST2_DRAW(13, n1, n2, n3)
         MCF_FAST2_DRAW(14, n2, n3, w0)
@@ -1091,6 +1100,12 @@ MCF_HD double terminal_value(Each each, const GbmDerived &g) {
     case MCF_NORMAL_SUM: {
         double acc = 0.0;
         each([&](double z) { acc = xadd(acc, z); });
+        return acc;
+    }
+    case MCF_NORMAL_LOC_SCALE: {  // rng.normal(loc, scale) = loc + scale*z, summed over the replication's draws
+        double acc = 0.0;
+        const double a = g.a, b = g.b;
+        each([&](double z) { acc = xadd(acc, xadd(a, xmul(b, z))); });
         return acc;
     }
     case MCF_BS_EURO_CALL:

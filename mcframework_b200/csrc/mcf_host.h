@@ -104,6 +104,10 @@ static inline int derive_spec(const mcf_gbm_spec &s, int64_t n_steps, mcf::GbmDe
     }
     case MCF_NORMAL_SUM:
         return MCF_OK;
+    case MCF_NORMAL_LOC_SCALE:
+        g->a = s.p[0];
+        g->b = s.p[1];
+        return MCF_OK;
     default:
         return MCF_ERR_BAD_ARG;
     }

@@ -32,6 +32,7 @@ struct ScanShared {
     ZigShared z;
     ZigKW kws[512];
     uint64_t park[3 * MCF_PARK_CAP * 256];
+    uint64_t first[2 * 256];  // every thread's first two draws: the previous thread's look-ahead
 };
 
 __device__ __forceinline__ ZigTables load_zig_tables(ZigShared &sh) {
@@ -188,7 +189,12 @@ __global__ void __launch_bounds__(256, 3) plan_scan_kernel(const mcf_stream *__r
                 c = pc.v2;
                 d = pc.v3;
             },
-            blk0, t, park, zsum + id * MCF_SUBS, &valid, [](unsigned) { return 0u; });
+            blk0, t, park, zsum + id * MCF_SUBS, &valid, [](unsigned) { return 0u; }, [](uint64_t, uint64_t) {},
+            [&](uint64_t &a, uint64_t &b) {
+                pc.load_block(blk0 + 16);
+                a = pc.v0;
+                b = pc.v1;
+            });
         startmask[id] = ci.startmask;
         emitmask[id] = ci.emitmask;
         exit_[id] = (uint8_t)ci.exit;
@@ -226,10 +232,25 @@ __global__ void __launch_bounds__(256, 4) plan_scan_philox_stream_kernel(const _
     const uint64_t blk0 = (K.off + (uint64_t)c * MCF_CHUNK) >> 2;
     const ChunkInfo ci = scan_chunk_fast2(
         [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &cc, uint64_t &d) { philox_block_folded(K, blk, a, b, cc, d); },
-        blk0, t, park, zsum + id * MCF_SUBS, &valid, [&](unsigned exit_spec) {
+        blk0, t, park, zsum + id * MCF_SUBS, &valid,
+        [&](unsigned exit_spec) {
             // the previous chunk of the stream is the neighbouring lane's; lane 0 cannot know it (entry 0, fixed up later)
             const unsigned prev = __shfl_up_sync(0xffffffffu, exit_spec, 1);
             return (threadIdx.x & 31) == 0 ? 0u : prev;
+        },
+        [&](uint64_t a, uint64_t b) {
+            sh.first[threadIdx.x] = a;
+            sh.first[256 + threadIdx.x] = b;
+            __syncthreads();  // whole CTAs are live (cps is a multiple of 1024)
+        },
+        [&](uint64_t &a, uint64_t &b) {
+            if (threadIdx.x == 255) {  // the CTA's last chunk: its successor belongs to another CTA
+                uint64_t c2, d2;
+                philox_block_folded(K, blk0 + 16, a, b, c2, d2);
+            } else {
+                a = sh.first[threadIdx.x + 1];
+                b = sh.first[256 + threadIdx.x + 1];
+            }
         });
     startmask[id] = ci.startmask;
     emitmask[id] = ci.emitmask;
@@ -549,6 +570,8 @@ __global__ void __launch_bounds__(256, 3) gbm_terminal_kernel(const mcf_stream *
         double v;
         if (g.mode == MCF_NORMAL_SUM) {
             v = zsum;
+        } else if (g.mode == MCF_NORMAL_LOC_SCALE) {
+            v = acc;
         } else if (g.mode == MCF_PATH_TERMINAL) {
             v = exp(xadd(g.logs0, acc));
         } else {
@@ -608,6 +631,8 @@ __global__ void __launch_bounds__(256, 4)
         double v;
         if (g.mode == MCF_NORMAL_SUM) {
             v = zsum;
+        } else if (g.mode == MCF_NORMAL_LOC_SCALE) {
+            v = acc;
         } else if (g.mode == MCF_PATH_TERMINAL) {
             v = exp(xadd(g.logs0, acc));
         } else {

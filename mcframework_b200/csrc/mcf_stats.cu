@@ -825,6 +825,42 @@ __global__ void boot_finalize_kernel(double *__restrict__ sums, int64_t B, doubl
     if (i < B) sums[i] = __ddiv_rn(sums[i], n);
 }
 
+// ============================================================================ declared integer draws
+// Replication i of a stream reads the 32-bit slots [i*k, (i+1)*k) of its stream (jump-ahead, no state carried from
+// one replication to the next) through NumPy's 32-bit Lemire rule.  A rejected slot would shift all later ones: it is
+// only flagged here (the caller then runs the reference's own loop), never papered over.
+template <int KIND>
+__global__ void __launch_bounds__(256) draw_integers_kernel(const mcf_stream *__restrict__ streams, int n_streams,
+                                                            int64_t n_total, int64_t hint, uint32_t span, int64_t low,
+                                                            int32_t k, int32_t op, int64_t match, double *__restrict__ out,
+                                                            int *__restrict__ rejected) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    int64_t g = hint > 0 ? i / hint : 0;
+    int si;
+    if (g < n_streams && streams[g].first_sim <= i && i < streams[g].first_sim + streams[g].n_sims)
+        si = (int)g;
+    else
+        si = find_stream(streams, n_streams, i);
+    const mcf_stream st = streams[si];
+    const uint64_t s0 = (uint64_t)(i - st.first_sim) * (uint64_t)k;
+    SlotWalker<KIND> w;
+    w.init(st, s0);
+    const SlotRule rule = slot_rule(span);
+    int64_t sum = 0, run = 0, best = 0;
+    bool bad = false;
+    for (int32_t t = 0; t < k; t++) {
+        uint32_t idx;
+        bad |= !slot_accept(rule, w.get(s0 + (uint64_t)t), idx);
+        const int64_t v = low + (int64_t)idx;
+        sum += v;
+        run = v == match ? run + 1 : 0;
+        best = run > best ? run : best;
+    }
+    if (bad) atomicExch(rejected, 1);
+    out[i] = (double)(op == 0 ? sum : best);
+}
+
 // =========================================================================================== lsm
 struct LsmState {
     double sums[8];    // n, Su, Su2, Su3, Su4, Sy, Suy, Su2y   (u = (S-K)/K)
@@ -1507,6 +1543,26 @@ int mcf_bootstrap_finalize(double *d_sums, int64_t n_resamples, int64_t n, void 
     if (!d_sums || n_resamples <= 0 || n <= 0) return MCF_ERR_BAD_ARG;
     boot_finalize_kernel<<<(unsigned)((n_resamples + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(d_sums, n_resamples,
                                                                                                     (double)n);
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+int mcf_draw_integers(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total,
+                      int64_t sims_per_stream_hint, int64_t low, int64_t high, int32_t size, int32_t op, int64_t match,
+                      double *d_out, int32_t *d_rejected, void *cuda_stream) {
+    if (!d_streams || n_streams <= 0 || n_total <= 0 || size <= 0 || high - low < 2 || high - low > 0xFFFFFFFFLL ||
+        (op != 0 && op != 1) || !d_out || !d_rejected)
+        return MCF_ERR_BAD_ARG;
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    MCF_CUDA_OK(cudaMemsetAsync(d_rejected, 0, 4, cs));
+    const unsigned grid = (unsigned)((n_total + 255) / 256);
+    const uint32_t span = (uint32_t)(high - low);
+    if (gen_kind == MCF_GEN_PCG64)
+        draw_integers_kernel<MCF_GEN_PCG64><<<grid, 256, 0, cs>>>(d_streams, n_streams, n_total, sims_per_stream_hint, span,
+                                                                  low, size, op, match, d_out, d_rejected);
+    else
+        draw_integers_kernel<MCF_GEN_PHILOX><<<grid, 256, 0, cs>>>(d_streams, n_streams, n_total, sims_per_stream_hint, span,
+                                                                   low, size, op, match, d_out, d_rejected);
     MCF_CUDA_OK(cudaGetLastError());
     return MCF_OK;
 }

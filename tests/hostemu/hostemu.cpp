@@ -139,6 +139,14 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
                     const unsigned e = (c0 & 31) == 0 ? 0u : prev_exit_spec;
                     prev_exit_spec = exit_spec;
                     return e;
+                },
+                [](uint64_t, uint64_t) {},
+                [&](uint64_t &a, uint64_t &b) {  // the next chunk's first two draws (the device reads its neighbour's)
+                    uint64_t c2, d2;
+                    if (K.fold_ok)
+                        philox_block_folded(K, blk0 + 16, a, b, c2, d2);
+                    else
+                        philox_block_keys(K, blk0 + 16, a, b, c2, d2);
                 });
             if (valid) {  // the speculative walk must agree with the general one from the same entry
                 double zref[MCF_SUBS];
@@ -300,6 +308,8 @@ static int terminal_impl(const mcf_stream *streams, int n_streams, int64_t n_tot
             double v;
             if (g.mode == MCF_NORMAL_SUM)
                 v = zsum;
+            else if (g.mode == MCF_NORMAL_LOC_SCALE)
+                v = acc;
             else if (g.mode == MCF_PATH_TERMINAL)
                 v = exp(xadd(g.logs0, acc));
             else {

@@ -148,6 +148,87 @@ def test_results_can_stay_on_the_device_until_somebody_reads_them(m, golden):
     bs.keep_results_on_device = False
 
 
+def test_declared_draw_programs_run_as_kernels_and_match_the_python_hooks(m, golden):
+    """user simulations that DECLARE their draws (dice of core.py:22-25, coin-flip streak of the
+    getting-started guide, SimpleSim of the reference tests) run on the device, bit-identical to looping their Python
+    hook like the reference does -- sequential PCG64 layout, Philox blocks, odd sizes (half-draw buffer), and a span
+    whose Lemire rejections force the host loop."""
+    from mcframework_b200 import _device as D, programs
+
+    _, a = golden
+
+    class Dice(m.MonteCarloSimulation):
+        size = 2
+
+        def single_simulation(self, _rng=None, **kw):
+            return float(self._rng(_rng, self.rng).integers(1, 7, size=self.size).sum())
+
+    class DeclaredDice(Dice):
+        def draw_program(self, **kw):
+            return programs.integers_sum(1, 7, size=self.size)
+
+    class Streak(m.MonteCarloSimulation):
+        def single_simulation(self, n_flips=100, _rng=None, **kw):
+            best = cur = 0
+            for f in self._rng(_rng, self.rng).integers(0, 2, size=n_flips):
+                cur = cur + 1 if f == 1 else 0
+                best = max(best, cur)
+            return float(best)
+
+    class DeclaredStreak(Streak):
+        def draw_program(self, n_flips=100, **kw):
+            return programs.integers_longest_run(0, 2, size=n_flips, value=1)
+
+    class Simple(m.MonteCarloSimulation):
+        def single_simulation(self, mean=0.0, std=1.0, _rng=None, **kw):
+            return float(self._rng(_rng, self.rng).normal(mean, std))
+
+    class DeclaredSimple(Simple):
+        def draw_program(self, mean=0.0, std=1.0, **kw):
+            return programs.normal(mean, std)
+
+    class Wide(Dice):  # 3e9 values: 30 % of the slots are rejected -> the engine must fall back to the hook
+        def single_simulation(self, _rng=None, **kw):
+            return float(self._rng(_rng, self.rng).integers(0, 3_000_000_000, size=3).sum())
+
+        def draw_program(self, **kw):
+            return programs.integers_sum(0, 3_000_000_000, size=3)
+
+    before = D.LAUNCHES["pi"]
+    d = DeclaredDice()
+    d.set_seed(42)
+    assert np.array_equal(d.run(10_000, compute_stats=False).results, a["G3_dice_seq"])
+    d.set_seed(42)
+    assert np.array_equal(d.run(20_000, parallel=True, n_workers=4, compute_stats=False).results, a["G3_dice_par"])
+    assert D.LAUNCHES["pi"] == before + 2  # both ran as kernels
+    for size, n in ((3, 1001), (1, 777)):  # odd slot counts: replications start in the middle of a 64-bit draw
+        ref, dev = Dice(), DeclaredDice()
+        ref.size = dev.size = size
+        ref.set_seed(7)
+        dev.set_seed(7)
+        r1, r2 = ref.run(n, compute_stats=False), dev.run(n, compute_stats=False)
+        assert np.array_equal(r1.results, r2.results)
+        assert np.array_equal(ref.run(5, compute_stats=False).results, dev.run(5, compute_stats=False).results)  # stream continues
+    for kw in (dict(), dict(parallel=True, n_workers=3)):
+        n = 20_011 if kw else 3000
+        ref, dev = Streak(), DeclaredStreak()
+        ref.set_seed(5)
+        dev.set_seed(5)
+        assert np.array_equal(ref.run(n, n_flips=37, compute_stats=False, **kw).results,
+                              dev.run(n, n_flips=37, compute_stats=False, **kw).results)
+        ref, dev = Simple(), DeclaredSimple()
+        ref.set_seed(9)
+        dev.set_seed(9)
+        assert np.array_equal(ref.run(n, mean=5.0, std=2.0, compute_stats=False, **kw).results,
+                              dev.run(n, mean=5.0, std=2.0, compute_stats=False, **kw).results)
+    ref, dev = Wide(), Wide()
+    ref.draw_program = lambda **kw: None
+    ref.set_seed(3)
+    dev.set_seed(3)
+    assert np.array_equal(ref.run(500, compute_stats=False).results, dev.run(500, compute_stats=False).results)
+    assert np.array_equal(ref.run(3, compute_stats=False).results, dev.run(3, compute_stats=False).results)
+
+
 def test_greeks(m, golden):
     j, _ = golden
     bs = m.BlackScholesSimulation()

@@ -163,6 +163,34 @@ def test_builtin_hooks_map_to_programs():
     assert Custom()._program_for({}) is None  # replaced hook => user Python code, looped on the host
 
 
+def test_declared_draw_programs_host_logic():
+    """`draw_program` declarations: validation, and that a declaration wins over the 'hook was
+    replaced => arbitrary Python' rule while an undeclared subclass still loops on the host."""
+    import mcframework_b200 as mcf
+    from mcframework_b200 import _native as N, programs
+
+    p = programs.integers_sum(1, 7, size=2)
+    assert (p.kind, p.low, p.high, p.size, p.op) == ("integers", 1, 7, 2, 0)
+    q = programs.integers_longest_run(0, 2, size=100, value=1)
+    assert (q.op, q.match, q.size) == (1, 1, 100)
+    z = programs.normal(5.0, 2.0)
+    assert z.kind == "normals" and z.n_steps == 1 and z.specs == [(N.NORMAL_LOC_SCALE, [5.0, 2.0])]
+    for bad in (dict(low=0, high=1, size=3), dict(low=0, high=1 << 33, size=1), dict(low=0, high=6, size=0)):
+        with pytest.raises(ValueError):
+            programs.integers_sum(**bad)
+
+    class Plain(mcf.MonteCarloSimulation):
+        def single_simulation(self, _rng=None, **kw):
+            return 1.0
+
+    class Declared(Plain):
+        def draw_program(self, **kw):
+            return p
+
+    assert Plain().draw_program() is None and Plain()._program_for({}) is None
+    assert Declared()._program_for({}) is p
+
+
 # ------------------------------------------------------------------------------------- hostemu
 @pytest.fixture(scope="module")
 def emu():
