@@ -909,8 +909,12 @@ MCF_HD double zig_value_of_start_t(Tail tail, uint64_t p, uint64_t r, const doub
 }
 template <int KIND>
 MCF_HD double zig_value_of_start(const mcf_stream &st, uint64_t p, uint64_t r, const double *wi, uint64_t ki0) {
-    return zig_value_of_start_t([&](uint64_t pp, uint64_t rabs) { return zig_tail_value<KIND>(st, pp, rabs); }, p, r, wi,
-                                ki0);
+    const unsigned idx = (unsigned)(r & 0xffULL);
+    const unsigned sign = (unsigned)((r >> 8) & 1ULL);
+    const uint64_t rabs = (r >> 9) & 0x000fffffffffffffULL;
+    if (idx == 0 && rabs >= ki0) return zig_tail_value<KIND>(st, p, rabs);  // 3e-4 of the emits
+    const double v = xmul(u52_to_double(rabs), wi[idx]);
+    return sign ? -v : v;
 }
 
 // Block-aligned Philox streams (off % 4 == 0): f(z) for every normal emitted by attempts starting in [start, end), whole

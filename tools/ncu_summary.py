@@ -36,6 +36,9 @@ def main():
                     d[w] = float(v)
                 except ValueError:
                     d[w] = v
+                u = units[hdr.index(w)]
+                if "byte" in u.lower() and isinstance(d[w], float):  # normalise Kbyte/Mbyte/Gbyte to bytes
+                    d[w] *= {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u.lower(), 1.0)
         d["unit:gpu__time_duration.sum"] = units[hdr.index("gpu__time_duration.sum")]
         stalls = []
         for i, h in enumerate(hdr):

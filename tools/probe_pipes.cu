@@ -98,10 +98,8 @@ int main() {
     run<2>("lop3", 1, p.multiProcessorCount, mhz);
     run<3>("imad_wide_plus_lop3", 2, p.multiProcessorCount, mhz);
     run<4>("dfma", 1, p.multiProcessorCount, mhz);
-    run<5>("mul_wide_u32_no_addend", 1, p.multiProcessorCount, mhz);
     run<6>("imad_wide_plus_independent_lop3", 2, p.multiProcessorCount, mhz);
     run<7>("imad_hi", 1, p.multiProcessorCount, mhz);
-    run<8>("mul_wide_plus_independent_lop3", 2, p.multiProcessorCount, mhz);
     run<9>("imad_wide_plus_two_independent_lop3", 3, p.multiProcessorCount, mhz);
     printf("  \"note\": \"8 independent chains per thread, 4 CTAs x 256 threads per SM, best of 5\"\n}\n");
     return 0;
