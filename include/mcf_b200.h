@@ -147,6 +147,19 @@ int mcf_gbm_slices(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_str
                    const mcf_gbm_spec *h_spec, int64_t slice_stride, int32_t time_major, double *d_out,
                    void *cuda_stream);
 
+/* Stored path slices from segment sums (BASELINE cfg 3).  mcf_normal_relocate re-runs only the locate step of a finished
+ * plan for `new_normals_per_sim` (the same streams cut into shorter pseudo-replications; `d_streams_new` carries the scaled
+ * first_sim / n_sims; max_sims_per_stream, normals_per_sim and slack are the ORIGINAL plan's).  With it every path is cut into
+ * n_steps/stride segments, mcf_gbm_terminal(MCF_NORMAL_SUM) returns the segment sums at two Philox blocks per segment, and
+ * mcf_gbm_slices_from_sums accumulates them into the slice values V0*exp(...) (MCF_PORTFOLIO_GBM) or exp(log S0 + ...)
+ * (MCF_PATH_TERMINAL): d_out is (n_segments+1, n_total) when time_major, else (n_total, n_segments+1). */
+int mcf_normal_relocate(const mcf_stream *d_streams_new, int32_t n_streams, int64_t max_sims_per_stream,
+                        int64_t normals_per_sim, double slack, int64_t new_normals_per_sim, void *d_workspace,
+                        uint64_t *d_sim_start_new, void *cuda_stream);
+int mcf_gbm_slices_from_sums(const double *d_segment_sums, int64_t n_total, int64_t n_segments, int64_t segment_steps,
+                             int64_t n_steps, const mcf_gbm_spec *h_spec, int32_t time_major, double *d_out,
+                             void *cuda_stream);
+
 /* ---- (2b) declared integer draw programs ------------------------------------------------
  * A user simulation whose hook is `rng.integers(low, high, size=k)` followed by a reduction (the reference's dice
  * fixture core.py:22-25, the coin-flip streak of docs/source/getting-started.md:139-183) can declare that instead of

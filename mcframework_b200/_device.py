@@ -72,6 +72,7 @@ class NormalPlan:
     stream_end: "object"  # torch int64 [n_streams]: 64-bit draws consumed per stream
     normals_per_sim: int
     workspace: "object" = None  # torch uint8: emit masks etc. -- the replay kernels read it
+    slack: float = 0.03  # window slack the workspace geometry was computed with (mcf_normal_relocate needs it)
 
 
 def normal_plan(dl: DeviceLayout, normals_per_sim: int, slack: float = 0.03, resolve_iters: int = 3,
@@ -96,7 +97,7 @@ def normal_plan(dl: DeviceLayout, normals_per_sim: int, slack: float = 0.03, res
         LAUNCHES["plan"] += 4 + 2 * resolve_iters + (lay.n_streams if lay.kind == 1 and lay.n_streams <= 1024 else 1)
         status = lib.mcf_workspace_status(_ptr(ws), _stream_ptr())
         if status == N.OK:
-            return NormalPlan(sim_start, stream_end, int(normals_per_sim), ws)
+            return NormalPlan(sim_start, stream_end, int(normals_per_sim), ws, float(slack))
         del ws
         if status == N.ERR_WINDOW_TOO_SMALL:
             slack = slack * 2 + 0.02
@@ -168,6 +169,30 @@ def gbm_slices(dl: DeviceLayout, n_steps: int, plan: NormalPlan, mode: int, para
     n_slices = int(n_steps) // int(slice_stride) + 1
     shape = (n_slices, lay.n_total) if time_major else (lay.n_total, n_slices)
     out = torch.empty(shape, dtype=torch.float64, device="cuda")
+    k = int(n_steps) // int(slice_stride)
+    if (lay.kind == 1 and lay.n_streams <= 1024 and int(slice_stride) >= 16 and k * int(slice_stride) == int(n_steps)
+            and k > 1 and int(mode) in (N.PORTFOLIO_GBM, N.PATH_TERMINAL) and bool((lay.records["buf_pos"] % 4 == 0).all())):
+        # Segment form: every path is cut into k pseudo-replications of `stride` steps.  Re-locating the finished plan
+        # gives their stream positions, the boundary-form replay their normal sums (two Philox blocks per segment
+        # instead of stride/4), and one accumulation pass the slice values.
+        recs = lay.records.copy()
+        recs["first_sim"] *= k
+        recs["n_sims"] *= k
+        lay2 = StreamLayout(lay.kind, recs, lay.n_total * k, lay.hint * k)
+        dl2 = DeviceLayout(lay2, upload_records(lay2))
+        starts = torch.empty(lay2.n_total, dtype=torch.int64, device="cuda")
+        rc = N.lib().mcf_normal_relocate(_ptr(dl2.records), lay.n_streams, lay.max_sims, int(plan.normals_per_sim),
+                                         float(plan.slack), int(slice_stride), _ptr(plan.workspace), _ptr(starts), _stream_ptr())
+        N.check("mcf_normal_relocate", rc)
+        LAUNCHES["plan"] += 1
+        plan2 = NormalPlan(starts, plan.stream_end, int(slice_stride), plan.workspace, plan.slack)
+        seg = gbm_terminal(dl2, int(slice_stride), plan2, [(N.NORMAL_SUM, [])])[0]
+        del starts, plan2
+        rc = N.lib().mcf_gbm_slices_from_sums(_ptr(seg), lay.n_total, k, int(slice_stride), int(n_steps),
+                                              _spec_array([(mode, params)]), int(bool(time_major)), _ptr(out), _stream_ptr())
+        N.check("mcf_gbm_slices_from_sums", rc)
+        LAUNCHES["paths"] += 1
+        return out
     rc = N.lib().mcf_gbm_slices(lay.kind, _ptr(dl.records), lay.n_streams, lay.n_total, int(n_steps), lay.hint,
                                 _ptr(plan.sim_start), _ptr(plan.workspace), _spec_array([(mode, params)]), int(slice_stride),
                                 int(bool(time_major)), _ptr(out), _stream_ptr())

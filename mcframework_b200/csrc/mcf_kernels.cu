@@ -671,6 +671,27 @@ __global__ void __launch_bounds__(256, 3) gbm_paths_kernel(const mcf_stream *__r
     });
 }
 
+// Slices from segment sums: seg[i*k + j] = sum of the normals of steps (j*stride, (j+1)*stride] of path i (what the
+// boundary-form replay returns when every path is cut into k pseudo-replications of `stride` steps).  One thread per
+// path accumulates the k segments and writes the k+1 slice values; time-major output is fully coalesced.
+__global__ void __launch_bounds__(256) gbm_slices_from_sums_kernel(const double *__restrict__ seg, int64_t n_total, int64_t k,
+                                                                  GbmDerived g, double stride_f, int time_major,
+                                                                  double *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    const bool portfolio = g.mode == MCF_PORTFOLIO_GBM;
+    const int64_t step = time_major ? n_total : 1;
+    double *p = out + (time_major ? i : i * (k + 1));
+    const double drift = xmul(stride_f, g.a);
+    double acc = 0.0;
+    *p = portfolio ? g.s0 : exp(g.logs0);
+    for (int64_t j = 0; j < k; j++) {
+        acc = xadd(acc, xadd(drift, xmul(g.b, __ldg(&seg[i * k + j]))));
+        p += step;
+        *p = portfolio ? xmul(g.s0, exp(acc)) : exp(xadd(g.logs0, acc));
+    }
+}
+
 // Stored path slices (BASELINE cfg 3): value at steps 0, stride, 2*stride, ... <= n_steps.  Time-major output
 // (n_slices, n_total) gives fully coalesced 8-byte stores per warp; row-major (n_total, n_slices) is what a
 // host caller reshapes most easily.  mode: MCF_PORTFOLIO_GBM -> V0*exp(sum), MCF_PATH_TERMINAL -> exp(log S0 + sum).
@@ -946,6 +967,40 @@ int mcf_gbm_paths(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_stre
 
 
 }  // extern "C"
+
+// Re-run only the locate step of a finished plan for another normals-per-replication count: `d_streams_new` describes the
+// same streams cut into n_sims*old_nps/new_nps pseudo-replications (first_sim/n_sims scaled by the caller).  The masks,
+// entries and tile prefix sums of the workspace are reused; only sim_start is recomputed (one pass over the masks).
+extern "C" int mcf_normal_relocate(const mcf_stream *d_streams_new, int32_t n_streams, int64_t max_sims_per_stream,
+                                   int64_t normals_per_sim, double slack, int64_t new_normals_per_sim, void *d_workspace,
+                                   uint64_t *d_sim_start_new, void *cuda_stream) {
+    if (!d_streams_new || n_streams <= 0 || max_sims_per_stream <= 0 || normals_per_sim <= 0 || new_normals_per_sim <= 0 ||
+        !d_workspace || !d_sim_start_new)
+        return MCF_ERR_BAD_ARG;
+    const PlanGeom g = plan_geom(n_streams, max_sims_per_stream, normals_per_sim, slack);
+    char *ws = (char *)d_workspace;
+    plan_locate_kernel<<<(unsigned)g.n_tiles, 256, 0, (cudaStream_t)cuda_stream>>>(
+        d_streams_new, g.cps, g.tps, new_normals_per_sim, (const uint64_t *)(ws + g.off_start),
+        (const uint64_t *)(ws + g.off_emit), (const uint8_t *)(ws + g.off_exit), (const uint8_t *)(ws + g.off_entry),
+        (const uint64_t *)(ws + g.off_tpre), d_sim_start_new, nullptr, (uint64_t *)(ws + g.off_send));
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+extern "C" int mcf_gbm_slices_from_sums(const double *d_segment_sums, int64_t n_total, int64_t n_segments, int64_t segment_steps,
+                                        int64_t n_steps, const mcf_gbm_spec *h_spec, int32_t time_major, double *d_out,
+                                        void *cuda_stream) {
+    if (!d_segment_sums || n_total <= 0 || n_segments <= 0 || segment_steps <= 0 || n_steps != n_segments * segment_steps ||
+        !h_spec || !d_out || (h_spec->mode != MCF_PORTFOLIO_GBM && h_spec->mode != MCF_PATH_TERMINAL))
+        return MCF_ERR_BAD_ARG;
+    GbmDerived g;
+    int rc = derive_spec(*h_spec, n_steps, &g);
+    if (rc) return rc;
+    gbm_slices_from_sums_kernel<<<grid_for(n_total, 256), 256, 0, (cudaStream_t)cuda_stream>>>(
+        d_segment_sums, n_total, n_segments, g, (double)segment_steps, time_major, d_out);
+    MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
 
 extern "C" int mcf_gbm_slices(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_streams, int64_t n_total,
                               int64_t n_steps, int64_t sims_per_stream_hint, const uint64_t *d_sim_start,

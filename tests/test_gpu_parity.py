@@ -342,6 +342,30 @@ def test_path_slices_are_strided_paths(dev):
     np.testing.assert_allclose(pf[1], term, rtol=FP_RTOL)  # strictly sequential sum vs chunk sums
 
 
+@pytest.mark.parametrize("steps,stride", [(96, 24), (64, 16), (2520, 21), (85, 17)])
+def test_path_slices_from_segment_sums(dev, steps, stride):
+    """Strides of at least one sub-chunk that divide the step count take the segment form (plan re-located for
+    `stride` normals per pseudo-replication, boundary-form sums, one accumulation pass): same values as every
+    stride-th column of the full paths, up to the summation order."""
+    D, N, S = dev
+    n = 20_000 if steps < 1000 else 20_000
+    lay = S.parallel_layout(np.random.SeedSequence(33), n + 7, 3)
+    dl = D.DeviceLayout.of(lay)
+    plan = D.normal_plan(dl, steps)
+    before = D.LAUNCHES["plan"]
+    tm = D.gbm_slices(dl, steps, plan, N.PATH_TERMINAL, [100.0, 0.05, 0.2, 1.0], stride, time_major=True).cpu().numpy()
+    assert D.LAUNCHES["plan"] == before + 1  # the re-locate: this call took the segment form
+    rm = D.gbm_slices(dl, steps, plan, N.PATH_TERMINAL, [100.0, 0.05, 0.2, 1.0], stride, time_major=False).cpu().numpy()
+    assert tm.shape == (steps // stride + 1, lay.n_total) and np.array_equal(tm.T, rm)
+    full = D.gbm_paths(dl, steps, plan, 100.0, 0.05, 0.2, 1.0).cpu().numpy()
+    np.testing.assert_allclose(rm, full[:, ::stride], rtol=1e-12)
+    if steps == 2520:
+        pf = D.gbm_slices(dl, steps, plan, N.PORTFOLIO_GBM, [1e4, 0.07, 0.2], stride).cpu().numpy()
+        term = D.gbm_terminal(dl, steps, plan, [(N.PORTFOLIO_GBM, [1e4, 0.07, 0.2])])[0].cpu().numpy()
+        assert np.all(pf[0] == 1e4)
+        np.testing.assert_allclose(pf[-1], term, rtol=1e-11)
+
+
 @pytest.mark.parametrize("n,B,shift,cs", [(50_000, 40, 12, 64), (120_000, 25, 13, 256), (3_000_000, 6, 18, 1024)])
 def test_bootstrap_binned_path_is_the_same_index_stream(sd, n, B, shift, cs):
     """The binned gather (queues per resample and per region of x, regions summed one after the other) draws the
