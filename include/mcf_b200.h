@@ -224,6 +224,14 @@ int mcf_select_choose(void *d_workspace, void *cuda_stream);
 int mcf_select_finish(const void *d_workspace, double *d_out, void *cuda_stream);
 int mcf_select(const double *d_x, int64_t n, int32_t omit_nonfinite, const int64_t *h_ranks, int32_t k, double *d_out,
                void *d_workspace, int64_t workspace_bytes, void *cuda_stream);
+/* The same selection with a scratch buffer of mcf_select_compact_bytes(n) bytes (d_compact may be NULL = mcf_select): after
+ * the second pass the candidates that still share a tracked 16-bit prefix (a few per cent of a smooth sample) are
+ * compacted and the six remaining passes read only those; if they do not fit (heavily tied data) the passes keep
+ * reading x.  Results are identical. */
+int64_t mcf_select_compact_bytes(int64_t n);
+int mcf_select_compacting(const double *d_x, int64_t n, int32_t omit_nonfinite, const int64_t *h_ranks, int32_t k,
+                          double *d_out, void *d_workspace, int64_t workspace_bytes, void *d_compact, int64_t compact_bytes,
+                          void *cuda_stream);
 
 /* Bootstrap means, replaces _bootstrap_means (stats_engine.py:1019-1041):
  *   idx = rng.integers(0, n, size=(B, n)); means = x[idx].mean(axis=1)

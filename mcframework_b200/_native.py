@@ -76,6 +76,8 @@ SIGNATURES = {
     "mcf_select_choose": (C.c_int, [_vp, _vp]),
     "mcf_select_finish": (C.c_int, [_vp, _vp, _vp]),
     "mcf_select": (C.c_int, [_vp, _i64, _i32, C.POINTER(_i64), _i32, _vp, _vp, _i64, _vp]),
+    "mcf_select_compact_bytes": (_i64, [_i64]),
+    "mcf_select_compacting": (C.c_int, [_vp, _i64, _i32, C.POINTER(_i64), _i32, _vp, _vp, _i64, _vp, _i64, _vp]),
     "mcf_set_l2_fetch_granularity": (C.c_int, [_i32]),
     "mcf_bootstrap_workspace_bytes": (_i64, [_i64, _i32]),
     "mcf_bootstrap_count": (C.c_int, [_u32, _vp, _i64, _u64, _u64, _i32, _vp, _i64, _vp, _vp]),

@@ -108,6 +108,10 @@ def moments(x, target: float = 0.0, group=None) -> MomentSummary:
 
 
 # ---------------------------------------------------------------------------------------- select
+#: samples of at least this many values compact the surviving candidates after the second radix pass
+SELECT_COMPACT_MIN_N = 1 << 20
+
+
 def select(x, ranks, omit_nonfinite: bool = False, group=None):
     """Order statistics ``sorted(x)[ranks]`` (float64 device tensor) by radix selection.
 
@@ -122,6 +126,15 @@ def select(x, ranks, omit_nonfinite: bool = False, group=None):
     arr = (C.c_int64 * k)(*ranks)
     n = int(x.numel())
     if group is None:
+        if n >= SELECT_COMPACT_MIN_N:  # large samples: passes 3..8 read only the candidates left after two digits
+            cbytes = int(lib.mcf_select_compact_bytes(n))
+            scratch = torch.empty(cbytes, dtype=torch.uint8, device=x.device)
+            rc = lib.mcf_select_compacting(_ptr(x), n, int(bool(omit_nonfinite)), arr, k, _ptr(out), _ptr(ws), nbytes,
+                                           _ptr(scratch), cbytes, _stream_ptr())
+            N.check("mcf_select_compacting", rc)
+            LAUNCHES["stats"] += 4 + 2 * int(lib.mcf_select_passes())
+            del scratch
+            return out
         rc = lib.mcf_select(_ptr(x), n, int(bool(omit_nonfinite)), arr, k, _ptr(out), _ptr(ws), nbytes, _stream_ptr())
         N.check("mcf_select", rc)
         LAUNCHES["stats"] += 2 + 2 * int(lib.mcf_select_passes())

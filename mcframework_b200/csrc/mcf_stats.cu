@@ -209,6 +209,8 @@ struct SelectState {
     uint64_t prefix[MCF_SELECT_MAX_RANKS];   // bits decided so far (right aligned)
     int32_t uniq_of[MCF_SELECT_MAX_RANKS];   // rank -> index into uniq[]
     uint64_t uniq[MCF_SELECT_MAX_RANKS];     // sorted distinct prefixes
+    unsigned long long compact_n;            // candidates appended by select_compact_kernel (may exceed its capacity)
+    int32_t compact_done, pad2;              // 1 once the compaction pass ran
 };
 
 struct SelectGeom {
@@ -228,9 +230,8 @@ __global__ void select_init_kernel(SelectState *st, unsigned long long *hist, Se
     if (threadIdx.x == 0) *st = init;
 }
 
-__device__ __forceinline__ int select_slot(double v, int omit, int pass, int shift, int n_uniq,
-                                           const uint64_t *__restrict__ sh_uniq, const unsigned *__restrict__ sh_bloom) {
-    const uint64_t key = select_key(v, omit);
+__device__ __forceinline__ int select_slot_key(uint64_t key, int pass, int shift, int n_uniq,
+                                               const uint64_t *__restrict__ sh_uniq, const unsigned *__restrict__ sh_bloom) {
     if (pass == 0) return (int)(key >> 56);
     const uint64_t pre = key >> (shift + SEL_BITS);
     // cheap reject: the last decided digit of the element must be the last digit of SOME tracked prefix
@@ -247,10 +248,17 @@ __device__ __forceinline__ int select_slot(double v, int omit, int pass, int shi
     if (sh_uniq[lo] != pre) return -1;
     return lo * SEL_BINS + (int)((unsigned)(key >> shift) & (SEL_BINS - 1));
 }
+__device__ __forceinline__ int select_slot(double v, int omit, int pass, int shift, int n_uniq,
+                                           const uint64_t *__restrict__ sh_uniq, const unsigned *__restrict__ sh_bloom) {
+    return select_slot_key(select_key(v, omit), pass, shift, n_uniq, sh_uniq, sh_bloom);
+}
 
+// `keys` (may be NULL): candidates compacted after the second pass (select_compact_kernel); when that pass ran and its
+// buffer did not overflow, the remaining passes read those few keys instead of all of x.
 __global__ void __launch_bounds__(512) select_hist_kernel(const double *__restrict__ x, int64_t n, int omit,
                                                           const SelectState *__restrict__ st,
-                                                          unsigned long long *__restrict__ hist) {
+                                                          unsigned long long *__restrict__ hist,
+                                                          const uint64_t *__restrict__ keys, int64_t keys_cap) {
     __shared__ unsigned int sh_hist[MCF_SELECT_MAX_RANKS * SEL_BINS];
     __shared__ uint64_t sh_uniq[MCF_SELECT_MAX_RANKS];
     __shared__ unsigned sh_bloom[SEL_BINS / 32];
@@ -267,20 +275,22 @@ __global__ void __launch_bounds__(512) select_hist_kernel(const double *__restri
     const int shift = 64 - SEL_BITS * (pass + 1);  // digit position of this pass
     const int lane = threadIdx.x & 31;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    const bool from_keys = keys != nullptr && st->compact_done && (int64_t)st->compact_n <= keys_cap;
+    if (from_keys) n = (int64_t)st->compact_n;
     constexpr int UNROLL = 4;
     for (int64_t i0 = tid - lane; i0 < n; i0 += UNROLL * nthr) {  // warp-uniform trip count, UNROLL loads in flight
-        double v[UNROLL];
+        uint64_t key[UNROLL];
         int slot[UNROLL];
         bool any = false;
 #pragma unroll
         for (int k = 0; k < UNROLL; k++) {
             const int64_t i = i0 + lane + k * nthr;
-            v[k] = i < n ? __ldg(&x[i]) : 0.0;
+            key[k] = i < n ? (from_keys ? __ldg(&keys[i]) : select_key(__ldg(&x[i]), omit)) : 0ULL;
         }
 #pragma unroll
         for (int k = 0; k < UNROLL; k++) {
             const int64_t i = i0 + lane + k * nthr;
-            slot[k] = i < n ? select_slot(v[k], omit, pass, shift, n_uniq, sh_uniq, sh_bloom) : -1;
+            slot[k] = i < n ? select_slot_key(key[k], pass, shift, n_uniq, sh_uniq, sh_bloom) : -1;
             any |= slot[k] >= 0;
         }
         if (__ballot_sync(0xffffffffu, any) == 0u) continue;  // later passes: nothing of interest in 128 elements
@@ -298,6 +308,63 @@ __global__ void __launch_bounds__(512) select_hist_kernel(const double *__restri
         if (v) atomicAdd(&hist[i], (unsigned long long)v);
     }
 }
+
+// After the second pass the tracked prefixes (16 bits: sign, exponent, 4 mantissa bits) hold a few per cent of a
+// smooth sample.  Append the keys of those candidates to `keys` (warp-aggregated: one global atomic per warp and trip)
+// so that the six remaining passes stream a few per cent of the data.  More candidates than `cap` (constant or heavily
+// tied data): nothing is lost, the later passes simply keep reading x.
+__global__ void __launch_bounds__(512) select_compact_kernel(const double *__restrict__ x, int64_t n, int omit,
+                                                             SelectState *__restrict__ st, uint64_t *__restrict__ keys,
+                                                             int64_t cap) {
+    __shared__ uint64_t sh_uniq[MCF_SELECT_MAX_RANKS];
+    __shared__ unsigned sh_bloom[SEL_BINS / 32];
+    const int n_uniq = st->n_uniq, pass = st->pass;  // pass = number of digits already decided
+    if (threadIdx.x < SEL_BINS / 32) sh_bloom[threadIdx.x] = 0u;
+    __syncthreads();
+    if (threadIdx.x < n_uniq) {
+        const uint64_t u = st->uniq[threadIdx.x];
+        sh_uniq[threadIdx.x] = u;
+        atomicOr(&sh_bloom[((unsigned)u & (SEL_BINS - 1)) >> 5], 1u << ((unsigned)u & 31u));
+    }
+    __syncthreads();
+    const int shift = 64 - SEL_BITS * (pass + 1);
+    const int lane = threadIdx.x & 31;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    constexpr int UNROLL = 4;
+    // per-CTA staging: the hits of one round (UNROLL * 512 elements) are collected in shared memory and appended with ONE
+    // global atomic (a per-warp atomic on the single counter costs 2 ms at 1e8 elements)
+    __shared__ uint64_t stage[UNROLL * 512];
+    __shared__ unsigned sh_cnt;
+    __shared__ unsigned long long sh_base;
+    for (int64_t b0 = (int64_t)blockIdx.x * blockDim.x; b0 < n; b0 += UNROLL * nthr) {  // CTA-uniform trip count
+        if (threadIdx.x == 0) sh_cnt = 0u;
+        __syncthreads();
+        uint64_t key[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) {
+            const int64_t i = b0 + threadIdx.x + k * nthr;
+            key[k] = i < n ? select_key(__ldg(&x[i]), omit) : 0ULL;
+        }
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) {
+            const int64_t i = b0 + threadIdx.x + k * nthr;
+            const bool hit = i < n && select_slot_key(key[k], pass, shift, n_uniq, sh_uniq, sh_bloom) >= 0;
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m == 0u) continue;
+            unsigned base = 0;
+            if (lane == __ffs(m) - 1) base = atomicAdd(&sh_cnt, (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (hit) stage[base + (unsigned)__popc(m & ((1u << lane) - 1u))] = key[k];
+        }
+        __syncthreads();
+        const unsigned cnt = sh_cnt;
+        if (threadIdx.x == 0 && cnt) sh_base = atomicAdd(&st->compact_n, (unsigned long long)cnt);
+        __syncthreads();
+        for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x)
+            if ((int64_t)(sh_base + j) < cap) keys[sh_base + j] = stage[j];
+    }
+}
+__global__ void select_compact_done_kernel(SelectState *st) { st->compact_done = 1; }
 
 // one CTA: every rank walks the histogram of its prefix, picks its digit, then prefixes are re-uniqued
 __global__ void __launch_bounds__(1024) select_choose_kernel(SelectState *st, unsigned long long *hist) {
@@ -1327,16 +1394,21 @@ int mcf_select_begin(const int64_t *h_ranks, int32_t k, void *d_workspace, int64
     return MCF_OK;
 }
 
-int mcf_select_hist(const double *d_x, int64_t n, int32_t omit_nonfinite, void *d_workspace, void *cuda_stream) {
-    if (!d_x || n <= 0 || !d_workspace) return MCF_ERR_BAD_ARG;
+static int select_hist_launch(const double *d_x, int64_t n, int32_t omit_nonfinite, void *d_workspace, const uint64_t *keys,
+                              int64_t keys_cap, void *cuda_stream) {
     const SelectGeom g = select_geom();
     char *ws = (char *)d_workspace;
     const int blocks = grid_cap(n, 512 * 8, MCF_SM_COUNT * 4);
     select_hist_kernel<<<blocks, 512, 0, (cudaStream_t)cuda_stream>>>(d_x, n, omit_nonfinite,
                                                                       (const SelectState *)(ws + g.off_state),
-                                                                      (unsigned long long *)(ws + g.off_hist));
+                                                                      (unsigned long long *)(ws + g.off_hist), keys, keys_cap);
     MCF_CUDA_OK(cudaGetLastError());
     return MCF_OK;
+}
+
+int mcf_select_hist(const double *d_x, int64_t n, int32_t omit_nonfinite, void *d_workspace, void *cuda_stream) {
+    if (!d_x || n <= 0 || !d_workspace) return MCF_ERR_BAD_ARG;
+    return select_hist_launch(d_x, n, omit_nonfinite, d_workspace, nullptr, 0, cuda_stream);
 }
 
 int mcf_select_choose(void *d_workspace, void *cuda_stream) {
@@ -1358,17 +1430,39 @@ int mcf_select_finish(const void *d_workspace, double *d_out, void *cuda_stream)
     return MCF_OK;
 }
 
-int mcf_select(const double *d_x, int64_t n, int32_t omit_nonfinite, const int64_t *h_ranks, int32_t k, double *d_out,
-               void *d_workspace, int64_t workspace_bytes, void *cuda_stream) {
+int64_t mcf_select_compact_bytes(int64_t n) { return n <= 0 ? MCF_ERR_BAD_ARG : align256((n / 8 + 1024) * 8); }
+
+// d_compact (may be NULL): scratch of mcf_select_compact_bytes(n) bytes.  With it the candidates left after the second
+// pass are compacted and passes 3..8 read only those.
+int mcf_select_compacting(const double *d_x, int64_t n, int32_t omit_nonfinite, const int64_t *h_ranks, int32_t k,
+                          double *d_out, void *d_workspace, int64_t workspace_bytes, void *d_compact, int64_t compact_bytes,
+                          void *cuda_stream) {
+    if (!d_x || n <= 0) return MCF_ERR_BAD_ARG;
     int rc = mcf_select_begin(h_ranks, k, d_workspace, workspace_bytes, cuda_stream);
     if (rc) return rc;
+    const SelectGeom g = select_geom();
+    SelectState *st = (SelectState *)((char *)d_workspace + g.off_state);
+    const uint64_t *keys = (const uint64_t *)d_compact;
+    const int64_t cap = d_compact ? compact_bytes / 8 : 0;
     for (int p = 0; p < SEL_PASSES; p++) {
-        rc = mcf_select_hist(d_x, n, omit_nonfinite, d_workspace, cuda_stream);
+        if (p == 2 && cap > 0) {
+            select_compact_kernel<<<grid_cap(n, 512 * 8, MCF_SM_COUNT * 4), 512, 0, (cudaStream_t)cuda_stream>>>(
+                d_x, n, omit_nonfinite, st, (uint64_t *)d_compact, cap);
+            select_compact_done_kernel<<<1, 1, 0, (cudaStream_t)cuda_stream>>>(st);
+            MCF_CUDA_OK(cudaGetLastError());
+        }
+        rc = select_hist_launch(d_x, n, omit_nonfinite, d_workspace, p >= 2 ? keys : nullptr, cap, cuda_stream);
         if (rc) return rc;
         rc = mcf_select_choose(d_workspace, cuda_stream);
         if (rc) return rc;
     }
     return mcf_select_finish(d_workspace, d_out, cuda_stream);
+}
+
+int mcf_select(const double *d_x, int64_t n, int32_t omit_nonfinite, const int64_t *h_ranks, int32_t k, double *d_out,
+               void *d_workspace, int64_t workspace_bytes, void *cuda_stream) {
+    return mcf_select_compacting(d_x, n, omit_nonfinite, h_ranks, k, d_out, d_workspace, workspace_bytes, nullptr, 0,
+                                 cuda_stream);
 }
 
 // Device-wide hint: how many bytes L2 fetches from DRAM on a miss (32, 64 or 128).  Random gathers want 32.

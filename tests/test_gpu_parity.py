@@ -231,7 +231,10 @@ def test_moments_nonfinite_and_skewed(sd):
 
 
 @pytest.mark.parametrize("n,dist", [(1, "normal"), (2, "normal"), (1001, "normal"), (250_000, "payoff"), (3_000_000, "normal"),
-                                    (100_000, "const"), (65_537, "ints")])
+                                    (100_000, "const"), (65_537, "ints"),
+                                    # >= 2^20 values: candidates are compacted after the second radix pass; tied data
+                                    # (zeros, a constant, few distinct integers) overflow the scratch and keep reading x
+                                    (2_500_000, "payoff"), (1_100_000, "const"), (1_300_001, "ints"), (1_048_576, "normal")])
 def test_percentiles_bit_exact_vs_numpy(sd, n, dist):
     rng = np.random.default_rng(n)
     if dist == "normal":
