@@ -7,7 +7,6 @@ bootstrap intervals within BOOT_RTOL (identical index stream, different summatio
 """
 import logging
 import math
-import os
 
 import numpy as np
 import pytest

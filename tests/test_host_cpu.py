@@ -4,7 +4,6 @@ Nothing here launches a kernel.  The hostemu harness compiles the SAME ``__host_
 kernels call (mcf_device.cuh) with g++ and walks them with the kernels' work decomposition, so stream
 positions, jump-ahead and the planning pass are checked against the oracle without a GPU.
 """
-import ctypes as C
 import os
 import re
 
