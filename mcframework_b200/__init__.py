@@ -24,7 +24,8 @@ def __getattr__(name):
         value = getattr(_import_module(f"{__name__}.{_WHERE[name]}"), name)
         globals()[name] = value
         return value
-    if name in _EXPORTS or name in ("_device", "_native", "_stats_device", "_streams", "_programs", "_multi", "build"):
+    if name in _EXPORTS or name in ("_device", "_native", "_stats_device", "_streams", "_programs", "_multi", "build",
+                                    "programs"):  # `programs`: declared draw programs for user simulations (additive)
         return _import_module(f"{__name__}.{name}")
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
 
