@@ -553,11 +553,13 @@ MCF_HD int find_stream(const mcf_stream *streams, int n_streams, int64_t sim) {
 // ---------------------------------------------------------------------------------------
 // Pi: hits among `npts` consecutive points starting at the cursor (sims/pi.py:71-72)
 // ---------------------------------------------------------------------------------------
-// x = -1 + 2*((v >> 11) * 2^-53) = fma(k, 2^-52, -1) with k = v >> 11 exact in a double (one rounding, the same one)
+// x = -1 + 2*((v >> 11) * 2^-53) = k*2^-52 - 1 with k = v >> 11: exactly representable, so any exact evaluation equals
+// NumPy's two roundings.  With k = m + top*2^52 (m the low 52 bits, top the 53rd): x = (k - 2^52)*2^-52 = d*2^-52 - (top ? 1 : 2) where
+// d = 2^52 + m is built from the bits -- one logic operation and ONE exact FMA per coordinate (the product lies in [1, 2),
+// the difference is a multiple of 2^-52 below 1 in magnitude, so nothing is rounded anywhere).
 MCF_HD double pi_coord(uint64_t v) {
-    const uint64_t k = v >> 11;  // < 2^53
-    const double kd = fma(u52_to_double(k >> 32), 4294967296.0, u52_to_double(k & 0xFFFFFFFFULL));  // exact
-    return fma(kd, 1.0 / 4503599627370496.0, -1.0);
+    const double d = bits_to_double(0x4330000000000000ULL | ((v >> 11) & 0x000fffffffffffffULL));
+    return fma(d, 1.0 / 4503599627370496.0, (v >> 63) ? -1.0 : -2.0);
 }
 template <class Cur>
 MCF_HD int64_t pi_count_hits(Cur &cur, int64_t npts) {
@@ -565,7 +567,7 @@ MCF_HD int64_t pi_count_hits(Cur &cur, int64_t npts) {
     int64_t hits = 0, left = 2 * npts;
     double x = 0.0;
     consume_draws(cur, [&](uint64_t r) {
-        const double c = pi_coord(r);  // == -1 + 2*next_double, one rounding either way
+        const double c = pi_coord(r);  // == -1 + 2*next_double exactly
         if (left & 1) {  // second coordinate of the point
             hits += (xadd(xmul(x, x), xmul(c, c)) <= 1.0) ? 1 : 0;
         } else {
@@ -578,8 +580,7 @@ MCF_HD int64_t pi_count_hits(Cur &cur, int64_t npts) {
 }
 
 // Block form for block-aligned Philox streams whose lanes start on block boundaries: two points per Philox block,
-// no per-draw bookkeeping.  One coordinate costs 2 exact integer->double conversions and 2 FMAs:
-//   x = -1 + 2*((v >> 11) * 2^-53) = fma(k, 2^-52, -1) with k = v >> 11 exact in a double (one rounding, the same one).
+// no per-draw bookkeeping; one coordinate costs a shift, one logic operation and one FMA (pi_coord).
 MCF_HD int pi_inside(uint64_t vx, uint64_t vy) {
     const double x = pi_coord(vx), y = pi_coord(vy);
     return (xadd(xmul(x, x), xmul(y, y)) <= 1.0) ? 1 : 0;
