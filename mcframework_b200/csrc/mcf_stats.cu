@@ -336,6 +336,17 @@ __global__ void __launch_bounds__(512) select_compact_kernel(const double *__res
     __shared__ uint64_t stage[UNROLL * 512];
     __shared__ unsigned sh_cnt;
     __shared__ unsigned long long sh_base;
+    __shared__ unsigned sh_map[2048];
+    const bool use_map = pass == 2;
+    if (use_map) {
+        for (int i = threadIdx.x; i < 2048; i += blockDim.x) sh_map[i] = 0u;
+        __syncthreads();
+        if (threadIdx.x < n_uniq) {
+            const unsigned u = (unsigned)sh_uniq[threadIdx.x] & 0xFFFFu;
+            atomicOr(&sh_map[u >> 5], 1u << (u & 31u));
+        }
+        __syncthreads();
+    }
     for (int64_t b0 = (int64_t)blockIdx.x * blockDim.x; b0 < n; b0 += UNROLL * nthr) {  // CTA-uniform trip count
         if (threadIdx.x == 0) sh_cnt = 0u;
         __syncthreads();
@@ -348,7 +359,13 @@ __global__ void __launch_bounds__(512) select_compact_kernel(const double *__res
 #pragma unroll
         for (int k = 0; k < UNROLL; k++) {
             const int64_t i = b0 + threadIdx.x + k * nthr;
-            const bool hit = i < n && select_slot_key(key[k], pass, shift, n_uniq, sh_uniq, sh_bloom) >= 0;
+            bool hit;
+            if (use_map) {  // two decided digits: exact membership from a 65536-bit map, one shared-memory load
+                const unsigned pre = (unsigned)(key[k] >> 48);
+                hit = i < n && ((sh_map[pre >> 5] >> (pre & 31u)) & 1u);
+            } else {
+                hit = i < n && select_slot_key(key[k], pass, shift, n_uniq, sh_uniq, sh_bloom) >= 0;
+            }
             const unsigned m = __ballot_sync(0xffffffffu, hit);
             if (m == 0u) continue;
             unsigned base = 0;
