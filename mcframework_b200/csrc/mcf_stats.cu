@@ -1569,6 +1569,11 @@ static inline uint32_t bin_region_shift(int64_t n, int32_t requested) {
     return s;
 }
 
+// Two queue sets: while the gather kernels of batch k drain one (L2-request bound, the SMs mostly idle), the bin kernel of
+// batch k+1 fills the other on the caller's stream (instruction bound).
+static inline int64_t bin_set_bytes(int64_t window, int64_t R, int64_t cap) {
+    return align256(window * R * cap * 4) + align256(window * R * 4);
+}
 int64_t mcf_bootstrap_binned_workspace_bytes(int64_t n, int32_t resamples_per_batch, int32_t region_shift) {
     if (n < 2 || resamples_per_batch < 1) return MCF_ERR_BAD_ARG;
     const uint32_t sh = bin_region_shift(n, region_shift);
@@ -1577,7 +1582,7 @@ int64_t mcf_bootstrap_binned_workspace_bytes(int64_t n, int32_t resamples_per_ba
     const int64_t region_len = 1LL << sh;
     const int64_t cap = region_len + 8 * (int64_t)sqrt((double)region_len) + 4096;
     const int64_t window = resamples_per_batch + 2;
-    return align256(window * R * cap * 4) + align256(window * R * 4) + 256;
+    return 2 * bin_set_bytes(window, R, cap) + 256;
 }
 
 int mcf_bootstrap_accumulate_binned(uint32_t gen_kind, const mcf_stream *d_stream, const double *d_x, int64_t n,
@@ -1600,17 +1605,44 @@ int mcf_bootstrap_accumulate_binned(uint32_t gen_kind, const mcf_stream *d_strea
     const int64_t cap = region_len + 8 * (int64_t)sqrt((double)region_len) + 4096;
     const int64_t window = resamples_per_batch + 2;
     char *bws = (char *)d_bin_workspace;
-    uint32_t *queues = (uint32_t *)bws;
-    unsigned int *tails = (unsigned int *)(bws + align256(window * R * cap * 4));
-    int *overflow = (int *)(bws + align256(window * R * cap * 4) + align256(window * R * 4));
+    const int64_t set_bytes = bin_set_bytes(window, R, cap);
+    uint32_t *queues[2];
+    unsigned int *tails[2];
+    for (int b = 0; b < 2; b++) {
+        queues[b] = (uint32_t *)(bws + b * set_bytes);
+        tails[b] = (unsigned int *)(bws + b * set_bytes + align256(window * R * cap * 4));
+    }
+    int *overflow = (int *)(bws + 2 * set_bytes);
     const char *ws = (const char *)d_workspace;
     const uint32_t *counts = (const uint32_t *)(ws + g.off_counts);
     const unsigned long long *bbase = (const unsigned long long *)(ws + g.off_bbase);
     cudaStream_t cs = (cudaStream_t)cuda_stream;
     MCF_CUDA_OK(cudaMemsetAsync(overflow, 0, 4, cs));
     const uint64_t total_needed = (uint64_t)n_resamples * (uint64_t)n;
+
+    // The gathers run on a side stream of their own (created per call: the entry point stays re-entrant). Measured at
+    // n = 1e8, 128 resamples: 111.6 ms serial, 103.7 ms overlapped; capping the bin kernel below 4 CTAs per SM to leave
+    // room for gather CTAs made it slower (150-164 ms), so the bin kernel keeps its full occupancy.
+    const bool overlap = true;
+    const int pad = 0;
+    cudaStream_t side = cs;
+    cudaEvent_t ev_bin[2] = {nullptr, nullptr}, ev_gat[2] = {nullptr, nullptr}, ev_start = nullptr;
+    if (overlap) {
+        int lo_pri = 0, hi_pri = 0;
+        MCF_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+        MCF_CUDA_OK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi_pri));
+        for (int b = 0; b < 2; b++) {
+            MCF_CUDA_OK(cudaEventCreateWithFlags(&ev_bin[b], cudaEventDisableTiming));
+            MCF_CUDA_OK(cudaEventCreateWithFlags(&ev_gat[b], cudaEventDisableTiming));
+        }
+        MCF_CUDA_OK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+        MCF_CUDA_OK(cudaEventRecord(ev_start, cs));  // x and the zeroed sums are ready
+        MCF_CUDA_OK(cudaStreamWaitEvent(side, ev_start, 0));
+    }
     // batches = runs of CTAs whose slots start inside `resamples_per_batch` consecutive resamples
     int64_t blk = 0;
+    int k = 0;
+    int rc = MCF_OK;
     while (blk < g.n_blocks) {
         const uint64_t ord0 = ordinal_base + h_block_base[blk];
         if (ord0 >= total_needed) break;
@@ -1627,26 +1659,50 @@ int mcf_bootstrap_accumulate_binned(uint32_t gen_kind, const mcf_stream *d_strea
         bp.b_first = b_first;
         bp.cap = (uint64_t)cap;
         bp.n_resamples = (uint64_t)n_resamples;
-        MCF_CUDA_OK(cudaMemsetAsync(tails, 0, (size_t)(window * R * 4), cs));
+        const int buf = overlap ? (k & 1) : 0;
+        if (overlap && k >= 2) cudaStreamWaitEvent(cs, ev_gat[buf], 0);  // this queue set has been drained
+        cudaMemsetAsync(tails[buf], 0, (size_t)(window * R * 4), cs);
         if (gen_kind == MCF_GEN_PCG64)
-            boot_bin_kernel<MCF_GEN_PCG64><<<(unsigned)(end - blk), BOOT_THREADS, 0, cs>>>(
-                d_stream, bp, slot_lo, slot_hi, chunk_slots, g.n_chunks, blk, ordinal_base, counts, bbase, queues, tails,
-                (unsigned long long *)d_end_slot, overflow);
+            boot_bin_kernel<MCF_GEN_PCG64><<<(unsigned)(end - blk), BOOT_THREADS, pad, cs>>>(
+                d_stream, bp, slot_lo, slot_hi, chunk_slots, g.n_chunks, blk, ordinal_base, counts, bbase, queues[buf],
+                tails[buf], (unsigned long long *)d_end_slot, overflow);
         else
-            boot_bin_kernel<MCF_GEN_PHILOX><<<(unsigned)(end - blk), BOOT_THREADS, 0, cs>>>(
-                d_stream, bp, slot_lo, slot_hi, chunk_slots, g.n_chunks, blk, ordinal_base, counts, bbase, queues, tails,
-                (unsigned long long *)d_end_slot, overflow);
-        MCF_CUDA_OK(cudaGetLastError());
+            boot_bin_kernel<MCF_GEN_PHILOX><<<(unsigned)(end - blk), BOOT_THREADS, pad, cs>>>(
+                d_stream, bp, slot_lo, slot_hi, chunk_slots, g.n_chunks, blk, ordinal_base, counts, bbase, queues[buf],
+                tails[buf], (unsigned long long *)d_end_slot, overflow);
+        if (overlap) {
+            cudaEventRecord(ev_bin[buf], cs);
+            cudaStreamWaitEvent(side, ev_bin[buf], 0);
+        }
         for (uint32_t r = 0; r < (uint32_t)R; r++) {
             dim3 grid(64, (unsigned)window);
-            boot_gather_kernel<<<grid, 256, 0, cs>>>(d_x, bp, r, queues, tails, d_sums);
+            boot_gather_kernel<<<grid, 256, 0, side>>>(d_x, bp, r, queues[buf], tails[buf], d_sums);
         }
-        MCF_CUDA_OK(cudaGetLastError());
+        if (overlap) cudaEventRecord(ev_gat[buf], side);
+        if (cudaGetLastError() != cudaSuccess) {
+            rc = MCF_ERR_CUDA;
+            break;
+        }
         blk = end;
+        k++;
+    }
+    if (overlap) {  // join the side stream into the caller's, then release it
+        for (int b = 0; b < 2; b++)
+            if (k > b) cudaStreamWaitEvent(cs, ev_gat[b], 0);
     }
     int h_over = 0;
-    MCF_CUDA_OK(cudaMemcpyAsync(&h_over, overflow, 4, cudaMemcpyDeviceToHost, cs));
-    MCF_CUDA_OK(cudaStreamSynchronize(cs));
+    cudaMemcpyAsync(&h_over, overflow, 4, cudaMemcpyDeviceToHost, cs);
+    const cudaError_t e1 = cudaStreamSynchronize(cs);
+    if (overlap) {
+        cudaStreamSynchronize(side);
+        cudaStreamDestroy(side);
+        for (int b = 0; b < 2; b++) {
+            cudaEventDestroy(ev_bin[b]);
+            cudaEventDestroy(ev_gat[b]);
+        }
+        cudaEventDestroy(ev_start);
+    }
+    if (e1 != cudaSuccess || rc != MCF_OK) return MCF_ERR_CUDA;
     return h_over ? MCF_ERR_WINDOW_TOO_SMALL : MCF_OK;
 }
 
