@@ -119,5 +119,38 @@ def run_blocks(prog: ReplicationProgram, blocks, children, n: int, group=None):
     return values
 
 
+def run_blocks_pipelined(prog: ReplicationProgram, blocks, children, n: int, n_groups: int = 4):
+    """``run_blocks`` for one GPU and a host-resident result: the spawned streams are replayed in ``n_groups``
+    contiguous groups and the device->host copy of group g (pinned memory, side stream) overlaps the kernels of
+    group g+1, so only the last group's copy is exposed; the plan workspace shrinks by the same factor.  Streams are
+    independent, so the values are those of ``run_blocks`` bit for bit.  Returns (device results, host ndarray)."""
+    import torch
+
+    lay = S.StreamLayout(S.GEN_PHILOX, S.philox_records(children, blocks), n, blocks[0][1] - blocks[0][0])
+    n_groups = max(1, min(int(n_groups), lay.n_streams))
+    values = torch.empty(n, dtype=torch.float64, device="cuda")
+    host = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    main = torch.cuda.current_stream()
+    side = torch.cuda.Stream()
+    at = 0
+    for g in range(n_groups):
+        part = lay.shard(g, n_groups)
+        if part.n_total == 0:
+            continue
+        out, _ = prog.execute(D.DeviceLayout.of(part))
+        piece = values[at:at + part.n_total]
+        piece.copy_(out)
+        del out
+        done = torch.cuda.Event()
+        done.record(main)
+        side.wait_event(done)
+        with torch.cuda.stream(side):
+            host[at:at + part.n_total].copy_(piece, non_blocking=True)
+        at += part.n_total
+    assert at == n, (at, n)
+    side.synchronize()
+    return values, host.numpy()
+
+
 __all__ = ["ReplicationProgram", "HostLoopRequired", "SlotCount", "pi_program", "normals_program", "integers_program",
-           "run_sequential", "run_blocks", "N"]
+           "run_sequential", "run_blocks", "run_blocks_pipelined", "N"]

@@ -154,6 +154,10 @@ class MonteCarloSimulation(ABC):
     _PCTS = (5, 25, 50, 75, 95)
     _PARALLEL_THRESHOLD = 20_000
     _CHUNKS_PER_WORKER = 8
+    #: block-parallel runs with at least this many replications copy their result vector to the host in
+    #: ``_PIPELINE_GROUPS`` pieces, each behind the kernels of the next group of streams (one GPU, host-resident result)
+    _PIPELINE_MIN_SIMS = 1 << 24
+    _PIPELINE_GROUPS = 4
 
     @staticmethod
     def _rng(rng: np.random.Generator | None, default: np.random.Generator | None = None) -> np.random.Generator:
@@ -319,9 +323,12 @@ class MonteCarloSimulation(ABC):
         host.copy_(t, non_blocking=False)
         return host.numpy()
 
-    def _finish_device_run(self, values_dev, group=None) -> np.ndarray:
-        """Device results -> (a) DeviceSample kept for the statistics, (b) the host ndarray of the result."""
-        if group is not None:
+    def _finish_device_run(self, values_dev, group=None, host=None) -> np.ndarray:
+        """Device results -> (a) DeviceSample kept for the statistics, (b) the host ndarray of the result
+        (``host``: already copied by the pipelined block run)."""
+        if host is not None:
+            self._device_sample = DeviceSample(values_dev, host, None)
+        elif group is not None:
             from . import _multi
 
             # "all": every rank returns the full vector (reference semantics on every rank);
@@ -453,12 +460,19 @@ class MonteCarloSimulation(ABC):
             from . import _programs
 
             group = self._shard_group()
+            host = None
             try:
-                values = _programs.run_blocks(prog, blocks, children, n_simulations, group)
+                if (group is None and prog.kind != "integers" and not getattr(self, "keep_results_on_device", False)
+                        and n_simulations >= self._PIPELINE_MIN_SIMS and len(blocks) >= 2):
+                    # large host-resident result: copy it out group by group while the next group is computed
+                    values, host = _programs.run_blocks_pipelined(prog, blocks, children, n_simulations,
+                                                                  self._PIPELINE_GROUPS)
+                else:
+                    values = _programs.run_blocks(prog, blocks, children, n_simulations, group)
             except _programs.HostLoopRequired:
                 values = None  # spawned children are untouched: loop the hook over the same blocks below
         if prog is not None and values is not None:
-            results = self._finish_device_run(values, group)
+            results = self._finish_device_run(values, group, host)
             if progress_callback:
                 done = 0
                 for a, b in blocks:

@@ -1585,6 +1585,30 @@ int64_t mcf_bootstrap_binned_workspace_bytes(int64_t n, int32_t resamples_per_ba
     return 2 * bin_set_bytes(window, R, cap) + 256;
 }
 
+// A high-priority side stream and the events that order it against the caller's stream; released on scope exit.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_bin[2] = {nullptr, nullptr}, ev_gat[2] = {nullptr, nullptr};
+    bool open(cudaStream_t caller) {
+        int lo_pri = 0, hi_pri = 0;
+        if (cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri) != cudaSuccess) return false;
+        if (cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, hi_pri) != cudaSuccess) return false;
+        for (int b = 0; b < 2; b++)
+            if (cudaEventCreateWithFlags(&ev_bin[b], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ev_gat[b], cudaEventDisableTiming) != cudaSuccess)
+                return false;
+        // everything queued on the caller's stream so far (x, the zeroed sums) precedes the side stream's work
+        return cudaEventRecord(ev_bin[0], caller) == cudaSuccess && cudaStreamWaitEvent(stream, ev_bin[0], 0) == cudaSuccess;
+    }
+    ~SideStream() {
+        for (int b = 0; b < 2; b++) {
+            if (ev_bin[b]) cudaEventDestroy(ev_bin[b]);
+            if (ev_gat[b]) cudaEventDestroy(ev_gat[b]);
+        }
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
 int mcf_bootstrap_accumulate_binned(uint32_t gen_kind, const mcf_stream *d_stream, const double *d_x, int64_t n,
                                     int64_t n_resamples, uint64_t slot_lo, uint64_t slot_hi, int32_t chunk_slots,
                                     uint64_t ordinal_base, const void *d_workspace, int64_t workspace_bytes,
@@ -1624,21 +1648,10 @@ int mcf_bootstrap_accumulate_binned(uint32_t gen_kind, const mcf_stream *d_strea
     // n = 1e8, 128 resamples: 111.6 ms serial, 103.7 ms overlapped; capping the bin kernel below 4 CTAs per SM to leave
     // room for gather CTAs made it slower (150-164 ms), so the bin kernel keeps its full occupancy.
     const bool overlap = true;
-    const int pad = 0;
-    cudaStream_t side = cs;
-    cudaEvent_t ev_bin[2] = {nullptr, nullptr}, ev_gat[2] = {nullptr, nullptr}, ev_start = nullptr;
-    if (overlap) {
-        int lo_pri = 0, hi_pri = 0;
-        MCF_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
-        MCF_CUDA_OK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi_pri));
-        for (int b = 0; b < 2; b++) {
-            MCF_CUDA_OK(cudaEventCreateWithFlags(&ev_bin[b], cudaEventDisableTiming));
-            MCF_CUDA_OK(cudaEventCreateWithFlags(&ev_gat[b], cudaEventDisableTiming));
-        }
-        MCF_CUDA_OK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
-        MCF_CUDA_OK(cudaEventRecord(ev_start, cs));  // x and the zeroed sums are ready
-        MCF_CUDA_OK(cudaStreamWaitEvent(side, ev_start, 0));
-    }
+    SideStream ss;
+    if (overlap && !ss.open(cs)) return MCF_ERR_CUDA;  // the destructor releases whatever was created
+    const cudaStream_t side = overlap ? ss.stream : cs;
+    cudaEvent_t *ev_bin = ss.ev_bin, *ev_gat = ss.ev_gat;
     // batches = runs of CTAs whose slots start inside `resamples_per_batch` consecutive resamples
     int64_t blk = 0;
     int k = 0;
@@ -1663,11 +1676,11 @@ int mcf_bootstrap_accumulate_binned(uint32_t gen_kind, const mcf_stream *d_strea
         if (overlap && k >= 2) cudaStreamWaitEvent(cs, ev_gat[buf], 0);  // this queue set has been drained
         cudaMemsetAsync(tails[buf], 0, (size_t)(window * R * 4), cs);
         if (gen_kind == MCF_GEN_PCG64)
-            boot_bin_kernel<MCF_GEN_PCG64><<<(unsigned)(end - blk), BOOT_THREADS, pad, cs>>>(
+            boot_bin_kernel<MCF_GEN_PCG64><<<(unsigned)(end - blk), BOOT_THREADS, 0, cs>>>(
                 d_stream, bp, slot_lo, slot_hi, chunk_slots, g.n_chunks, blk, ordinal_base, counts, bbase, queues[buf],
                 tails[buf], (unsigned long long *)d_end_slot, overflow);
         else
-            boot_bin_kernel<MCF_GEN_PHILOX><<<(unsigned)(end - blk), BOOT_THREADS, pad, cs>>>(
+            boot_bin_kernel<MCF_GEN_PHILOX><<<(unsigned)(end - blk), BOOT_THREADS, 0, cs>>>(
                 d_stream, bp, slot_lo, slot_hi, chunk_slots, g.n_chunks, blk, ordinal_base, counts, bbase, queues[buf],
                 tails[buf], (unsigned long long *)d_end_slot, overflow);
         if (overlap) {
@@ -1693,15 +1706,7 @@ int mcf_bootstrap_accumulate_binned(uint32_t gen_kind, const mcf_stream *d_strea
     int h_over = 0;
     cudaMemcpyAsync(&h_over, overflow, 4, cudaMemcpyDeviceToHost, cs);
     const cudaError_t e1 = cudaStreamSynchronize(cs);
-    if (overlap) {
-        cudaStreamSynchronize(side);
-        cudaStreamDestroy(side);
-        for (int b = 0; b < 2; b++) {
-            cudaEventDestroy(ev_bin[b]);
-            cudaEventDestroy(ev_gat[b]);
-        }
-        cudaEventDestroy(ev_start);
-    }
+    if (overlap) cudaStreamSynchronize(side);
     if (e1 != cudaSuccess || rc != MCF_OK) return MCF_ERR_CUDA;
     return h_over ? MCF_ERR_WINDOW_TOO_SMALL : MCF_OK;
 }

@@ -121,6 +121,34 @@ def test_black_scholes_runs(m, golden):
         bs.run(10, exercise_type="bermudan")
 
 
+def test_pipelined_block_runs_equal_plain_runs(m, golden):
+    """Large block-parallel runs copy their result to the host group by group behind the next group's kernels
+    (core._PIPELINE_MIN_SIMS).  Forced on at fixture size: same vectors bit for bit, same statistics, same spawn
+    side effects, with 1..5 groups and more groups than streams; Pi and Black-Scholes programs."""
+    _, a = golden
+    bs = m.BlackScholesSimulation()
+    bs.set_seed(11)
+    plain = bs.run(20_000, parallel=True, n_workers=4, n_steps=64, percentiles=(10, 90))
+    np.testing.assert_allclose(plain.results, a["G4_bs_call_par"], rtol=RES_RTOL, atol=PAY_ATOL)
+    for groups in (1, 2, 3, 5, 64):
+        piped = m.BlackScholesSimulation()
+        piped._PIPELINE_MIN_SIMS, piped._PIPELINE_GROUPS = 1, groups
+        piped.set_seed(11)
+        r = piped.run(20_000, parallel=True, n_workers=4, n_steps=64, percentiles=(10, 90))
+        assert isinstance(r.results, np.ndarray) and r.results.dtype == np.float64 and r.results.flags.writeable
+        assert np.array_equal(r.results, plain.results), groups
+        assert (r.mean, r.std, r.percentiles) == (plain.mean, plain.std, plain.percentiles)
+        assert piped.seed_seq.n_children_spawned == bs.seed_seq.n_children_spawned
+    pi = m.PiEstimationSimulation()
+    pi._PIPELINE_MIN_SIMS, pi._PIPELINE_GROUPS = 1, 3
+    pi.set_seed(123)
+    assert np.array_equal(pi.run(20_000, n_points=100, parallel=True, n_workers=8, compute_stats=False).results,
+                          a["G2_pi_parallel_results"])
+    pi.set_seed(5)  # ragged last block (20_001 = 3*8 blocks of 833 + 9)
+    assert np.array_equal(pi.run(20_001, n_points=33, antithetic=True, parallel=True, n_workers=3, compute_stats=False).results,
+                          a["G2b_pi_antithetic_parallel_results"])
+
+
 def test_results_can_stay_on_the_device_until_somebody_reads_them(m, golden):
     """SURVEY 8(f).2: opt-in device-resident results.  Statistics, percentiles and compare_results need no host copy;
     the ndarray appears (once) when the caller touches it, and equals the one an ordinary run returns."""

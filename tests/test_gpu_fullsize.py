@@ -68,6 +68,23 @@ def test_config2_black_scholes_1e8_paths(m):
     np.testing.assert_allclose(z_fast, both[2][:4096].cpu().numpy(), rtol=0, atol=0)  # same streams, same plan geometry
 
 
+def test_large_runs_pipeline_their_host_copy(m):
+    """2^24 + 5 paths through the public API (above core._PIPELINE_MIN_SIMS: four stream groups, host copy of each
+    behind the kernels of the next) == one plan + replay over the whole layout, bit for bit."""
+    from mcframework_b200 import _device as D, _native as N, _streams as S
+
+    n, steps = (1 << 24) + 5, 16
+    P = [100.0, 100.0, 1.0, 0.05, 0.2]
+    bs = m.BlackScholesSimulation()
+    assert n >= bs._PIPELINE_MIN_SIMS
+    bs.set_seed(42)
+    res = bs.run(n, parallel=True, n_workers=8, n_steps=steps, compute_stats=False)
+    lay = S.parallel_layout(np.random.SeedSequence(42), n, 8)
+    dl = D.DeviceLayout.of(lay)
+    whole = D.gbm_terminal(dl, steps, D.normal_plan(dl, steps), [(N.BS_EURO_CALL, P)])[0].cpu().numpy()
+    assert res.results.shape == (n,) and np.array_equal(res.results, whole)
+
+
 def test_config1_pi_scaled_2e6_sims(m):
     from mcframework_b200 import _device as D, _stats_device as SD, _streams as S
 
