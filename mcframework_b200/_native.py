@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcf_b200.so")
+#: developer override for A/B runs of alternative builds of the same ABI (tools/ab_variants.sh); unset in normal use
+LIB_PATH = os.environ.get("MCF_B200_LIB") or os.path.join(_HERE, "libmcf_b200.so")
 
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_WORKSPACE_TOO_SMALL, ERR_WINDOW_TOO_SMALL, ERR_NOT_CONVERGED = 0, -1, -2, -3, -4, -5
 _ERR_NAMES = {

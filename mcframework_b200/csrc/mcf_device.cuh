@@ -76,6 +76,45 @@ MCF_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
 #endif
 }
 
+// Full 64x64 -> 128 product with a compile-time-constant multiplier (the Philox round multipliers).
+// CHAIN = false: mul.hi.u64 + mul.lo.u64 as ptxas expands them -- four IMAD.WIDE.U32 plus IMAD.X, IMAD.MOV (both on the
+// multiplier pipe, the busiest one of the RNG kernels) and one IADD3.
+// CHAIN = true (device only): the same four wide multiplications written as a carry chain, so that the carry of the
+// middle sum is materialised by SEL on the integer ALU instead of IMAD.X: B = xl*ml, A = xh*ml, C = xl*mh + A (carry cy),
+// w1 = B.hi + C.lo (carry k), (w3:w2) = xh*mh + (cy:C.hi) + k.  Measured in the planning scan: 204 -> 192 ms per two
+// plans of 1e8 x 252.  Kernels at the register limit with more live state (the 8-set replay) spill with it and keep
+// CHAIN = false.
+template <bool CHAIN = false>
+MCF_HD void mul64_full(uint64_t m, uint64_t x, uint64_t &hi, uint64_t &lo) {
+#if defined(__CUDA_ARCH__)
+    if (CHAIN) {
+        const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32), ml = (uint32_t)m, mh = (uint32_t)(m >> 32);
+        uint32_t w0, w1, w2, w3;
+        asm("{\n\t"
+            ".reg .u32 b1, a0, a1, c0, c1, cy;\n\t"
+            ".reg .u64 tb, ta;\n\t"
+            "mul.wide.u32 tb, %4, %6;\n\t"
+            "mul.wide.u32 ta, %5, %6;\n\t"
+            "mov.b64 {%0, b1}, tb;\n\t"
+            "mov.b64 {a0, a1}, ta;\n\t"
+            "mad.lo.cc.u32 c0, %4, %7, a0;\n\t"
+            "madc.hi.cc.u32 c1, %4, %7, a1;\n\t"
+            "addc.u32 cy, 0, 0;\n\t"
+            "add.cc.u32 %1, b1, c0;\n\t"
+            "madc.lo.cc.u32 %2, %5, %7, c1;\n\t"
+            "madc.hi.u32 %3, %5, %7, cy;\n\t"
+            "}"
+            : "=&r"(w0), "=&r"(w1), "=&r"(w2), "=&r"(w3)
+            : "r"(xl), "r"(xh), "r"(ml), "r"(mh));
+        lo = ((uint64_t)w1 << 32) | w0;
+        hi = ((uint64_t)w3 << 32) | w2;
+        return;
+    }
+#endif
+    hi = mulhi64(m, x);
+    lo = m * x;
+}
+
 MCF_HD int popc64(uint64_t v) {
 #if defined(__CUDA_ARCH__)
     return __popcll(v);
@@ -171,8 +210,9 @@ MCF_HD void philox4x64_10(uint64_t c0, uint64_t c1, uint64_t c2, uint64_t c3, ui
                           uint64_t out[4]) {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
-        uint64_t hi0 = mulhi64(MCF_PHILOX_M0, c0), lo0 = MCF_PHILOX_M0 * c0;
-        uint64_t hi1 = mulhi64(MCF_PHILOX_M1, c2), lo1 = MCF_PHILOX_M1 * c2;
+        uint64_t hi0, lo0, hi1, lo1;
+        mul64_full(MCF_PHILOX_M0, c0, hi0, lo0);
+        mul64_full(MCF_PHILOX_M1, c2, hi1, lo1);
         c0 = hi1 ^ c1 ^ k0;
         c1 = lo1;
         c2 = hi0 ^ c3 ^ k1;
@@ -230,8 +270,9 @@ MCF_HD void philox_block_keys(const PhiloxKeys &K, uint64_t blk, uint64_t &o0, u
     uint64_t c3 = K.b3;
 #pragma unroll
     for (int r = 0; r < 10; r++) {
-        const uint64_t hi0 = mulhi64(MCF_PHILOX_M0, c0), lo0 = MCF_PHILOX_M0 * c0;
-        const uint64_t hi1 = mulhi64(MCF_PHILOX_M1, c2), lo1 = MCF_PHILOX_M1 * c2;
+        uint64_t hi0, lo0, hi1, lo1;
+        mul64_full(MCF_PHILOX_M0, c0, hi0, lo0);
+        mul64_full(MCF_PHILOX_M1, c2, hi1, lo1);
         c0 = hi1 ^ c1 ^ K.rk[2 * r];
         c1 = lo1;
         c2 = hi0 ^ c3 ^ K.rk[2 * r + 1];
@@ -246,16 +287,21 @@ MCF_HD void philox_block_keys(const PhiloxKeys &K, uint64_t blk, uint64_t &o0, u
 // Block `blk` of a stream whose low counter word never carries (K.fold_ok): 18 wide multiplications instead of 20.
 //   round 0: (x, b1, b2, b3)      -> (A0,              M1*b2,      mulhi(M0,x) ^ b3 ^ rk1, M0*x)     A0 constant
 //   round 1: (A0, M1*b2, c2, c3)  -> (mulhi(M1,c2) ^ M1*b2 ^ rk2, M1*c2, mulhi(M0,A0) ^ c3 ^ rk3, M0*A0)
+template <bool CHAIN = false>
 MCF_HD void philox_block_folded(const PhiloxKeys &K, uint64_t blk, uint64_t &o0, uint64_t &o1, uint64_t &o2, uint64_t &o3) {
     const uint64_t x = K.b0 + blk;
-    uint64_t c2 = mulhi64(MCF_PHILOX_M0, x) ^ K.f0_c2x, c3 = MCF_PHILOX_M0 * x;  // round 0
-    uint64_t c0 = mulhi64(MCF_PHILOX_M1, c2) ^ K.f1_c0x, c1 = MCF_PHILOX_M1 * c2;  // round 1
+    uint64_t c0, c1, c2, c3;
+    mul64_full<CHAIN>(MCF_PHILOX_M0, x, c2, c3);  // round 0
+    c2 ^= K.f0_c2x;
+    mul64_full<CHAIN>(MCF_PHILOX_M1, c2, c0, c1);  // round 1
+    c0 ^= K.f1_c0x;
     c2 = c3 ^ K.f1_c2x;
     c3 = K.f1_c3;
 #pragma unroll
     for (int r = 2; r < 10; r++) {
-        const uint64_t hi0 = mulhi64(MCF_PHILOX_M0, c0), lo0 = MCF_PHILOX_M0 * c0;
-        const uint64_t hi1 = mulhi64(MCF_PHILOX_M1, c2), lo1 = MCF_PHILOX_M1 * c2;
+        uint64_t hi0, lo0, hi1, lo1;
+        mul64_full<CHAIN>(MCF_PHILOX_M0, c0, hi0, lo0);
+        mul64_full<CHAIN>(MCF_PHILOX_M1, c2, hi1, lo1);
         c0 = hi1 ^ c1 ^ K.rk[2 * r];
         c1 = lo1;
         c2 = hi0 ^ c3 ^ K.rk[2 * r + 1];
@@ -682,6 +728,11 @@ MCF_HD ChunkInfo scan_chunk(Cur &cur, uint64_t chunk_base, uint32_t entry, const
 // for the general re-walk, as before.  The sums differ from scan_chunk's by summation order only (deterministic).
 // ---------------------------------------------------------------------------------------
 #define MCF_PARK_CAP 4
+#ifndef MCF_SCAN_UNROLL
+#define MCF_SCAN_UNROLL 1  // sub-chunk iterations of the phase-1 loop per loop body
+#endif
+#define MCF_PRAGMA(x) _Pragma(#x)
+#define MCF_UNROLL(n) MCF_PRAGMA(unroll n)
 struct ParkSlots {  // slot k of this thread: a[k * stride], b[k * stride], c[k * stride]
     uint64_t *a, *b, *c;
     unsigned stride;
@@ -705,7 +756,8 @@ MCF_HD double zig_fast_value(uint64_t w, const ZigTables &t) {  // signed value 
 // chunk is generated by one thread per CTA only; the host build simply generates it.
 template <class Load, class EntryOf, class ShareFirst, class LookAhead>
 MCF_HD ChunkInfo scan_chunk_fast2(Load load, uint64_t blk0, const ZigTables &t, const ParkSlots &park, double *zsub_out,
-                                  bool *valid, EntryOf entry_of, ShareFirst share_first, LookAhead lookahead) {
+                                  bool *valid, EntryOf entry_of, ShareFirst share_first, LookAhead lookahead,
+                                  const uint64_t bias = MCF_U52_BIAS) {
     uint64_t F = 0;   // fast-looking draws
     unsigned np = 0;  // parked draws
     double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
@@ -715,7 +767,7 @@ MCF_HD ChunkInfo scan_chunk_fast2(Load load, uint64_t blk0, const ZigTables &t, 
     share_first(w0, w1);
 #define MCF_FAST2_DRAW(J, WA, WB, WC)                                                             \
     {                                                                                             \
-        const uint64_t dbits = (((WA) >> 9) & 0x000fffffffffffffULL) | MCF_U52_BIAS;              \
+        const uint64_t dbits = (((WA) >> 9) & 0x000fffffffffffffULL) | bias;                      \
         const ZigKW kw = t.kws[(unsigned)(WA)&0x1ffu];                                            \
         const double v = xmul(xadd(bits_to_double(dbits), -4503599627370496.0), kw.wi);           \
         if ((J) == 0 && sub == 0) vk0 = v;                                                        \
@@ -732,7 +784,7 @@ MCF_HD ChunkInfo scan_chunk_fast2(Load load, uint64_t blk0, const ZigTables &t, 
             np++;                                                                                 \
         }                                                                                         \
     }
-#pragma unroll 1
+MCF_UNROLL(MCF_SCAN_UNROLL)
     for (unsigned sub = 0; sub < MCF_SUBS; sub++) {
         double zc = 0.0;
         unsigned f16 = 0;

@@ -71,6 +71,17 @@ __device__ __forceinline__ int stream_of(const mcf_stream *streams, int n_stream
     return find_stream(streams, n_streams, sim);
 }
 
+// code-generation choices of the Philox kernels (tools/ab_variants.sh measures the alternatives)
+#ifndef MCF_PI_CHAIN
+#define MCF_PI_CHAIN false      // carry-chain form of the round multiplications (mul64_full<true>) in the Pi kernel
+#endif
+#ifndef MCF_REPLAY_CHAIN
+#define MCF_REPLAY_CHAIN false  // ... in the boundary-form replay
+#endif
+#ifndef MCF_SCAN_CTAS
+#define MCF_SCAN_CTAS 4         // resident CTAs per SM of the planning scan (64 registers per thread)
+#endif
+
 // ===================================================================================== Pi
 template <int KIND>
 __global__ void __launch_bounds__(256) pi_kernel(const mcf_stream *__restrict__ streams, int n_streams, int64_t n_total,
@@ -116,7 +127,7 @@ __global__ void __launch_bounds__(256) pi_philox_stream_kernel(const __grid_cons
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n_units = n_sims * parts;
-    auto load = [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) { philox_block_folded(K, blk, a, b, c, d); };
+    auto load = [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) { philox_block_folded<MCF_PI_CHAIN>(K, blk, a, b, c, d); };
     for (int64_t unit = warp0; unit < n_units; unit += n_warps) {
         const int64_t sim = unit / parts, part = unit - sim * parts;
         const uint64_t base = K.off + (uint64_t)sim * (uint64_t)draws_per_sim;  // multiple of 4
@@ -216,7 +227,7 @@ __global__ void __launch_bounds__(256, 3) plan_scan_kernel(const mcf_stream *__r
 
 // One launch per stream: the stream's ten Philox round keys and base counter are kernel parameters, i.e. operands
 // in the constant bank -- the key schedule costs no instruction and no register.
-__global__ void __launch_bounds__(256, 4) plan_scan_philox_stream_kernel(const __grid_constant__ PhiloxKeys K, int64_t row0,
+__global__ void __launch_bounds__(256, MCF_SCAN_CTAS) plan_scan_philox_stream_kernel(const __grid_constant__ PhiloxKeys K, int64_t row0,
                                                                          int64_t cps, uint64_t *__restrict__ startmask,
                                                                          uint64_t *__restrict__ emitmask,
                                                                          uint8_t *__restrict__ exit_,
@@ -231,7 +242,7 @@ __global__ void __launch_bounds__(256, 4) plan_scan_philox_stream_kernel(const _
     bool valid;
     const uint64_t blk0 = (K.off + (uint64_t)c * MCF_CHUNK) >> 2;
     const ChunkInfo ci = scan_chunk_fast2(
-        [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &cc, uint64_t &d) { philox_block_folded(K, blk, a, b, cc, d); },
+        [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &cc, uint64_t &d) { philox_block_folded<true>(K, blk, a, b, cc, d); },
         blk0, t, park, zsum + id * MCF_SUBS, &valid,
         [&](unsigned exit_spec) {
             // the previous chunk of the stream is the neighbouring lane's; lane 0 cannot know it (entry 0, fixed up later)
@@ -246,12 +257,18 @@ __global__ void __launch_bounds__(256, 4) plan_scan_philox_stream_kernel(const _
         [&](uint64_t &a, uint64_t &b) {
             if (threadIdx.x == 255) {  // the CTA's last chunk: its successor belongs to another CTA
                 uint64_t c2, d2;
-                philox_block_folded(K, blk0 + 16, a, b, c2, d2);
+                philox_block_folded<true>(K, blk0 + 16, a, b, c2, d2);
             } else {
                 a = sh.first[threadIdx.x + 1];
                 b = sh.first[256 + threadIdx.x + 1];
             }
-        });
+        }
+#ifdef MCF_SCAN_OPAQUE_BIAS
+        // the 2^52 exponent bias as a launch-time value (fold_ok is 0 or 1): ptxas keeps it in a uniform register and
+        // merges mask and bias of the high word into one logic operation instead of re-materialising two immediates
+        , MCF_U52_BIAS | ((uint64_t)(K.fold_ok >> 1) << 32)
+#endif
+        );
     startmask[id] = ci.startmask;
     emitmask[id] = ci.emitmask;
     exit_[id] = (uint8_t)ci.exit;
@@ -606,7 +623,7 @@ __global__ void __launch_bounds__(256, 4)
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = j < n_sims;
     const int64_t i = first_sim + j;
-    auto load = [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) { philox_block_folded(K, blk, a, b, c, d); };
+    auto load = [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) { philox_block_folded<MCF_REPLAY_CHAIN>(K, blk, a, b, c, d); };
     auto tail = [&](uint64_t p, uint64_t rabs) { return zig_tail_value<MCF_GEN_PHILOX>(streams[si], p, rabs); };
     uint64_t start = 0, end = 0;
     BoundarySums be;
