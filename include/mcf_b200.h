@@ -261,8 +261,11 @@ int mcf_bootstrap_finalize(double *d_sums, int64_t n_resamples, int64_t n, void 
  * resamples are first appended (4 bytes each) to per-(resample, 2^region_shift-element region of x) queues, then
  * summed region by region.  Same index stream, bit for bit; only the order of a resample's additions differs.
  * h_block_base: host copy of the per-CTA ordinal prefix of the count pass (mcf_bootstrap_blocks entries, filled by
- * mcf_bootstrap_block_base).  region_shift 0 = automatic (64 MB regions, at most 16).  Needs 256*chunk_slots <= n,
- * chunk_slots % 8 == 0.  Synchronises the stream (reads the queue-overflow flag). */
+ * mcf_bootstrap_block_base).  region_shift 0 = automatic (2^22-element = 32 MB regions, doubled until at most 32 regions cover x).  Needs 256*chunk_slots <= n,
+ * chunk_slots % 8 == 0.  The workspace holds TWO queue sets: the gathers of one batch run on an internal
+ * high-priority side stream while the bin pass of the next batch fills the other set on the caller's stream; the
+ * side stream is joined into the caller's before the call returns.  Synchronises the stream (reads the
+ * queue-overflow flag). */
 int64_t mcf_bootstrap_blocks(int64_t n_slots, int32_t chunk_slots);
 int mcf_bootstrap_block_base(const void *d_workspace, int64_t n_slots, int32_t chunk_slots, uint64_t *h_block_base,
                              void *cuda_stream);
