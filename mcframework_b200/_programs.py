@@ -22,7 +22,7 @@ class HostLoopRequired(RuntimeError):
 
 @dataclass
 class ReplicationProgram:
-    kind: str  # "pi" | "normals" | "integers"
+    kind: str  # "pi" | "normals" | "integers" | "constant"
     # pi
     n_points: int = 0
     antithetic: bool = False
@@ -35,9 +35,15 @@ class ReplicationProgram:
     size: int = 0
     op: int = 0      # 0: sum of the values, 1: longest run of `match`
     match: int = 0
+    # constant: a replication that draws nothing (a zero-step horizon)
+    value: float = 0.0
 
     def execute(self, dl: D.DeviceLayout):
         """-> (float64[n] device tensor of results, int64[n_streams] device tensor of draws per stream | fixed int)"""
+        if self.kind == "constant":
+            import torch
+
+            return torch.full((dl.layout.n_total,), self.value, dtype=torch.float64, device="cuda"), 0
         if self.kind == "pi":
             _, out = D.pi_hits(dl, self.n_points, self.antithetic)
             m = self.n_points // 2 if self.antithetic else self.n_points
@@ -76,6 +82,11 @@ def normals_program(n_steps: int, specs) -> ReplicationProgram:
     if n_steps <= 0:
         raise ValueError("n_steps must be positive")
     return ReplicationProgram("normals", n_steps=n_steps, specs=list(specs))
+
+
+def constant_program(value: float) -> ReplicationProgram:
+    """Every replication returns ``value`` and leaves its stream untouched (``rng.normal(size=0)`` in the reference)."""
+    return ReplicationProgram("constant", value=float(value))
 
 
 def run_sequential(prog: ReplicationProgram, rng: np.random.Generator, n: int):
@@ -153,4 +164,4 @@ def run_blocks_pipelined(prog: ReplicationProgram, blocks, children, n: int, n_g
 
 
 __all__ = ["ReplicationProgram", "HostLoopRequired", "SlotCount", "pi_program", "normals_program", "integers_program",
-           "run_sequential", "run_blocks", "run_blocks_pipelined", "N"]
+           "constant_program", "run_sequential", "run_blocks", "run_blocks_pipelined", "N"]

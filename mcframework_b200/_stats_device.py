@@ -187,6 +187,9 @@ def percentiles(x, pcts, n_valid: int | None = None, has_nan: bool = False, omit
     ``n_valid``: number of values taking part (all of them, or the finite ones with ``omit_nonfinite``).
     ``has_nan`` (and not omitting): NumPy returns NaN for every percentile."""
     pcts = list(pcts)
+    q = np.asarray(pcts, dtype=np.float64)
+    if q.size and not (np.all(q >= 0.0) and np.all(q <= 100.0)):  # NaN fails both tests, as in np.percentile
+        raise ValueError("Percentiles must be in the range [0, 100]")
     n = int(x.numel()) if n_valid is None else int(n_valid)
     if n == 0 or (has_nan and not omit_nonfinite):
         return np.full(len(pcts), np.nan)

@@ -26,6 +26,8 @@ class PortfolioSimulation(MonteCarloSimulation):
                              volatility: float = 0.20, years: int = 10, use_gbm: bool = True, **_ignored):
         dt = 1.0 / 252.0
         n_steps = int(years / dt)  # computed exactly as the reference's Python expression
+        if n_steps == 0:  # a horizon below one day: `rng.normal(size=0)` draws nothing, exp(0) * V0 (:81-84)
+            return _programs.constant_program(initial_value)
         mode = N.PORTFOLIO_GBM if use_gbm else N.PORTFOLIO_LOG1P
         return _programs.normals_program(n_steps, [(mode, [initial_value, annual_return, volatility])])
 

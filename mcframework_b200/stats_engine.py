@@ -497,10 +497,13 @@ def ci_mean_bootstrap(x, ctx: StatsContext) -> dict[str, float | str] | None:
     lo_q, hi_q = ctx.q_bound()
     # a population with NaN/inf under "propagate" poisons the resample means: NumPy's percentile then returns NaN
     poisoned = bool(v.tainted and SD.moments(means).n_nan > 0)
-    if ctx.bootstrap == "percentile" or v.size < 3 or v.tainted:
-        label = "bootstrap-percentile" if (ctx.bootstrap == "percentile" or v.size < 3) else "bootstrap-bca"
+    if ctx.bootstrap == "percentile" or v.size < 3:
         low, high = SD.percentiles(means, [lo_q, hi_q], has_nan=poisoned)
-        return _CIResult(ctx.confidence, label, low, high).as_dict()
+        return _CIResult(ctx.confidence, "bootstrap-percentile", low, high).as_dict()
+    if v.tainted:
+        # NaN/inf taking part ("propagate") make the jackknife acceleration NaN, the adjusted percentiles with it, and
+        # np.percentile rejects them (:1197) -- after the resamples were drawn, so the generator has moved as well
+        raise ValueError("Percentiles must be in the range [0, 100]")
     low, high = _compute_bca_interval(v, means, ctx.confidence)
     return _CIResult(ctx.confidence, "bootstrap-bca", low, high).as_dict()
 

@@ -1,0 +1,299 @@
+"""TEST INFRASTRUCTURE ONLY -- differential run: the UNMODIFIED reference (imported from ``/root/reference/src``) and
+``mcframework_b200`` on the oracle-backed stand-in device (``fakedev``) are driven through the same public calls with
+the same seeds; every output is compared.  Run as a script in its own process (``fakedev.install()`` patches globally):
+
+    python tests/refsuite/differential.py [n_cases [seed]]
+
+Exit code 0 and a last line ``differential: <k> comparisons, 0 mismatches`` on success.
+"""
+from __future__ import annotations
+
+import math
+import os
+import re
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+for p in (ROOT, os.path.join(ROOT, "tests"), "/root/reference/src"):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import logging  # noqa: E402
+
+import mcframework as ref  # noqa: E402  (the reference itself)
+from refsuite import fakedev  # noqa: E402
+
+fakedev.install()
+import mcframework_b200 as new  # noqa: E402
+
+for name in ("mcframework.core", "mcframework_b200.core", "mcframework.stats_engine", "mcframework_b200.stats_engine"):
+    logging.getLogger(name).setLevel(logging.CRITICAL)
+
+RTOL = 1e-9  # host-side assembly; the stand-in sums in NumPy order, the reference in its own
+mismatches: list[str] = []
+n_cmp = 0
+
+
+def same(a, b, where: str, rtol: float = RTOL) -> None:
+    """Deep comparison: structure, keys, types of leaves (str/None/bool exactly, numbers within rtol, NaN == NaN)."""
+    global n_cmp
+    if isinstance(a, dict) or isinstance(b, dict):
+        if not (isinstance(a, dict) and isinstance(b, dict)) or set(a) != set(b):
+            mismatches.append(f"{where}: keys {sorted(map(str, a)) if isinstance(a, dict) else a!r} vs "
+                              f"{sorted(map(str, b)) if isinstance(b, dict) else b!r}")
+            return
+        for k in a:
+            same(a[k], b[k], f"{where}[{k!r}]", rtol)
+        return
+    if isinstance(a, (list, tuple)) or isinstance(b, (list, tuple)):
+        if not (isinstance(a, (list, tuple)) and isinstance(b, (list, tuple))) or len(a) != len(b):
+            mismatches.append(f"{where}: {a!r} vs {b!r}")
+            return
+        for i, (x, y) in enumerate(zip(a, b)):
+            same(x, y, f"{where}[{i}]", rtol)
+        return
+    if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+        a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+        n_cmp += 1
+        if a.shape != b.shape or not np.allclose(a, b, rtol=rtol, atol=1e-12, equal_nan=True):
+            mismatches.append(f"{where}: arrays differ (shapes {a.shape} {b.shape})")
+        return
+    n_cmp += 1
+    if a is None or b is None or isinstance(a, (str, bool)) or isinstance(b, (str, bool)):
+        if a != b:
+            mismatches.append(f"{where}: {a!r} vs {b!r}")
+        return
+    try:
+        fa, fb = float(a), float(b)
+    except (TypeError, ValueError):
+        if a != b:
+            mismatches.append(f"{where}: {a!r} vs {b!r}")
+        return
+    if math.isnan(fa) and math.isnan(fb):
+        return
+    if fa == fb or abs(fa - fb) <= rtol * max(abs(fa), abs(fb)) + 1e-12:
+        return
+    mismatches.append(f"{where}: {fa!r} vs {fb!r}")
+
+
+def outcome(fn):
+    """(kind, payload): the value, or the exception type name and message."""
+    try:
+        return "ok", fn()
+    except Exception as exc:  # noqa: BLE001
+        return "raise", (type(exc).__name__, str(exc))
+
+
+def both(where, f_ref, f_new, rtol: float = RTOL):
+    a, b = outcome(f_ref), outcome(f_new)
+    if a[0] != b[0]:
+        mismatches.append(f"{where}: reference {a!r} vs drop-in {b!r}")
+        return None, None
+    if a[0] == "raise":
+        # same exception family (MissingContextError subclasses ValueError in both) and same message
+        same(a[1][1], b[1][1], where + " (message)")
+        if a[1][0] != b[1][0]:
+            mismatches.append(f"{where}: exception {a[1][0]} vs {b[1][0]}")
+        return None, None
+    same(a[1], b[1], where, rtol)
+    return a[1], b[1]
+
+
+def result_fields(r, seeded_bootstrap: bool):
+    meta = {k: v for k, v in r.metadata.items() if k != "timestamp"}
+    stats = dict(r.stats)
+    if not seeded_bootstrap and isinstance(stats.get("ci_mean_bootstrap"), dict):  # fresh OS entropy on both sides
+        stats["ci_mean_bootstrap"] = {k: v for k, v in stats["ci_mean_bootstrap"].items() if k not in ("low", "high")}
+    return {"results": np.asarray(r.results), "n": r.n_simulations, "mean": r.mean, "std": r.std,
+            "percentiles": r.percentiles, "stats": stats, "metadata": meta}
+
+
+# ------------------------------------------------------------------------------------------------ scenarios
+def engine_cases(rng: np.random.Generator, n_cases: int):
+    for case in range(n_cases):
+        n = int(rng.choice([0, 1, 2, 3, 4, 7, 29, 30, 31, 200]))
+        x = rng.normal(3.0, 2.0, n) if rng.random() < 0.7 else np.round(rng.normal(0, 3, n))  # ties
+        taint = rng.random()
+        if n >= 3 and taint < 0.25:
+            x[rng.integers(0, n)] = np.nan
+        elif n >= 3 and taint < 0.35:
+            x[rng.integers(0, n)] = np.inf
+        kw = dict(n=n, confidence=float(rng.choice([0.5, 0.9, 0.95, 0.99])),
+                  ci_method=str(rng.choice(["auto", "z", "t", "bootstrap"])),
+                  nan_policy=str(rng.choice(["propagate", "omit"])),
+                  bootstrap=str(rng.choice(["percentile", "bca"])), n_bootstrap=int(rng.choice([100, 128])),
+                  percentiles=tuple(int(p) for p in rng.choice([1, 5, 25, 50, 75, 95, 99], size=int(rng.integers(0, 4)),
+                                                                replace=False)))
+        if rng.random() < 0.6:
+            kw["target"] = float(rng.normal(3.0, 1.0))
+        if rng.random() < 0.6:
+            kw["eps"] = float(rng.choice([0.01, 0.5]))
+        if rng.random() < 0.3:
+            kw["ess"] = int(rng.integers(1, max(2, n + 1)))
+        if rng.random() < 0.3:
+            kw["ddof"] = int(rng.choice([0, 1]))
+        seed = int(rng.integers(0, 2 ** 31))
+        where = f"engine[{case}] n={n} {kw}"
+
+        def run(mod, as_dict):
+            ctx_kw = dict(kw, rng=seed)
+            ctx = ctx_kw if as_dict else mod.StatsContext(**ctx_kw)
+            res = mod.stats_engine.build_default_engine().compute(x.copy(), ctx)
+            return {"metrics": res.metrics, "skipped": sorted(n_ for n_, _ in res.skipped),
+                    "errors": sorted(n_ for n_, _ in res.errors)}
+
+        as_dict = bool(rng.random() < 0.3)
+        both(where, lambda: run(ref, as_dict), lambda: run(new, as_dict))
+        sel = [str(s) for s in rng.choice(["mean", "std", "percentiles", "skew", "kurtosis", "ci_mean", "ci_mean_chebyshev",
+                                           "markov_error_prob", "bias_to_target", "mse_to_target", "chebyshev_required_n"],
+                                          size=3, replace=False)]
+
+        def run_sel(mod):
+            res = mod.stats_engine.build_default_engine().compute(x.copy(), mod.StatsContext(**dict(kw, rng=seed)), select=sel)
+            return res.metrics
+
+        both(where + f" select={sel}", lambda: run_sel(ref), lambda: run_sel(new))
+
+
+def run_cases(rng: np.random.Generator, n_cases: int):
+    def sims(mod):
+        return {"pi": mod.PiEstimationSimulation, "portfolio": mod.PortfolioSimulation, "bs": mod.BlackScholesSimulation,
+                "path": mod.BlackScholesPathSimulation}
+
+    for case in range(n_cases):
+        which = str(rng.choice(["pi", "portfolio", "bs", "path"]))
+        seed = int(rng.integers(0, 10_000))
+        parallel = bool(rng.random() < 0.3)
+        n = int(rng.choice([20_000, 20_011])) if parallel else int(rng.choice([1, 2, 17, 300]))
+        sim_kw = {"pi": dict(n_points=int(rng.choice([1, 2, 7, 50])), antithetic=bool(rng.random() < 0.5)),
+                  "portfolio": dict(years=float(rng.choice([0, 0.01, 0.1, 1])), use_gbm=bool(rng.random() < 0.5),
+                                    volatility=float(rng.choice([0.0, 0.2]))),
+                  "bs": dict(option_type=str(rng.choice(["call", "put"])), exercise_type=str(rng.choice(["european", "american"])),
+                             n_steps=int(rng.choice([1, 5, 16, 33])), K=float(rng.choice([90.0, 100.0, 130.0]))),
+                  "path": dict(n_steps=int(rng.choice([1, 12])), sigma=float(rng.choice([0.1, 0.4])))}[which]
+        if parallel and which == "pi":
+            sim_kw["n_points"] = min(sim_kw["n_points"], 7)
+        run_kw = dict(parallel=parallel, compute_stats=bool(rng.random() < 0.8), confidence=float(rng.choice([0.9, 0.95])),
+                      ci_method=str(rng.choice(["auto", "z", "t", "bootstrap"])))
+        if parallel:
+            run_kw["n_workers"] = int(rng.choice([2, 3, 8]))
+        if rng.random() < 0.6:
+            run_kw["percentiles"] = [int(p) for p in rng.choice([1, 5, 10, 50, 90, 99], size=int(rng.integers(0, 4)), replace=False)]
+            if run_kw["percentiles"] and rng.random() < 0.3:
+                run_kw["percentiles"] = run_kw["percentiles"] + run_kw["percentiles"][:1]  # a duplicate, unsorted
+        if rng.random() < 0.5:
+            run_kw["extra_context"] = dict(target=float(rng.normal(3, 1)), eps=0.05, n_bootstrap=100, rng=int(seed),
+                                           bootstrap=str(rng.choice(["percentile", "bca"])))
+        where = f"run[{case}] {which} seed={seed} n={n} {sim_kw} {run_kw}"
+
+        def go(mod):
+            sim = sims(mod)[which]()
+            sim.set_seed(seed)
+            fw = mod.MonteCarloFramework()
+            fw.register_simulation(sim)
+            ticks = []
+            first = fw.run_simulation(sim.name, n, progress_callback=lambda d, t: ticks.append((d, t)), **run_kw, **sim_kw)
+            second = sim.run(3, compute_stats=False, **sim_kw)  # un-reseeded continuation of the stream
+            cmp_ = {}
+            for metric in ("mean", "std", "var", "se", "p50", "p7"):
+                cmp_[metric] = outcome(lambda: fw.compare_results([sim.name], metric))
+            # the report prints floats at full precision: keep its structure, round the numbers to 9 significant digits
+            text = [re.sub(r"-?\d+\.\d+(?:e[-+]?\d+)?", lambda m_: f"{float(m_.group()):.9g}", ln)
+                    for ln in first.result_to_string().splitlines()
+                    if "Execution time" not in ln and "timestamp" not in ln and "ci_mean_bootstrap" not in ln]
+            return {"first": result_fields(first, "extra_context" in run_kw), "second": np.asarray(second.results),
+                    "compare": cmp_, "text": text, "spawned": sim.seed_seq.n_children_spawned,
+                    # thread completion order decides the intermediate counts of a parallel run (ragged last block)
+                    "ticks": ticks if not parallel else [len(ticks), max(ticks), sorted({t for _, t in ticks})]}
+
+        import contextlib
+        import io
+
+        def quiet(mod):
+            with contextlib.redirect_stdout(io.StringIO()):
+                return go(mod)
+
+        both(where, lambda: quiet(ref), lambda: quiet(new), rtol=1e-9)
+
+
+def hook_cases(rng: np.random.Generator):
+    """User plugin code (arbitrary Python hooks): looped on the host by both, on the same streams."""
+    def make(mod):
+        class Dice(mod.MonteCarloSimulation):
+            def single_simulation(self, _rng=None, n_dice=2, **kw):
+                g = self._rng(_rng, self.rng)
+                return float(g.integers(1, 7, size=n_dice).sum())
+
+        return Dice("Dice")
+
+    for n, par, workers, backend in ((50, False, None, "auto"), (20_000, True, 2, "thread"), (20_003, True, 3, "auto"),
+                                     (19_999, True, 4, "thread"), (20_000, True, 1, "thread")):
+        seed = int(rng.integers(0, 1000))
+
+        def go(mod):
+            sim = make(mod)
+            sim.parallel_backend = backend
+            sim.set_seed(seed)
+            kw = dict(parallel=par, percentiles=(10, 90), n_dice=3)
+            if workers:
+                kw["n_workers"] = workers
+            r = sim.run(n, **kw)
+            r2 = sim.run(7, compute_stats=False)
+            return {"a": result_fields(r, False), "b": np.asarray(r2.results)}
+
+        both(f"hook n={n} parallel={par} workers={workers} backend={backend}", lambda: go(ref), lambda: go(new))
+
+
+def misc_cases():
+    for conf, n, method in [(0.95, 10, "auto"), (0.95, 30, "auto"), (0.9, 5, "z"), (0.99, 100, "t"), (0.95, 10, "bootstrap"),
+                            (0.95, 10, "nope")]:
+        both(f"autocrit{(conf, n, method)}", lambda: ref.utils.autocrit(conf, n, method), lambda: new.utils.autocrit(conf, n, method))
+    both("z_crit", lambda: ref.utils.z_crit(0.9), lambda: new.utils.z_crit(0.9))
+    both("t_crit", lambda: ref.utils.t_crit(0.9, 7), lambda: new.utils.t_crit(0.9, 7))
+    for bad in (dict(n=5, confidence=1.5), dict(n=5, percentiles=(101,)), dict(n=5, n_bootstrap=0), dict(n=5, ddof=-1),
+                dict(n=5, eps=-1.0), dict(n=5, ess=0), dict(n=5, nan_policy="zap")):
+        both(f"StatsContext{bad}", lambda: vars(ref.StatsContext(**bad)) and None, lambda: vars(new.StatsContext(**bad)) and None)
+    for call in (dict(n_simulations=0), dict(n_simulations=5, n_workers=0), dict(n_simulations=5, confidence=1.0),
+                 dict(n_simulations=5, ci_method="x")):
+        both(f"run{call}", lambda: ref.PiEstimationSimulation().run(**call) and None,
+             lambda: new.PiEstimationSimulation().run(**call) and None)
+    greeks_kw = dict(n_simulations=200, n_steps=8, option_type="put")
+    for par in (False,):
+        def g(mod):
+            s = mod.BlackScholesSimulation()
+            s.set_seed(5)
+            before = s.rng.bit_generator.state["state"]["state"]
+            out = s.calculate_greeks(parallel=par, **greeks_kw)
+            return {"greeks": out, "rng_restored": s.rng.bit_generator.state["state"]["state"] == before}
+        both(f"greeks parallel={par}", lambda: g(ref), lambda: g(new), rtol=1e-7)
+
+    def paths(mod):
+        s = mod.BlackScholesPathSimulation()
+        s.set_seed(9)
+        p = s.simulate_paths(40, n_steps=20)
+        from importlib import import_module
+        bsm = import_module(mod.__name__ + ".sims.black_scholes")
+        return {"paths": p, "put": bsm._american_exercise_lsm(p, 100.0, 0.05, 1.0 / 20, "put"),
+                "call": bsm._american_exercise_lsm(p, 100.0, 0.05, 1.0 / 20, "call"),
+                "one": bsm._simulate_gbm_path(100.0, 0.05, 0.2, 1.0, 6, np.random.default_rng(4))}
+    both("paths+lsm", lambda: paths(ref), lambda: paths(new), rtol=1e-9)
+
+
+def main():
+    n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 20240601)
+    misc_cases()
+    hook_cases(rng)
+    engine_cases(rng, n_cases)
+    run_cases(rng, max(8, n_cases // 3))
+    for m in mismatches[:40]:
+        print("MISMATCH", m)
+    print(f"differential: {n_cmp} comparisons, {len(mismatches)} mismatches")
+    return 1 if mismatches else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

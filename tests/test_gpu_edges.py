@@ -59,6 +59,14 @@ def test_single_replication_and_direct_hook_calls(m):
     rng = np.random.default_rng(np.random.SeedSequence(3))
     np.testing.assert_allclose(pf.single_simulation(years=0.5), np_port.portfolio_once(rng, years=0.5), rtol=RTOL)
     np.testing.assert_allclose(pf.single_simulation(years=1, use_gbm=False), np_port.portfolio_once(rng, years=1, use_gbm=False), rtol=RTOL)
+    # zero-step horizon (reference tests/test_errors_and_edge_cases.py::test_zero_year_portfolio): the initial value, no draw
+    before = pf.rng.bit_generator.state
+    assert pf.single_simulation(initial_value=10_000, annual_return=0.07, volatility=0.2, years=0) == 10_000.0
+    r0 = pf.run(50, years=0, initial_value=123.5, percentiles=(50,))
+    assert np.array_equal(r0.results, np.full(50, 123.5)) and r0.mean == 123.5 and r0.percentiles[50] == 123.5
+    rp = pf.run(20_000, years=0, parallel=True, n_workers=2, compute_stats=False)
+    assert np.array_equal(rp.results, np.full(20_000, 10_000.0))
+    assert pf.rng.bit_generator.state == before
     # a Philox generator handed in through _rng (what a reference worker thread does)
     g1, g2 = (np.random.Generator(np.random.Philox(5)) for _ in range(2))
     pi = m.PiEstimationSimulation()
@@ -87,6 +95,9 @@ def test_stats_engine_edge_inputs(m):
     x[[1, 50]] = [np.nan, np.inf]
     prop = eng.compute(x, m.StatsContext(n=x.size, rng=1, n_bootstrap=100)).metrics
     assert math.isnan(prop["mean"]) and math.isnan(prop["std"]) and all(math.isnan(v) for v in prop["percentiles"].values())
+    # ... and with BCa the reference's np.percentile rejects the NaN-adjusted percentiles: the engine re-raises ValueError
+    with pytest.raises(ValueError, match=r"Percentiles must be in the range \[0, 100\]"):
+        eng.compute(x, m.StatsContext(n=x.size, rng=1, n_bootstrap=100, bootstrap="bca"))
     omit = eng.compute(x, m.StatsContext(n=x.size, rng=1, n_bootstrap=100, nan_policy="omit")).metrics
     f = x[np.isfinite(x)]
     assert omit["mean"] == pytest.approx(f.mean(), rel=1e-13) and omit["percentiles"][50] == np.percentile(f, 50)

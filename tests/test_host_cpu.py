@@ -150,6 +150,13 @@ def test_builtin_hooks_map_to_programs():
 
     p = m.PortfolioSimulation()._program_for(dict(years=5, use_gbm=False))
     assert p.kind == "normals" and p.n_steps == int(5 / (1.0 / 252.0)) and p.specs[0][0] == N.PORTFOLIO_LOG1P
+    # a horizon below one trading day has no steps: `rng.normal(size=0)` in the reference, a constant program here
+    # (reference tests/test_errors_and_edge_cases.py::test_zero_year_portfolio)
+    z = m.PortfolioSimulation()._program_for(dict(years=0, initial_value=10_000))
+    assert z.kind == "constant" and z.value == 10_000.0
+    assert m.PortfolioSimulation()._program_for(dict(years=0.003, use_gbm=False)).kind == "constant"
+    with pytest.raises(ValueError):  # NumPy: "negative dimensions are not allowed"
+        m.PortfolioSimulation()._program_for(dict(years=-1))
     b = m.BlackScholesSimulation()._program_for(dict(option_type="put", exercise_type="american", n_steps=10))
     assert b.specs[0][0] == N.BS_AMER_PUT and b.n_steps == 10
     with pytest.raises(ValueError, match="option_type must be 'call' or 'put'"):
