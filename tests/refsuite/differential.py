@@ -247,6 +247,72 @@ def hook_cases(rng: np.random.Generator):
         both(f"hook n={n} parallel={par} workers={workers} backend={backend}", lambda: go(ref), lambda: go(new))
 
 
+def api_surface():
+    """Every public name of the reference (module ``__all__`` lists) exists in the drop-in with the same call signature:
+    functions, class constructors and public methods (parameter names, kinds and defaults; extra keyword-only
+    parameters with defaults are allowed on the drop-in side, they cannot break a caller of the reference)."""
+    import dataclasses
+    import inspect
+    from importlib import import_module
+
+    def params(fn):
+        try:
+            sig = inspect.signature(fn)
+        except (TypeError, ValueError):
+            return None
+        return [(p.name, str(p.kind), None if p.default is inspect._empty else repr(p.default)) for p in sig.parameters.values()]
+
+    def compatible(where, pr, pn):
+        global n_cmp
+        n_cmp += 1
+        if pr is None or pn is None:
+            return
+        extra = [q for q in pn[len(pr):]] if pn[:len(pr)] == pr else None
+        if pn == pr:
+            return
+        names_r = [q[0] for q in pr]
+        rest = [q for q in pn if q[0] not in names_r]
+        kept = [q for q in pn if q[0] in names_r]
+        ok = kept == pr and all(q[1] in ("KEYWORD_ONLY", "VAR_KEYWORD") or q[2] is not None for q in rest) and \
+            all(q[1] == "KEYWORD_ONLY" or q[1] == "VAR_KEYWORD" for q in rest)
+        if not ok:
+            mismatches.append(f"{where}: signature {pr} vs {pn}")
+
+    for modname in ("", ".core", ".stats_engine", ".utils", ".sims", ".sims.pi", ".sims.portfolio", ".sims.black_scholes"):
+        mr, mn = import_module("mcframework" + modname), import_module("mcframework_b200" + modname)
+        names = list(getattr(mr, "__all__", []))
+        same(sorted(n_ for n_ in names if not hasattr(mn, n_)), [], f"api{modname}: names missing in the drop-in")
+        for name in names:
+            a, b = getattr(mr, name), getattr(mn, name, None)
+            if b is None:
+                continue
+            if inspect.isclass(a):
+                if dataclasses.is_dataclass(a):
+                    same([(f.name, repr(f.default) if f.default is not dataclasses.MISSING else None) for f in dataclasses.fields(a)],
+                         [(f.name, repr(f.default) if f.default is not dataclasses.MISSING else None) for f in dataclasses.fields(b)],
+                         f"api{modname}.{name} fields")
+                elif issubclass(a, BaseException) or hasattr(a, "__members__"):
+                    same([c.__name__ for c in a.__mro__[1:3]], [c.__name__ for c in b.__mro__[1:3]], f"api{modname}.{name} bases")
+                    if hasattr(a, "__members__"):
+                        same({k: v.value for k, v in a.__members__.items()}, {k: v.value for k, v in b.__members__.items()},
+                             f"api{modname}.{name} members")
+                else:
+                    compatible(f"api{modname}.{name}.__init__", params(a.__init__), params(b.__init__))
+                for meth, fn in inspect.getmembers(a, predicate=inspect.isfunction):
+                    if meth.startswith("_") and meth not in ("__call__",):
+                        continue
+                    other = getattr(b, meth, None)
+                    if other is None:
+                        mismatches.append(f"api{modname}.{name}.{meth}: missing in the drop-in")
+                        continue
+                    compatible(f"api{modname}.{name}.{meth}", params(fn), params(other))
+                for attr in ("_PCTS", "_PARALLEL_THRESHOLD", "_CHUNKS_PER_WORKER"):
+                    if hasattr(a, attr):
+                        same(getattr(a, attr), getattr(b, attr, None), f"api{modname}.{name}.{attr}")
+            elif callable(a):
+                compatible(f"api{modname}.{name}", params(a), params(b))
+
+
 def misc_cases():
     for conf, n, method in [(0.95, 10, "auto"), (0.95, 30, "auto"), (0.9, 5, "z"), (0.99, 100, "t"), (0.95, 10, "bootstrap"),
                             (0.95, 10, "nope")]:
@@ -285,6 +351,7 @@ def misc_cases():
 def main():
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 20240601)
+    api_surface()
     misc_cases()
     hook_cases(rng)
     engine_cases(rng, n_cases)
