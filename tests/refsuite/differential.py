@@ -336,6 +336,24 @@ def misc_cases():
             return {"greeks": out, "rng_restored": s.rng.bit_generator.state["state"]["state"] == before}
         both(f"greeks parallel={par}", lambda: g(ref), lambda: g(new), rtol=1e-7)
 
+    def pickled(mod):
+        import pickle
+
+        sim = mod.PiEstimationSimulation()
+        sim.set_seed(77)
+        sim.run(5, n_points=10, compute_stats=False)  # moves self.rng; the copy restarts from seed_seq (:318-330)
+        copy = pickle.loads(pickle.dumps(sim))
+        return {"copy": np.asarray(copy.run(4, n_points=10, compute_stats=False).results),
+                "orig": np.asarray(sim.run(4, n_points=10, compute_stats=False).results), "name": copy.name,
+                "entropy": copy.seed_seq.entropy}
+    both("pickle round trip", lambda: pickled(ref), lambda: pickled(new))
+
+    def unseeded(mod):
+        sim = mod.PiEstimationSimulation()
+        r = sim.run(3, n_points=5, compute_stats=False)
+        return {"seed_entropy": r.metadata.get("seed_entropy"), "seq": sim.seed_seq is None, "n": len(r.results)}
+    both("unseeded run", lambda: unseeded(ref), lambda: unseeded(new))
+
     def paths(mod):
         s = mod.BlackScholesPathSimulation()
         s.set_seed(9)
