@@ -458,9 +458,22 @@ struct ZigTables {
     const ZigKW *kws;
 };
 #define MCF_U52_BIAS 0x4330000000000000ULL
+// Candidate for the next round (off by default, not measured yet): MCF_SCAN_DENORM reads the 52 bits of `rabs` as the bit
+// pattern of a SUBNORMAL double (value rabs * 2^-1074, exact) instead of OR-ing the 2^52 exponent in: the compare against
+// ki works on the subnormals as they are, and rabs * wi becomes (d * 2^1000) * (wi * 2^74) -- two exact power-of-two
+// scalings, so the one rounding is NumPy's rounding of rabs * wi.  Saves one logic operation per draw of the scan.
+#ifdef MCF_SCAN_DENORM
+#define MCF_SCAN_BIAS 0ULL
+#define MCF_SCAN_WI_SCALE 0x1p74
+#define MCF_SCAN_VALUE(d, wi) xmul(xmul((d), 0x1p1000), (wi))
+#else
+#define MCF_SCAN_BIAS MCF_U52_BIAS
+#define MCF_SCAN_WI_SCALE 1.0
+#define MCF_SCAN_VALUE(d, wi) xmul(xadd((d), -4503599627370496.0), (wi))
+#endif
 MCF_HD void zig_fill_kws(ZigKW *kws, unsigned e, uint64_t ki, double wi) {
-    kws[e].ki = ki | MCF_U52_BIAS;
-    kws[e].wi = (e & 0x100u) ? -wi : wi;
+    kws[e].ki = ki | MCF_SCAN_BIAS;
+    kws[e].wi = ((e & 0x100u) ? -wi : wi) * MCF_SCAN_WI_SCALE;
 }
 #define MCF_ZIG_R 3.6541528853610088
 #define MCF_ZIG_INV_R 0.27366123732975828
@@ -736,11 +749,79 @@ MCF_HD ChunkInfo scan_chunk(Cur &cur, uint64_t chunk_base, uint32_t entry, const
 struct ParkSlots {  // slot k of this thread: a[k * stride], b[k * stride], c[k * stride]
     uint64_t *a, *b, *c;
     unsigned stride;
+#ifdef MCF_P2_COOP
+    uint8_t *f;  // flags of the evaluated slot (MCF_P2_COOP), same indexing
+#endif
 };
+#ifdef MCF_P2_COOP
+#define MCF_PARK_HAS_FLAGS 1
+#endif
 MCF_HD double zig_fast_value(uint64_t w, const ZigTables &t) {  // signed value of a fast-looking draw
-    const uint64_t dbits = ((w >> 9) & 0x000fffffffffffffULL) | MCF_U52_BIAS;
-    return xmul(xadd(bits_to_double(dbits), -4503599627370496.0), t.kws[(unsigned)w & 0x1ffu].wi);
+    const uint64_t dbits = ((w >> 9) & 0x000fffffffffffffULL) | MCF_SCAN_BIAS;
+    return MCF_SCAN_VALUE(bits_to_double(dbits), t.kws[(unsigned)w & 0x1ffu].wi);
 }
+
+#ifdef MCF_P2_COOP
+// Candidate for the next round (off by default; host logic checked by the emulation tests, the warp-cooperative
+// distribution in mcf_kernels.cu NOT yet run on hardware).  Phase 2 costs ~14 % of the scan's instructions because every
+// warp repeats the wedge arithmetic for its unluckiest lane (3.3-3.7 rounds of ~140 instructions, a third of the lanes
+// busy).  What a parked draw yields -- accepted or not, its normal, how many draws it consumes, the fast values of the two
+// draws behind it -- does not depend on the chain, so it can be evaluated EAGERLY for every parked draw, by any lane
+// (`eval_parked`: on the device the warp's parked draws are compacted and spread over the lanes, ~1.5 dense rounds), and
+// the chain walk that is left only reads results and updates masks (~45 instructions per round).
+#define MCF_PE_ACC 1u   // the attempt emits a normal
+#define MCF_PE_LEN2 2u  // tail attempt: consumes the next two draws (else wedge: the next one)
+#define MCF_PE_BAD 4u   // tail whose first pair is rejected: the chunk goes to the general walk
+struct ParkEval {
+    double x, fv1, fv2;
+    unsigned flags;
+};
+MCF_HD ParkEval park_eval(uint64_t a, uint64_t u, uint64_t u2, const ZigTables &t) {
+    ParkEval r;
+    r.x = 0.0;
+    r.flags = 0;
+    if ((a & 0xffULL) != 0) {  // wedge: same arithmetic and decision as zig_feed, state 1
+        ZigFsm f;
+        zig_reset(f);
+        double x = 0.0;
+        zig_feed(f, a, t, x);
+        if (zig_feed(f, u, t, x)) {
+            r.flags = MCF_PE_ACC;
+            r.x = x;
+        }
+    } else {  // tail, first pair
+        const uint64_t rabs = (a >> 9) & 0x000fffffffffffffULL;
+        const double xx = xmul(-MCF_ZIG_INV_R, log1p(-u64_to_unit_double(u)));
+        const double yy = -log1p(-u64_to_unit_double(u2));
+        const double m = xadd(MCF_ZIG_R, xx);
+        r.x = ((rabs >> 8) & 1ULL) ? -m : m;
+        r.flags = MCF_PE_LEN2 | ((xadd(yy, yy) > xmul(xx, xx)) ? MCF_PE_ACC : MCF_PE_BAD);
+    }
+    r.fv1 = zig_fast_value(u, t);
+    r.fv2 = zig_fast_value(u2, t);
+    return r;
+}
+MCF_HD void park_eval_store(const ParkSlots &park, unsigned slot, const ParkEval &r) {
+    union {
+        double d;
+        uint64_t u;
+    } cv;
+    cv.d = r.x;
+    park.a[slot] = cv.u;
+    cv.d = r.fv1;
+    park.b[slot] = cv.u;
+    cv.d = r.fv2;
+    park.c[slot] = cv.u;
+    park.f[slot] = (uint8_t)r.flags;
+}
+// every thread evaluates its own parked draws (host emulation, kernels whose warps may be partial)
+MCF_HD void eval_parked_local(const ParkSlots &park, unsigned n_parked, const ZigTables &t) {
+    for (unsigned k = 0; k < n_parked; k++) {
+        const unsigned slot = k * park.stride;
+        park_eval_store(park, slot, park_eval(park.a[slot], park.b[slot], park.c[slot], t));
+    }
+}
+#endif
 
 //
 // Entry patch.  `entry_of(exit)` is called once, with the chunk's speculative exit, and returns the exit of the
@@ -754,10 +835,18 @@ MCF_HD double zig_fast_value(uint64_t w, const ZigTables &t) {  // signed value 
 // `share_first(w0, w1)` is called once with the chunk's own first two draws and `lookahead(a, b)` must later return
 // the next chunk's: on the device the neighbouring thread's (through shared memory), so the 17th Philox block per
 // chunk is generated by one thread per CTA only; the host build simply generates it.
+#ifdef MCF_P2_COOP
+// `eval_parked(n)`: afterwards slot k < n of this thread holds {x, fv1, fv2} (bit patterns in a/b/c) and its flags
+template <class Load, class EntryOf, class ShareFirst, class LookAhead, class EvalParked>
+MCF_HD ChunkInfo scan_chunk_fast2(Load load, uint64_t blk0, const ZigTables &t, const ParkSlots &park, double *zsub_out,
+                                  bool *valid, EntryOf entry_of, ShareFirst share_first, LookAhead lookahead,
+                                  EvalParked eval_parked, const uint64_t bias = MCF_SCAN_BIAS) {
+#else
 template <class Load, class EntryOf, class ShareFirst, class LookAhead>
 MCF_HD ChunkInfo scan_chunk_fast2(Load load, uint64_t blk0, const ZigTables &t, const ParkSlots &park, double *zsub_out,
                                   bool *valid, EntryOf entry_of, ShareFirst share_first, LookAhead lookahead,
-                                  const uint64_t bias = MCF_U52_BIAS) {
+                                  const uint64_t bias = MCF_SCAN_BIAS) {
+#endif
     uint64_t F = 0;   // fast-looking draws
     unsigned np = 0;  // parked draws
     double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
@@ -769,7 +858,7 @@ MCF_HD ChunkInfo scan_chunk_fast2(Load load, uint64_t blk0, const ZigTables &t, 
     {                                                                                             \
         const uint64_t dbits = (((WA) >> 9) & 0x000fffffffffffffULL) | bias;                      \
         const ZigKW kw = t.kws[(unsigned)(WA)&0x1ffu];                                            \
-        const double v = xmul(xadd(bits_to_double(dbits), -4503599627370496.0), kw.wi);           \
+        const double v = MCF_SCAN_VALUE(bits_to_double(dbits), kw.wi);                            \
         if ((J) == 0 && sub == 0) vk0 = v;                                                        \
         if ((J) == 1 && sub == 0) vk1 = v;                                                        \
         if (bits_to_double(dbits) < bits_to_double(kw.ki)) {                                      \
@@ -830,6 +919,32 @@ MCF_UNROLL(MCF_SCAN_UNROLL)
         z2 = sub == 2 ? xadd(z2, x) : z2;
         z3 = sub == 3 ? xadd(z3, x) : z3;
     };
+#ifdef MCF_P2_COOP
+    eval_parked(np < MCF_PARK_CAP ? np : (unsigned)MCF_PARK_CAP);
+    while (N != 0 && k < MCF_PARK_CAP) {
+        const unsigned j = (unsigned)ctz64(N);
+        N &= N - 1;
+        const unsigned slot = k * park.stride;
+        k++;
+        if (!((S >> j) & 1ULL)) continue;  // consumed by an earlier attempt
+        const unsigned fl = park.f[slot];
+        const unsigned len = (fl & MCF_PE_LEN2) ? 2u : 1u;
+        if (fl & MCF_PE_BAD) ok = false;  // longer tail: general re-walk
+        if (fl & MCF_PE_ACC) {
+            A |= 1ULL << j;
+            add_to_sub(j >> MCF_SUB_SHIFT, bits_to_double(park.a[slot]));
+        }
+        for (unsigned q = 1; q <= len; q++) {
+            const unsigned f = j + q;
+            if (f >= MCF_CHUNK) {
+                exitv++;
+                continue;
+            }
+            S &= ~(1ULL << f);
+            if ((F >> f) & 1ULL) add_to_sub(f >> MCF_SUB_SHIFT, -bits_to_double(q == 1 ? park.b[slot] : park.c[slot]));
+        }
+    }
+#else
     while (N != 0 && k < MCF_PARK_CAP) {
         const unsigned j = (unsigned)ctz64(N);
         N &= N - 1;
@@ -869,6 +984,7 @@ MCF_UNROLL(MCF_SCAN_UNROLL)
             if ((F >> f) & 1ULL) add_to_sub(f >> MCF_SUB_SHIFT, -zig_fast_value(q == 1 ? u : u2, t));
         }
     }
+#endif
     const unsigned e = entry_of(exitv);
     unsigned gen_entry = 0;
     if (e != 0) {

@@ -33,6 +33,10 @@ struct ScanShared {
     ZigKW kws[512];
     uint64_t park[3 * MCF_PARK_CAP * 256];
     uint64_t first[2 * 256];  // every thread's first two draws: the previous thread's look-ahead
+#ifdef MCF_P2_COOP
+    uint8_t park_flags[MCF_PARK_CAP * 256];  // flags of the evaluated parked draws
+    uint8_t items[MCF_PARK_CAP * 256];       // per warp: (lane << 2 | slot) of its parked draws, compacted
+#endif
 };
 
 __device__ __forceinline__ ZigTables load_zig_tables(ZigShared &sh) {
@@ -59,6 +63,9 @@ __device__ __forceinline__ ZigTables load_scan_tables(ScanShared &sh, ParkSlots 
     park.b = park.a + MCF_PARK_CAP * 256;
     park.c = park.b + MCF_PARK_CAP * 256;
     park.stride = 256;
+#ifdef MCF_P2_COOP
+    park.f = sh.park_flags + threadIdx.x;
+#endif
     return t;
 }
 
@@ -205,7 +212,11 @@ __global__ void __launch_bounds__(256, 3) plan_scan_kernel(const mcf_stream *__r
                 pc.load_block(blk0 + 16);
                 a = pc.v0;
                 b = pc.v1;
-            });
+            }
+#ifdef MCF_P2_COOP
+            , [&](unsigned n_parked) { eval_parked_local(park, n_parked, t); }  // warps may be partial here
+#endif
+            );
         startmask[id] = ci.startmask;
         emitmask[id] = ci.emitmask;
         exit_[id] = (uint8_t)ci.exit;
@@ -263,10 +274,34 @@ __global__ void __launch_bounds__(256, MCF_SCAN_CTAS) plan_scan_philox_stream_ke
                 b = sh.first[256 + threadIdx.x + 1];
             }
         }
-#ifdef MCF_SCAN_OPAQUE_BIAS
-        // the 2^52 exponent bias as a launch-time value (fold_ok is 0 or 1): ptxas keeps it in a uniform register and
-        // merges mask and bias of the high word into one logic operation instead of re-materialising two immediates
-        , MCF_U52_BIAS | ((uint64_t)(K.fold_ok >> 1) << 32)
+#ifdef MCF_P2_COOP
+        // Warp-cooperative evaluation of the parked draws (whole warps are live here): an exclusive prefix of the lanes'
+        // counts compacts (lane, slot) pairs into the warp's item list; item i is evaluated by lane i mod 32 from the
+        // owner's shared-memory slot and written back in place.
+        , [&](unsigned n_parked) {
+            const unsigned lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u;
+            unsigned incl = n_parked;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (unsigned)d) incl += v;
+            }
+            const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+            uint8_t *items = sh.items + wbase * MCF_PARK_CAP;
+            for (unsigned k = 0; k < n_parked; k++) items[incl - n_parked + k] = (uint8_t)((lane << 2) | k);
+            __syncwarp();
+            ParkSlots all;  // slot index = k * 256 + thread
+            all.a = sh.park;
+            all.b = all.a + MCF_PARK_CAP * 256;
+            all.c = all.b + MCF_PARK_CAP * 256;
+            all.f = sh.park_flags;
+            all.stride = 256;
+            for (unsigned i = lane; i < total; i += 32) {
+                const unsigned it = items[i], slot = (it & 3u) * 256u + wbase + (it >> 2);
+                park_eval_store(all, slot, park_eval(all.a[slot], all.b[slot], all.c[slot], t));
+            }
+            __syncwarp();
+        }
 #endif
         );
     startmask[id] = ci.startmask;

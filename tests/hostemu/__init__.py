@@ -8,7 +8,10 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "_build", "libhostemu.so")
+#: extra compiler flags (e.g. "-DMCF_SCAN_DENORM") select a code-generation variant of the device headers; each set of
+#: flags gets its own library
+_FLAGS = os.environ.get("MCF_HOSTEMU_FLAGS", "").split()
+_SO = os.path.join(_HERE, "_build", "libhostemu%s.so" % ("_" + "".join(c for c in "".join(_FLAGS) if c.isalnum()) if _FLAGS else ""))
 _SRC = [os.path.join(_HERE, "hostemu.cpp")] + [
     os.path.join(_HERE, "..", "..", "mcframework_b200", "csrc", f) for f in ("mcf_device.cuh", "mcf_host.h", "zig_tables.h")
 ]
@@ -17,8 +20,8 @@ _SRC = [os.path.join(_HERE, "hostemu.cpp")] + [
 def build():
     os.makedirs(os.path.dirname(_SO), exist_ok=True)
     if not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in _SRC):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
-                               "-x", "c++", _SRC[0], "-o", _SO, "-lm"])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math"] + _FLAGS +
+                              ["-x", "c++", _SRC[0], "-o", _SO, "-lm"])
     return _SO
 
 

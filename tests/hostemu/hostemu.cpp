@@ -127,6 +127,10 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
             park.b = slots + MCF_PARK_CAP;
             park.c = slots + 2 * MCF_PARK_CAP;
             park.stride = 1;
+#ifdef MCF_P2_COOP
+            uint8_t slot_flags[MCF_PARK_CAP];
+            park.f = slot_flags;
+#endif
             ChunkInfo ci = scan_chunk_fast2(
                 [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &cc, uint64_t &d) {
                     if (K.fold_ok)
@@ -147,7 +151,11 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
                         philox_block_folded(K, blk0 + 16, a, b, c2, d2);
                     else
                         philox_block_keys(K, blk0 + 16, a, b, c2, d2);
-                });
+                }
+#ifdef MCF_P2_COOP
+                , [&](unsigned n_parked) { eval_parked_local(park, n_parked, t); }
+#endif
+                );
             if (valid) {  // the speculative walk must agree with the general one from the same entry
                 double zref[MCF_SUBS];
                 Cursor<KIND> c2;
