@@ -352,7 +352,7 @@ def test_hostemu_folded_philox_blocks_equal_numpy_raw_draws(emu):
         assert rc == 0 and np.array_equal(got, bg.random_raw(32))
 
 
-@pytest.mark.parametrize("flags", ["-DMCF_P2_COOP", "-DMCF_SCAN_DENORM", "-DMCF_P2_COOP -DMCF_SCAN_DENORM"])
+@pytest.mark.parametrize("flags", ["-DMCF_P2_COOP", "-DMCF_SCAN_DENORM", "-DMCF_P2_COOP -DMCF_SCAN_DENORM -DMCF_SCAN_NMASK"])
 def test_scan_candidates_stay_bit_exact_on_the_host(flags):
     """The not-yet-measured code-generation candidates of the planning scan must keep passing the
     host-emulation checks (positions, decisions and sums against the oracle; fast walk == general walk)."""
