@@ -817,10 +817,36 @@ static int normal_plan_impl(const mcf_stream *d_streams, const mcf_stream *h_str
     for (int64_t si = 0; per_stream && si < n_streams; si++)
         per_stream = (h_streams[si].buf_pos & 3u) == 0 && h_streams[si].s[2] < (1ULL << 62);  // aligned, foldable counter
     if (per_stream) {
+#ifdef MCF_SCAN_TWO_STREAMS
+        // Candidate for the next round (off by default, not measured): odd streams are scanned on a side stream, so the
+        // tail of one launch (the last partial wave of its 41.8) overlaps the head of the next one.
+        cudaStream_t side = nullptr;
+        cudaEvent_t fork = nullptr, join = nullptr;
+        const bool two = n_streams > 1 && cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) == cudaSuccess &&
+                         cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
+                         cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess;
+        if (two) {
+            cudaEventRecord(fork, cs);  // plan_init_kernel precedes every scan
+            cudaStreamWaitEvent(side, fork, 0);
+        }
+        for (int64_t si = 0; si < n_streams; si++) {
+            const PhiloxKeys K = philox_keys_of(h_streams[si]);
+            plan_scan_philox_stream_kernel<<<grid_for(g.cps, 256), 256, 0, (two && (si & 1)) ? side : cs>>>(
+                K, si * g.cps, g.cps, sm, em, ex, gen, zs);
+        }
+        if (two) {
+            cudaEventRecord(join, side);
+            cudaStreamWaitEvent(cs, join, 0);
+        }
+        if (fork) cudaEventDestroy(fork);
+        if (join) cudaEventDestroy(join);
+        if (side) cudaStreamDestroy(side);  // deferred by the runtime until its work has drained
+#else
         for (int64_t si = 0; si < n_streams; si++) {
             const PhiloxKeys K = philox_keys_of(h_streams[si]);
             plan_scan_philox_stream_kernel<<<grid_for(g.cps, 256), 256, 0, cs>>>(K, si * g.cps, g.cps, sm, em, ex, gen, zs);
         }
+#endif
     } else {
         plan_scan_kernel<KIND, RUN><<<grid_for(n_runs, 256), 256, 0, cs>>>(d_streams, g.cps, n_runs, sm, em, ex, gen, zs,
                                                                           hdr);
