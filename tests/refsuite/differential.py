@@ -313,6 +313,52 @@ def api_surface():
                 compatible(f"api{modname}.{name}", params(a), params(b))
 
 
+def declared_cases(rng: np.random.Generator):
+    """Declared draw programs (a drop-in extra): the reference runs the Python hook, the drop-in the declaration of the
+    same hook through the device entry points -- results, statistics and the state the generator is left in must agree."""
+    from mcframework_b200 import programs
+
+    hooks = {
+        "dice": (lambda self, g, kw: float(g.integers(1, 7, size=kw.get("n_dice", 2)).sum()),
+                 lambda kw: programs.integers_sum(1, 7, size=kw.get("n_dice", 2))),
+        "streak": (lambda self, g, kw: float(max((len(r) for r in "".join(map(str, g.integers(0, 2, size=31))).split("0")), default=0)),
+                   lambda kw: programs.integers_longest_run(0, 2, size=31, value=1)),
+        "normal": (lambda self, g, kw: float(g.normal(kw.get("loc", 1.5), 2.0)),
+                   lambda kw: programs.normal(kw.get("loc", 1.5), 2.0)),
+        "wide": (lambda self, g, kw: float(g.integers(0, 3_000_000_000, size=3).sum()),  # rejections: host loop on both sides
+                 lambda kw: programs.integers_sum(0, 3_000_000_000, size=3)),
+    }
+
+    def make(mod, which, declare):
+        hook, decl = hooks[which]
+
+        class Sim(mod.MonteCarloSimulation):
+            def single_simulation(self, _rng=None, **kw):
+                return hook(self, self._rng(_rng, self.rng), kw)
+
+        if declare:
+            Sim.draw_program = lambda self, **kw: decl(kw)
+        return Sim(which)
+
+    for which in hooks:
+        for n, par, workers in ((1, False, None), (37, False, None), (20_000, True, 2), (20_005, True, 5)):
+            seed = int(rng.integers(0, 1000))
+            kw = {"dice": dict(n_dice=3), "normal": dict(loc=-0.5)}.get(which, {})
+
+            def go(mod, declare):
+                sim = make(mod, which, declare)
+                sim.set_seed(seed)
+                run_kw = dict(parallel=par, percentiles=(25,), **kw)
+                if workers:
+                    run_kw["n_workers"] = workers
+                first = sim.run(n, **run_kw)
+                second = sim.run(5, compute_stats=False, **kw)  # continues the stream (odd slot counts included)
+                return {"first": result_fields(first, False), "second": np.asarray(second.results),
+                        "next_raw": int(sim.rng.bit_generator.random_raw())}
+
+            both(f"declared {which} n={n} parallel={par} workers={workers}", lambda: go(ref, False), lambda: go(new, True))
+
+
 def misc_cases():
     for conf, n, method in [(0.95, 10, "auto"), (0.95, 30, "auto"), (0.9, 5, "z"), (0.99, 100, "t"), (0.95, 10, "bootstrap"),
                             (0.95, 10, "nope")]:
@@ -372,6 +418,7 @@ def main():
     api_surface()
     misc_cases()
     hook_cases(rng)
+    declared_cases(rng)
     engine_cases(rng, n_cases)
     run_cases(rng, max(8, n_cases // 3))
     for m in mismatches[:40]:

@@ -97,8 +97,10 @@ def draw_integers(dl, low, high, size, op, match=0):
         n = int(rec["n_sims"])
         g = _gen_of(rec)
         vals = g.integers(int(low), int(high), n * int(size)).reshape(n, int(size))
-        fresh = n * int(size) - int(rec["has_uint32"])  # 32-bit slots taken from new 64-bit draws when nothing is rejected
-        if int(rec["kind"]) == S.GEN_PCG64 and g.consumed != (fresh + 1) // 2:
+        # the kernel's flag: does any of the first n*size 32-bit slots fail NumPy's Lemire test?
+        span = int(high) - int(low)
+        slots = _gen_of(rec).raw32(n * int(size)).astype(np.uint64)
+        if np.any(((slots * np.uint64(span)) & np.uint64(0xFFFFFFFF)) < np.uint64(((1 << 32) - span) % span)):
             rejected = 1
         if int(op) == 0:
             outs.append(vals.sum(axis=1).astype(np.float64))
