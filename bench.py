@@ -209,7 +209,9 @@ def b200_arm(args):
     fw = mcf.MonteCarloFramework()
     fw.register_simulation(sim)
     if world > 1:
-        sim.gather_mode = "root"
+        # "root": rank 0 receives every shard through NCCL and copies the whole vector out; "shm" (opt-in, A/B): every
+        # rank copies its own shard into one shared-memory buffer (mcframework_b200/_multi.py)
+        sim.gather_mode = os.environ.get("MCF_BENCH_GATHER", "root")
 
     def e2e_step():
         sim.set_seed(42)

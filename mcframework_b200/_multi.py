@@ -43,3 +43,157 @@ def gather_results_to_root(local, group):
     if rank != 0:
         return None
     return torch.cat([p[:k] for p, k in zip(parts, sizes)])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Shared-memory gather (opt-in: ``sim.gather_mode = "shm"``; host logic covered by the gloo tests, the pinned copies not
+# yet timed on hardware).  ``gather_results_to_root`` funnels the whole result vector through ONE GPU's PCIe link (8 GPUs:
+# 6.4 GB, ~130 ms per 1e8-path shard set).  Here rank 0 owns a POSIX shared-memory segment, every rank maps it and copies
+# its own shard device->host into its slice over its own link, in parallel; no data-path collective, two tiny ones for
+# the bookkeeping.  Segments are pooled: a segment goes back to the pool when the ndarray handed to the caller is garbage
+# collected, so steady-state runs reuse mappings that are already page-locked (``cudaHostRegister`` is paid once).
+# ------------------------------------------------------------------------------------------------------------------
+class _Segment:
+    __slots__ = ("shm", "nbytes", "registered", "owner")
+
+    def __init__(self, shm, nbytes, owner):
+        self.shm, self.nbytes, self.registered, self.owner = shm, nbytes, False, owner
+
+
+class _Attachment:
+    """A plain mapping of somebody else's segment.  ``SharedMemory(name=...)`` would also register the name with this
+    process's resource tracker (Python < 3.13), which then unlinks the owner's segment when this process exits."""
+
+    def __init__(self, name: str, nbytes: int):
+        import mmap
+        import os
+
+        import _posixshmem
+
+        self.name = name
+        fd = _posixshmem.shm_open("/" + name.lstrip("/"), os.O_RDWR, mode=0o600)
+        try:
+            self._mmap = mmap.mmap(fd, nbytes)
+        finally:
+            os.close(fd)
+        self.buf = memoryview(self._mmap)
+
+    def close(self) -> None:
+        self.buf.release()
+        self._mmap.close()
+
+
+class SharedResultPool:
+    """Per-process cache of shared-memory result segments (rank 0 creates and recycles, the others attach by name)."""
+
+    def __init__(self):
+        self._free: list[_Segment] = []    # rank 0: segments whose result array is gone
+        self._attached: dict[str, _Segment] = {}  # other ranks: name -> mapping
+        self._all: list[_Segment] = []
+        import atexit
+
+        atexit.register(self.close)
+
+    # -- rank 0 ---------------------------------------------------------------------------------------------------
+    def acquire(self, nbytes: int) -> _Segment:
+        from multiprocessing import shared_memory
+
+        best = None
+        for seg in self._free:
+            if seg.nbytes >= nbytes and (best is None or seg.nbytes < best.nbytes):
+                best = seg
+        if best is not None:
+            self._free.remove(best)
+            return best
+        seg = _Segment(shared_memory.SharedMemory(create=True, size=max(int(nbytes), 8)), max(int(nbytes), 8), True)
+        self._all.append(seg)
+        return seg
+
+    def release(self, seg: _Segment) -> None:
+        self._free.append(seg)
+
+    # -- other ranks ----------------------------------------------------------------------------------------------
+    def attach(self, name: str, nbytes: int) -> _Segment:
+        seg = self._attached.get(name)
+        if seg is None:
+            seg = _Segment(_Attachment(name, int(nbytes)), int(nbytes), False)
+            self._attached[name] = seg
+            self._all.append(seg)
+        return seg
+
+    @staticmethod
+    def page_lock(seg: _Segment) -> None:
+        """Register the mapping with CUDA once, so device->host copies into it run at pinned-memory speed."""
+        if seg.registered:
+            return
+        import ctypes
+
+        import torch
+
+        if torch.cuda.is_available():
+            addr = ctypes.addressof(ctypes.c_char.from_buffer(seg.shm.buf))
+            rc = torch.cuda.cudart().cudaHostRegister(addr, seg.nbytes, 0)
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister failed with error {int(rc)}")
+        seg.registered = True
+
+    def close(self) -> None:
+        import ctypes
+
+        for seg in self._all:
+            try:
+                if seg.registered:
+                    import torch
+
+                    if torch.cuda.is_available():
+                        addr = ctypes.addressof(ctypes.c_char.from_buffer(seg.shm.buf))
+                        torch.cuda.cudart().cudaHostUnregister(addr)
+                seg.shm.close()
+                if seg.owner:
+                    seg.shm.unlink()
+            except Exception:  # noqa: BLE001 - interpreter shutdown: nothing useful to do
+                pass
+        self._all, self._free, self._attached = [], [], {}
+
+
+_POOL = None
+
+
+def _pool() -> SharedResultPool:
+    global _POOL
+    if _POOL is None:
+        _POOL = SharedResultPool()
+    return _POOL
+
+
+def gather_results_shared(local, group):
+    """Rank 0 returns the concatenation (rank order) as a host float64 ndarray backed by shared memory; the other ranks
+    return ``None``.  Every rank copies only its own shard, straight from its device into the shared buffer."""
+    import weakref
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_local = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    sizes = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(sizes, n_local, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    total, offset = sum(sizes), sum(sizes[:rank])
+    pool = _pool()
+    seg = pool.acquire(total * 8) if rank == 0 else None
+    box = [(seg.shm.name, seg.nbytes) if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    if rank != 0:
+        seg = pool.attach(*box[0])
+    pool.page_lock(seg)
+    whole = np.ndarray((total,), dtype=np.float64, buffer=seg.shm.buf)
+    if sizes[rank]:
+        torch.from_numpy(whole[offset:offset + sizes[rank]]).copy_(local.to(torch.float64), non_blocking=False)
+    dist.barrier(group=group)  # every shard has landed
+    if rank != 0:
+        del whole
+        return None
+    weakref.finalize(whole, pool.release, seg)  # the segment is reusable once the caller has dropped the result
+    return whole

@@ -332,9 +332,14 @@ class MonteCarloSimulation(ABC):
             from . import _multi
 
             # "all": every rank returns the full vector (reference semantics on every rank);
-            # "root": only rank 0 does, the others return their own shard (saves N-1 host copies)
+            # "root": only rank 0 does, the others return their own shard (saves N-1 host copies);
+            # "shm": as "root", without funnelling the vector through rank 0's GPU (opt-in)
             local = values_dev
-            if getattr(self, "gather_mode", "all") == "root":
+            mode = getattr(self, "gather_mode", "all")
+            if mode == "shm":  # every rank copies its own shard into one shared-memory buffer (see _multi)
+                full = _multi.gather_results_shared(local, group)
+                host = full if full is not None else self._to_host(local)
+            elif mode == "root":
                 full = _multi.gather_results_to_root(local, group)
                 host = self._to_host(full if full is not None else local)
             else:

@@ -48,6 +48,35 @@ def _worker(rank, world, port, q):
         if rank == 0:
             assert torch.equal(root, torch.arange(n, dtype=torch.float64))
 
+        # (2b) shared-memory gather: every rank writes its own shard into rank 0's segment; the segment is recycled once
+        #      the result array is gone, and never while somebody still holds it
+        import gc
+
+        shared = _multi.gather_results_shared(local, dist.group.WORLD)
+        assert (shared is None) == (rank != 0)
+        if rank == 0:
+            assert shared.dtype == np.float64 and np.array_equal(shared, np.arange(n, dtype=np.float64))
+            pool = _multi._pool()
+            assert len(pool._all) == 1 and not pool._free
+        del shared
+        gc.collect()
+        again = _multi.gather_results_shared(local * 2.0, dist.group.WORLD)
+        if rank == 0:
+            assert len(pool._all) == 1, "the released segment must be reused"
+            assert np.array_equal(again, 2.0 * np.arange(n))
+        third = _multi.gather_results_shared(local + 1.0, dist.group.WORLD)  # `again` is still alive on rank 0
+        if rank == 0:
+            assert len(pool._all) == 2 and np.array_equal(again, 2.0 * np.arange(n)) and np.array_equal(third, np.arange(n) + 1.0)
+        else:
+            assert again is None and third is None and len(_multi._pool()._attached) == 2
+        view = third[5:9] if rank == 0 else None
+        del third, again
+        gc.collect()
+        if rank == 0:
+            assert len(pool._free) == 1, "a live view keeps its segment out of the pool"
+            assert view.tolist() == [6.0, 7.0, 8.0, 9.0]
+        del view
+
         # (3) moment partials: all-gather 12 doubles per rank, merge with the pairwise update formulas
         x = np.random.default_rng(0).lognormal(0, 1, n)
         part = torch.from_numpy(_summary_of(x[first:first + mine.n_total]).to_array())
