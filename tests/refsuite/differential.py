@@ -382,6 +382,26 @@ def misc_cases():
             return {"greeks": out, "rng_restored": s.rng.bit_generator.state["state"]["state"] == before}
         both(f"greeks parallel={par}", lambda: g(ref), lambda: g(new), rtol=1e-7)
 
+    # input types the engine accepts: lists, tuples, integer / bool / float32 arrays, empty input.  (Known superset, not
+    # compared: a 2-D array -- the reference records errors for skew, kurtosis and the bootstrap interval because SciPy
+    # and the index gather work along axis 0 there; the drop-in treats the sample as flat and returns all twelve.)
+    for label, data in (("list", [1.0, 2.5, 4.0, 8.0]), ("ints", np.arange(12)),
+                        ("tuple", (3.0, 1.0, 2.0)), ("bools", np.array([True, False, True, True])),
+                        ("float32", np.linspace(0, 1, 9, dtype=np.float32)), ("empty", [])):
+        def shaped(mod, data=data):
+            n = int(np.asarray(data).size)
+            res = mod.stats_engine.build_default_engine().compute(
+                np.asarray(data) if label != "list" and label != "tuple" else data,
+                mod.StatsContext(n=n, rng=5, n_bootstrap=100, target=1.0, eps=0.5, percentiles=(10, 50)))
+            return {"metrics": res.metrics, "skipped": sorted(k for k, _ in res.skipped), "errors": sorted(k for k, _ in res.errors)}
+        both(f"engine input {label}", lambda: shaped(ref), lambda: shaped(new))
+    for conf in (0.001, 0.999, 0.5):
+        def extreme(mod, conf=conf):
+            x = np.random.default_rng(3).standard_t(3, 400)
+            return mod.stats_engine.build_default_engine().compute(
+                x, mod.StatsContext(n=400, confidence=conf, rng=9, n_bootstrap=200, bootstrap="bca", target=0.1, eps=0.2)).metrics
+        both(f"engine confidence {conf}", lambda: extreme(ref), lambda: extreme(new))
+
     def pickled(mod):
         import pickle
 
