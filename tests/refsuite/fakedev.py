@@ -133,6 +133,12 @@ def moments_raw(x, target=0.0):
 
 def select(x, ranks, omit_nonfinite=False, group=None):
     a = x.numpy().reshape(-1)
+    if group is not None:  # sharded sample: the order statistics of the union (the kernels all-reduce digit histograms)
+        import torch.distributed as dist
+
+        parts = [None] * dist.get_world_size(group)
+        dist.all_gather_object(parts, a, group=group)
+        a = np.concatenate(parts)
     if omit_nonfinite:
         a = a[np.isfinite(a)]
     return _t(np.sort(a)[[int(r) for r in ranks]].astype(np.float64))

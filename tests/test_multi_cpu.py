@@ -148,3 +148,73 @@ def test_two_rank_host_logic_gloo():
     for p in procs:
         p.join(60)
     assert out == {0: "ok", 1: "ok"}, out
+
+
+def _run_worker(rank, world, port, q):
+    """Block-parallel public-API runs on 2 ranks (stand-in device of tests/refsuite, gloo): every gather mode returns the
+    reference-ordered vector where it should, equal to the single-process run."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import logging
+        import sys
+
+        here = os.path.dirname(os.path.abspath(__file__))
+        for p_ in (os.path.dirname(here), here):
+            if p_ not in sys.path:
+                sys.path.insert(0, p_)
+        from refsuite import fakedev
+
+        fakedev.install()
+        import mcframework_b200 as m
+        from oracle import np_port
+
+        logging.getLogger("mcframework_b200.core").setLevel(logging.WARNING)
+        n, workers = 20_003, 3  # 24 blocks of 833 + a ragged one: 12 / 13 blocks per rank
+        want = np_port.Runner("pi", seed=9).run(n, parallel=True, n_workers=workers, n_points=40)
+        first = {0: 0, 1: 12 * 833}[rank]
+        for mode in ("all", "root", "shm"):
+            sim = m.PiEstimationSimulation()
+            sim.gather_mode = mode
+            sim.set_seed(9)
+            got = sim.run(n, parallel=True, n_workers=workers, n_points=40, compute_stats=False).results
+            if mode == "all" or rank == 0:
+                assert got.shape == (n,) and np.array_equal(got, want), (mode, rank)
+            else:  # the other ranks keep their own shard
+                assert np.array_equal(got, want[first:first + got.size]) and got.size in (12 * 833, n - 12 * 833), (mode, rank)
+            assert sim.seed_seq.n_children_spawned == 25
+        # sharded statistics: moments, percentiles, z/t interval, seeded BCa bootstrap, distribution-free bounds --
+        # every rank reports what the single-process run (the oracle's port of the reference engine) reports
+        ctx_kw = dict(target=3.1, eps=0.01, rng=4, n_bootstrap=100, bootstrap="bca")
+        sim = m.PiEstimationSimulation()
+        sim.set_seed(9)
+        res = sim.run(n, parallel=True, n_workers=workers, n_points=40, percentiles=(1, 99), extra_context=ctx_kw)
+        ref = np_port.default_metrics(want, n=n, percentiles=(5, 25, 50, 75, 95), **ctx_kw)
+        for key in ("mean", "std", "skew", "kurtosis", "bias_to_target", "mse_to_target", "markov_error_prob",
+                    "chebyshev_required_n"):
+            np.testing.assert_allclose(res.stats[key], ref[key], rtol=1e-9, err_msg=key)
+        for key in ("ci_mean", "ci_mean_bootstrap", "ci_mean_chebyshev"):
+            for f in ("low", "high"):
+                np.testing.assert_allclose(res.stats[key][f], ref[key][f], rtol=1e-9, err_msg=key)
+        assert res.percentiles == {int(p): float(np.percentile(want, p)) for p in (1, 5, 25, 50, 75, 95, 99)}
+        assert (res.mean, res.n_simulations) == (res.stats["mean"], n)
+        q.put((rank, "ok"))
+    except Exception as exc:  # noqa: BLE001
+        import traceback
+
+        q.put((rank, traceback.format_exc() + repr(exc)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_public_api_runs_and_gather_modes_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_run_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert out == {0: "ok", 1: "ok"}, out
