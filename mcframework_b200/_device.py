@@ -18,6 +18,14 @@ from ._streams import StreamLayout
 LAUNCHES = {"pi": 0, "plan": 0, "gbm": 0, "paths": 0, "stats": 0, "lsm": 0}
 
 
+KEY_BATCH = 112  # streams per launch of the launch-constant-key kernels (MCF_KEY_BATCH in csrc/mcf_kernels.cu)
+
+
+def _batches(lay) -> int:
+    """Launches one pass over the layout's streams takes: Philox streams go 112 per launch, anything else in one."""
+    return -(-lay.n_streams // KEY_BATCH) if lay.kind == 1 else 1
+
+
 def _torch():
     import torch
 
@@ -60,7 +68,7 @@ def pi_hits(dl: DeviceLayout, n_points: int, antithetic: bool = False):
     rc = N.lib().mcf_pi_hits(lay.kind, _ptr(dl.records), host_records.ctypes.data_as(C.c_void_p), lay.n_streams, lay.n_total,
                              int(n_points), int(bool(antithetic)), lay.hint, _ptr(hits), _ptr(out), _stream_ptr())
     N.check("mcf_pi_hits", rc)
-    LAUNCHES["pi"] += 1 + (lay.n_streams if lay.kind == 1 and lay.n_streams <= 1024 else 1)
+    LAUNCHES["pi"] += 1 + _batches(lay)
     return hits, out
 
 
@@ -75,12 +83,24 @@ class NormalPlan:
     slack: float = 0.03  # window slack the workspace geometry was computed with (mcf_normal_relocate needs it)
 
 
-def normal_plan(dl: DeviceLayout, normals_per_sim: int, slack: float = 0.03, resolve_iters: int = 3,
+#: NumPy's ziggurat consumes 1.02201 64-bit draws per normal on average (measured over 2e8 normals; variance of the
+#: count per normal ~0.04): the scan window of a stream is its expected consumption plus 8 standard deviations
+ZIG_DRAWS_PER_NORMAL = 1.02201
+
+
+def default_slack(normals_per_stream: int) -> float:
+    need = max(1.0, float(normals_per_stream))
+    return (ZIG_DRAWS_PER_NORMAL - 1.0) + 0.0004 + 8.0 * (0.04 / need) ** 0.5
+
+
+def normal_plan(dl: DeviceLayout, normals_per_sim: int, slack: float | None = None, resolve_iters: int = 3,
                 max_retries: int = 4) -> NormalPlan:
     """Planning pass for ziggurat-consuming replications ("stream-exact planning")."""
     torch = _torch()
     lay = dl.layout
     lib = N.lib()
+    if slack is None:  # a window that turns out too small is re-planned with a wider one below
+        slack = default_slack(int(lay.max_sims) * int(normals_per_sim))
     sim_start = torch.empty(lay.n_total, dtype=torch.int64, device="cuda")
     stream_end = torch.zeros(lay.n_streams, dtype=torch.int64, device="cuda")
     for _ in range(max_retries):
@@ -94,7 +114,7 @@ def normal_plan(dl: DeviceLayout, normals_per_sim: int, slack: float = 0.03, res
                                  int(normals_per_sim), float(slack), int(resolve_iters), _ptr(ws), int(nbytes),
                                  _ptr(sim_start), _ptr(stream_end), _stream_ptr())
         N.check("mcf_normal_plan", rc)
-        LAUNCHES["plan"] += 4 + 2 * resolve_iters + (lay.n_streams if lay.kind == 1 and lay.n_streams <= 1024 else 1)
+        LAUNCHES["plan"] += 4 + 2 * resolve_iters + _batches(lay)
         status = lib.mcf_workspace_status(_ptr(ws), _stream_ptr())
         if status == N.OK:
             return NormalPlan(sim_start, stream_end, int(normals_per_sim), ws, float(slack))
@@ -128,8 +148,8 @@ def gbm_terminal(dl: DeviceLayout, n_steps: int, plan: NormalPlan, specs):
                                   _spec_array(specs), len(specs), _ptr(out), _stream_ptr())
     N.check("mcf_gbm_terminal", rc)
     affine = all(int(m) not in (N.BS_AMER_CALL, N.BS_AMER_PUT, N.PORTFOLIO_LOG1P) for m, _ in specs)
-    per_stream = lay.kind == 1 and lay.n_streams <= 1024 and affine and int(n_steps) >= 16
-    LAUNCHES["gbm"] += lay.n_streams if per_stream else 1  # boundary-form replay: one launch per stream
+    per_stream = lay.kind == 1 and affine and int(n_steps) >= 16
+    LAUNCHES["gbm"] += _batches(lay) if per_stream else 1  # boundary-form replay: one launch per batch of streams
     return out
 
 
@@ -170,7 +190,7 @@ def gbm_slices(dl: DeviceLayout, n_steps: int, plan: NormalPlan, mode: int, para
     shape = (n_slices, lay.n_total) if time_major else (lay.n_total, n_slices)
     out = torch.empty(shape, dtype=torch.float64, device="cuda")
     k = int(n_steps) // int(slice_stride)
-    if (lay.kind == 1 and lay.n_streams <= 1024 and int(slice_stride) >= 16 and k * int(slice_stride) == int(n_steps)
+    if (lay.kind == 1 and int(slice_stride) >= 16 and k * int(slice_stride) == int(n_steps)
             and k > 1 and int(mode) in (N.PORTFOLIO_GBM, N.PATH_TERMINAL) and bool((lay.records["buf_pos"] % 4 == 0).all())):
         # Segment form: every path is cut into k pseudo-replications of `stride` steps.  Re-locating the finished plan
         # gives their stream positions, the boundary-form replay their normal sums (two Philox blocks per segment

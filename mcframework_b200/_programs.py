@@ -109,15 +109,16 @@ def run_blocks(prog: ReplicationProgram, blocks, children, n: int, group=None):
         import torch.distributed as dist
 
         lay = lay.shard(dist.get_rank(group), dist.get_world_size(group))
-    if lay.n_total == 0:
+    if lay.n_total == 0:  # more ranks than blocks: an empty shard still takes part in the collectives below
         import torch
 
-        return torch.empty(0, dtype=torch.float64, device="cuda")
-    try:
-        values, _ = prog.execute(D.DeviceLayout.of(lay))
-        failed = False
-    except HostLoopRequired:
-        values, failed = None, True
+        values, failed = torch.empty(0, dtype=torch.float64, device="cuda"), False
+    else:
+        try:
+            values, _ = prog.execute(D.DeviceLayout.of(lay))
+            failed = False
+        except HostLoopRequired:
+            values, failed = None, True
     if group is not None:  # every rank takes the same path
         import torch
         import torch.distributed as dist

@@ -135,6 +135,23 @@ def generator_record(gen: np.random.Generator, first_sim: int = 0, n_sims: int =
     raise NotImplementedError(f"device streams support PCG64 and Philox bit generators, got {name!r}")
 
 
+def _restore_buffered_half(bg, before) -> None:
+    """``advance``/``random_raw`` drop NumPy's buffered 32-bit half draw (``has_uint32``/``uinteger``); the reference's
+    ``random``/``standard_normal`` calls keep it, so it is written back after a jump over 64-bit draws."""
+    if int(before.get("has_uint32", 0)):
+        st = bg.state
+        st["has_uint32"], st["uinteger"] = before["has_uint32"], before["uinteger"]
+        bg.state = st
+
+
+def advance_keeping_buffer(gen: np.random.Generator, draws: int) -> None:
+    """PCG64: jump ``draws`` 64-bit outputs ahead; a buffered ``integers`` half survives, as in the reference."""
+    bg = gen.bit_generator
+    before = bg.state
+    bg.advance(int(draws))
+    _restore_buffered_half(bg, before)
+
+
 def consume_draws(gen: np.random.Generator, draws: int) -> int:
     """Advance ``gen`` by ``draws`` 64-bit outputs without producing them; returns the LAST of those outputs
     (NumPy's buffered ``next_uint32`` needs its upper half).  PCG64: O(log n) jump.  Philox: counter arithmetic."""
@@ -144,19 +161,23 @@ def consume_draws(gen: np.random.Generator, draws: int) -> int:
     st = bg.state
     if st["bit_generator"] == "PCG64":
         bg.advance(draws - 1)
-        return int(bg.random_raw())
+        last = int(bg.random_raw())
+        _restore_buffered_half(bg, st)
+        return last
     if st["bit_generator"] == "Philox":
         q = int(st["buffer_pos"]) + draws  # position after consumption, in units of 64-bit outputs
         ctr = sum(int(c) << (64 * i) for i, c in enumerate(st["state"]["counter"]))
         blk = (q - 1) // 4  # block (relative to the counter) holding the last consumed output
         if blk == 0:  # still inside the buffered block
             last = int(st["buffer"][q - 1])
-            st["buffer_pos"] = q
+            st["buffer_pos"] = q  # (the state dict written back still carries the buffered half)
             bg.state = st
             return last
         new_ctr = (ctr + blk - 1) % (1 << 256)  # pre-increment: the next generated block is new_ctr + 1
         st["state"]["counter"] = np.array([(new_ctr >> (64 * i)) & _M64 for i in range(4)], dtype=np.uint64)
         st["buffer_pos"] = 4
         bg.state = st
-        return int(bg.random_raw((q - 1) % 4 + 1)[-1])
+        last = int(bg.random_raw((q - 1) % 4 + 1)[-1])
+        _restore_buffered_half(bg, st)
+        return last
     raise NotImplementedError(st["bit_generator"])

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmcf_b200.so")
 SOURCES = ["mcf_kernels.cu", "mcf_stats.cu"]  # missing files are skipped until they exist
-HEADERS = ["mcf_device.cuh", "mcf_host.h", "zig_tables.h", os.path.join("..", "..", "include", "mcf_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "mcf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -174,6 +174,8 @@ class MonteCarloSimulation(ABC):
         state = self.__dict__.copy()
         state["rng"] = None
         state.pop("_device_sample", None)
+        if not isinstance(state.get("shard_group"), (str, type(None))):
+            state.pop("shard_group")  # a process group does not travel to worker processes
         return state
 
     def __setstate__(self, state):
@@ -211,15 +213,27 @@ class MonteCarloSimulation(ABC):
             return None  # the subclass replaced the hook: its Python body is the definition now
         return prog
 
+    #: Multi-GPU sharding is OPT-IN: set ``sim.shard_group`` to a ``torch.distributed`` process group (one process per
+    #: GPU), or to the string ``"world"`` for the default group.  While it is set, ``run(parallel=True)`` and
+    #: ``calculate_greeks(parallel=True)`` are COLLECTIVE calls: every rank of the group must make them with identical
+    #: arguments (``n_simulations``, ``n_workers``, seed, simulation kwargs); each rank replays a contiguous range of the
+    #: spawned blocks.  ``None`` (default): an initialised process group is ignored and every process runs the whole job.
+    shard_group = None
+
     def _shard_group(self):
         """Process group over which a parallel run is sharded (one process per GPU), else None."""
-        try:
-            import torch.distributed as dist
-        except Exception:  # pragma: no cover
+        group = getattr(self, "shard_group", None)
+        if group is None:
             return None
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            return dist.group.WORLD
-        return None
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("shard_group is set but torch.distributed is not initialised")
+        if isinstance(group, str):
+            if group != "world":
+                raise ValueError("shard_group must be a process group, 'world' or None")
+            group = dist.group.WORLD
+        return group if dist.get_world_size(group) > 1 else None
 
     # ------------------------------------------------------------------ validation / stats
     def _validate_run_params(self, n_simulations: int, n_workers: int | None, confidence: float, ci_method: str) -> None:
@@ -291,26 +305,27 @@ class MonteCarloSimulation(ABC):
         """Run ``n_simulations`` replications and summarise them (:486-581)."""
         self._validate_run_params(n_simulations, n_workers, confidence, ci_method)
         self._device_sample = None
-        started = time.time()
-        if parallel:
-            if n_workers is None:
-                n_workers = mp.cpu_count()
-            logger.info("Computing %d simulations in parallel using %d workers...", n_simulations, n_workers)
-            results = self._run_parallel(n_simulations, n_workers, progress_callback, **simulation_kwargs)
-        else:
-            logger.info("Computing %d simulations sequentially...", n_simulations)
-            results = self._run_sequential(n_simulations, progress_callback, **simulation_kwargs)
-        elapsed = time.time() - started
+        try:
+            started = time.time()
+            if parallel:
+                if n_workers is None:
+                    n_workers = mp.cpu_count()
+                logger.info("Computing %d simulations in parallel using %d workers...", n_simulations, n_workers)
+                results = self._run_parallel(n_simulations, n_workers, progress_callback, **simulation_kwargs)
+            else:
+                logger.info("Computing %d simulations sequentially...", n_simulations)
+                results = self._run_sequential(n_simulations, progress_callback, **simulation_kwargs)
+            elapsed = time.time() - started
 
-        stats: dict[str, Any] = {}
-        pmap: dict[int, float] = {}
-        if compute_stats:
-            stats, pmap = self._compute_stats_with_engine(results, n_simulations, confidence, ci_method, stats_engine,
-                                                          extra_context)
-        pmap, requested, defaults_used = self._handle_percentiles(results, percentiles, compute_stats, pmap)
-        out = self._create_result(results, n_simulations, elapsed, pmap, stats, requested, defaults_used)
-        self._device_sample = None
-        return out
+            stats: dict[str, Any] = {}
+            pmap: dict[int, float] = {}
+            if compute_stats:
+                stats, pmap = self._compute_stats_with_engine(results, n_simulations, confidence, ci_method, stats_engine,
+                                                              extra_context)
+            pmap, requested, defaults_used = self._handle_percentiles(results, percentiles, compute_stats, pmap)
+            return self._create_result(results, n_simulations, elapsed, pmap, stats, requested, defaults_used)
+        finally:
+            self._device_sample = None  # also when the statistics raise: the device copy must not outlive the call
 
     # ------------------------------------------------------------------ replication loop
     @staticmethod
@@ -366,8 +381,10 @@ class MonteCarloSimulation(ABC):
             except _programs.HostLoopRequired:
                 values = None  # the generator was not advanced: loop the hook below, exactly like the reference
             if values is not None:
-                if draws:  # (advance() also clears NumPy's buffered half draw: integer programs advance themselves)
-                    self.rng.bit_generator.advance(int(draws))  # leave the stream where the reference would
+                if draws:  # leave the stream where the reference would (64-bit draws never touch the buffered half)
+                    from ._streams import advance_keeping_buffer
+
+                    advance_keeping_buffer(self.rng, int(draws))
                 results = self._finish_device_run(values)
                 if progress_callback:
                     for done in range(step, n_simulations + 1, step):

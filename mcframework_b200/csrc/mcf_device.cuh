@@ -287,6 +287,40 @@ MCF_HD void philox_block_keys(const PhiloxKeys &K, uint64_t blk, uint64_t &o0, u
 // Block `blk` of a stream whose low counter word never carries (K.fold_ok): 18 wide multiplications instead of 20.
 //   round 0: (x, b1, b2, b3)      -> (A0,              M1*b2,      mulhi(M0,x) ^ b3 ^ rk1, M0*x)     A0 constant
 //   round 1: (A0, M1*b2, c2, c3)  -> (mulhi(M1,c2) ^ M1*b2 ^ rk2, M1*c2, mulhi(M0,A0) ^ c3 ^ rk3, M0*A0)
+// `r0hi:r0lo` = M0 * (b0 + blk), the one product of round 0 that depends on the block index.  A thread that walks
+// consecutive blocks keeps it as a running 128-bit value (philox_r0_next: + M0 per block) instead of multiplying.
+template <bool CHAIN = false>
+MCF_HD void philox_block_folded_r0(const PhiloxKeys &K, uint64_t r0hi, uint64_t r0lo, uint64_t &o0, uint64_t &o1, uint64_t &o2,
+                                   uint64_t &o3) {
+    uint64_t c0, c1, c2 = r0hi ^ K.f0_c2x, c3 = r0lo;
+    mul64_full<CHAIN>(MCF_PHILOX_M1, c2, c0, c1);  // round 1
+    c0 ^= K.f1_c0x;
+    c2 = c3 ^ K.f1_c2x;
+    c3 = K.f1_c3;
+#pragma unroll
+    for (int r = 2; r < 10; r++) {
+        uint64_t hi0, lo0, hi1, lo1;
+        mul64_full<CHAIN>(MCF_PHILOX_M0, c0, hi0, lo0);
+        mul64_full<CHAIN>(MCF_PHILOX_M1, c2, hi1, lo1);
+        c0 = hi1 ^ c1 ^ K.rk[2 * r];
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ K.rk[2 * r + 1];
+        c3 = lo0;
+    }
+    o0 = c0;
+    o1 = c1;
+    o2 = c2;
+    o3 = c3;
+}
+MCF_HD void philox_r0_next(uint64_t &r0hi, uint64_t &r0lo) {  // (hi:lo) += M0
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, 0;" : "+l"(r0lo), "+l"(r0hi) : "l"(MCF_PHILOX_M0));
+#else
+    r0lo += MCF_PHILOX_M0;
+    r0hi += r0lo < MCF_PHILOX_M0 ? 1ULL : 0ULL;
+#endif
+}
+
 template <bool CHAIN = false>
 MCF_HD void philox_block_folded(const PhiloxKeys &K, uint64_t blk, uint64_t &o0, uint64_t &o1, uint64_t &o2, uint64_t &o3) {
     const uint64_t x = K.b0 + blk;
@@ -458,19 +492,14 @@ struct ZigTables {
     const ZigKW *kws;
 };
 #define MCF_U52_BIAS 0x4330000000000000ULL
-// Candidate for the next round (off by default, not measured yet): MCF_SCAN_DENORM reads the 52 bits of `rabs` as the bit
-// pattern of a SUBNORMAL double (value rabs * 2^-1074, exact) instead of OR-ing the 2^52 exponent in: the compare against
-// ki works on the subnormals as they are, and rabs * wi becomes (d * 2^1000) * (wi * 2^74) -- two exact power-of-two
-// scalings, so the one rounding is NumPy's rounding of rabs * wi.  Saves one logic operation per draw of the scan.
-#ifdef MCF_SCAN_DENORM
+// The scan reads the 52 bits of `rabs` as the bit pattern of a SUBNORMAL double d = rabs * 2^-1074 (no exponent bias to
+// OR in) and keeps the table weight as wi' = wi * 2^974, so d * wi' = x * 2^-100 -- a normal number, rounded exactly like
+// rabs * wi -- and the sub-chunk sums are accumulated with ONE fused multiply-add per fast draw in that scaled range
+// (rescaled by 2^100, exactly, after the loop): two FP64 operations per draw (compare + FMA) instead of four.
+// Measured: 97.4 -> 93.8 ms per plan of 1e8 x 252 (profiles/r2_scan_variants.jsonl).
 #define MCF_SCAN_BIAS 0ULL
-#define MCF_SCAN_WI_SCALE 0x1p74
-#define MCF_SCAN_VALUE(d, wi) xmul(xmul((d), 0x1p1000), (wi))
-#else
-#define MCF_SCAN_BIAS MCF_U52_BIAS
-#define MCF_SCAN_WI_SCALE 1.0
-#define MCF_SCAN_VALUE(d, wi) xmul(xadd((d), -4503599627370496.0), (wi))
-#endif
+#define MCF_SCAN_WI_SCALE 0x1p974
+#define MCF_SCAN_VALUE(d, wi) xmul(xmul((d), (wi)), 0x1p100)
 MCF_HD void zig_fill_kws(ZigKW *kws, unsigned e, uint64_t ki, double wi) {
     kws[e].ki = ki | MCF_SCAN_BIAS;
     kws[e].wi = ((e & 0x100u) ? -wi : wi) * MCF_SCAN_WI_SCALE;
@@ -723,22 +752,26 @@ MCF_HD ChunkInfo scan_chunk(Cur &cur, uint64_t chunk_base, uint32_t entry, const
 
 // ---------------------------------------------------------------------------------------
 // Speculative walk of one chunk of a block-aligned Philox stream (entry offset 0), branch-light form.
-// Same result as scan_chunk(cur, chunk_base, 0, ...) up to the summation order of the sub-chunk sums.
-// `load(blk, a, b, c, d)` yields the four draws of Philox block `blk` (relative to the stream's base counter);
-// `blk0` is the block holding the chunk's first draw; one block of look-ahead is always loaded.
+// Same result as scan_chunk(cur, chunk_base, 0, ...) up to the rounding of the sub-chunk sums.
+// `load(blk, a, b, c, d)` yields the four draws of Philox block `blk` (relative to the stream's base counter) and is
+// called for CONSECUTIVE blocks starting at `blk0`, the block holding the chunk's first draw (the device keeps round 0's
+// product as a running value, philox_r0_next); one block of look-ahead is always loaded.
 //
-// Phase 1 touches every draw once and has no dependence between draws: the draw is converted as if an attempt
-// started there (one 16-byte table load, one 64-bit compare, DADD + DMUL), its value is added to the sub-chunk sum
-// when it is "fast-looking" (rabs < ki), and a draw that is not (1.57 %) is parked in a per-thread slot together
-// with its two successors.  Phase 2 resolves the chain from the parked draws alone, in order:
-//   * a parked draw that an earlier attempt consumed is not a start -- drop it;
-//   * otherwise it starts a wedge attempt (consumes the next draw) or a tail attempt (the next two); the draws it
-//     consumes stop being starts, and where they were fast-looking their value leaves the sum again;
-//   * the acceptance test decides its emit bit and adds its normal.
+// Phase 1 touches every draw once and has no dependence between draws: the draw is looked at as if an attempt started
+// there (one 16-byte table load, one FP64 compare); when it is "fast-looking" (rabs < ki) its value joins the sub-chunk
+// sum with one fused multiply-add (see MCF_SCAN_VALUE), and a draw that is not (1.57 %) is parked in a per-thread slot
+// together with its two successors.  Phase 2 resolves the chain from the parked draws alone, in order:
+//   * what a parked draw yields -- accepted or not, its normal, how many draws it consumes, the fast values of the two
+//     draws behind it -- does not depend on the chain, so `eval_parked` evaluates every parked draw EAGERLY (on the
+//     device the warp's parked draws are compacted and spread over the lanes: ~1.5 dense rounds of the wedge
+//     arithmetic instead of 3.3-3.7 sparse ones);
+//   * the chain walk then only reads results: a parked draw that an earlier attempt consumed is not a start -- drop it;
+//     otherwise the draws it consumes stop being starts (where they were fast-looking their value leaves the sum
+//     again) and its flags give its emit bit and normal.
 // Fast-looking draws that nobody consumed are exactly the fast attempts, so
 //     startmask = ~consumed,  emitmask = (fast-looking & ~consumed) | accepted.
 // More parked draws than slots (4e-3 of the chunks) or a tail whose first pair is rejected mark the chunk invalid
-// for the general re-walk, as before.  The sums differ from scan_chunk's by summation order only (deterministic).
+// for the general re-walk.
 // ---------------------------------------------------------------------------------------
 #define MCF_PARK_CAP 4
 #ifndef MCF_SCAN_UNROLL
@@ -746,32 +779,20 @@ MCF_HD ChunkInfo scan_chunk(Cur &cur, uint64_t chunk_base, uint32_t entry, const
 #endif
 #define MCF_PRAGMA(x) _Pragma(#x)
 #define MCF_UNROLL(n) MCF_PRAGMA(unroll n)
-struct ParkSlots {  // slot k of this thread: a[k * stride], b[k * stride], c[k * stride]
+struct ParkSlots {  // slot k of this thread: a[k * stride], b[k * stride], c[k * stride], f[k * stride]
     uint64_t *a, *b, *c;
     unsigned stride;
-#ifdef MCF_P2_COOP
-    uint8_t *f;  // flags of the evaluated slot (MCF_P2_COOP), same indexing
-#endif
+    uint8_t *f;  // flags of the evaluated slot
 };
-#ifdef MCF_P2_COOP
-#define MCF_PARK_HAS_FLAGS 1
-#endif
 MCF_HD double zig_fast_value(uint64_t w, const ZigTables &t) {  // signed value of a fast-looking draw
     const uint64_t dbits = ((w >> 9) & 0x000fffffffffffffULL) | MCF_SCAN_BIAS;
     return MCF_SCAN_VALUE(bits_to_double(dbits), t.kws[(unsigned)w & 0x1ffu].wi);
 }
 
-#ifdef MCF_P2_COOP
-// Candidate for the next round (off by default; host logic checked by the emulation tests, the warp-cooperative
-// distribution in mcf_kernels.cu NOT yet run on hardware).  Phase 2 costs ~14 % of the scan's instructions because every
-// warp repeats the wedge arithmetic for its unluckiest lane (3.3-3.7 rounds of ~140 instructions, a third of the lanes
-// busy).  What a parked draw yields -- accepted or not, its normal, how many draws it consumes, the fast values of the two
-// draws behind it -- does not depend on the chain, so it can be evaluated EAGERLY for every parked draw, by any lane
-// (`eval_parked`: on the device the warp's parked draws are compacted and spread over the lanes, ~1.5 dense rounds), and
-// the chain walk that is left only reads results and updates masks (~45 instructions per round).
 #define MCF_PE_ACC 1u   // the attempt emits a normal
 #define MCF_PE_LEN2 2u  // tail attempt: consumes the next two draws (else wedge: the next one)
 #define MCF_PE_BAD 4u   // tail whose first pair is rejected: the chunk goes to the general walk
+#define MCF_PE_LEN0 8u  // a fast attempt after all (never set by the FP64 compare of phase 1; kept for exactness)
 struct ParkEval {
     double x, fv1, fv2;
     unsigned flags;
@@ -780,11 +801,13 @@ MCF_HD ParkEval park_eval(uint64_t a, uint64_t u, uint64_t u2, const ZigTables &
     ParkEval r;
     r.x = 0.0;
     r.flags = 0;
-    if ((a & 0xffULL) != 0) {  // wedge: same arithmetic and decision as zig_feed, state 1
-        ZigFsm f;
-        zig_reset(f);
-        double x = 0.0;
-        zig_feed(f, a, t, x);
+    ZigFsm f;
+    zig_reset(f);
+    double x = 0.0;
+    if (zig_feed(f, a, t, x)) {
+        r.flags = MCF_PE_ACC | MCF_PE_LEN0;
+        r.x = x;
+    } else if ((a & 0xffULL) != 0) {  // wedge: same arithmetic and decision as zig_feed, state 1
         if (zig_feed(f, u, t, x)) {
             r.flags = MCF_PE_ACC;
             r.x = x;
@@ -821,7 +844,6 @@ MCF_HD void eval_parked_local(const ParkSlots &park, unsigned n_parked, const Zi
         park_eval_store(park, slot, park_eval(park.a[slot], park.b[slot], park.c[slot], t));
     }
 }
-#endif
 
 //
 // Entry patch.  `entry_of(exit)` is called once, with the chunk's speculative exit, and returns the exit of the
@@ -835,55 +857,33 @@ MCF_HD void eval_parked_local(const ParkSlots &park, unsigned n_parked, const Zi
 // `share_first(w0, w1)` is called once with the chunk's own first two draws and `lookahead(a, b)` must later return
 // the next chunk's: on the device the neighbouring thread's (through shared memory), so the 17th Philox block per
 // chunk is generated by one thread per CTA only; the host build simply generates it.
-#ifdef MCF_P2_COOP
 // `eval_parked(n)`: afterwards slot k < n of this thread holds {x, fv1, fv2} (bit patterns in a/b/c) and its flags
 template <class Load, class EntryOf, class ShareFirst, class LookAhead, class EvalParked>
 MCF_HD ChunkInfo scan_chunk_fast2(Load load, uint64_t blk0, const ZigTables &t, const ParkSlots &park, double *zsub_out,
                                   bool *valid, EntryOf entry_of, ShareFirst share_first, LookAhead lookahead,
-                                  EvalParked eval_parked, const uint64_t bias = MCF_SCAN_BIAS) {
-#else
-template <class Load, class EntryOf, class ShareFirst, class LookAhead>
-MCF_HD ChunkInfo scan_chunk_fast2(Load load, uint64_t blk0, const ZigTables &t, const ParkSlots &park, double *zsub_out,
-                                  bool *valid, EntryOf entry_of, ShareFirst share_first, LookAhead lookahead,
-                                  const uint64_t bias = MCF_SCAN_BIAS) {
-#endif
+                                  EvalParked eval_parked) {
     uint64_t F = 0;   // fast-looking draws
     unsigned np = 0;  // parked draws
     double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
-    double vk0 = 0.0, vk1 = 0.0;  // values of the chunk's first two draws (entry patch)
     uint64_t w0, w1, w2, w3, n0, n1, n2, n3;
     load(blk0, w0, w1, w2, w3);
     share_first(w0, w1);
-// Candidate for the next round (off by default): MCF_SCAN_NMASK records the 1.6 % parked positions in the rare branch
-// instead of the 98.4 % fast ones on the common path (one predicated logic operation less per draw).
-#ifdef MCF_SCAN_NMASK
-#define MCF_FAST2_MARK_FAST(J)
-#define MCF_FAST2_MARK_PARKED(J) f16 |= 1u << (J);
-#define MCF_FAST2_F16(f16) (~(f16) & 0xffffu)
-#else
-#define MCF_FAST2_MARK_FAST(J) f16 |= 1u << (J);
-#define MCF_FAST2_MARK_PARKED(J)
-#define MCF_FAST2_F16(f16) (f16)
-#endif
-#define MCF_FAST2_DRAW(J, WA, WB, WC)                                                             \
-    {                                                                                             \
-        const uint64_t dbits = (((WA) >> 9) & 0x000fffffffffffffULL) | bias;                      \
-        const ZigKW kw = t.kws[(unsigned)(WA)&0x1ffu];                                            \
-        const double v = MCF_SCAN_VALUE(bits_to_double(dbits), kw.wi);                            \
-        if ((J) == 0 && sub == 0) vk0 = v;                                                        \
-        if ((J) == 1 && sub == 0) vk1 = v;                                                        \
-        if (bits_to_double(dbits) < bits_to_double(kw.ki)) {                                      \
-            MCF_FAST2_MARK_FAST(J)                                                                \
-            zc = xadd(zc, v);                                                                     \
-        } else {                                                                                  \
-            MCF_FAST2_MARK_PARKED(J)                                                              \
-            if (np < MCF_PARK_CAP) {                                                              \
-                park.a[np * park.stride] = (WA);                                                  \
-                park.b[np * park.stride] = (WB);                                                  \
-                park.c[np * park.stride] = (WC);                                                  \
-            }                                                                                     \
-            np++;                                                                                 \
-        }                                                                                         \
+    const double vk0 = zig_fast_value(w0, t), vk1 = zig_fast_value(w1, t);  // the first two draws (entry patch)
+#define MCF_FAST2_DRAW(J, WA, WB, WC)                                                       \
+    {                                                                                       \
+        const uint64_t dbits = (((WA) >> 9) & 0x000fffffffffffffULL) | MCF_SCAN_BIAS;       \
+        const ZigKW kw = t.kws[(unsigned)(WA)&0x1ffu];                                      \
+        if (bits_to_double(dbits) < bits_to_double(kw.ki)) {                                \
+            f16 |= 1u << (J);                                                               \
+            zc = fma(bits_to_double(dbits), kw.wi, zc); /* x * 2^-100, one rounding */      \
+        } else {                                                                            \
+            if (np < MCF_PARK_CAP) {                                                        \
+                park.a[np * park.stride] = (WA);                                            \
+                park.b[np * park.stride] = (WB);                                            \
+                park.c[np * park.stride] = (WC);                                            \
+            }                                                                               \
+            np++;                                                                           \
+        }                                                                                   \
     }
 MCF_UNROLL(MCF_SCAN_UNROLL)
     for (unsigned sub = 0; sub < MCF_SUBS; sub++) {
@@ -914,13 +914,17 @@ MCF_UNROLL(MCF_SCAN_UNROLL)
         MCF_FAST2_DRAW(13, n1, n2, n3)
         MCF_FAST2_DRAW(14, n2, n3, w0)
         MCF_FAST2_DRAW(15, n3, w0, w1)
-        F |= (uint64_t)MCF_FAST2_F16(f16) << (16 * sub);
+        F |= (uint64_t)f16 << (16 * sub);
         z0 = z1;
         z1 = z2;
         z2 = z3;
         z3 = zc;
     }
 #undef MCF_FAST2_DRAW
+    z0 = xmul(z0, 0x1p100);  // exact: back from the scaled accumulation range
+    z1 = xmul(z1, 0x1p100);
+    z2 = xmul(z2, 0x1p100);
+    z3 = xmul(z3, 0x1p100);
     // phase 2: the chain, from the parked draws
     bool ok = np <= MCF_PARK_CAP;
     uint64_t S = ~0ULL, A = 0, N = ~F;
@@ -931,7 +935,6 @@ MCF_UNROLL(MCF_SCAN_UNROLL)
         z2 = sub == 2 ? xadd(z2, x) : z2;
         z3 = sub == 3 ? xadd(z3, x) : z3;
     };
-#ifdef MCF_P2_COOP
     eval_parked(np < MCF_PARK_CAP ? np : (unsigned)MCF_PARK_CAP);
     while (N != 0 && k < MCF_PARK_CAP) {
         const unsigned j = (unsigned)ctz64(N);
@@ -940,7 +943,7 @@ MCF_UNROLL(MCF_SCAN_UNROLL)
         k++;
         if (!((S >> j) & 1ULL)) continue;  // consumed by an earlier attempt
         const unsigned fl = park.f[slot];
-        const unsigned len = (fl & MCF_PE_LEN2) ? 2u : 1u;
+        const unsigned len = (fl & MCF_PE_LEN0) ? 0u : ((fl & MCF_PE_LEN2) ? 2u : 1u);
         if (fl & MCF_PE_BAD) ok = false;  // longer tail: general re-walk
         if (fl & MCF_PE_ACC) {
             A |= 1ULL << j;
@@ -956,47 +959,6 @@ MCF_UNROLL(MCF_SCAN_UNROLL)
             if ((F >> f) & 1ULL) add_to_sub(f >> MCF_SUB_SHIFT, -bits_to_double(q == 1 ? park.b[slot] : park.c[slot]));
         }
     }
-#else
-    while (N != 0 && k < MCF_PARK_CAP) {
-        const unsigned j = (unsigned)ctz64(N);
-        N &= N - 1;
-        const uint64_t a = park.a[k * park.stride], u = park.b[k * park.stride], u2 = park.c[k * park.stride];
-        k++;
-        if (!((S >> j) & 1ULL)) continue;  // consumed by an earlier attempt
-        unsigned len;
-        bool acc;
-        double x;
-        if ((a & 0xffULL) != 0) {  // wedge: same arithmetic and decision as zig_feed, state 1
-            len = 1;
-            ZigFsm f;
-            zig_reset(f);
-            zig_feed(f, a, t, x);
-            acc = zig_feed(f, u, t, x);
-        } else {  // tail, first pair
-            len = 2;
-            const uint64_t rabs = (a >> 9) & 0x000fffffffffffffULL;
-            const double xx = xmul(-MCF_ZIG_INV_R, log1p(-u64_to_unit_double(u)));
-            const double yy = -log1p(-u64_to_unit_double(u2));
-            acc = xadd(yy, yy) > xmul(xx, xx);
-            const double m = xadd(MCF_ZIG_R, xx);
-            x = ((rabs >> 8) & 1ULL) ? -m : m;
-            if (!acc) ok = false;  // longer tail: general re-walk
-        }
-        if (acc) {
-            A |= 1ULL << j;
-            add_to_sub(j >> MCF_SUB_SHIFT, x);
-        }
-        for (unsigned q = 1; q <= len; q++) {
-            const unsigned f = j + q;
-            if (f >= MCF_CHUNK) {
-                exitv++;
-                continue;
-            }
-            S &= ~(1ULL << f);
-            if ((F >> f) & 1ULL) add_to_sub(f >> MCF_SUB_SHIFT, -zig_fast_value(q == 1 ? u : u2, t));
-        }
-    }
-#endif
     const unsigned e = entry_of(exitv);
     unsigned gen_entry = 0;
     if (e != 0) {

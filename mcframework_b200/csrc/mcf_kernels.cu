@@ -33,10 +33,8 @@ struct ScanShared {
     ZigKW kws[512];
     uint64_t park[3 * MCF_PARK_CAP * 256];
     uint64_t first[2 * 256];  // every thread's first two draws: the previous thread's look-ahead
-#ifdef MCF_P2_COOP
     uint8_t park_flags[MCF_PARK_CAP * 256];  // flags of the evaluated parked draws
     uint8_t items[MCF_PARK_CAP * 256];       // per warp: (lane << 2 | slot) of its parked draws, compacted
-#endif
 };
 
 __device__ __forceinline__ ZigTables load_zig_tables(ZigShared &sh) {
@@ -63,9 +61,7 @@ __device__ __forceinline__ ZigTables load_scan_tables(ScanShared &sh, ParkSlots 
     park.b = park.a + MCF_PARK_CAP * 256;
     park.c = park.b + MCF_PARK_CAP * 256;
     park.stride = 256;
-#ifdef MCF_P2_COOP
     park.f = sh.park_flags + threadIdx.x;
-#endif
     return t;
 }
 
@@ -88,6 +84,52 @@ __device__ __forceinline__ int stream_of(const mcf_stream *streams, int n_stream
 #ifndef MCF_SCAN_CTAS
 #define MCF_SCAN_CTAS 4         // resident CTAs per SM of the planning scan (64 registers per thread)
 #endif
+
+// Block-aligned Philox streams are replayed by kernels whose round keys are LAUNCH CONSTANTS (kernel parameters, i.e.
+// operands in the constant bank).  One launch takes a whole batch of streams: blockIdx.y (or a uniform loop index)
+// selects the stream, so its keys still reach the instructions as uniform-register operands, and a parallel run of any
+// width is a handful of launches instead of one per stream.  112 x (240 + 16) B stays below the 32 764-byte parameter limit.
+// Streams long enough to fill the GPU by themselves keep one launch each (NB = 1: the keys are direct constant-bank
+// operands; with an indexed batch the compiler re-loads part of them inside the hot loop, +3 % instructions).
+#define MCF_KEY_BATCH 112
+#define MCF_BATCH_BELOW_CTAS 2048  // streams with fewer CTAs of work than this are launched in batches
+template <int NB>
+struct PhiloxKeyBatch {
+    PhiloxKeys k[NB];
+};
+template <int NB>
+struct StreamSpanBatch {  // first replication and replication count of every stream of the batch
+    int64_t first_sim[NB];
+    int64_t n_sims[NB];
+};
+// `launch(tag, first_stream, count)` is called with tag.value == 1 (count == 1) or MCF_KEY_BATCH
+template <int NB>
+struct BatchTag {
+    static constexpr int value = NB;
+};
+template <class Launch>
+static void for_each_stream_batch(int64_t n_streams, bool batched, Launch launch) {
+    if (!batched) {
+        for (int64_t s = 0; s < n_streams; s++) launch(BatchTag<1>(), s, 1);
+        return;
+    }
+    for (int64_t s0 = 0; s0 < n_streams; s0 += MCF_KEY_BATCH)
+        launch(BatchTag<MCF_KEY_BATCH>(), s0, (int)(n_streams - s0 < MCF_KEY_BATCH ? n_streams - s0 : MCF_KEY_BATCH));
+}
+template <int NB>
+static void fill_batch(const mcf_stream *h_streams, int64_t s0, int cnt, PhiloxKeyBatch<NB> &KB, StreamSpanBatch<NB> *SB,
+                       int64_t *longest) {
+    int64_t big = 0;
+    for (int k = 0; k < cnt; k++) {
+        KB.k[k] = philox_keys_of(h_streams[s0 + k]);
+        if (SB) {
+            SB->first_sim[k] = h_streams[s0 + k].first_sim;
+            SB->n_sims[k] = h_streams[s0 + k].n_sims;
+        }
+        if (h_streams[s0 + k].n_sims > big) big = h_streams[s0 + k].n_sims;
+    }
+    if (longest) *longest = big;
+}
 
 // ===================================================================================== Pi
 template <int KIND>
@@ -126,10 +168,14 @@ __global__ void __launch_bounds__(256) pi_kernel(const mcf_stream *__restrict__ 
 
 // One launch per block-aligned Philox stream (round keys = launch constants), lanes on Philox block boundaries:
 // requires draws_per_sim % 4 == 0 (ppt is even by construction).
-__global__ void __launch_bounds__(256) pi_philox_stream_kernel(const __grid_constant__ PhiloxKeys K, int64_t first_sim,
-                                                               int64_t n_sims, int64_t m, int64_t draws_per_sim, int64_t ppt,
-                                                               int64_t parts, int weight, int extra_point,
-                                                               unsigned long long *__restrict__ hits) {
+template <int NB>
+__global__ void __launch_bounds__(256) pi_philox_stream_kernel(const __grid_constant__ PhiloxKeyBatch<NB> KB,
+                                                               const __grid_constant__ StreamSpanBatch<NB> SB, int64_t m,
+                                                               int64_t draws_per_sim, int64_t ppt, int64_t parts, int weight,
+                                                               int extra_point, unsigned long long *__restrict__ hits) {
+    const unsigned sb = NB == 1 ? 0u : blockIdx.y;
+    const PhiloxKeys &K = KB.k[sb];
+    const int64_t first_sim = SB.first_sim[sb], n_sims = SB.n_sims[sb];
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -213,9 +259,7 @@ __global__ void __launch_bounds__(256, 3) plan_scan_kernel(const mcf_stream *__r
                 a = pc.v0;
                 b = pc.v1;
             }
-#ifdef MCF_P2_COOP
             , [&](unsigned n_parked) { eval_parked_local(park, n_parked, t); }  // warps may be partial here
-#endif
             );
         startmask[id] = ci.startmask;
         emitmask[id] = ci.emitmask;
@@ -238,7 +282,8 @@ __global__ void __launch_bounds__(256, 3) plan_scan_kernel(const mcf_stream *__r
 
 // One launch per stream: the stream's ten Philox round keys and base counter are kernel parameters, i.e. operands
 // in the constant bank -- the key schedule costs no instruction and no register.
-__global__ void __launch_bounds__(256, MCF_SCAN_CTAS) plan_scan_philox_stream_kernel(const __grid_constant__ PhiloxKeys K, int64_t row0,
+template <int NB>
+__global__ void __launch_bounds__(256, MCF_SCAN_CTAS) plan_scan_philox_stream_kernel(const __grid_constant__ PhiloxKeyBatch<NB> KB, int64_t stream0,
                                                                          int64_t cps, uint64_t *__restrict__ startmask,
                                                                          uint64_t *__restrict__ emitmask,
                                                                          uint8_t *__restrict__ exit_,
@@ -247,13 +292,27 @@ __global__ void __launch_bounds__(256, MCF_SCAN_CTAS) plan_scan_philox_stream_ke
     __shared__ ScanShared sh;
     ParkSlots park;
     const ZigTables t = load_scan_tables(sh, park);
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // cps is a multiple of 1024: whole warps are live
+    const unsigned sb = NB == 1 ? 0u : blockIdx.y;
+    const PhiloxKeys &K = KB.k[sb];
+#ifdef MCF_SCAN_PERSIST
+    // A/B candidate: resident CTAs walk the stream's 256-chunk tiles with a grid stride, so the tables are set up once
+    for (int64_t tile = blockIdx.x; tile < cps / 256; tile += gridDim.x) {
+    const int64_t c = tile * 256 + threadIdx.x;
+#else
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // cps is a multiple of 1024: whole CTAs are live
     if (c >= cps) return;
-    const int64_t id = row0 + c;
+#endif
+    const int64_t id = (stream0 + sb) * cps + c;
     bool valid;
     const uint64_t blk0 = (K.off + (uint64_t)c * MCF_CHUNK) >> 2;
+    // the walk asks for consecutive blocks: round 0's product M0 * (b0 + blk) is carried along (+ M0 per block)
+    uint64_t r0hi, r0lo;
+    mul64_full<true>(MCF_PHILOX_M0, K.b0 + blk0, r0hi, r0lo);
     const ChunkInfo ci = scan_chunk_fast2(
-        [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &cc, uint64_t &d) { philox_block_folded<true>(K, blk, a, b, cc, d); },
+        [&](uint64_t, uint64_t &a, uint64_t &b, uint64_t &cc, uint64_t &d) {
+            philox_block_folded_r0<true>(K, r0hi, r0lo, a, b, cc, d);
+            philox_r0_next(r0hi, r0lo);
+        },
         blk0, t, park, zsum + id * MCF_SUBS, &valid,
         [&](unsigned exit_spec) {
             // the previous chunk of the stream is the neighbouring lane's; lane 0 cannot know it (entry 0, fixed up later)
@@ -274,7 +333,6 @@ __global__ void __launch_bounds__(256, MCF_SCAN_CTAS) plan_scan_philox_stream_ke
                 b = sh.first[256 + threadIdx.x + 1];
             }
         }
-#ifdef MCF_P2_COOP
         // Warp-cooperative evaluation of the parked draws (whole warps are live here): an exclusive prefix of the lanes'
         // counts compacts (lane, slot) pairs into the warp's item list; item i is evaluated by lane i mod 32 from the
         // owner's shared-memory slot and written back in place.
@@ -302,12 +360,15 @@ __global__ void __launch_bounds__(256, MCF_SCAN_CTAS) plan_scan_philox_stream_ke
             }
             __syncwarp();
         }
-#endif
         );
     startmask[id] = ci.startmask;
     emitmask[id] = ci.emitmask;
     exit_[id] = (uint8_t)ci.exit;
     gen[id] = valid ? (uint8_t)ci.gen_entry : (uint8_t)MCF_GEN_ENTRY_INVALID;
+#ifdef MCF_SCAN_PERSIST
+    __syncthreads();  // the first-draw exchange and the parking slots are reused by the next tile
+    }
+#endif
 }
 
 // Fix chunk entries: a chunk's true entry offset is its predecessor's exit.  Two kernels per iteration so that the
@@ -640,13 +701,18 @@ __global__ void __launch_bounds__(256, 3) gbm_terminal_kernel(const mcf_stream *
 // Affine bodies on block-aligned Philox streams, one launch per stream (round keys and base counter in the constant
 // bank, rounds 0/1 folded): every thread regenerates only the shorter side of the boundary at the END of its
 // replication (at most two Philox blocks) and takes the other side of the boundary at its START from its neighbour.
+template <int NB>
 __global__ void __launch_bounds__(256, 4)
-    gbm_terminal_affine_stream_kernel(const __grid_constant__ PhiloxKeys K, const mcf_stream *__restrict__ streams, int64_t si,
-                                      int64_t first_sim, int64_t n_sims, int64_t n_total,
+    gbm_terminal_affine_stream_kernel(const __grid_constant__ PhiloxKeyBatch<NB> KB, const __grid_constant__ StreamSpanBatch<NB> SB,
+                                      const mcf_stream *__restrict__ streams, int64_t stream0, int64_t n_total,
                                       const uint64_t *__restrict__ sim_start, const char *__restrict__ plan_ws,
                                       const __grid_constant__ SpecPack specs, double n_steps_f, double *__restrict__ out) {
     __shared__ WiShared sh;
     __shared__ double sh_after[8];
+    const unsigned sb = NB == 1 ? 0u : blockIdx.y;
+    const PhiloxKeys &K = KB.k[sb];
+    const int64_t si = stream0 + sb, first_sim = SB.first_sim[sb], n_sims = SB.n_sims[sb];
+    if ((int64_t)blockIdx.x * blockDim.x >= n_sims) return;  // the grid is sized for the longest stream of the batch
     const double *wi = load_wi_table(sh);
     const uint64_t ki0 = g_zig_ki[0];
     const PlanLayout *lay = reinterpret_cast<const PlanLayout *>(plan_ws + MCF_LAYOUT_OFFSET);
@@ -813,27 +879,35 @@ static int normal_plan_impl(const mcf_stream *d_streams, const mcf_stream *h_str
     constexpr int RUN = KIND == MCF_GEN_PCG64 ? 8 : 1;  // PCG64 pays an O(log n) jump per thread
     const int64_t n_runs = g.n_chunks / RUN;
     const int64_t n_streams = g.n_chunks / g.cps;
-    bool per_stream = KIND == MCF_GEN_PHILOX && h_streams != nullptr && n_streams <= 1024;
+    bool per_stream = KIND == MCF_GEN_PHILOX && h_streams != nullptr;
     for (int64_t si = 0; per_stream && si < n_streams; si++)
         per_stream = (h_streams[si].buf_pos & 3u) == 0 && h_streams[si].s[2] < (1ULL << 62);  // aligned, foldable counter
     if (per_stream) {
-#ifdef MCF_SCAN_TWO_STREAMS
-        // Candidate for the next round (off by default, not measured): odd streams are scanned on a side stream, so the
-        // tail of one launch (the last partial wave of its 41.8) overlaps the head of the next one.
+        // Streams that get a launch of their own alternate between the caller's stream and a side stream, so that the tail
+        // of one launch (the last partial wave of its ~42) overlaps the head of the next (-0.8 % per plan of 1e8 x 252).
+        const bool batched = g.cps / 256 < MCF_BATCH_BELOW_CTAS;
         cudaStream_t side = nullptr;
         cudaEvent_t fork = nullptr, join = nullptr;
-        const bool two = n_streams > 1 && cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) == cudaSuccess &&
+        const bool two = !batched && n_streams > 1 && cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) == cudaSuccess &&
                          cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
                          cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess;
         if (two) {
             cudaEventRecord(fork, cs);  // plan_init_kernel precedes every scan
             cudaStreamWaitEvent(side, fork, 0);
         }
-        for (int64_t si = 0; si < n_streams; si++) {
-            const PhiloxKeys K = philox_keys_of(h_streams[si]);
-            plan_scan_philox_stream_kernel<<<grid_for(g.cps, 256), 256, 0, (two && (si & 1)) ? side : cs>>>(
-                K, si * g.cps, g.cps, sm, em, ex, gen, zs);
-        }
+        int nb = 0;
+        for_each_stream_batch(n_streams, batched, [&](auto tag, int64_t s0, int cnt) {
+            constexpr int NB = decltype(tag)::value;
+            PhiloxKeyBatch<NB> KB;  // host staging of the parameter block (the launch copies it)
+            fill_batch<NB>(h_streams, s0, cnt, KB, nullptr, nullptr);
+#ifdef MCF_SCAN_PERSIST
+            const unsigned gx = NB == 1 ? (unsigned)(g.cps / 256 < 148 * MCF_SCAN_CTAS ? g.cps / 256 : 148 * MCF_SCAN_CTAS) : grid_for(g.cps, 256);
+#else
+            const unsigned gx = grid_for(g.cps, 256);
+#endif
+            plan_scan_philox_stream_kernel<NB><<<dim3(gx, cnt), 256, 0, (two && (nb++ & 1)) ? side : cs>>>(
+                KB, s0, g.cps, sm, em, ex, gen, zs);
+        });
         if (two) {
             cudaEventRecord(join, side);
             cudaStreamWaitEvent(cs, join, 0);
@@ -841,12 +915,6 @@ static int normal_plan_impl(const mcf_stream *d_streams, const mcf_stream *h_str
         if (fork) cudaEventDestroy(fork);
         if (join) cudaEventDestroy(join);
         if (side) cudaStreamDestroy(side);  // deferred by the runtime until its work has drained
-#else
-        for (int64_t si = 0; si < n_streams; si++) {
-            const PhiloxKeys K = philox_keys_of(h_streams[si]);
-            plan_scan_philox_stream_kernel<<<grid_for(g.cps, 256), 256, 0, cs>>>(K, si * g.cps, g.cps, sm, em, ex, gen, zs);
-        }
-#endif
     } else {
         plan_scan_kernel<KIND, RUN><<<grid_for(n_runs, 256), 256, 0, cs>>>(d_streams, g.cps, n_runs, sm, em, ex, gen, zs,
                                                                           hdr);
@@ -900,19 +968,24 @@ int mcf_pi_hits(uint32_t gen_kind, const mcf_stream *d_streams, const mcf_stream
     int64_t blocks = (n_units + 7) / 8;  // 8 warps per CTA
     const int64_t max_blocks = 148LL * 8 * 64;
     if (blocks > max_blocks) blocks = max_blocks;
-    bool per_stream = gen_kind == MCF_GEN_PHILOX && h_streams != nullptr && n_streams <= 1024 && (pg.draws_per_sim % 4) == 0;
+    bool per_stream = gen_kind == MCF_GEN_PHILOX && h_streams != nullptr && (pg.draws_per_sim % 4) == 0;
     for (int si = 0; per_stream && si < n_streams; si++)
         per_stream = (h_streams[si].buf_pos & 3u) == 0 && h_streams[si].s[2] < (1ULL << 62);  // aligned, foldable counter
     if (per_stream) {
-        for (int si = 0; si < n_streams; si++) {
-            const PhiloxKeys K = philox_keys_of(h_streams[si]);
-            int64_t b = (h_streams[si].n_sims * pg.parts + 7) / 8;
-            if (b > max_blocks) b = max_blocks;
-            if (b < 1) continue;
-            pi_philox_stream_kernel<<<(unsigned)b, 256, 0, cs>>>(K, h_streams[si].first_sim, h_streams[si].n_sims, pg.m,
-                                                                 pg.draws_per_sim, pg.ppt, pg.parts, pg.weight, pg.extra,
-                                                                 (unsigned long long *)d_hits);
-        }
+        int64_t biggest = 0;
+        for (int si = 0; si < n_streams; si++) biggest = h_streams[si].n_sims > biggest ? h_streams[si].n_sims : biggest;
+        for_each_stream_batch(n_streams, (biggest * pg.parts + 7) / 8 < MCF_BATCH_BELOW_CTAS, [&](auto tag, int64_t s0, int cnt) {
+            constexpr int NB = decltype(tag)::value;
+            PhiloxKeyBatch<NB> KB;
+            StreamSpanBatch<NB> SB;
+            int64_t longest = 0;
+            fill_batch<NB>(h_streams, s0, cnt, KB, &SB, &longest);
+            int64_t b = (longest * pg.parts + 7) / 8;
+            if (b > max_blocks / cnt + 1) b = max_blocks / cnt + 1;  // grid-stride over the (replication, slice) units
+            if (b < 1) return;
+            pi_philox_stream_kernel<NB><<<dim3((unsigned)b, cnt), 256, 0, cs>>>(KB, SB, pg.m, pg.draws_per_sim, pg.ppt, pg.parts,
+                                                                                pg.weight, pg.extra, (unsigned long long *)d_hits);
+        });
     } else if (gen_kind == MCF_GEN_PCG64)
         pi_kernel<MCF_GEN_PCG64><<<(unsigned)blocks, 256, 0, cs>>>(
             d_streams, n_streams, n_total, pg.m, pg.draws_per_sim, pg.ppt, pg.parts, pg.weight, pg.extra,
@@ -990,18 +1063,22 @@ int mcf_gbm_terminal(uint32_t gen_kind, const mcf_stream *d_streams, const mcf_s
     }
     cudaStream_t cs = (cudaStream_t)cuda_stream;
     // affine bodies of at least one sub-chunk per replication on aligned, foldable Philox streams: boundary form
-    bool per_stream = gen_kind == MCF_GEN_PHILOX && pack.affine && n_steps >= (1 << MCF_SUB_SHIFT) && h_streams != nullptr &&
-                      n_streams <= 1024;
+    bool per_stream = gen_kind == MCF_GEN_PHILOX && pack.affine && n_steps >= (1 << MCF_SUB_SHIFT) && h_streams != nullptr;
     for (int si = 0; per_stream && si < n_streams; si++)
         per_stream = (h_streams[si].buf_pos & 3u) == 0 && h_streams[si].s[2] < (1ULL << 62);
     if (per_stream) {
-        for (int si = 0; si < n_streams; si++) {
-            if (h_streams[si].n_sims <= 0) continue;
-            const PhiloxKeys K = philox_keys_of(h_streams[si]);
-            gbm_terminal_affine_stream_kernel<<<grid_for(h_streams[si].n_sims, 256), 256, 0, cs>>>(
-                K, d_streams, si, h_streams[si].first_sim, h_streams[si].n_sims, n_total, d_sim_start,
-                (const char *)d_plan_workspace, pack, (double)n_steps, d_out);
-        }
+        int64_t biggest = 0;
+        for (int si = 0; si < n_streams; si++) biggest = h_streams[si].n_sims > biggest ? h_streams[si].n_sims : biggest;
+        for_each_stream_batch(n_streams, grid_for(biggest, 256) < MCF_BATCH_BELOW_CTAS, [&](auto tag, int64_t s0, int cnt) {
+            constexpr int NB = decltype(tag)::value;
+            PhiloxKeyBatch<NB> KB;
+            StreamSpanBatch<NB> SB;
+            int64_t longest = 0;
+            fill_batch<NB>(h_streams, s0, cnt, KB, &SB, &longest);
+            if (longest <= 0) return;
+            gbm_terminal_affine_stream_kernel<NB><<<dim3(grid_for(longest, 256), cnt), 256, 0, cs>>>(
+                KB, SB, d_streams, s0, n_total, d_sim_start, (const char *)d_plan_workspace, pack, (double)n_steps, d_out);
+        });
         MCF_CUDA_OK(cudaGetLastError());
         return MCF_OK;
     }
@@ -1029,7 +1106,8 @@ int mcf_gbm_paths(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_stre
     s.mode = MCF_PATH_TERMINAL;
     for (int k = 0; k < 4; k++) s.p[k] = h_p4[k];
     GbmDerived g;
-    derive_spec(s, n_steps, &g);
+    const int rc = derive_spec(s, n_steps, &g);
+    if (rc) return rc;
     cudaStream_t cs = (cudaStream_t)cuda_stream;
     if (gen_kind == MCF_GEN_PCG64)
         gbm_paths_kernel<MCF_GEN_PCG64><<<grid_for(n_total, 256), 256, 0, cs>>>(

@@ -135,13 +135,19 @@ class BlackScholesSimulation(MonteCarloSimulation):
                 lay = lay.shard(dist.get_rank(group), dist.get_world_size(group))
         else:
             lay = S.sequential_layout(self.rng, n_simulations)
-        dl = D.DeviceLayout.of(lay)
-        plan = D.normal_plan(dl, int(n_steps))
-        if exercise_type == "european":
-            values = D.gbm_terminal(dl, int(n_steps), plan, [(mode, p) for p in sets])
-            means = [SD.moments(values[k], group=group).mean for k in range(len(sets))]
-        else:  # path-dependent payoff: one replay per parameter set, same plan
-            means = [SD.moments(D.gbm_terminal(dl, int(n_steps), plan, [(mode, p)])[0], group=group).mean for p in sets]
+        if lay.n_total == 0:  # more ranks than blocks: nothing to replay here, but the moment collectives still run
+            import torch
+
+            empty = torch.empty(0, dtype=torch.float64, device="cuda")
+            means = [SD.moments(empty, group=group).mean for _ in sets]
+        else:
+            dl = D.DeviceLayout.of(lay)
+            plan = D.normal_plan(dl, int(n_steps))
+            if exercise_type == "european":
+                values = D.gbm_terminal(dl, int(n_steps), plan, [(mode, p) for p in sets])
+                means = [SD.moments(values[k], group=group).mean for k in range(len(sets))]
+            else:  # path-dependent payoff: one replay per parameter set, same plan
+                means = [SD.moments(D.gbm_terminal(dl, int(n_steps), plan, [(mode, p)])[0], group=group).mean for p in sets]
         v0, v_up, v_dn, v_sig_up, v_sig_dn, v_r_up, v_r_dn = means[:7]
         greeks = {
             "price": float(v0),

@@ -127,12 +127,19 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
             park.b = slots + MCF_PARK_CAP;
             park.c = slots + 2 * MCF_PARK_CAP;
             park.stride = 1;
-#ifdef MCF_P2_COOP
             uint8_t slot_flags[MCF_PARK_CAP];
             park.f = slot_flags;
-#endif
+            uint64_t r0hi, r0lo, next_blk = blk0;
+            mul64_full(MCF_PHILOX_M0, K.b0 + blk0, r0hi, r0lo);
             ChunkInfo ci = scan_chunk_fast2(
                 [&](uint64_t blk, uint64_t &a, uint64_t &b, uint64_t &cc, uint64_t &d) {
+                    if (K.fold_ok) {  // as the device kernel: consecutive blocks, running round-0 product
+                        if (blk != next_blk) status = -1001;  // harness-only: the walk must ask for consecutive blocks
+                        next_blk++;
+                        philox_block_folded_r0(K, r0hi, r0lo, a, b, cc, d);
+                        philox_r0_next(r0hi, r0lo);
+                        return;
+                    }
                     if (K.fold_ok)
                         philox_block_folded(K, blk, a, b, cc, d);
                     else
@@ -152,9 +159,7 @@ static int plan_impl(const mcf_stream *streams, int n_streams, int64_t max_sims,
                     else
                         philox_block_keys(K, blk0 + 16, a, b, c2, d2);
                 }
-#ifdef MCF_P2_COOP
                 , [&](unsigned n_parked) { eval_parked_local(park, n_parked, t); }
-#endif
                 );
             if (valid) {  // the speculative walk must agree with the general one from the same entry
                 double zref[MCF_SUBS];

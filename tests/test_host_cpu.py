@@ -350,16 +350,3 @@ def test_hostemu_folded_philox_blocks_equal_numpy_raw_draws(emu):
         bg.state = g.bit_generator.state
         bg.advance((1 << 40) - 64)  # the generator above already consumed 64 blocks
         assert rc == 0 and np.array_equal(got, bg.random_raw(32))
-
-
-@pytest.mark.parametrize("flags", ["-DMCF_P2_COOP", "-DMCF_SCAN_DENORM", "-DMCF_P2_COOP -DMCF_SCAN_DENORM -DMCF_SCAN_NMASK"])
-def test_scan_candidates_stay_bit_exact_on_the_host(flags):
-    """The not-yet-measured code-generation candidates of the planning scan must keep passing the
-    host-emulation checks (positions, decisions and sums against the oracle; fast walk == general walk)."""
-    import subprocess
-    import sys
-
-    env = dict(os.environ, MCF_HOSTEMU_FLAGS=flags)
-    run = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-p", "no:cacheprovider", "-k",
-                          "hostemu and not candidates"], env=env, capture_output=True, text=True, timeout=900)
-    assert run.returncode == 0 and " passed" in run.stdout, run.stdout[-2000:]

@@ -53,6 +53,38 @@ def jsonable(o):
     return o
 
 
+def lsm_large(provenance, n_paths=1_000_000, n_steps=252):
+    """G9: Longstaff-Schwartz at 1e6 paths x 252 steps on the UNMODIFIED reference (black_scholes.py:109-193, 403-418):
+    ``simulate_paths(1_000_000)`` with seed 1, American put K=100.  The reference returns the price only; the exercise-step
+    histogram comes from the oracle port run on the SAME matrix, after its price has been checked to equal the
+    reference's bit for bit (which also pins the port at this size).  -> tests/golden/reference_lsm_1e6.json"""
+    import time
+
+    sys.path.insert(0, ROOT)
+    from oracle import np_port
+
+    ps = ref.BlackScholesPathSimulation()
+    ps.set_seed(1)
+    t0 = time.perf_counter()
+    paths = ps.simulate_paths(n_paths, n_steps=n_steps)
+    t_paths = time.perf_counter() - t0
+    out = {"provenance": provenance, "n_paths": n_paths, "n_steps": n_steps, "seed": 1, "K": 100.0, "r": 0.05,
+           "paths_checksum": float(paths.sum()), "paths_last": float(paths[-1, -1]), "paths_col_means": {
+               str(t): float(paths[:, t].mean()) for t in (1, 63, 126, 252)}}
+    for opt in ("put", "call"):
+        t0 = time.perf_counter()
+        price = _american_exercise_lsm(paths, 100.0, 0.05, 1.0 / n_steps, opt)
+        t_lsm = time.perf_counter() - t0
+        port_price, ex = np_port.lsm_price(paths, 100.0, 0.05, 1.0 / n_steps, opt)
+        assert port_price == price, (opt, port_price, price)  # bit for bit on the same matrix
+        out["lsm_" + opt] = {"price": float(price), "exercise_step_histogram": np.bincount(ex, minlength=n_steps + 1).tolist(),
+                             "reference_seconds": t_lsm}
+    out["reference_simulate_paths_seconds"] = t_paths
+    with open(os.path.join(ROOT, "tests", "golden", "reference_lsm_1e6.json"), "w") as f:
+        json.dump(jsonable(out), f, indent=1, sort_keys=True)
+    print("wrote tests/golden/reference_lsm_1e6.json:", {k: v["price"] for k, v in out.items() if k.startswith("lsm_")})
+
+
 def main():
     J, A = {}, {}
     J["provenance"] = {
@@ -173,6 +205,10 @@ def main():
         "bca_rng321_B200": eng.compute(six, StatsContext(n=6, rng=321, n_bootstrap=200, bootstrap="bca"),
                                        select=["ci_mean_bootstrap"]).metrics,
     }
+
+    if "--lsm-large" in sys.argv:
+        lsm_large(J["provenance"])
+        return
 
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     with open(os.path.join(ROOT, "tests", "golden", "reference_golden.json"), "w") as f:
