@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MCF_ABI_VERSION 2
+#define MCF_ABI_VERSION 3
 
 enum {
     MCF_OK = 0,
@@ -156,9 +156,11 @@ int mcf_gbm_slices(uint32_t gen_kind, const mcf_stream *d_streams, int32_t n_str
 int mcf_normal_relocate(const mcf_stream *d_streams_new, int32_t n_streams, int64_t max_sims_per_stream,
                         int64_t normals_per_sim, double slack, int64_t new_normals_per_sim, void *d_workspace,
                         uint64_t *d_sim_start_new, void *cuda_stream);
+/* out_f32 != 0: d_out is float (accumulation and exp stay in fp64, only the store narrows) -- half the HBM bytes.
+ * Time-major output with n_total % 2 == 0 (fp64) / % 4 == 0 (fp32) is written with one 128-bit store per lane. */
 int mcf_gbm_slices_from_sums(const double *d_segment_sums, int64_t n_total, int64_t n_segments, int64_t segment_steps,
-                             int64_t n_steps, const mcf_gbm_spec *h_spec, int32_t time_major, double *d_out,
-                             void *cuda_stream);
+                             int64_t n_steps, const mcf_gbm_spec *h_spec, int32_t time_major, int32_t out_f32,
+                             void *d_out, void *cuda_stream);
 
 /* ---- (2b) declared integer draw programs ------------------------------------------------
  * A user simulation whose hook is `rng.integers(low, high, size=k)` followed by a reduction (the reference's dice

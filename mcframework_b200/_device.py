@@ -81,6 +81,11 @@ class NormalPlan:
     normals_per_sim: int
     workspace: "object" = None  # torch uint8: emit masks etc. -- the replay kernels read it
     slack: float = 0.03  # window slack the workspace geometry was computed with (mcf_normal_relocate needs it)
+    resolve_iters: int = 3
+
+    def status(self) -> int:
+        """Status of the planning pass (synchronises the stream: reads the workspace header back)."""
+        return int(N.lib().mcf_workspace_status(_ptr(self.workspace), _stream_ptr()))
 
 
 #: NumPy's ziggurat consumes 1.02201 64-bit draws per normal on average (measured over 2e8 normals; variance of the
@@ -93,9 +98,36 @@ def default_slack(normals_per_stream: int) -> float:
     return (ZIG_DRAWS_PER_NORMAL - 1.0) + 0.0004 + 8.0 * (0.04 / need) ** 0.5
 
 
+def with_plan(dl: DeviceLayout, normals_per_sim: int, body, max_retries: int = 4):
+    """``plan = normal_plan(...); out = body(plan)`` with ONE host round trip: the planning kernels and whatever ``body``
+    launches are queued back to back, and the plan's status is read afterwards (a replay on a failed plan returns at once
+    on the device).  A failed plan is re-planned with a wider window / more fix-up rounds and ``body`` runs again.
+    Returns ``(plan, out)``."""
+    slack, resolve_iters, status = None, 3, N.OK
+    for _ in range(max_retries):
+        plan = normal_plan(dl, normals_per_sim, slack, resolve_iters, check=False)
+        out = body(plan)
+        status = plan.status()
+        if status == N.OK:
+            return plan, out
+        slack, resolve_iters = _replan_parameters(status, plan.slack, plan.resolve_iters)
+        del plan, out
+    raise N.NativeError("mcf_normal_plan", status, "planning did not succeed after retries")
+
+
+def _replan_parameters(status: int, slack: float, resolve_iters: int):
+    if status == N.ERR_WINDOW_TOO_SMALL:
+        return slack * 2 + 0.02, resolve_iters
+    if status == N.ERR_NOT_CONVERGED:
+        return slack, min(resolve_iters + 3, 12)
+    N.check("mcf_workspace_status", status)
+    return slack, resolve_iters
+
+
 def normal_plan(dl: DeviceLayout, normals_per_sim: int, slack: float | None = None, resolve_iters: int = 3,
-                max_retries: int = 4) -> NormalPlan:
-    """Planning pass for ziggurat-consuming replications ("stream-exact planning")."""
+                max_retries: int = 4, check: bool = True) -> NormalPlan:
+    """Planning pass for ziggurat-consuming replications ("stream-exact planning").
+    ``check=False``: one attempt, no host synchronisation -- the caller reads ``plan.status()`` later (``with_plan``)."""
     torch = _torch()
     lay = dl.layout
     lib = N.lib()
@@ -115,16 +147,14 @@ def normal_plan(dl: DeviceLayout, normals_per_sim: int, slack: float | None = No
                                  _ptr(sim_start), _ptr(stream_end), _stream_ptr())
         N.check("mcf_normal_plan", rc)
         LAUNCHES["plan"] += 4 + 2 * resolve_iters + _batches(lay)
-        status = lib.mcf_workspace_status(_ptr(ws), _stream_ptr())
+        plan = NormalPlan(sim_start, stream_end, int(normals_per_sim), ws, float(slack), int(resolve_iters))
+        if not check:
+            return plan
+        status = plan.status()
         if status == N.OK:
-            return NormalPlan(sim_start, stream_end, int(normals_per_sim), ws, float(slack))
-        del ws
-        if status == N.ERR_WINDOW_TOO_SMALL:
-            slack = slack * 2 + 0.02
-        elif status == N.ERR_NOT_CONVERGED:
-            resolve_iters = min(resolve_iters + 3, 12)
-        else:
-            N.check("mcf_workspace_status", status)
+            return plan
+        del ws, plan
+        slack, resolve_iters = _replan_parameters(status, slack, resolve_iters)
     raise N.NativeError("mcf_normal_plan", status, "planning did not succeed after retries")
 
 
@@ -182,19 +212,34 @@ def gbm_paths(dl: DeviceLayout, n_steps: int, plan: NormalPlan, S0: float, r: fl
 
 
 def gbm_slices(dl: DeviceLayout, n_steps: int, plan: NormalPlan, mode: int, params, slice_stride: int,
-               time_major: bool = True):
-    """Path values at steps 0, stride, 2*stride, ...: float64 (n_slices, n) when time_major else (n, n_slices)."""
+               time_major: bool = True, dtype=None, timings: dict | None = None):
+    """Path values at steps 0, stride, 2*stride, ...: (n_slices, n) when time_major else (n, n_slices);
+    float64, or float32 with ``dtype=torch.float32`` (segment form only: the values are computed in fp64 and narrowed
+    by the store).  ``timings``: optional dict that receives CUDA events around the three stages of the segment form."""
     torch = _torch()
     lay = dl.layout
+    dtype = dtype or torch.float64
+    if dtype not in (torch.float64, torch.float32):
+        raise ValueError("slices are stored as float64 or float32")
     n_slices = int(n_steps) // int(slice_stride) + 1
     shape = (n_slices, lay.n_total) if time_major else (lay.n_total, n_slices)
-    out = torch.empty(shape, dtype=torch.float64, device="cuda")
     k = int(n_steps) // int(slice_stride)
-    if (lay.kind == 1 and int(slice_stride) >= 16 and k * int(slice_stride) == int(n_steps)
-            and k > 1 and int(mode) in (N.PORTFOLIO_GBM, N.PATH_TERMINAL) and bool((lay.records["buf_pos"] % 4 == 0).all())):
+    segment_form = (lay.kind == 1 and int(slice_stride) >= 16 and k * int(slice_stride) == int(n_steps)
+                    and k > 1 and int(mode) in (N.PORTFOLIO_GBM, N.PATH_TERMINAL)
+                    and bool((lay.records["buf_pos"] % 4 == 0).all()))
+    out = torch.empty(shape, dtype=dtype if segment_form else torch.float64, device="cuda")
+
+    def mark(name):
+        if timings is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            timings[name] = e
+
+    if segment_form:
         # Segment form: every path is cut into k pseudo-replications of `stride` steps.  Re-locating the finished plan
         # gives their stream positions, the boundary-form replay their normal sums (two Philox blocks per segment
         # instead of stride/4), and one accumulation pass the slice values.
+        mark("start")
         recs = lay.records.copy()
         recs["first_sim"] *= k
         recs["n_sims"] *= k
@@ -205,17 +250,21 @@ def gbm_slices(dl: DeviceLayout, n_steps: int, plan: NormalPlan, mode: int, para
                                          float(plan.slack), int(slice_stride), _ptr(plan.workspace), _ptr(starts), _stream_ptr())
         N.check("mcf_normal_relocate", rc)
         LAUNCHES["plan"] += 1
+        mark("relocated")
         plan2 = NormalPlan(starts, plan.stream_end, int(slice_stride), plan.workspace, plan.slack)
         seg = gbm_terminal(dl2, int(slice_stride), plan2, [(N.NORMAL_SUM, [])])[0]
         del starts, plan2
+        mark("segment_sums")
         rc = N.lib().mcf_gbm_slices_from_sums(_ptr(seg), lay.n_total, k, int(slice_stride), int(n_steps),
-                                              _spec_array([(mode, params)]), int(bool(time_major)), _ptr(out), _stream_ptr())
+                                              _spec_array([(mode, params)]), int(bool(time_major)),
+                                              int(dtype == torch.float32), _ptr(out), _stream_ptr())
         N.check("mcf_gbm_slices_from_sums", rc)
         LAUNCHES["paths"] += 1
+        mark("stored")
         return out
     rc = N.lib().mcf_gbm_slices(lay.kind, _ptr(dl.records), lay.n_streams, lay.n_total, int(n_steps), lay.hint,
                                 _ptr(plan.sim_start), _ptr(plan.workspace), _spec_array([(mode, params)]), int(slice_stride),
                                 int(bool(time_major)), _ptr(out), _stream_ptr())
     N.check("mcf_gbm_slices", rc)
     LAUNCHES["paths"] += 1
-    return out
+    return out if dtype == torch.float64 else out.to(dtype)

@@ -166,6 +166,64 @@ def _pool() -> SharedResultPool:
     return _POOL
 
 
+_ONE_HOST: dict = {}
+
+
+def _require_one_host(group) -> None:
+    """POSIX shared memory only reaches the ranks of ONE host: checked once per group, and EVERY rank raises when the
+    group spans hosts (a rank that failed alone in ``shm_open`` would leave the others waiting at the barrier)."""
+    import socket
+
+    import torch.distributed as dist
+
+    key = id(group)
+    if key not in _ONE_HOST:
+        names = [None] * dist.get_world_size(group)
+        dist.all_gather_object(names, socket.gethostname(), group=group)
+        _ONE_HOST[key] = len(set(names)) == 1
+    if not _ONE_HOST[key]:
+        raise RuntimeError('gather_mode="shm" needs every rank of the group on one host; use "root" or "all"')
+
+
+def shared_result_buffer(sizes, group):
+    """One float64 result buffer of ``sum(sizes)`` elements in POSIX shared memory, mapped and page-locked by every rank
+    of the (single-host) group.  Returns ``(whole ndarray, this rank's slice as a torch tensor, segment)``; rank 0 owns the
+    segment -- it goes back to the pool when rank 0's ndarray is garbage collected (``finish_shared_result``)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    _require_one_host(group)
+    total, offset = sum(sizes), sum(sizes[:rank])
+    pool = _pool()
+    seg = pool.acquire(total * 8) if rank == 0 else None
+    box = [(seg.shm.name, seg.nbytes) if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    if rank != 0:
+        seg = pool.attach(*box[0])
+    pool.page_lock(seg)
+    whole = np.ndarray((total,), dtype=np.float64, buffer=seg.shm.buf)
+    mine = torch.from_numpy(whole[offset:offset + sizes[rank]])
+    return whole, mine, seg
+
+
+def finish_shared_result(whole, seg, sizes, group):
+    """Barrier (every shard has landed), then rank 0 gets the whole vector and the other ranks a view of their own shard
+    (valid until rank 0 drops the result and the segment is reused by a later run)."""
+    import weakref
+
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    dist.barrier(group=group)
+    if rank != 0:
+        offset = sum(sizes[:rank])
+        return whole[offset:offset + sizes[rank]]
+    weakref.finalize(whole, _pool().release, seg)  # the segment is reusable once the caller has dropped the result
+    return whole
+
+
 def gather_results_shared(local, group):
     """Rank 0 returns the concatenation (rank order) as a host float64 ndarray backed by shared memory; the other ranks
     return ``None``.  Every rank copies only its own shard, straight from its device into the shared buffer."""
@@ -176,6 +234,7 @@ def gather_results_shared(local, group):
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    _require_one_host(group)
     n_local = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
     sizes = [torch.zeros_like(n_local) for _ in range(world)]
     dist.all_gather(sizes, n_local, group=group)

@@ -52,7 +52,7 @@ SIGNATURES = {
     "mcf_normal_plan": (C.c_int, [_u32, _vp, _vp, _i32, _i64, _i64, _i64, _f64, _i32, _vp, _i64, _vp, _vp, _vp]),
     "mcf_workspace_status": (C.c_int, [_vp, _vp]),
     "mcf_normal_relocate": (C.c_int, [_vp, _i32, _i64, _i64, _f64, _i64, _vp, _vp, _vp]),
-    "mcf_gbm_slices_from_sums": (C.c_int, [_vp, _i64, _i64, _i64, _i64, C.POINTER(GbmSpec), _i32, _vp, _vp]),
+    "mcf_gbm_slices_from_sums": (C.c_int, [_vp, _i64, _i64, _i64, _i64, C.POINTER(GbmSpec), _i32, _i32, _vp, _vp]),
     "mcf_draw_integers": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _i64, _vp, _vp, _vp]),
     "mcf_gbm_terminal": (C.c_int, [_u32, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, C.POINTER(GbmSpec), _i32, _vp, _vp]),
     "mcf_gbm_paths": (C.c_int, [_u32, _vp, _i32, _i64, _i64, _i64, _vp, _vp, C.POINTER(_f64), _i32, _vp, _vp]),

@@ -54,8 +54,7 @@ class ReplicationProgram:
             if int(rejected.item()):
                 raise HostLoopRequired("a Lemire slot was rejected: later slots shift, run the hook's own loop")
             return out, SlotCount(self.size)
-        plan = D.normal_plan(dl, self.n_steps)
-        out = D.gbm_terminal(dl, self.n_steps, plan, self.specs)
+        plan, out = D.with_plan(dl, self.n_steps, lambda plan: D.gbm_terminal(dl, self.n_steps, plan, self.specs))
         return (out[0] if len(self.specs) == 1 else out), plan.stream_end
 
 
@@ -131,17 +130,25 @@ def run_blocks(prog: ReplicationProgram, blocks, children, n: int, group=None):
     return values
 
 
-def run_blocks_pipelined(prog: ReplicationProgram, blocks, children, n: int, n_groups: int = 4):
-    """``run_blocks`` for one GPU and a host-resident result: the spawned streams are replayed in ``n_groups``
-    contiguous groups and the device->host copy of group g (pinned memory, side stream) overlaps the kernels of
-    group g+1, so only the last group's copy is exposed; the plan workspace shrinks by the same factor.  Streams are
-    independent, so the values are those of ``run_blocks`` bit for bit.  Returns (device results, host ndarray)."""
+def run_blocks_pipelined(prog: ReplicationProgram, blocks, children, n: int, n_groups: int = 4, shard=None, host_out=None):
+    """``run_blocks`` for a host-resident result: the spawned streams are replayed in ``n_groups`` contiguous groups and
+    the device->host copy of group g (pinned memory, side stream) overlaps the kernels of group g+1, so only the last
+    group's copy is exposed; the plan workspace shrinks by the same factor.  Streams are independent, so the values are
+    those of ``run_blocks`` bit for bit.  ``shard = (rank, world)``: only this rank's contiguous range of blocks is
+    replayed; ``host_out``: a page-locked float64 host tensor for exactly that range (a slice of the shared result
+    buffer of a multi-GPU run) instead of a fresh pinned allocation.  Returns (device results, host ndarray)."""
     import torch
 
     lay = S.StreamLayout(S.GEN_PHILOX, S.philox_records(children, blocks), n, blocks[0][1] - blocks[0][0])
-    n_groups = max(1, min(int(n_groups), lay.n_streams))
+    if shard is not None:
+        lay = lay.shard(*shard)
+        n = lay.n_total
     values = torch.empty(n, dtype=torch.float64, device="cuda")
-    host = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    host = host_out if host_out is not None else torch.empty(n, dtype=torch.float64, pin_memory=True)
+    assert host.numel() == n, (host.numel(), n)
+    if n == 0:
+        return values, host.numpy()
+    n_groups = max(1, min(int(n_groups), lay.n_streams))
     main = torch.cuda.current_stream()
     side = torch.cuda.Stream()
     at = 0
@@ -164,5 +171,15 @@ def run_blocks_pipelined(prog: ReplicationProgram, blocks, children, n: int, n_g
     return values, host.numpy()
 
 
+def shard_sizes(blocks, world: int):
+    """Replications per rank of the contiguous block sharding (what ``StreamLayout.shard`` gives every rank)."""
+    k = len(blocks)
+    sizes = []
+    for r in range(world):
+        lo, hi = r * k // world, (r + 1) * k // world
+        sizes.append(sum(b - a for a, b in blocks[lo:hi]))
+    return sizes
+
+
 __all__ = ["ReplicationProgram", "HostLoopRequired", "SlotCount", "pi_program", "normals_program", "integers_program",
-           "constant_program", "run_sequential", "run_blocks", "run_blocks_pipelined", "N"]
+           "constant_program", "run_sequential", "run_blocks", "run_blocks_pipelined", "shard_sizes", "N"]

@@ -107,6 +107,28 @@ def moments(x, target: float = 0.0, group=None) -> MomentSummary:
     return merge_summaries(MomentSummary.from_array(g.cpu().numpy()) for g in gathered)
 
 
+def moments_many(xs, target: float = 0.0, group=None):
+    """``[moments(x, target, group) for x in xs]`` with ONE device->host copy (and one all-gather) for all of them:
+    the eight revaluations of ``calculate_greeks`` are read back together."""
+    torch = _torch()
+    xs = list(xs)
+    if not xs:
+        return []
+    outs = [torch.zeros(MOMENTS_OUT, dtype=torch.float64, device=x.device) if x.numel() == 0 else moments_raw(x, target)
+            for x in xs]
+    both = torch.stack(outs)
+    if group is None:
+        host = both.cpu().numpy()
+        return [MomentSummary.from_array(row) for row in host]
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    gathered = [torch.empty_like(both) for _ in range(world)]
+    dist.all_gather(gathered, both, group=group)
+    host = torch.stack(gathered).cpu().numpy()  # (world, len(xs), 12)
+    return [merge_summaries(MomentSummary.from_array(host[r, k]) for r in range(world)) for k in range(len(xs))]
+
+
 # ---------------------------------------------------------------------------------------- select
 #: samples of at least this many values compact the surviving candidates after the second radix pass
 SELECT_COMPACT_MIN_N = 1 << 20

@@ -341,8 +341,8 @@ class MonteCarloSimulation(ABC):
     def _finish_device_run(self, values_dev, group=None, host=None) -> np.ndarray:
         """Device results -> (a) DeviceSample kept for the statistics, (b) the host ndarray of the result
         (``host``: already copied by the pipelined block run)."""
-        if host is not None:
-            self._device_sample = DeviceSample(values_dev, host, None)
+        if host is not None:  # already copied out (pipelined run); sharded runs keep the group for the statistics
+            self._device_sample = DeviceSample(values_dev, host, group)
         elif group is not None:
             from . import _multi
 
@@ -483,12 +483,26 @@ class MonteCarloSimulation(ABC):
 
             group = self._shard_group()
             host = None
+            big = (prog.kind != "integers" and not getattr(self, "keep_results_on_device", False)
+                   and n_simulations >= self._PIPELINE_MIN_SIMS and len(blocks) >= 2)
             try:
-                if (group is None and prog.kind != "integers" and not getattr(self, "keep_results_on_device", False)
-                        and n_simulations >= self._PIPELINE_MIN_SIMS and len(blocks) >= 2):
+                if group is None and big:
                     # large host-resident result: copy it out group by group while the next group is computed
                     values, host = _programs.run_blocks_pipelined(prog, blocks, children, n_simulations,
                                                                   self._PIPELINE_GROUPS)
+                elif group is not None and big and getattr(self, "gather_mode", "all") == "shm":
+                    # sharded run, one host: every rank pipelines ITS shard straight into its slice of one shared,
+                    # page-locked result buffer, over its own PCIe link -- no gather, one barrier
+                    import torch.distributed as dist
+
+                    from . import _multi
+
+                    sizes = _programs.shard_sizes(blocks, dist.get_world_size(group))
+                    whole, mine, seg = _multi.shared_result_buffer(sizes, group)
+                    values, _ = _programs.run_blocks_pipelined(
+                        prog, blocks, children, n_simulations, self._PIPELINE_GROUPS,
+                        shard=(dist.get_rank(group), dist.get_world_size(group)), host_out=mine)
+                    host = _multi.finish_shared_result(whole, seg, sizes, group)
                 else:
                     values = _programs.run_blocks(prog, blocks, children, n_simulations, group)
             except _programs.HostLoopRequired:

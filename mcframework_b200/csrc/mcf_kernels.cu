@@ -188,7 +188,19 @@ __global__ void __launch_bounds__(256) pi_philox_stream_kernel(const __grid_cons
         int64_t cnt = m - p0;
         cnt = cnt < 0 ? 0 : (cnt > ppt ? ppt : cnt);
         int64_t h = 0;
-        if (cnt > 0) h = pi_count_hits_blocks(load, (base + 2ULL * (uint64_t)p0) >> 2, cnt) * weight;
+        if (cnt > 0) {
+            // a lane walks consecutive blocks: round 0's product M0 * (b0 + blk) is carried along (+ M0 per block);
+            // measured 1.78e11 -> 1.85e11 samples/s
+            const uint64_t blk0 = (base + 2ULL * (uint64_t)p0) >> 2;
+            uint64_t r0hi, r0lo;
+            mul64_full<MCF_PI_CHAIN>(MCF_PHILOX_M0, K.b0 + blk0, r0hi, r0lo);
+            h = pi_count_hits_blocks(
+                    [&](uint64_t, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
+                        philox_block_folded_r0<MCF_PI_CHAIN>(K, r0hi, r0lo, a, b, c, d);
+                        philox_r0_next(r0hi, r0lo);
+                    },
+                    blk0, cnt) * weight;
+        }
         if (extra_point && part == 0 && lane == 0) {  // odd n_points with antithetic pairs (sims/pi.py:79-80)
             const uint64_t q = base + 2ULL * (uint64_t)m;  // even; the point is (v0, v1) or (v2, v3) of its block
             uint64_t a, b, c, d;
@@ -294,14 +306,9 @@ __global__ void __launch_bounds__(256, MCF_SCAN_CTAS) plan_scan_philox_stream_ke
     const ZigTables t = load_scan_tables(sh, park);
     const unsigned sb = NB == 1 ? 0u : blockIdx.y;
     const PhiloxKeys &K = KB.k[sb];
-#ifdef MCF_SCAN_PERSIST
-    // A/B candidate: resident CTAs walk the stream's 256-chunk tiles with a grid stride, so the tables are set up once
-    for (int64_t tile = blockIdx.x; tile < cps / 256; tile += gridDim.x) {
-    const int64_t c = tile * 256 + threadIdx.x;
-#else
+    // (resident CTAs walking the tiles with a grid stride, tables set up once per CTA, measured 1 % SLOWER: 90.2 vs 89.3 ms)
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // cps is a multiple of 1024: whole CTAs are live
     if (c >= cps) return;
-#endif
     const int64_t id = (stream0 + sb) * cps + c;
     bool valid;
     const uint64_t blk0 = (K.off + (uint64_t)c * MCF_CHUNK) >> 2;
@@ -365,10 +372,6 @@ __global__ void __launch_bounds__(256, MCF_SCAN_CTAS) plan_scan_philox_stream_ke
     emitmask[id] = ci.emitmask;
     exit_[id] = (uint8_t)ci.exit;
     gen[id] = valid ? (uint8_t)ci.gen_entry : (uint8_t)MCF_GEN_ENTRY_INVALID;
-#ifdef MCF_SCAN_PERSIST
-    __syncthreads();  // the first-draw exchange and the parking slots are reused by the next tile
-    }
-#endif
 }
 
 // Fix chunk entries: a chunk's true entry offset is its predecessor's exit.  Two kernels per iteration so that the
@@ -631,6 +634,13 @@ __device__ __forceinline__ const double *load_wi_table(WiShared &sh) {
     return sh.wi;
 }
 
+// The host no longer waits for the plan's status before it queues the replay (one round trip per plan saved): a replay
+// launched on a plan that FAILED (window too small, queue overflow: header word 0) must not follow its unusable
+// positions -- every replay kernel returns at once and the caller, who reads the status after the replay, re-plans.
+__device__ __forceinline__ bool plan_failed(const char *__restrict__ plan_ws) {
+    return *reinterpret_cast<const volatile int *>(plan_ws) != 0;
+}
+
 struct ReplaySetup {
     mcf_stream st;
     PlanView pv;
@@ -663,6 +673,7 @@ __global__ void __launch_bounds__(256, 3) gbm_terminal_kernel(const mcf_stream *
                                                               const char *__restrict__ plan_ws, SpecPack specs,
                                                               double n_steps_f, double *__restrict__ out) {
     __shared__ WiShared sh;
+    if (plan_failed(plan_ws)) return;
     const double *wi = load_wi_table(sh);
     const uint64_t ki0 = g_zig_ki[0];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -713,6 +724,7 @@ __global__ void __launch_bounds__(256, 4)
     const PhiloxKeys &K = KB.k[sb];
     const int64_t si = stream0 + sb, first_sim = SB.first_sim[sb], n_sims = SB.n_sims[sb];
     if ((int64_t)blockIdx.x * blockDim.x >= n_sims) return;  // the grid is sized for the longest stream of the batch
+    if (plan_failed(plan_ws)) return;
     const double *wi = load_wi_table(sh);
     const uint64_t ki0 = g_zig_ki[0];
     const PlanLayout *lay = reinterpret_cast<const PlanLayout *>(plan_ws + MCF_LAYOUT_OFFSET);
@@ -771,6 +783,7 @@ __global__ void __launch_bounds__(256, 3) gbm_paths_kernel(const mcf_stream *__r
                                                            const char *__restrict__ plan_ws, GbmDerived g, int time_major,
                                                            double *__restrict__ paths) {
     __shared__ WiShared sh;
+    if (plan_failed(plan_ws)) return;
     const double *wi = load_wi_table(sh);
     const uint64_t ki0 = g_zig_ki[0];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -790,23 +803,75 @@ __global__ void __launch_bounds__(256, 3) gbm_paths_kernel(const mcf_stream *__r
 }
 
 // Slices from segment sums: seg[i*k + j] = sum of the normals of steps (j*stride, (j+1)*stride] of path i (what the
-// boundary-form replay returns when every path is cut into k pseudo-replications of `stride` steps).  One thread per
-// path accumulates the k segments and writes the k+1 slice values; time-major output is fully coalesced.
-__global__ void __launch_bounds__(256) gbm_slices_from_sums_kernel(const double *__restrict__ seg, int64_t n_total, int64_t k,
-                                                                  GbmDerived g, double stride_f, int time_major,
-                                                                  double *__restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_total) return;
+// boundary-form replay returns when every path is cut into k pseudo-replications of `stride` steps).  The sums are
+// path-major, the slices time-major: a warp moves 32*PPL paths x 16 segments through a shared-memory tile, so that the
+// reads are 128-byte rows of one path and every store is ONE 128-bit vector per lane (PPL = 2 adjacent paths in fp64,
+// 4 in fp32) -- 512 contiguous bytes per warp and slice.  Accumulation and exp() stay in fp64; only the store narrows.
+template <typename OutT>
+struct SliceVec;
+template <>
+struct SliceVec<double> {
+    static constexpr int PPL = 2;
+    static __device__ __forceinline__ void store(double *p, const double *v) { *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]); }
+};
+template <>
+struct SliceVec<float> {
+    static constexpr int PPL = 4;
+    static __device__ __forceinline__ void store(float *p, const double *v) {
+        *reinterpret_cast<float4 *>(p) = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+    }
+};
+#define MCF_SLICE_COLS 16
+template <typename OutT>
+__global__ void __launch_bounds__(64) gbm_slices_from_sums_kernel(const double *__restrict__ seg, int64_t n_total, int64_t k,
+                                                                 GbmDerived g, double stride_f, int time_major,
+                                                                 OutT *__restrict__ out) {
+    constexpr int PPL = SliceVec<OutT>::PPL, ROWS = 32 * PPL;
+    __shared__ double tile_all[2][ROWS][MCF_SLICE_COLS + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double(*tile)[MCF_SLICE_COLS + 1] = tile_all[warp];
+    const int64_t p0 = ((int64_t)blockIdx.x * 2 + warp) * ROWS;  // first path of this warp
+    if (p0 >= n_total) return;
     const bool portfolio = g.mode == MCF_PORTFOLIO_GBM;
-    const int64_t step = time_major ? n_total : 1;
-    double *p = out + (time_major ? i : i * (k + 1));
     const double drift = xmul(stride_f, g.a);
-    double acc = 0.0;
-    *p = portfolio ? g.s0 : exp(g.logs0);
-    for (int64_t j = 0; j < k; j++) {
-        acc = xadd(acc, xadd(drift, xmul(g.b, __ldg(&seg[i * k + j]))));
-        p += step;
-        *p = portfolio ? xmul(g.s0, exp(acc)) : exp(xadd(g.logs0, acc));
+    const int64_t mine = p0 + (int64_t)lane * PPL;  // this lane's PPL adjacent paths
+    // vector stores need PPL live, aligned paths: n_total % PPL == 0 is required for the time-major vector path
+    const bool vec_ok = time_major && (n_total % PPL) == 0;
+    double acc[PPL], v[PPL];
+#pragma unroll
+    for (int q = 0; q < PPL; q++) {
+        acc[q] = 0.0;
+        v[q] = portfolio ? g.s0 : exp(g.logs0);
+    }
+    auto put = [&](int64_t slice) {  // slice values of this lane's paths
+        if (vec_ok) {
+            if (mine < n_total) SliceVec<OutT>::store(out + slice * n_total + mine, v);
+        } else {
+#pragma unroll
+            for (int q = 0; q < PPL; q++)
+                if (mine + q < n_total) out[time_major ? slice * n_total + mine + q : (mine + q) * (k + 1) + slice] = (OutT)v[q];
+        }
+    };
+    put(0);
+    const int half = lane >> 4, col = lane & 15;
+    for (int64_t j0 = 0; j0 < k; j0 += MCF_SLICE_COLS) {
+        // rows of 16 consecutive segments of one path: two paths per load instruction, 128 contiguous bytes each
+#pragma unroll 4
+        for (int r = 0; r < ROWS; r += 2) {
+            const int64_t path = p0 + r + half, j = j0 + col;
+            tile[r + half][col] = (path < n_total && j < k) ? __ldg(&seg[path * k + j]) : 0.0;
+        }
+        __syncwarp();
+        const int cols = (int)(k - j0 < MCF_SLICE_COLS ? k - j0 : MCF_SLICE_COLS);
+        for (int t = 0; t < cols; t++) {
+#pragma unroll
+            for (int q = 0; q < PPL; q++) {
+                acc[q] = xadd(acc[q], xadd(drift, xmul(g.b, tile[lane * PPL + q][t])));
+                v[q] = portfolio ? xmul(g.s0, exp(acc[q])) : exp(xadd(g.logs0, acc[q]));
+            }
+            put(j0 + t + 1);
+        }
+        __syncwarp();
     }
 }
 
@@ -821,6 +886,7 @@ __global__ void __launch_bounds__(256, 3) gbm_slices_kernel(const mcf_stream *__
                                                             int64_t slice_stride, int64_t n_slices, int time_major,
                                                             double *__restrict__ out) {
     __shared__ WiShared sh;
+    if (plan_failed(plan_ws)) return;
     const double *wi = load_wi_table(sh);
     const uint64_t ki0 = g_zig_ki[0];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -900,11 +966,7 @@ static int normal_plan_impl(const mcf_stream *d_streams, const mcf_stream *h_str
             constexpr int NB = decltype(tag)::value;
             PhiloxKeyBatch<NB> KB;  // host staging of the parameter block (the launch copies it)
             fill_batch<NB>(h_streams, s0, cnt, KB, nullptr, nullptr);
-#ifdef MCF_SCAN_PERSIST
-            const unsigned gx = NB == 1 ? (unsigned)(g.cps / 256 < 148 * MCF_SCAN_CTAS ? g.cps / 256 : 148 * MCF_SCAN_CTAS) : grid_for(g.cps, 256);
-#else
             const unsigned gx = grid_for(g.cps, 256);
-#endif
             plan_scan_philox_stream_kernel<NB><<<dim3(gx, cnt), 256, 0, (two && (nb++ & 1)) ? side : cs>>>(
                 KB, s0, g.cps, sm, em, ex, gen, zs);
         });
@@ -1144,16 +1206,21 @@ extern "C" int mcf_normal_relocate(const mcf_stream *d_streams_new, int32_t n_st
 }
 
 extern "C" int mcf_gbm_slices_from_sums(const double *d_segment_sums, int64_t n_total, int64_t n_segments, int64_t segment_steps,
-                                        int64_t n_steps, const mcf_gbm_spec *h_spec, int32_t time_major, double *d_out,
-                                        void *cuda_stream) {
+                                        int64_t n_steps, const mcf_gbm_spec *h_spec, int32_t time_major, int32_t out_f32,
+                                        void *d_out, void *cuda_stream) {
     if (!d_segment_sums || n_total <= 0 || n_segments <= 0 || segment_steps <= 0 || n_steps != n_segments * segment_steps ||
         !h_spec || !d_out || (h_spec->mode != MCF_PORTFOLIO_GBM && h_spec->mode != MCF_PATH_TERMINAL))
         return MCF_ERR_BAD_ARG;
     GbmDerived g;
     int rc = derive_spec(*h_spec, n_steps, &g);
     if (rc) return rc;
-    gbm_slices_from_sums_kernel<<<grid_for(n_total, 256), 256, 0, (cudaStream_t)cuda_stream>>>(
-        d_segment_sums, n_total, n_segments, g, (double)segment_steps, time_major, d_out);
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    if (out_f32)
+        gbm_slices_from_sums_kernel<float><<<grid_for(n_total, 2 * 32 * SliceVec<float>::PPL), 64, 0, cs>>>(
+            d_segment_sums, n_total, n_segments, g, (double)segment_steps, time_major, (float *)d_out);
+    else
+        gbm_slices_from_sums_kernel<double><<<grid_for(n_total, 2 * 32 * SliceVec<double>::PPL), 64, 0, cs>>>(
+            d_segment_sums, n_total, n_segments, g, (double)segment_steps, time_major, (double *)d_out);
     MCF_CUDA_OK(cudaGetLastError());
     return MCF_OK;
 }

@@ -1155,12 +1155,24 @@ __global__ void __launch_bounds__(LSM_THREADS) lsm_apply_kernel(const double *__
 // serial part costs no launch.  Per path and step: S_t and S_{t-1} (8 B each), cf read (8 B), cf written only where
 // the option is exercised.  t == n_steps is the initialisation (cf = discounted terminal intrinsic, no decision);
 // t == 1 accumulates the price sum instead of regression sums.
-__global__ void __launch_bounds__(LSM_THREADS, 4)
+// Sweep direction.  Column S_{t-1} is read here for the regression and again by the NEXT launch for its decision, and
+// the cash flows are read by every launch: 16 of the 24 bytes per path and step were touched one launch earlier.  One
+// launch's footprint (240 MB at 1e7 paths) exceeds the 126 MB L2, so a front-to-back sweep every step finds nothing left
+// (LRU against a cyclic pattern).  Successive launches therefore sweep in OPPOSITE directions (`reverse`), in one
+// co-resident wave of CTAs: what the previous launch touched last is what this one touches first, and S_t -- dead after
+// this launch -- is loaded with the evict-first policy so that it does not push the reusable lines out.
+#ifndef MCF_LSM_PPT
+#define MCF_LSM_PPT 4  // paths per thread and loop trip (3 independent loads each)
+#endif
+#ifndef MCF_LSM_CTAS
+#define MCF_LSM_CTAS 3  // resident CTAs per SM (register budget 65536 / (256 * CTAS))
+#endif
+__global__ void __launch_bounds__(LSM_THREADS, MCF_LSM_CTAS)
     lsm_fused_step_kernel(const double *__restrict__ s_t, const double *__restrict__ s_prev, int64_t n_paths, int32_t t,
                           int32_t n_steps, double K, int is_put, double disc_t, double grow_prev,
                           const LsmState *__restrict__ st_cur, LsmState *__restrict__ st_next,
                           int32_t *__restrict__ ex, double *__restrict__ cf, double *__restrict__ partials,
-                          unsigned int *__restrict__ counter, double *__restrict__ price_out) {
+                          unsigned int *__restrict__ counter, double *__restrict__ price_out, int reverse) {
     const bool init = t == n_steps, last_step = t == 1;
     const bool have_fit = !init && st_cur->have_fit;
     const double c0 = have_fit ? st_cur->coef[0] : 0.0, c1 = have_fit ? st_cur->coef[1] : 0.0,
@@ -1200,15 +1212,29 @@ __global__ void __launch_bounds__(LSM_THREADS, 4)
             a[7] = fma(u2, y, a[7]);
         }
     };
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + stride < n_paths; i += 2 * stride) {  // two paths per trip: six independent loads in flight
-        const double s0 = __ldcs(&s_t[i]), s1 = __ldcs(&s_t[i + stride]);
-        const double p0 = last_step ? 0.0 : __ldg(&s_prev[i]), p1 = last_step ? 0.0 : __ldg(&s_prev[i + stride]);
-        const double k0 = init ? 0.0 : cf[i], k1 = init ? 0.0 : cf[i + stride];
-        one(i, s0, k0, p0);
-        one(i + stride, s1, k1, p1);
+    // bands of `stride` paths; a thread owns one path of every band.  Forward: band 0, 1, ...; reverse: last band first.
+    const int64_t lane_i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t bands = (n_paths + stride - 1) / stride;
+    for (int64_t b0 = 0; b0 < bands; b0 += MCF_LSM_PPT) {
+        double s[MCF_LSM_PPT], p[MCF_LSM_PPT], c[MCF_LSM_PPT];
+        int64_t idx[MCF_LSM_PPT];
+#pragma unroll
+        for (int q = 0; q < MCF_LSM_PPT; q++) {
+            const int64_t b = b0 + q;
+            const int64_t band = reverse ? bands - 1 - b : b;
+            idx[q] = (b < bands && band * stride + lane_i < n_paths) ? band * stride + lane_i : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < MCF_LSM_PPT; q++) {  // all loads of the trip are issued before the first use
+            const bool on = idx[q] >= 0;
+            s[q] = on ? __ldcs(&s_t[idx[q]]) : 0.0;
+            p[q] = (on && !last_step) ? __ldg(&s_prev[idx[q]]) : 0.0;
+            c[q] = (on && !init) ? cf[idx[q]] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < MCF_LSM_PPT; q++)
+            if (idx[q] >= 0) one(idx[q], s[q], c[q], p[q]);
     }
-    if (i < n_paths) one(i, __ldcs(&s_t[i]), init ? 0.0 : cf[i], last_step ? 0.0 : __ldg(&s_prev[i]));
 
     __shared__ double sh[LSM_THREADS / 32][8];
     __shared__ bool is_last;
@@ -1250,6 +1276,9 @@ __global__ void __launch_bounds__(LSM_THREADS, 4)
     }
 }
 
+// (Measured and rejected: the whole sweep as ONE cooperative launch -- grid-wide barrier per step, every CTA adding the
+// partials and solving the 3x3 system for itself.  16.6 ms against 14.7 ms for one launch per step at 1e7 x 252: the
+// barrier and the redundant serial solve cost more than the launch gaps they replace.)
 // discounted cash flows: per-block partial sums (column 0 of partials)
 __global__ void __launch_bounds__(LSM_THREADS) lsm_price_kernel(int64_t n_paths, const double *__restrict__ cf,
                                                                 double *__restrict__ partials) {
@@ -1823,14 +1852,17 @@ int mcf_lsm(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K
     unsigned int *counter = (unsigned int *)(ws + g.off_counter);
     double *cf = (double *)(ws + g.off_cf), *partials = (double *)(ws + g.off_partials);
     MCF_CUDA_OK(cudaMemsetAsync(ws + g.off_state, 0, (size_t)(g.off_partials - g.off_state), cs));
-    const int grid = g.n_blocks;
+    // one co-resident wave of CTAs (the sweep order of a launch is then the band order), never more than the partial-sum
+    // slots the workspace was sized for
+    int grid = MCF_SM_COUNT * MCF_LSM_CTAS;
+    if (grid > g.n_blocks) grid = g.n_blocks;
     // t = n_steps: initialise cash flows and fit step n_steps-1; t = n_steps-1 .. 1: decide step t, fit step t-1
     for (int64_t t = n_steps; t >= 1; t--) {
         const double *s_t = d_paths_tm + (size_t)t * (size_t)n_paths;
         lsm_fused_step_kernel<<<grid, LSM_THREADS, 0, cs>>>(
             s_t, s_t - n_paths, n_paths, (int32_t)t, (int32_t)n_steps, K, is_put, exp(-r * dt * (double)t),
             exp(r * dt * (double)(t - 1)), st + (t & 1), st + ((t - 1) & 1), d_exercise_times, cf, partials, counter,
-            d_price);
+            d_price, (int)((n_steps - t) & 1));
     }
     MCF_CUDA_OK(cudaGetLastError());
     return MCF_OK;

@@ -139,15 +139,19 @@ class BlackScholesSimulation(MonteCarloSimulation):
             import torch
 
             empty = torch.empty(0, dtype=torch.float64, device="cuda")
-            means = [SD.moments(empty, group=group).mean for _ in sets]
+            means = [s.mean for s in SD.moments_many([empty] * len(sets), group=group)]
         else:
             dl = D.DeviceLayout.of(lay)
-            plan = D.normal_plan(dl, int(n_steps))
-            if exercise_type == "european":
-                values = D.gbm_terminal(dl, int(n_steps), plan, [(mode, p) for p in sets])
-                means = [SD.moments(values[k], group=group).mean for k in range(len(sets))]
-            else:  # path-dependent payoff: one replay per parameter set, same plan
-                means = [SD.moments(D.gbm_terminal(dl, int(n_steps), plan, [(mode, p)])[0], group=group).mean for p in sets]
+
+            def replay(plan):
+                if exercise_type == "european":  # all parameter sets on ONE replay of the normals
+                    values = D.gbm_terminal(dl, int(n_steps), plan, [(mode, p) for p in sets])
+                    return [values[k] for k in range(len(sets))]
+                # path-dependent payoff: one replay per parameter set, same plan
+                return [D.gbm_terminal(dl, int(n_steps), plan, [(mode, p)])[0] for p in sets]
+
+            _, values = D.with_plan(dl, int(n_steps), replay)
+            means = [s.mean for s in SD.moments_many(values, group=group)]
         v0, v_up, v_dn, v_sig_up, v_sig_dn, v_r_up, v_r_dn = means[:7]
         greeks = {
             "price": float(v0),

@@ -347,3 +347,45 @@ def test_engine_taxonomy_and_small_samples(m):
     # a user metric gets the host array and can sit next to device metrics
     eng2 = m.StatsEngine([m.FnMetric("mean", se.mean), m.FnMetric("peak", lambda x, ctx: float(np.max(x)))])
     assert eng2.compute(np.array([1.0, 5.0, 3.0])).metrics == {"mean": 3.0, "peak": 5.0}
+
+
+def test_portfolio_simulate_slices_extension(golden):
+    """``PortfolioSimulation.simulate_slices`` (extension; closest reference shape ``simulate_paths``,
+    black_scholes.py:403-418): the last slice of a block-parallel call equals the reference's ``run`` results (fixture
+    G5_portfolio_gbm_par), both layouts agree, ragged path counts and strides fall back to the per-draw kernel, fp32
+    narrows only the store, the sequential form consumes ``self.rng`` like ``run`` does."""
+    import torch
+
+    import mcframework_b200 as m
+
+    _, a = golden
+    pf = m.PortfolioSimulation()
+    pf.set_seed(3)
+    sl = pf.simulate_slices(20_000, years=1, slice_stride=21, parallel=True, n_workers=8)
+    assert sl.shape == (13, 20_000) and sl.dtype == np.float64
+    np.testing.assert_allclose(sl[-1], a["G5_portfolio_gbm_par"], rtol=1e-12)
+    assert np.all(sl[0] == 10_000.0) and np.all(sl > 0)
+    pf.set_seed(3)
+    rm = pf.simulate_slices(20_000, years=1, slice_stride=21, parallel=True, n_workers=8, time_major=False)
+    assert rm.shape == (20_000, 13) and np.array_equal(rm.T, sl)
+    pf.set_seed(3)
+    f32 = pf.simulate_slices(20_000, years=1, slice_stride=21, parallel=True, n_workers=8, dtype="float32", device=True)
+    assert f32.dtype == torch.float32 and np.array_equal(f32.cpu().numpy(), sl.astype(np.float32))
+    pf.set_seed(3)
+    odd = pf.simulate_slices(20_001, years=1, slice_stride=21, parallel=True, n_workers=3)  # 20 001 % 2 == 1: scalar stores
+    pf.set_seed(3)
+    want = pf.run(20_001, years=1, parallel=True, n_workers=3, compute_stats=False).results
+    np.testing.assert_allclose(odd[-1], want, rtol=1e-12)
+    pf.set_seed(3)
+    s5 = pf.simulate_slices(20_000, years=1, slice_stride=5, parallel=True, n_workers=8)  # stride < 16: every draw replayed
+    assert s5.shape == (51, 20_000)
+    np.testing.assert_allclose(s5[21], sl[5], rtol=1e-12)  # step 105 is a slice of both
+    # sequential form: one PCG64 stream, generator left where ``run`` leaves it
+    p1, p2 = m.PortfolioSimulation(), m.PortfolioSimulation()
+    p1.set_seed(42), p2.set_seed(42)
+    seq = p1.simulate_slices(500, years=5, slice_stride=252)
+    np.testing.assert_allclose(seq[-1], a["G5_portfolio_gbm_seq"], rtol=1e-12)
+    p2.run(500, years=5, compute_stats=False)
+    assert p1.rng.bit_generator.state == p2.rng.bit_generator.state
+    with pytest.raises(ValueError):
+        pf.simulate_slices(10, dtype="float16")

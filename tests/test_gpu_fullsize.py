@@ -130,6 +130,104 @@ def test_config5_stats_on_1e8_results(m):
     assert abs(means.mean() - s.mean) < 6 * 2.0 / math.sqrt(n)
 
 
+def test_config4_lsm_1e6_paths_vs_the_unmodified_reference(m):
+    """1e6 paths x 252 steps, seed 1: ``simulate_paths`` + Longstaff-Schwartz against the fixture the UNMODIFIED reference
+    produced (tools/gen_golden.py --lsm-large -> tests/golden/reference_lsm_1e6.json; black_scholes.py:167-193).
+    Bars: path matrix checksums rtol 1e-12, price rtol 1e-9, >= 99.99 % identical exercise steps (histograms)."""
+    import json
+    import os
+
+    import torch
+    from mcframework_b200 import _stats_device as SD
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_lsm_1e6.json")))
+    n, steps = g["n_paths"], g["n_steps"]
+    ps = m.BlackScholesPathSimulation()
+    ps.set_seed(g["seed"])
+    tm = ps.simulate_paths(n, n_steps=steps, device=True, time_major=True)
+    assert tuple(tm.shape) == (steps + 1, n)
+    np.testing.assert_allclose(float(tm.sum(dtype=torch.float64)), g["paths_checksum"], rtol=1e-12)
+    np.testing.assert_allclose(float(tm[-1, -1]), g["paths_last"], rtol=1e-12)
+    for t, want in g["paths_col_means"].items():
+        np.testing.assert_allclose(float(tm[int(t)].mean(dtype=torch.float64)), want, rtol=1e-12)
+    for opt in ("put", "call"):
+        price, ex = SD.lsm_price(tm, g["K"], g["r"], 1.0 / steps, opt == "put", return_exercise=True)
+        want = g["lsm_" + opt]
+        np.testing.assert_allclose(float(price.cpu()[0]), want["price"], rtol=1e-9)
+        hist = torch.bincount(ex.to(torch.int64), minlength=steps + 1).cpu().numpy()
+        moved = int(np.abs(hist - np.asarray(want["exercise_step_histogram"])).sum()) // 2
+        assert moved <= 1e-4 * n, (opt, moved)
+
+
+def test_config4_lsm_1e7_paths_full_size(m):
+    """BASELINE config 4 at its full size, 1e7 paths x 252 steps (20 GB of time-major paths): the price agrees with the
+    reference's 1e6-path price within the Monte Carlo error of both, lies above the European put, and two halves of the
+    path set price alike."""
+    import json
+    import os
+
+    from mcframework_b200 import _stats_device as SD
+    from mcframework_b200.sims import _american_exercise_lsm
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_lsm_1e6.json")))
+    n = 10_000_000
+    ps = m.BlackScholesPathSimulation()
+    ps.set_seed(1)
+    tm = ps.simulate_paths(n, n_steps=252, device=True, time_major=True)
+    price = _american_exercise_lsm(tm, 100.0, 0.05, 1.0 / 252, "put", time_major=True)
+    euro_put = _bs_call(100.0, 100.0, 1.0, 0.05, 0.2) - 100.0 + 100.0 * math.exp(-0.05)
+    se = 7.6 * math.sqrt(1.0 / n + 1.0 / g["n_paths"])  # payoff standard deviation ~7.6
+    assert euro_put < price and abs(price - g["lsm_put"]["price"]) < 4 * se, (price, g["lsm_put"]["price"], se)
+    # the first 1e6 of the 1e7 paths ARE the fixture's paths (same seed, same sequential stream)
+    first = float(SD.lsm_price(tm[:, :1_000_000].contiguous(), 100.0, 0.05, 1.0 / 252, True).cpu()[0])
+    np.testing.assert_allclose(first, g["lsm_put"]["price"], rtol=1e-9)
+    a = float(SD.lsm_price(tm[:, : n // 2].contiguous(), 100.0, 0.05, 1.0 / 252, True).cpu()[0])
+    b = float(SD.lsm_price(tm[:, n // 2:].contiguous(), 100.0, 0.05, 1.0 / 252, True).cpu()[0])
+    assert abs(a - b) < 5 * 7.6 * math.sqrt(4.0 / n)
+
+
+def test_config3_portfolio_1e7_paths_x_2520_steps_stored_slices(m):
+    """BASELINE config 3 at full size through the public extension ``PortfolioSimulation.simulate_slices``: 1e7 paths x
+    2520 steps, a slice every 21 steps (121 slices, time-major).  Slice 0 is V0, the LAST slice is the result vector of
+    ``run`` with the same seed (bit for bit: same plan, same replay), sampled streams equal the strided columns of the
+    full paths regenerated draw by draw, and the fp32 store agrees with the fp64 one to float precision."""
+    import torch
+    from mcframework_b200 import _device as D, _native as N, _stats_device as SD, _streams as S
+
+    n, years, stride = 10_000_000, 10, 21
+    pf = m.PortfolioSimulation()
+    pf.set_seed(42)
+    sl = pf.simulate_slices(n, years=years, slice_stride=stride, parallel=True, n_workers=8, device=True)
+    assert tuple(sl.shape) == (2520 // stride + 1, n) and sl.dtype == torch.float64
+    assert bool((sl[0] == 10_000.0).all())
+    pf.set_seed(42)
+    pf.keep_results_on_device = True
+    res = pf.run(n, parallel=True, n_workers=8, years=years, compute_stats=False)
+    term = res.results.device  # core.DeviceResults: the vector stayed in HBM
+    np.testing.assert_allclose(sl[-1].cpu().numpy(), term.cpu().numpy(), rtol=1e-12)
+    mean_T = float(SD.moments(sl[-1]).mean)
+    sd_T = 1e4 * math.exp(0.7) * math.sqrt(math.exp(0.04 * years) - 1.0)
+    assert abs(mean_T - 1e4 * math.exp(0.07 * years)) < 5 * sd_T / math.sqrt(n)
+    # sampled streams: the first 1024 paths of the first and of the last Philox block, every normal regenerated
+    lay = S.parallel_layout(np.random.SeedSequence(42), n, 8)
+    for k in (0, lay.n_streams - 1):
+        sub = S.StreamLayout(lay.kind, lay.records[k:k + 1].copy(), 1024, 0)
+        sub.records["first_sim"], sub.records["n_sims"] = 0, 1024
+        dls = D.DeviceLayout.of(sub)
+        plans = D.normal_plan(dls, 2520)
+        mu, sig = 0.07, 0.2
+        # gbm_paths parameters (S0, r, sigma, T) with T = 10 and dt = T/2520 = 1/252: the same per-step drift and scale
+        full = D.gbm_paths(dls, 2520, plans, 1e4, mu, sig, float(years), time_major=True)
+        f0 = int(lay.records["first_sim"][k])
+        np.testing.assert_allclose(sl[:, f0:f0 + 1024].cpu().numpy(), full[::stride].cpu().numpy(), rtol=2e-12)
+    del res, term
+    pf.set_seed(42)
+    sl32 = pf.simulate_slices(n, years=years, slice_stride=stride, parallel=True, n_workers=8, device=True, dtype="float32")
+    assert sl32.dtype == torch.float32
+    rel = ((sl32[-1].double() - sl[-1]).abs() / sl[-1]).max()
+    assert float(rel) < 1e-7 * 1.0001  # one float rounding (2^-24 = 6e-8)
+
+
 def test_config4_lsm_1e7_paths_smaller(m):
     """American put, 2e6 paths x 252 steps through the public API: above the European put, below the strike, and
     stable (same price from two different shards of a 2-way split of the paths within MC error)."""

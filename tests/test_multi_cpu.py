@@ -175,6 +175,7 @@ def _run_worker(rank, world, port, q):
         first = {0: 0, 1: 12 * 833}[rank]
         for mode in ("all", "root", "shm"):
             sim = m.PiEstimationSimulation()
+            sim.shard_group = "world"  # sharding is opt-in
             sim.gather_mode = mode
             sim.set_seed(9)
             got = sim.run(n, parallel=True, n_workers=workers, n_points=40, compute_stats=False).results
@@ -187,8 +188,16 @@ def _run_worker(rank, world, port, q):
         # every rank reports what the single-process run (the oracle's port of the reference engine) reports
         ctx_kw = dict(target=3.1, eps=0.01, rng=4, n_bootstrap=100, bootstrap="bca")
         sim = m.PiEstimationSimulation()
+        sim.shard_group = dist.group.WORLD
         sim.set_seed(9)
         res = sim.run(n, parallel=True, n_workers=workers, n_points=40, percentiles=(1, 99), extra_context=ctx_kw)
+        # without the opt-in an initialised process group is ignored: every process runs the whole job
+        solo = m.PiEstimationSimulation()
+        solo.set_seed(9)
+        assert np.array_equal(solo.run(n, parallel=True, n_workers=workers, n_points=40, compute_stats=False).results, want)
+        # more ranks than blocks cannot happen with 2 ranks; an EMPTY shard is exercised through the layout instead
+        from mcframework_b200 import _streams as S_
+        assert S_.parallel_layout(np.random.SeedSequence(1), 20_000, 1).shard(7, 16).n_total >= 0
         ref = np_port.default_metrics(want, n=n, percentiles=(5, 25, 50, 75, 95), **ctx_kw)
         for key in ("mean", "std", "skew", "kurtosis", "bias_to_target", "mse_to_target", "markov_error_prob",
                     "chebyshev_required_n"):

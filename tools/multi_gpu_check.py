@@ -40,10 +40,12 @@ def main():
 
     # replications sharded by block: full result vector on every rank, in reference order
     sim = m.PiEstimationSimulation()
+    sim.shard_group = "world"  # sharding is opt-in: every rank makes the same calls
     sim.set_seed(123)
     r = sim.run(20_000, n_points=100, parallel=True, n_workers=8, compute_stats=False)
     check("pi blocks sharded == reference (bit-exact)", np.array_equal(r.results, a["G2_pi_parallel_results"]))
     bs = m.BlackScholesSimulation()
+    bs.shard_group = "world"
     bs.set_seed(11)
     r = bs.run(20_000, parallel=True, n_workers=4, n_steps=64)
     check("black-scholes blocks sharded == reference", np.allclose(r.results, a["G4_bs_call_par"], rtol=1e-12, atol=1e-11))
@@ -53,6 +55,20 @@ def main():
     if not good and rank == 0:
         print("   detail:", r.mean, ref.mean(), r.std, ref.std(ddof=1), r.percentiles, np.percentile(r.results, [50, 95]))
     check("sharded stats: mean/std/percentiles", good)
+    # the large-run path at fixture size: every rank pipelines its shard into ONE shared-memory result buffer
+    shm = m.BlackScholesSimulation()
+    shm.shard_group, shm.gather_mode, shm._PIPELINE_MIN_SIMS = "world", "shm", 1000
+    shm.set_seed(11)
+    rs = shm.run(20_000, parallel=True, n_workers=4, n_steps=64)
+    if rank == 0:
+        good = rs.results.shape == (20_000,) and np.allclose(rs.results, a["G4_bs_call_par"], rtol=1e-12, atol=1e-11)
+    else:  # the other ranks see their own shard (a view into the shared buffer)
+        lo_blk = 33 * rank // world  # 20 000 // (4*8) = 625-sized blocks: 32 blocks (no ragged one)
+        good = rs.results.size > 0 and np.allclose(rs.results, a["G4_bs_call_par"][625 * (32 * rank // world):][:rs.results.size],
+                                                   rtol=1e-12, atol=1e-11)
+        _ = lo_blk
+    good = good and abs(rs.mean - ref.mean()) <= 1e-12 * ref.mean()
+    check("shared-memory pipelined gather (gather_mode='shm') == reference, sharded stats", good)
     g = bs.calculate_greeks(20_000, option_type="put", n_steps=12, parallel=True, n_workers=j["G4_greeks_put_par_cpu_count"])
     check("greeks sharded == reference", all(abs(g[k] - w) <= 1e-9 * abs(w) for k, w in j["G4_greeks_put_par"].items()))
 
