@@ -38,6 +38,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# multi-GB result and workspace tensors are allocated and dropped every step: expandable segments keep PyTorch's caching
+# allocator from answering an occasional 6 GB request with cudaFree + cudaMalloc (a 150 ms stall inside one timed step)
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 
 BS = dict(S0=100.0, K=100.0, T=1.0, r=0.05, sigma=0.20)
 N_STEPS = 252
@@ -603,12 +606,16 @@ def cfg_stats(cx):
     t, p = best_of(cx, lambda: SD.percentiles(x, (1, 5, 50, 95, 99), group=cx.group), reps=3)
     out["percentiles"] = {"s": t, "values": [float(v) for v in p],
                           "roofline": cx.hbm_roofline(8 * (hi - lo) * 8, t, "select_hist/compact (8 radix passes, algorithmic)")}
+    # the bootstrap resamples the WHOLE sample: with N ranks every rank holds all of x (one all-gather of the shards, as
+    # the engine does) and generates/gathers 1/N of the single index stream's slots; the B partial sums are all-reduced
+    full = DeviceSample(x, None, cx.group).full() if cx.world > 1 else x
     gen = np.random.default_rng(7)
     cx.barrier()
     t0 = time.perf_counter()
-    means = SD.bootstrap_means(x, B, gen, group=cx.group)
+    means = SD.bootstrap_means(full, B, gen, group=cx.group)
     cx.barrier()
     tb = cx.max_over_ranks(time.perf_counter() - t0)
+    del full
     # the whole 12-metric engine, as run() calls it (ci_mean_bootstrap = BCa with its own B resamples)
     eng = mcf.stats_engine.build_default_engine()
     B_eng = max(100, B // 10)  # (the full-B bootstrap was timed above; the engine pass shows the other 11 metrics ride along)
@@ -624,7 +631,7 @@ def cfg_stats(cx):
                 "config": {"workload": "stats_engine_on_1e8_results", "n": n, "n_bootstrap": B, "percentiles": [1, 5, 50, 95, 99],
                            "bootstrap": "bca", "sharded_over_ranks": cx.world, "resident": "device"},
                 "gathers_per_s": B * n / tb,
-                "roofline": {**cx.hbm_roofline(B * (hi - lo) * 8.0, tb, "boot_count/boot_bin/boot_gather"),
+                "roofline": {**cx.hbm_roofline(B * n * 8.0 / cx.world, tb, "boot_count/boot_bin/boot_gather"),
                              "note": "algorithmic bytes = 8 B per gather; the binding resources are the SM->L2 request rate of the "
                                      "gather and the integer-multiply pipe of the PCG64 index stream (DESIGN.md section 3.5)"},
                 "engine_all_12_metrics_s": te, "engine_n_bootstrap": B_eng,

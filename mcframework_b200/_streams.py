@@ -58,16 +58,119 @@ def pcg64_record(state: dict, first_sim: int, n_sims: int) -> np.ndarray:
     return rec
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# SeedSequence child keys, all children at once.  ``Philox(child)`` takes its key from ``child.generate_state(2,
+# uint64)`` (core.py:659); with hundreds or thousands of spawned blocks (n_workers = cpu_count of a wide host) the
+# per-child Python call is the slowest part of a small run.  The children of one ``spawn`` call share the parent's
+# entropy and spawn-key prefix and differ in the LAST spawn-key word only, so NumPy's hash (bit_generator.pyx:
+# SeedSequence.mix_entropy / generate_state) is evaluated on arrays over the children.  Bit-identical to NumPy
+# (tests/test_host_cpu.py compares against ``generate_state`` itself); anything unusual falls back to NumPy.
+# ---------------------------------------------------------------------------------------------------------------
+_INIT_A, _MULT_A, _INIT_B, _MULT_B = 0x43B0D7E5, 0x931E8875, 0x8B51F9DD, 0x58F38DED
+_MIX_L, _MIX_R, _XSHIFT, _M32 = 0xCA01F9DD, 0x4973F715, 16, 0xFFFFFFFF
+
+
+def _uint32_words(value) -> list[int] | None:
+    """NumPy's ``_coerce_to_uint32_array`` for ints and flat sequences of ints (little-endian words, at least one)."""
+    if isinstance(value, (int, np.integer)):
+        v = int(value)
+        if v < 0:
+            return None
+        words = [v & _M32]
+        v >>= 32
+        while v:
+            words.append(v & _M32)
+            v >>= 32
+        return words
+    if isinstance(value, (tuple, list)):
+        out: list[int] = []
+        for item in value:
+            w = _uint32_words(item) if isinstance(item, (int, np.integer)) else None
+            if w is None:
+                return None
+            out += w
+        return out
+    return None
+
+
+def child_philox_keys(children) -> np.ndarray | None:
+    """``[c.generate_state(2, uint64) for c in children]`` as a (n, 2) uint64 array, for children of ONE spawn call
+    (same entropy, same spawn-key prefix, consecutive last word); ``None`` when the fast form does not apply."""
+    n = len(children)
+    if n < 8:
+        return None
+    first = children[0]
+    if first.pool_size != 4 or not first.spawn_key or children[-1].spawn_key[:-1] != first.spawn_key[:-1]:
+        return None
+    k0 = first.spawn_key[-1]
+    if not isinstance(k0, (int, np.integer)) or children[-1].spawn_key[-1] != k0 + n - 1 or k0 + n - 1 > _M32:
+        return None
+    if children[-1].entropy is not first.entropy and children[-1].entropy != first.entropy:
+        return None
+    run = _uint32_words(first.entropy)
+    prefix = _uint32_words(tuple(first.spawn_key[:-1]))
+    if run is None or prefix is None:
+        return None
+    if len(run) < 4:
+        run = run + [0] * (4 - len(run))  # spawned sequences pad the run entropy to the pool size
+    words = run + prefix  # + the child index, one uint32 word that differs per child
+    last = np.arange(k0, k0 + n, dtype=np.uint64).astype(np.uint32)
+    hash_const = _INIT_A
+
+    def hashmix(value):  # value: python int (shared by all children) or uint32 array
+        nonlocal hash_const
+        value = value ^ (hash_const if isinstance(value, int) else np.uint32(hash_const))
+        hash_const = (hash_const * _MULT_A) & _M32
+        if isinstance(value, int):
+            value = (value * hash_const) & _M32
+            return value ^ (value >> _XSHIFT)
+        value = value * np.uint32(hash_const)
+        return value ^ (value >> np.uint32(_XSHIFT))
+
+    def mix(x, y):
+        if isinstance(x, int) and isinstance(y, int):
+            r = (_MIX_L * x - _MIX_R * y) & _M32
+            return r ^ (r >> _XSHIFT)
+        x = np.uint32(x) if isinstance(x, int) else x
+        y = np.uint32(y) if isinstance(y, int) else y
+        r = np.uint32(_MIX_L) * x - np.uint32(_MIX_R) * y
+        return r ^ (r >> np.uint32(_XSHIFT))
+
+    entropy = words + [last]
+    with np.errstate(over="ignore"):
+        mixer = [hashmix(entropy[i]) if i < len(entropy) else hashmix(0) for i in range(4)]
+        for i_src in range(4):
+            for i_dst in range(4):
+                if i_src != i_dst:
+                    mixer[i_dst] = mix(mixer[i_dst], hashmix(mixer[i_src]))
+        for i_src in range(4, len(entropy)):
+            for i_dst in range(4):
+                mixer[i_dst] = mix(mixer[i_dst], hashmix(entropy[i_src]))
+        # generate_state(2, uint64): four 32-bit words from the pool, cycled
+        hc = _INIT_B
+        out32 = np.empty((n, 4), dtype=np.uint32)
+        for i_dst in range(4):
+            v = mixer[i_dst % 4]
+            v = (np.full(n, v, dtype=np.uint32) if isinstance(v, int) else v) ^ np.uint32(hc)
+            hc = (hc * _MULT_B) & _M32
+            v = v * np.uint32(hc)
+            out32[:, i_dst] = v ^ (v >> np.uint32(_XSHIFT))
+    return out32.view(np.uint64) if out32.dtype.byteorder in ("=", "<", "|") and np.little_endian else None
+
+
 def philox_records(children, blocks) -> np.ndarray:
     """Records for ``Philox(child)`` of every spawned child (core.py:659): key from
     ``child.generate_state(2, uint64)``, counter 0, empty output buffer."""
     rec = np.zeros(len(children), dtype=STREAM_DTYPE)
     rec["kind"] = GEN_PHILOX
     rec["buf_pos"] = 4
-    for k, (child, (a, b)) in enumerate(zip(children, blocks)):
-        rec["s"][k, :2] = child.generate_state(2, np.uint64)
-        rec["first_sim"][k] = a
-        rec["n_sims"][k] = b - a
+    keys = child_philox_keys(children)
+    if keys is None:
+        keys = np.array([child.generate_state(2, np.uint64) for child in children], dtype=np.uint64).reshape(len(children), 2)
+    rec["s"][:, :2] = keys
+    edges = np.asarray(blocks, dtype=np.int64).reshape(len(children), 2)
+    rec["first_sim"] = edges[:, 0]
+    rec["n_sims"] = edges[:, 1] - edges[:, 0]
     return rec
 
 

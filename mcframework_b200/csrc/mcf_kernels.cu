@@ -9,6 +9,7 @@
 //     speculatively -> fix chunk entries -> tile sums -> per-stream scan -> locate), then one
 //     thread per replication replays its draws with all path state in registers.
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdio.h>
 
 #include "mcf_device.cuh"
@@ -27,8 +28,31 @@ struct ZigShared {
     double wi[256];
     double fi[256];
 };
+// The scan's shared-memory tables as ONE 14 KB image in HBM, built at compile time from the generated lists: ki, wi,
+// fi (what ZigShared holds) followed by the 512 (layer, sign) entries {ki, +-wi * 2^974} of ZigTables::kws.  A CTA
+// copies it with 896 16-byte loads (3.5 per thread) instead of deriving its 512 entries from scratch -- the table
+// set-up was 3 % of the scan's instructions.
+struct ScanTableImage {
+    unsigned long long w[768 + 1024];
+};
+constexpr ScanTableImage make_scan_table_image() {
+    constexpr unsigned long long ki[256] = {MCF_ZIG_KI_LIST}, wi[256] = {MCF_ZIG_WI_BITS_LIST}, fi[256] = {MCF_ZIG_FI_BITS_LIST};
+    ScanTableImage t{};
+    for (int i = 0; i < 256; i++) {
+        t.w[i] = ki[i];
+        t.w[256 + i] = wi[i];
+        t.w[512 + i] = fi[i];
+    }
+    for (int e = 0; e < 512; e++) {  // zig_fill_kws: ki | MCF_SCAN_BIAS (= 0), (e & 256 ? -wi : wi) * 2^974 (exponent + 974)
+        t.w[768 + 2 * e] = ki[e & 255];
+        t.w[768 + 2 * e + 1] = (wi[e & 255] + (974ULL << 52)) | ((e & 256) ? (1ULL << 63) : 0ULL);
+    }
+    return t;
+}
+__device__ const ScanTableImage g_scan_table_image = make_scan_table_image();
+static_assert(MCF_SCAN_BIAS == 0ULL, "the table image assumes the subnormal (unbiased) form of rabs");
 // the speculative scan adds the (layer, sign)-indexed table and the per-thread parking slots (256 threads per CTA)
-struct ScanShared {
+struct alignas(16) ScanShared {
     ZigShared z;
     ZigKW kws[512];
     uint64_t park[3 * MCF_PARK_CAP * 256];
@@ -53,9 +77,20 @@ __device__ __forceinline__ ZigTables load_zig_tables(ZigShared &sh) {
 }
 
 __device__ __forceinline__ ZigTables load_scan_tables(ScanShared &sh, ParkSlots &park) {
-    for (int e = threadIdx.x; e < 512; e += blockDim.x)
-        zig_fill_kws(sh.kws, (unsigned)e, g_zig_ki[e & 255], __longlong_as_double((long long)g_zig_wi[e & 255]));
-    ZigTables t = load_zig_tables(sh.z);
+    static_assert(offsetof(ScanShared, kws) == sizeof(ZigShared) && sizeof(ZigShared) + sizeof(sh.kws) == sizeof(ScanTableImage),
+                  "z and kws must mirror the table image");
+    const uint4 *src = reinterpret_cast<const uint4 *>(g_scan_table_image.w);
+    uint4 *dst = reinterpret_cast<uint4 *>(&sh);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {  // 896 vectors, 256 threads per CTA (every scan kernel's launch bound)
+        const int j = (int)threadIdx.x + 256 * i;
+        if (j < (int)(sizeof(ScanTableImage) / 16)) dst[j] = __ldg(&src[j]);
+    }
+    __syncthreads();
+    ZigTables t;
+    t.ki = sh.z.ki;
+    t.wi = sh.z.wi;
+    t.fi = sh.z.fi;
     t.kws = sh.kws;
     park.a = sh.park + threadIdx.x;
     park.b = park.a + MCF_PARK_CAP * 256;

@@ -1047,6 +1047,33 @@ __global__ void __launch_bounds__(256) lsm_sum_partials_kernel(const double *__r
 
 // symmetric 3x3 eigen-decomposition (cyclic Jacobi) -> pseudo-inverse solve with lstsq's rcond=eps*max(M,N) spirit
 __device__ void lsm_solve3(const double G[3][3], const double rhs[3], double n_rows, double coef[3]) {
+    // Fast path (every step of an at-the-money sweep): the rescaled Gram matrix is safely positive definite, so an
+    // LDL^T factorisation -- three divisions, no square root, ~0.3 us -- gives the unique least-squares solution.
+    // The eigen-decomposition below (a serial ~7 us on the one thread that runs it: half of the fixed cost of a step)
+    // is only needed to reproduce lstsq's min-norm answer when the fit is rank deficient or nearly so; a pivot below
+    // 1e-4 of the largest diagonal entry (condition number above ~1e4) sends the step there.
+    {
+        const double a00 = G[0][0], a01 = G[0][1], a02 = G[0][2], a11 = G[1][1], a12 = G[1][2], a22 = G[2][2];
+        const double floor_ = 1e-4 * fmax(a00, fmax(a11, a22));
+        if (a00 > floor_) {
+            const double l10 = a01 / a00, l20 = a02 / a00;
+            const double d1 = a11 - l10 * a01;
+            if (d1 > floor_) {
+                const double l21 = (a12 - l20 * a01) / d1;
+                const double d2 = a22 - l20 * a02 - l21 * (a12 - l20 * a01);
+                if (d2 > floor_) {
+                    const double y0 = rhs[0], y1 = rhs[1] - l10 * y0, y2 = rhs[2] - l20 * y0 - l21 * y1;
+                    const double z2 = y2 / d2;
+                    const double z1 = y1 / d1 - l21 * z2;
+                    const double z0 = y0 / a00 - l10 * z1 - l20 * z2;
+                    coef[0] = z0;
+                    coef[1] = z1;
+                    coef[2] = z2;
+                    return;
+                }
+            }
+        }
+    }
     double A[3][3], V[3][3];
 #pragma unroll
     for (int i = 0; i < 3; i++)
@@ -1174,9 +1201,27 @@ __global__ void __launch_bounds__(LSM_THREADS, MCF_LSM_CTAS)
                           int32_t *__restrict__ ex, double *__restrict__ cf, double *__restrict__ partials,
                           unsigned int *__restrict__ counter, double *__restrict__ price_out, int reverse) {
     const bool init = t == n_steps, last_step = t == 1;
-    const bool have_fit = !init && st_cur->have_fit;
-    const double c0 = have_fit ? st_cur->coef[0] : 0.0, c1 = have_fit ? st_cur->coef[1] : 0.0,
-                 c2 = have_fit ? st_cur->coef[2] : 0.0;
+    // Programmatic dependent launch: this grid may start while the previous step's grid is still finishing (its last
+    // CTA is adding the partial sums and solving).  The path columns do not depend on it, so the first trip's loads of
+    // S_t / S_{t-1} are issued BEFORE `griddepcontrol.wait`; the coefficients and the cash flows are read after it.
+#ifndef MCF_LSM_NO_PDL
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+    bool have_fit = false, waited = false;
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    auto wait_for_previous_step = [&]() {
+        if (waited) return;
+        waited = true;
+#ifndef MCF_LSM_NO_PDL
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+        have_fit = !init && st_cur->have_fit;
+        if (have_fit) {
+            c0 = st_cur->coef[0];
+            c1 = st_cur->coef[1];
+            c2 = st_cur->coef[2];
+        }
+    };
     const double invK = 1.0 / K;
     double a[8];
 #pragma unroll
@@ -1229,12 +1274,15 @@ __global__ void __launch_bounds__(LSM_THREADS, MCF_LSM_CTAS)
             const bool on = idx[q] >= 0;
             s[q] = on ? __ldcs(&s_t[idx[q]]) : 0.0;
             p[q] = (on && !last_step) ? __ldg(&s_prev[idx[q]]) : 0.0;
-            c[q] = (on && !init) ? cf[idx[q]] : 0.0;
         }
+        wait_for_previous_step();
+#pragma unroll
+        for (int q = 0; q < MCF_LSM_PPT; q++) c[q] = (idx[q] >= 0 && !init) ? cf[idx[q]] : 0.0;
 #pragma unroll
         for (int q = 0; q < MCF_LSM_PPT; q++)
             if (idx[q] >= 0) one(idx[q], s[q], c[q], p[q]);
     }
+    wait_for_previous_step();  // (a grid with no band still orders itself behind the previous step)
 
     __shared__ double sh[LSM_THREADS / 32][8];
     __shared__ bool is_last;
@@ -1258,9 +1306,19 @@ __global__ void __launch_bounds__(LSM_THREADS, MCF_LSM_CTAS)
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    {  // 8 warps, warp k sums column k in a fixed order (as lsm_sum_partials_kernel)
+    {  // 8 warps, warp k sums column k in a fixed order (as lsm_sum_partials_kernel); the loads of a group of 16 are
+       // issued together -- this CTA is the serial tail of the step, a dependent load per addition cost ~4 us
         double v = 0.0;
-        for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(&partials[(size_t)b * 8 + wid]);
+        for (int b0 = lane; b0 < (int)gridDim.x; b0 += 32 * 16) {
+            double part[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int b = b0 + 32 * j;
+                part[j] = b < (int)gridDim.x ? __ldcg(&partials[(size_t)b * 8 + wid]) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j++) v += part[j];
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) st_next->sums[wid] = v;
@@ -1859,10 +1917,21 @@ int mcf_lsm(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K
     // t = n_steps: initialise cash flows and fit step n_steps-1; t = n_steps-1 .. 1: decide step t, fit step t-1
     for (int64_t t = n_steps; t >= 1; t--) {
         const double *s_t = d_paths_tm + (size_t)t * (size_t)n_paths;
-        lsm_fused_step_kernel<<<grid, LSM_THREADS, 0, cs>>>(
-            s_t, s_t - n_paths, n_paths, (int32_t)t, (int32_t)n_steps, K, is_put, exp(-r * dt * (double)t),
-            exp(r * dt * (double)(t - 1)), st + (t & 1), st + ((t - 1) & 1), d_exercise_times, cf, partials, counter,
-            d_price, (int)((n_steps - t) & 1));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(LSM_THREADS);
+        cfg.stream = cs;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+#ifndef MCF_LSM_NO_PDL
+        cfg.attrs = attr;
+        cfg.numAttrs = t == n_steps ? 0 : 1;  // the first step follows a memset, not a kernel of this chain
+#endif
+        MCF_CUDA_OK(cudaLaunchKernelEx(&cfg, lsm_fused_step_kernel, s_t, s_t - n_paths, n_paths, (int32_t)t, (int32_t)n_steps, K,
+                                       (int)is_put, exp(-r * dt * (double)t), exp(r * dt * (double)(t - 1)),
+                                       (const LsmState *)(st + (t & 1)), st + ((t - 1) & 1), d_exercise_times, cf, partials,
+                                       counter, d_price, (int)((n_steps - t) & 1)));
     }
     MCF_CUDA_OK(cudaGetLastError());
     return MCF_OK;

@@ -350,3 +350,29 @@ def test_hostemu_folded_philox_blocks_equal_numpy_raw_draws(emu):
         bg.state = g.bit_generator.state
         bg.advance((1 << 40) - 64)  # the generator above already consumed 64 blocks
         assert rc == 0 and np.array_equal(got, bg.random_raw(32))
+
+
+def test_child_philox_keys_equal_numpy_generate_state():
+    """``_streams.child_philox_keys`` evaluates SeedSequence's hash for all spawned children at once (NumPy
+    bit_generator.pyx: mix_entropy / generate_state; reference call site core.py:637,659): bit-identical keys for small
+    and 128-bit entropies, sequence entropies, nested spawn keys and children that do not start at index 0; shapes it
+    does not cover return None (the caller then asks NumPy)."""
+    from mcframework_b200 import _streams as S
+
+    for ent in (0, 1, 42, 123, 2**32 + 5, 2**100 + 12345, 2**127 - 1, [1, 2, 3], [5], (2**40, 7), np.random.SeedSequence().entropy):
+        for prefix in ((), (3,), (0, 17), (2**31, 4, 5, 6, 7)):
+            ss = np.random.SeedSequence(ent, spawn_key=prefix)
+            ss.spawn(3)
+            children = ss.spawn(70)
+            want = np.array([c.generate_state(2, np.uint64) for c in children])
+            got = S.child_philox_keys(children)
+            assert got is not None and np.array_equal(got, want), (ent, prefix)
+    assert S.child_philox_keys(np.random.SeedSequence(1).spawn(3)) is None  # too few: not worth it
+    mixed = np.random.SeedSequence(1).spawn(8) + np.random.SeedSequence(2).spawn(8)
+    assert S.child_philox_keys(mixed) is None  # children of different parents
+    assert S.child_philox_keys(np.random.SeedSequence(1, pool_size=8).spawn(9)) is None
+    blocks = [(i * 10, i * 10 + 10) for i in range(40)]
+    kids = np.random.SeedSequence(9).spawn(40)
+    rec = S.philox_records(kids, blocks)
+    assert np.array_equal(rec["s"][:, :2], np.array([c.generate_state(2, np.uint64) for c in kids]))
+    assert rec["first_sim"].tolist() == [a for a, _ in blocks] and rec["n_sims"].tolist() == [10] * 40
