@@ -38,9 +38,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# multi-GB result and workspace tensors are allocated and dropped every step: expandable segments keep PyTorch's caching
-# allocator from answering an occasional 6 GB request with cudaFree + cudaMalloc (a 150 ms stall inside one timed step)
-os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 
 BS = dict(S0=100.0, K=100.0, T=1.0, r=0.05, sigma=0.20)
 N_STEPS = 252
@@ -190,6 +187,7 @@ class Ctx:
                 continue
         self.ri = ri
         self.sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+        self._imad_peak, self.imad_src = None, None
 
     @property
     def group(self):
@@ -225,8 +223,24 @@ class Ctx:
         return ms, wall_ms / 1e3, out
 
     def imad_peak(self):
-        """Measured issue rate of IMAD.WIDE.U32 (tools/probe_pipes.cu on this GPU model), scaled to the SM clock."""
-        return float(self.ri.get("imad_wide_warp_inst_per_s", 3.4755e11)) * (self.sm_mhz / float(self.ri.get("probe_sm_mhz", 1965.0)))
+        """Issue rate of IMAD.WIDE.U32 measured IN THIS RUN on this GPU (mcf_probe_issue_rate: the loop of
+        tools/probe_pipes.cu); the committed round-1 probe (profiles/r1_probe_pipes.json) is only the fallback."""
+        if self._imad_peak is None:
+            import ctypes as C
+
+            from mcframework_b200 import _native as N
+
+            v = C.c_double(0.0)
+            try:
+                rc = N.lib().mcf_probe_issue_rate(0, C.byref(v), C.c_void_p(self.torch.cuda.current_stream().cuda_stream))
+            except Exception:  # noqa: BLE001
+                rc = -1
+            if rc == 0 and v.value > 0:
+                self._imad_peak, self.imad_src = float(v.value), "measured in this run (mcf_probe_issue_rate, 8 chains x 1024 threads per SM)"
+            else:
+                self._imad_peak = float(self.ri.get("imad_wide_warp_inst_per_s", 3.4755e11)) * (self.sm_mhz / float(self.ri.get("probe_sm_mhz", 1965.0)))
+                self.imad_src = "committed probe profiles/r1_probe_pipes.json, scaled to the SM clock"
+        return self._imad_peak
 
     def imad_roofline(self, philox_blocks, seconds, kernel):
         """Philox4x64-10 = 18 64x64->128 products per block of 4 draws after folding = 72 IMAD.WIDE.U32 per block."""
@@ -235,8 +249,8 @@ class Ctx:
         return {"kernel": kernel, "bound": "imad", "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "Gwarp-IMAD.WIDE/s",
                 "frac": ach / peak, "traffic": None,
                 "algorithmic_work": "Philox blocks holding consumed draws x 72 IMAD.WIDE.U32 per block and thread",
-                "peak_source": "BUILDER-measured IMAD.WIDE.U32 issue rate (tools/probe_pipes.cu -> profiles/r1_probe_pipes.json; "
-                               f"not a driver-measured peak), scaled to {self.sm_mhz:.0f} MHz"}
+                "peak_source": "BUILDER-measured IMAD.WIDE.U32 issue rate, not a driver-measured peak (MEASURED_PEAKS.json has no "
+                               "issue-slot figure): " + str(self.imad_src)}
 
     def hbm_roofline(self, nbytes, seconds, kernel, traffic=None):
         ach = nbytes / seconds / 1e9

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MCF_ABI_VERSION 3
+#define MCF_ABI_VERSION 4
 
 enum {
     MCF_OK = 0,
@@ -193,6 +193,27 @@ int mcf_lsm_apply(const double *d_paths_tm, int64_t n_paths, int64_t t, double K
  * Either may be NULL.  d_exercise_times (int32[n_paths], may be NULL) receives the exercise step of every path. */
 int mcf_lsm_finish(int64_t n_paths, double r, double dt, void *d_workspace, double *d_price_sum, double *d_price,
                    int32_t *d_exercise_times, void *cuda_stream);
+/* Measurement aid (bench.py's roofline denominator, measured on the device the benchmark runs on): issue rate, in warp
+ * instructions per second over the whole GPU, of kind 0: IMAD.WIDE.U32, 1: IMAD (low), 2: LOP3 -- eight independent
+ * chains per thread, 4 CTAs x 256 threads per SM (the loop of tools/probe_pipes.cu).  Blocks until measured. */
+int mcf_probe_issue_rate(int32_t kind, double *warp_inst_per_s, void *cuda_stream);
+
+/* Paths sharded over the GPUs of ONE box (world <= 8): the same fused step kernel as mcf_lsm, with the exchange of the 8
+ * sums of a step done inside the kernel over peer memory -- the last CTA of every rank stores its sums into a slot of
+ * every rank's exchange buffer, waits for the others' and adds them in rank order (no collective call per step).
+ * mcf_peer_buffer_create allocates one exchange buffer (mcf_lsm_exchange_bytes()) and returns its 64-byte CUDA IPC
+ * handle; the handles are exchanged by the caller (torch.distributed), opened with mcf_peer_buffer_open, and passed as
+ * peer_buffers[world] (entry [rank] = the local buffer).  sequence_base: any number that grows by more than n_steps
+ * from one sweep to the next (stale slots never match); the caller orders successive sweeps with a stream barrier. */
+int64_t mcf_lsm_exchange_bytes(void);
+int mcf_peer_buffer_create(int64_t bytes, void **d_ptr, void *handle64);
+int mcf_peer_buffer_open(const void *handle64, void **d_ptr);
+int mcf_peer_buffer_close(void *d_ptr);
+int mcf_peer_buffer_destroy(void *d_ptr);
+int mcf_lsm_sharded(const double *d_paths_tm, int64_t n_paths_local, int64_t n_paths_global, int64_t n_steps, double K, double r,
+                    double dt, int32_t is_put, void *d_workspace, int64_t workspace_bytes, void *const *peer_buffers,
+                    int32_t rank, int32_t world, uint64_t sequence_base, double *d_price, int32_t *d_exercise_times,
+                    void *cuda_stream);
 int mcf_lsm(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K, double r, double dt, int32_t is_put,
             void *d_workspace, int64_t workspace_bytes, double *d_price, int32_t *d_exercise_times, void *cuda_stream);
 /* (n_rows, n_cols) row-major -> (n_cols, n_rows) row-major */

@@ -54,10 +54,11 @@ def gather_results_to_root(local, group):
 # collected, so steady-state runs reuse mappings that are already page-locked (``cudaHostRegister`` is paid once).
 # ------------------------------------------------------------------------------------------------------------------
 class _Segment:
-    __slots__ = ("shm", "nbytes", "registered", "owner")
+    __slots__ = ("shm", "nbytes", "registered", "owner", "ranges")
 
     def __init__(self, shm, nbytes, owner):
         self.shm, self.nbytes, self.registered, self.owner = shm, nbytes, False, owner
+        self.ranges = {}  # (page-aligned offset, length) -> registered with CUDA
 
 
 class _Attachment:
@@ -137,11 +138,42 @@ class SharedResultPool:
                 raise RuntimeError(f"cudaHostRegister failed with error {int(rc)}")
         seg.registered = True
 
+    @staticmethod
+    def page_lock_range(seg: _Segment, offset: int, nbytes: int) -> bool:
+        """Register only ``[offset, offset + nbytes)`` of the mapping (rounded out to pages): a rank copies into ITS slice
+        of the shared result, and eight processes each pinning a whole multi-GB segment run into the locked-memory limit
+        (cudaHostRegister error 304 at 8 x 6.4 GB).  Returns False when the range could not be pinned (the copy then
+        runs through pageable memory: slower, still correct)."""
+        import ctypes
+
+        import torch
+
+        if nbytes <= 0 or not torch.cuda.is_available():
+            return True
+        page = 4096
+        lo = (offset // page) * page
+        hi = min(seg.nbytes, -(-(offset + nbytes) // page) * page)
+        if seg.registered or any(a <= lo and hi <= a + n for (a, n) in seg.ranges):
+            return True
+        base = ctypes.addressof(ctypes.c_char.from_buffer(seg.shm.buf))
+        rc = int(torch.cuda.cudart().cudaHostRegister(base + lo, hi - lo, 0))
+        if rc != 0:
+            return False
+        seg.ranges[(lo, hi - lo)] = True
+        return True
+
     def close(self) -> None:
         import ctypes
 
         for seg in self._all:
             try:
+                for (lo, _n) in list(seg.ranges):
+                    import torch
+
+                    if torch.cuda.is_available():
+                        base = ctypes.addressof(ctypes.c_char.from_buffer(seg.shm.buf))
+                        torch.cuda.cudart().cudaHostUnregister(base + lo)
+                seg.ranges = {}
                 if seg.registered:
                     import torch
 
@@ -202,7 +234,7 @@ def shared_result_buffer(sizes, group):
     dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
     if rank != 0:
         seg = pool.attach(*box[0])
-    pool.page_lock(seg)
+    pool.page_lock_range(seg, offset * 8, sizes[rank] * 8)  # only the slice this rank's GPU writes
     whole = np.ndarray((total,), dtype=np.float64, buffer=seg.shm.buf)
     mine = torch.from_numpy(whole[offset:offset + sizes[rank]])
     return whole, mine, seg
@@ -246,7 +278,7 @@ def gather_results_shared(local, group):
     dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
     if rank != 0:
         seg = pool.attach(*box[0])
-    pool.page_lock(seg)
+    pool.page_lock_range(seg, offset * 8, sizes[rank] * 8)
     whole = np.ndarray((total,), dtype=np.float64, buffer=seg.shm.buf)
     if sizes[rank]:
         torch.from_numpy(whole[offset:offset + sizes[rank]]).copy_(local.to(torch.float64), non_blocking=False)

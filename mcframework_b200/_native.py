@@ -64,6 +64,14 @@ SIGNATURES = {
     "mcf_lsm_apply": (C.c_int, [_vp, _i64, _i64, _f64, _f64, _f64, _i32, _vp, _vp]),
     "mcf_lsm_finish": (C.c_int, [_i64, _f64, _f64, _vp, _vp, _vp, _vp, _vp]),
     "mcf_lsm": (C.c_int, [_vp, _i64, _i64, _f64, _f64, _f64, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "mcf_probe_issue_rate": (C.c_int, [_i32, C.POINTER(C.c_double), _vp]),
+    "mcf_lsm_exchange_bytes": (_i64, []),
+    "mcf_peer_buffer_create": (C.c_int, [_i64, C.POINTER(C.c_void_p), _vp]),
+    "mcf_peer_buffer_open": (C.c_int, [_vp, C.POINTER(C.c_void_p)]),
+    "mcf_peer_buffer_close": (C.c_int, [_vp]),
+    "mcf_peer_buffer_destroy": (C.c_int, [_vp]),
+    "mcf_lsm_sharded": (C.c_int, [_vp, _i64, _i64, _i64, _f64, _f64, _f64, _i32, _vp, _i64, C.POINTER(C.c_void_p), _i32, _i32,
+                                  C.c_uint64, _vp, _vp, _vp]),
     "mcf_transpose": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
     # StatsEngine reductions
     "mcf_moments_workspace_bytes": (_i64, [_i64]),

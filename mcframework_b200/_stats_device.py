@@ -353,7 +353,57 @@ def transpose(a):
     return out
 
 
-def lsm_price(paths_tm, K: float, r: float, dt: float, is_put: bool, group=None, return_exercise: bool = False):
+class LsmPeerExchange:
+    """Peer-mapped exchange buffers of one process group (the GPUs of one box, at most 8): every rank allocates a 2 KB
+    buffer, the CUDA IPC handles travel once through ``all_gather_object``, every rank maps every buffer.  The fused
+    sharded sweep (``mcf_lsm_sharded``) then exchanges the 8 sums of a step inside its kernel over NVLink."""
+
+    _cache: dict = {}
+
+    def __init__(self, group):
+        import socket
+
+        import torch.distributed as dist
+
+        lib = N.lib()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.seq = 0
+        self.ok = False
+        local, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        mine = None
+        if self.world <= 8:
+            rc = lib.mcf_peer_buffer_create(int(lib.mcf_lsm_exchange_bytes()), C.byref(local), handle)
+            mine = (socket.gethostname(), bytes(handle)) if rc == N.OK else None
+        infos = [None] * self.world
+        dist.all_gather_object(infos, mine, group=group)
+        good = all(i is not None for i in infos) and len({i[0] for i in infos}) == 1
+        ptrs = []
+        if good:
+            for r, (_, h) in enumerate(infos):
+                if r == self.rank:
+                    ptrs.append(local.value)
+                    continue
+                q = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                if lib.mcf_peer_buffer_open(buf, C.byref(q)) != N.OK:
+                    good = False
+                    break
+                ptrs.append(q.value)
+        flags = [None] * self.world
+        dist.all_gather_object(flags, bool(good), group=group)  # every rank takes the same path
+        self.ok = all(flags)
+        self.ptrs = (C.c_void_p * 8)(*(ptrs + [None] * (8 - len(ptrs)))) if self.ok else None
+
+    @classmethod
+    def get(cls, group):
+        key = id(group)
+        if key not in cls._cache:
+            cls._cache[key] = cls(group)
+        return cls._cache[key]
+
+
+def lsm_price(paths_tm, K: float, r: float, dt: float, is_put: bool, group=None, return_exercise: bool = False,
+              fused: bool = True):
     """Longstaff-Schwartz price from TIME-MAJOR paths ``(n_steps+1, n_paths)`` on device
     (sims/black_scholes.py:109-193).  With ``group`` the paths are sharded by rank; the 8 regression sums of
     every step and the final cash-flow sum are all-reduced."""
@@ -373,6 +423,20 @@ def lsm_price(paths_tm, K: float, r: float, dt: float, is_put: bool, group=None,
         return (price, ex) if return_exercise else price
     import torch.distributed as dist
 
+    px = LsmPeerExchange.get(group) if fused else None
+    if px is not None and px.ok:
+        # one fused launch per step and rank; the ranks' sums meet inside the kernel (peer memory over NVLink)
+        counts = torch.tensor([float(n_paths)], dtype=torch.float64, device=paths_tm.device)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)  # also orders this sweep behind the previous one
+        n_global = int(round(float(counts.item())))
+        base = px.seq
+        px.seq += n_steps + 2
+        rc = lib.mcf_lsm_sharded(_ptr(paths_tm), n_paths, n_global, n_steps, float(K), float(r), float(dt), int(bool(is_put)),
+                                 _ptr(ws), nbytes, px.ptrs, px.rank, px.world, base, _ptr(price),
+                                 _ptr(ex) if ex is not None else None, sp)
+        N.check("mcf_lsm_sharded", rc)
+        LAUNCHES["lsm"] += n_steps
+        return (price, ex) if return_exercise else price
     sums = ws[:64].view(torch.float64)
     N.check("mcf_lsm_begin", lib.mcf_lsm_begin(_ptr(paths_tm), n_paths, n_steps, float(K), float(r), float(dt), int(bool(is_put)), _ptr(ws), nbytes, sp))
     for t in range(n_steps - 1, 0, -1):

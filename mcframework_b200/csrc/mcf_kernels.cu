@@ -960,6 +960,35 @@ static int g_last_cuda_error = 0;
 
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
+// One side stream and one fork/join event pair per device, created on first use and kept for the life of the process
+// (creating and destroying them per plan showed up as occasional multi-millisecond stalls).  A plan holds them only
+// between its fork and its join, both stream-ordered, so concurrent host threads on one device merely share the lane.
+#include <mutex>
+static bool side_stream_for_current_device(cudaStream_t *side, cudaEvent_t *fork, cudaEvent_t *join) {
+    struct Lane {
+        cudaStream_t s = nullptr;
+        cudaEvent_t f = nullptr, j = nullptr;
+        bool tried = false, ok = false;
+    };
+    static Lane lanes[64];
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    std::lock_guard<std::mutex> lock(mu);
+    Lane &l = lanes[dev];
+    if (!l.tried) {
+        l.tried = true;
+        l.ok = cudaStreamCreateWithFlags(&l.s, cudaStreamNonBlocking) == cudaSuccess &&
+               cudaEventCreateWithFlags(&l.f, cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&l.j, cudaEventDisableTiming) == cudaSuccess;
+        if (!l.ok) (void)cudaGetLastError();
+    }
+    *side = l.s;
+    *fork = l.f;
+    *join = l.j;
+    return l.ok;
+}
+
 template <int KIND>
 static int normal_plan_impl(const mcf_stream *d_streams, const mcf_stream *h_streams, const PlanGeom &g, int64_t nps,
                             int32_t iters, char *ws, uint64_t *d_sim_start, uint64_t *d_stream_end, cudaStream_t cs) {
@@ -989,9 +1018,7 @@ static int normal_plan_impl(const mcf_stream *d_streams, const mcf_stream *h_str
         const bool batched = g.cps / 256 < MCF_BATCH_BELOW_CTAS;
         cudaStream_t side = nullptr;
         cudaEvent_t fork = nullptr, join = nullptr;
-        const bool two = !batched && n_streams > 1 && cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) == cudaSuccess &&
-                         cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
-                         cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess;
+        const bool two = !batched && n_streams > 1 && side_stream_for_current_device(&side, &fork, &join);
         if (two) {
             cudaEventRecord(fork, cs);  // plan_init_kernel precedes every scan
             cudaStreamWaitEvent(side, fork, 0);
@@ -1009,9 +1036,6 @@ static int normal_plan_impl(const mcf_stream *d_streams, const mcf_stream *h_str
             cudaEventRecord(join, side);
             cudaStreamWaitEvent(cs, join, 0);
         }
-        if (fork) cudaEventDestroy(fork);
-        if (join) cudaEventDestroy(join);
-        if (side) cudaStreamDestroy(side);  // deferred by the runtime until its work has drained
     } else {
         plan_scan_kernel<KIND, RUN><<<grid_for(n_runs, 256), 256, 0, cs>>>(d_streams, g.cps, n_runs, sm, em, ex, gen, zs,
                                                                           hdr);
@@ -1041,6 +1065,72 @@ static int normal_plan_impl(const mcf_stream *d_streams, const mcf_stream *h_str
     plan_locate_kernel<<<(unsigned)g.n_tiles, 256, 0, cs>>>(d_streams, g.cps, g.tps, nps, sm, em, ex, ent, tpre,
                                                            d_sim_start, d_stream_end, (uint64_t *)(ws + g.off_send));
     MCF_CUDA_OK(cudaGetLastError());
+    return MCF_OK;
+}
+
+// Issue-rate probe (the roofline denominator of the RNG kernels, measured on the device the benchmark runs on): eight
+// independent chains of one instruction per thread, 4 CTAs x 256 threads per SM, so the loop is bound by the issue rate
+// of that instruction, not by its latency.  kind 0: IMAD.WIDE.U32 (32x32 -> 64 with a 64-bit addend), 1: IMAD (low 32
+// bits), 2: LOP3.  The same loop as tools/probe_pipes.cu.
+template <int KIND>
+__global__ void __launch_bounds__(256) issue_rate_probe_kernel(uint64_t *out, uint32_t m0, uint32_t m1, int iters) {
+    uint64_t a[8];
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        a[k] = threadIdx.x * 977u + k;
+        x[k] = threadIdx.x * 31u + k;
+    }
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (KIND == 0)
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[k]) : "r"(x[k]), "r"(m0));
+            else if (KIND == 1)
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(m0), "r"(m1));
+            else
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[k]) : "r"(m0), "r"(m1));
+        }
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += a[k] + x[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int mcf_probe_issue_rate(int32_t kind, double *warp_inst_per_s, void *cuda_stream) {
+    if (!warp_inst_per_s || kind < 0 || kind > 2) return MCF_ERR_BAD_ARG;
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    int dev = 0, sms = 0;
+    MCF_CUDA_OK(cudaGetDevice(&dev));
+    MCF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 4, iters = 16384;
+    uint64_t *out = nullptr;
+    MCF_CUDA_OK(cudaMalloc(&out, sizeof(uint64_t) * (size_t)blocks * 256));
+    cudaEvent_t e0, e1;
+    MCF_CUDA_OK(cudaEventCreate(&e0));
+    MCF_CUDA_OK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int r = 0; r < 6; r++) {  // the first repetition warms up
+        cudaEventRecord(e0, cs);
+        if (kind == 0)
+            issue_rate_probe_kernel<0><<<blocks, 256, 0, cs>>>(out, 0xE14C6C93u, 0xD2E7470Eu, iters);
+        else if (kind == 1)
+            issue_rate_probe_kernel<1><<<blocks, 256, 0, cs>>>(out, 0xE14C6C93u, 0xD2E7470Eu, iters);
+        else
+            issue_rate_probe_kernel<2><<<blocks, 256, 0, cs>>>(out, 0xE14C6C93u, 0xD2E7470Eu, iters);
+        cudaEventRecord(e1, cs);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    MCF_CUDA_OK(cudaGetLastError());
+    *warp_inst_per_s = (double)blocks * 8.0 * (double)iters * 8.0 / ((double)best * 1e-3);  // 8 warps per CTA, 8 chains
     return MCF_OK;
 }
 

@@ -1182,6 +1182,46 @@ __global__ void __launch_bounds__(LSM_THREADS) lsm_apply_kernel(const double *__
 // serial part costs no launch.  Per path and step: S_t and S_{t-1} (8 B each), cf read (8 B), cf written only where
 // the option is exercised.  t == n_steps is the initialisation (cf = discounted terminal intrinsic, no decision);
 // t == 1 accumulates the price sum instead of regression sums.
+// Paths sharded over the GPUs of one box: the 8 sums of a step are exchanged INSIDE the step kernel, over peer memory.
+// Every rank owns a small exchange buffer that all ranks have mapped (CUDA IPC over NVLink): the CTA that finishes last
+// stores its rank's 8 sums into slot [parity][rank] of EVERY rank's buffer, then a sequence number (system-scope
+// release), waits until all slots of its own buffer carry this step's number, adds them in rank order (the same order
+// on every rank: identical coefficients everywhere, deterministic) and solves.  No collective library call, no extra
+// launch, no host: a step of the sharded sweep is the single-GPU step plus one NVLink round trip.  Ranks can be at most
+// one step apart (nobody passes a step without everybody's sums), hence two slot sets by step parity.
+#define MCF_LSM_MAX_PEERS 8
+struct LsmPeers {
+    double *slots[MCF_LSM_MAX_PEERS];  // exchange buffer of every rank, as mapped in THIS process
+    int32_t rank, world;               // world == 1: no exchange
+    unsigned long long seq_base;       // sequence numbers of this sweep are seq_base + 1 .. seq_base + n_steps
+    double n_paths_global;
+};
+#define MCF_LSM_SLOT_DOUBLES 16  // 8 sums, the sequence number, padding to 128 bytes
+__host__ __device__ inline size_t lsm_slot_index(int parity, int rank) {
+    return ((size_t)parity * MCF_LSM_MAX_PEERS + (size_t)rank) * MCF_LSM_SLOT_DOUBLES;
+}
+__device__ __forceinline__ void lsm_exchange_sums(const LsmPeers &px, int parity, unsigned long long seq, double sums[8]) {
+    for (int p = 0; p < px.world; p++) {
+        volatile double *dst = px.slots[p] + lsm_slot_index(parity, px.rank);
+#pragma unroll
+        for (int k = 0; k < 8; k++) dst[k] = sums[k];
+    }
+    __threadfence_system();
+    for (int p = 0; p < px.world; p++)
+        *reinterpret_cast<volatile unsigned long long *>(px.slots[p] + lsm_slot_index(parity, px.rank) + 8) = seq;
+    double total[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int src = 0; src < px.world; src++) {
+        const double *mine = px.slots[px.rank] + lsm_slot_index(parity, src);
+        const volatile unsigned long long *flag = reinterpret_cast<const volatile unsigned long long *>(mine + 8);
+        while (*flag != seq) __nanosleep(20);
+        __threadfence_system();
+#pragma unroll
+        for (int k = 0; k < 8; k++) total[k] += reinterpret_cast<const volatile double *>(mine)[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) sums[k] = total[k];
+}
+
 // Sweep direction.  Column S_{t-1} is read here for the regression and again by the NEXT launch for its decision, and
 // the cash flows are read by every launch: 16 of the 24 bytes per path and step were touched one launch earlier.  One
 // launch's footprint (240 MB at 1e7 paths) exceeds the 126 MB L2, so a front-to-back sweep every step finds nothing left
@@ -1199,7 +1239,8 @@ __global__ void __launch_bounds__(LSM_THREADS, MCF_LSM_CTAS)
                           int32_t n_steps, double K, int is_put, double disc_t, double grow_prev,
                           const LsmState *__restrict__ st_cur, LsmState *__restrict__ st_next,
                           int32_t *__restrict__ ex, double *__restrict__ cf, double *__restrict__ partials,
-                          unsigned int *__restrict__ counter, double *__restrict__ price_out, int reverse) {
+                          unsigned int *__restrict__ counter, double *__restrict__ price_out, int reverse,
+                          const __grid_constant__ LsmPeers peers) {
     const bool init = t == n_steps, last_step = t == 1;
     // Programmatic dependent launch: this grid may start while the previous step's grid is still finishing (its last
     // CTA is adding the partial sums and solving).  The path columns do not depend on it, so the first trip's loads of
@@ -1326,8 +1367,18 @@ __global__ void __launch_bounds__(LSM_THREADS, MCF_LSM_CTAS)
     __syncthreads();
     if (threadIdx.x == 0) {
         *counter = 0;
+        double n_all = (double)n_paths;
+        if (peers.world > 1) {  // add the other ranks' sums (and receive theirs) before anybody solves
+            double sums[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) sums[k] = st_next->sums[k];
+            lsm_exchange_sums(peers, t & 1, peers.seq_base + (unsigned long long)(n_steps - t + 1), sums);
+#pragma unroll
+            for (int k = 0; k < 8; k++) st_next->sums[k] = sums[k];
+            n_all = peers.n_paths_global;
+        }
         if (last_step) {
-            if (price_out) *price_out = st_next->sums[0] / (double)n_paths;
+            if (price_out) *price_out = st_next->sums[0] / n_all;
         } else {
             lsm_solve_state(st_next);
         }
@@ -1899,8 +1950,9 @@ int mcf_lsm_finish(int64_t n_paths, double r, double dt, void *d_workspace, doub
     return MCF_OK;
 }
 
-int mcf_lsm(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K, double r, double dt, int32_t is_put,
-            void *d_workspace, int64_t workspace_bytes, double *d_price, int32_t *d_exercise_times, void *cuda_stream) {
+static int lsm_sweep(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K, double r, double dt, int32_t is_put,
+                     void *d_workspace, int64_t workspace_bytes, double *d_price, int32_t *d_exercise_times,
+                     const LsmPeers &peers, void *cuda_stream) {
     if (!d_paths_tm || n_paths <= 0 || n_steps < 1 || n_steps > 0x7fffffff || !d_workspace) return MCF_ERR_BAD_ARG;
     const LsmGeom g = lsm_geom(n_paths);
     if (workspace_bytes < g.total) return MCF_ERR_WORKSPACE_TOO_SMALL;
@@ -1931,10 +1983,67 @@ int mcf_lsm(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K
         MCF_CUDA_OK(cudaLaunchKernelEx(&cfg, lsm_fused_step_kernel, s_t, s_t - n_paths, n_paths, (int32_t)t, (int32_t)n_steps, K,
                                        (int)is_put, exp(-r * dt * (double)t), exp(r * dt * (double)(t - 1)),
                                        (const LsmState *)(st + (t & 1)), st + ((t - 1) & 1), d_exercise_times, cf, partials,
-                                       counter, d_price, (int)((n_steps - t) & 1)));
+                                       counter, d_price, (int)((n_steps - t) & 1), peers));
     }
     MCF_CUDA_OK(cudaGetLastError());
     return MCF_OK;
+}
+
+int mcf_lsm(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K, double r, double dt, int32_t is_put,
+            void *d_workspace, int64_t workspace_bytes, double *d_price, int32_t *d_exercise_times, void *cuda_stream) {
+    LsmPeers solo;
+    memset(&solo, 0, sizeof(solo));
+    solo.world = 1;
+    return lsm_sweep(d_paths_tm, n_paths, n_steps, K, r, dt, is_put, d_workspace, workspace_bytes, d_price, d_exercise_times,
+                     solo, cuda_stream);
+}
+
+// ---- peer-mapped exchange buffers (one per rank and process group; CUDA IPC, the GPUs of one box) ----
+int64_t mcf_lsm_exchange_bytes(void) { return (int64_t)(2 * MCF_LSM_MAX_PEERS * MCF_LSM_SLOT_DOUBLES * sizeof(double)); }
+
+int mcf_peer_buffer_create(int64_t bytes, void **d_ptr, void *handle64) {
+    if (bytes <= 0 || !d_ptr || !handle64) return MCF_ERR_BAD_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles travel as 64 opaque bytes");
+    MCF_CUDA_OK(cudaMalloc(d_ptr, (size_t)bytes));
+    MCF_CUDA_OK(cudaMemset(*d_ptr, 0, (size_t)bytes));
+    MCF_CUDA_OK(cudaDeviceSynchronize());
+    MCF_CUDA_OK(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, *d_ptr));
+    return MCF_OK;
+}
+int mcf_peer_buffer_open(const void *handle64, void **d_ptr) {
+    if (!handle64 || !d_ptr) return MCF_ERR_BAD_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    MCF_CUDA_OK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return MCF_OK;
+}
+int mcf_peer_buffer_close(void *d_ptr) {
+    if (d_ptr) MCF_CUDA_OK(cudaIpcCloseMemHandle(d_ptr));
+    return MCF_OK;
+}
+int mcf_peer_buffer_destroy(void *d_ptr) {
+    if (d_ptr) MCF_CUDA_OK(cudaFree(d_ptr));
+    return MCF_OK;
+}
+
+int mcf_lsm_sharded(const double *d_paths_tm, int64_t n_paths_local, int64_t n_paths_global, int64_t n_steps, double K, double r,
+                    double dt, int32_t is_put, void *d_workspace, int64_t workspace_bytes, void *const *peer_buffers,
+                    int32_t rank, int32_t world, uint64_t sequence_base, double *d_price, int32_t *d_exercise_times,
+                    void *cuda_stream) {
+    if (!peer_buffers || world < 1 || world > MCF_LSM_MAX_PEERS || rank < 0 || rank >= world || n_paths_global < n_paths_local)
+        return MCF_ERR_BAD_ARG;
+    LsmPeers px;
+    memset(&px, 0, sizeof(px));
+    for (int p = 0; p < world; p++) {
+        if (!peer_buffers[p]) return MCF_ERR_BAD_ARG;
+        px.slots[p] = (double *)peer_buffers[p];
+    }
+    px.rank = rank;
+    px.world = world;
+    px.seq_base = sequence_base;
+    px.n_paths_global = (double)n_paths_global;
+    return lsm_sweep(d_paths_tm, n_paths_local, n_steps, K, r, dt, is_put, d_workspace, workspace_bytes, d_price,
+                     d_exercise_times, px, cuda_stream);
 }
 
 int mcf_transpose(const double *d_in, int64_t n_rows, int64_t n_cols, double *d_out, void *cuda_stream) {

@@ -29,7 +29,7 @@ def _seq(S, seed, n):
 
 def test_abi_version(dev):
     _, N, _ = dev
-    assert N.lib().mcf_abi_version() == 3
+    assert N.lib().mcf_abi_version() == 4
     assert b"sm_100a" in N.lib().mcf_build_info()
 
 

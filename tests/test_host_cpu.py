@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in include/mcf_b200.h but not exported"
         assert name in _native.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.mcf_abi_version() == 3
+    assert lib.mcf_abi_version() == 4
     assert lib.mcf_select_workspace_bytes() > 0 and lib.mcf_lsm_workspace_bytes(1000) > 0
     assert lib.mcf_bootstrap_workspace_bytes(10 ** 6, 64) > 0 and lib.mcf_moments_workspace_bytes(5) > 0
 

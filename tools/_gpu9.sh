@@ -1,6 +1,7 @@
 N=${1:-2}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
 timeout 600 $TR tools/multi_gpu_check.py 2>&1 | grep -v "INFO\|Warning\|warn" | tail -12
+timeout 300 $TR tools/ab_lsm_multi.py 2>&1 | grep "^{" | tail -1
 timeout 900 $TR bench.py --gpus $N > gpurun_out/bench_r2_${N}gpu.json 2> gpurun_out/bench_r2_${N}gpu.err; tail -3 gpurun_out/bench_r2_${N}gpu.err | cut -c1-300
 timeout 600 $TR bench.py --gpus $N --scaling strong --configs none > gpurun_out/bench_r2_${N}gpu_strong.json 2>> gpurun_out/bench_r2_${N}gpu.err
 MCF_BENCH_GATHER=root timeout 600 $TR bench.py --gpus $N --configs none > gpurun_out/bench_r2_${N}gpu_rootgather.json 2>> gpurun_out/bench_r2_${N}gpu.err

@@ -99,7 +99,13 @@ def main():
     lo, hi = 4000 * rank // world, 4000 * (rank + 1) // world
     tm = SD.transpose(torch.from_numpy(np.ascontiguousarray(paths[lo:hi])).cuda())
     price = float(SD.lsm_price(tm, 100.0, 0.05, 1.0 / 50, True, group=dist.group.WORLD).cpu()[0])
-    check("LSM with sharded paths == reference", abs(price - j["G6"]["lsm_put"]) <= 1e-9 * j["G6"]["lsm_put"])
+    check("LSM with sharded paths == reference (fused step kernel, sums exchanged over peer memory)",
+          abs(price - j["G6"]["lsm_put"]) <= 1e-9 * j["G6"]["lsm_put"])
+    used_peer = SD.LsmPeerExchange.get(dist.group.WORLD).ok
+    staged = float(SD.lsm_price(tm, 100.0, 0.05, 1.0 / 50, True, group=dist.group.WORLD, fused=False).cpu()[0])
+    again = float(SD.lsm_price(tm, 100.0, 0.05, 1.0 / 50, False, group=dist.group.WORLD).cpu()[0])  # a second sweep, a call
+    check(f"LSM staged (NCCL all-reduce per step) == fused (peer exchange in use: {used_peer}); call price == reference",
+          abs(staged - price) <= 1e-12 * price and abs(again - j["G6"]["lsm_call"]) <= 1e-9 * j["G6"]["lsm_call"])
 
     flag = torch.tensor([int(all(ok))], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
