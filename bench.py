@@ -587,7 +587,8 @@ def cfg_lsm(cx):
            "paths_generation": {"s": t_paths, "path_steps_per_s": n * cx.world * steps / t_paths,
                                 "store_GBps_per_gpu": n * (steps + 1) * 8 / t_paths / 1e9,
                                 "includes": "planning pass of the sequential PCG64 stream + path kernel"},
-           "roofline": cx.hbm_roofline(alg, t, "lsm_fused_step_kernel" if cx.world == 1 else "lsm_reduce/solve/apply"),
+           "roofline": cx.hbm_roofline(alg, t, "lsm_fused_step_kernel" if cx.world == 1 else
+                                       "lsm_fused_step_kernel (the ranks' sums meet inside the kernel, over peer memory)"),
            "tensor_pipe_note": "3-column regression (8 sums per path): not tensor-core shaped, FP64 FMA; HBM binds",
            "checks": {"american_put_price": float(price.cpu()[0]), "reference_1e6_path_price": 6.053948135228681}}
     del paths
@@ -617,7 +618,7 @@ def cfg_stats(cx):
     out = {}
     t, _ = best_of(cx, lambda: SD.moments(x, 5.0, group=cx.group) if cx.world > 1 else SD.moments_raw(x, 5.0), reps=3)
     out["moments"] = {"s": t, "roofline": cx.hbm_roofline((hi - lo) * 8, t, "moments_kernel")}
-    t, p = best_of(cx, lambda: SD.percentiles(x, (1, 5, 50, 95, 99), group=cx.group), reps=3)
+    t, p = best_of(cx, lambda: SD.percentiles(x, (1, 5, 50, 95, 99), n_valid=n, group=cx.group), reps=3)
     out["percentiles"] = {"s": t, "values": [float(v) for v in p],
                           "roofline": cx.hbm_roofline(8 * (hi - lo) * 8, t, "select_hist/compact (8 radix passes, algorithmic)")}
     # the bootstrap resamples the WHOLE sample: with N ranks every rank holds all of x (one all-gather of the shards, as
