@@ -245,6 +245,16 @@ int mcf_select_begin(const int64_t *h_ranks, int32_t k, void *d_workspace, int64
 int mcf_select_hist(const double *d_x, int64_t n, int32_t omit_nonfinite, void *d_workspace, void *cuda_stream);
 int mcf_select_choose(void *d_workspace, void *cuda_stream);
 int mcf_select_finish(const void *d_workspace, double *d_out, void *cuda_stream);
+/* Large samples (n >= 2^22), NaN-free semantics: ONE pass over x instead of two radix passes plus a compaction pass.  A
+ * strided sub-sample of 2^20 values brackets every target rank (6 standard deviations of the sampling error); the pass
+ * counts the keys below / inside every bracket EXACTLY and appends the inside keys (a few per cent of x) to the scratch;
+ * the radix passes then run on those keys with rebased ranks.  h_ranks ascending, k <= 16.  *d_invalid != 0 afterwards:
+ * not decided here (ties heavier than the scratch, > 8 disjoint brackets, a sampling miss) -- run mcf_select_compacting.
+ * d_scratch: mcf_select_bracket_bytes(n).  Synchronises the stream once (uploads the bracket ranks). */
+int64_t mcf_select_bracket_bytes(int64_t n);
+int mcf_select_bracketed(const double *d_x, int64_t n, const int64_t *h_ranks, int32_t k, double *d_out, void *d_workspace,
+                         int64_t workspace_bytes, void *d_scratch, int64_t scratch_bytes, int32_t *d_invalid,
+                         void *cuda_stream);
 int mcf_select(const double *d_x, int64_t n, int32_t omit_nonfinite, const int64_t *h_ranks, int32_t k, double *d_out,
                void *d_workspace, int64_t workspace_bytes, void *cuda_stream);
 /* The same selection with a scratch buffer of mcf_select_compact_bytes(n) bytes (d_compact may be NULL = mcf_select): after

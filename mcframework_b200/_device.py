@@ -125,7 +125,7 @@ def _replan_parameters(status: int, slack: float, resolve_iters: int):
 
 
 def normal_plan(dl: DeviceLayout, normals_per_sim: int, slack: float | None = None, resolve_iters: int = 3,
-                max_retries: int = 4, check: bool = True) -> NormalPlan:
+                max_retries: int = 4, check: bool = True, buffers: dict | None = None) -> NormalPlan:
     """Planning pass for ziggurat-consuming replications ("stream-exact planning").
     ``check=False``: one attempt, no host synchronisation -- the caller reads ``plan.status()`` later (``with_plan``)."""
     torch = _torch()
@@ -133,13 +133,15 @@ def normal_plan(dl: DeviceLayout, normals_per_sim: int, slack: float | None = No
     lib = N.lib()
     if slack is None:  # a window that turns out too small is re-planned with a wider one below
         slack = default_slack(int(lay.max_sims) * int(normals_per_sim))
-    sim_start = torch.empty(lay.n_total, dtype=torch.int64, device="cuda")
+    # ``buffers``: optional dict a caller keeps across calls ({"sim_start", "workspace"} tensors are reused when they are
+    # large enough) -- a repeated plan of the same shape then allocates nothing
+    sim_start = _reuse(buffers, "sim_start", lay.n_total, torch.int64)
     stream_end = torch.zeros(lay.n_streams, dtype=torch.int64, device="cuda")
     for _ in range(max_retries):
         nbytes = lib.mcf_normal_plan_workspace_bytes(lay.n_streams, lay.max_sims, int(normals_per_sim), float(slack))
         if nbytes < 0:
             N.check("mcf_normal_plan_workspace_bytes", int(nbytes))
-        ws = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda")
+        ws = _reuse(buffers, "workspace", int(nbytes), torch.uint8)
         host_records = np.ascontiguousarray(lay.records)
         rc = lib.mcf_normal_plan(lay.kind, _ptr(dl.records), host_records.ctypes.data_as(C.c_void_p), lay.n_streams,
                                  lay.n_total, lay.max_sims,
@@ -167,11 +169,29 @@ def _spec_array(specs):
     return arr
 
 
-def gbm_terminal(dl: DeviceLayout, n_steps: int, plan: NormalPlan, specs):
-    """float64[(len(specs), n)] terminal values; ``specs`` = [(mode, params), ...] on common random numbers."""
+def _reuse(buffers, key: str, numel: int, dtype):
+    """A tensor of exactly ``numel`` elements: a view of ``buffers[key]`` when that exists and is large enough, else fresh
+    (and remembered in ``buffers`` for the next call)."""
+    torch = _torch()
+    if buffers is not None:
+        have = buffers.get(key)
+        if have is not None and have.dtype == dtype and have.numel() >= numel:
+            return have[:numel]
+    t = torch.empty(numel, dtype=dtype, device="cuda")
+    if buffers is not None:
+        buffers[key] = t
+    return t
+
+
+def gbm_terminal(dl: DeviceLayout, n_steps: int, plan: NormalPlan, specs, out=None):
+    """float64[(len(specs), n)] terminal values; ``specs`` = [(mode, params), ...] on common random numbers.
+    ``out``: optional float64 CUDA tensor of that shape to write into."""
     torch = _torch()
     lay = dl.layout
-    out = torch.empty((len(specs), lay.n_total), dtype=torch.float64, device="cuda")
+    if out is None:
+        out = torch.empty((len(specs), lay.n_total), dtype=torch.float64, device="cuda")
+    elif tuple(out.shape) != (len(specs), lay.n_total) or out.dtype != torch.float64 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float64 tensor of shape (len(specs), n)")
     host_records = np.ascontiguousarray(lay.records)
     rc = N.lib().mcf_gbm_terminal(lay.kind, _ptr(dl.records), host_records.ctypes.data_as(C.c_void_p), lay.n_streams,
                                   lay.n_total, int(n_steps), lay.hint, _ptr(plan.sim_start), _ptr(plan.workspace),

@@ -64,6 +64,8 @@ SIGNATURES = {
     "mcf_lsm_apply": (C.c_int, [_vp, _i64, _i64, _f64, _f64, _f64, _i32, _vp, _vp]),
     "mcf_lsm_finish": (C.c_int, [_i64, _f64, _f64, _vp, _vp, _vp, _vp, _vp]),
     "mcf_lsm": (C.c_int, [_vp, _i64, _i64, _f64, _f64, _f64, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "mcf_select_bracket_bytes": (_i64, [_i64]),
+    "mcf_select_bracketed": (C.c_int, [_vp, _i64, C.POINTER(C.c_int64), _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "mcf_probe_issue_rate": (C.c_int, [_i32, C.POINTER(C.c_double), _vp]),
     "mcf_lsm_exchange_bytes": (_i64, []),
     "mcf_peer_buffer_create": (C.c_int, [_i64, C.POINTER(C.c_void_p), _vp]),

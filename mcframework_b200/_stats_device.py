@@ -176,6 +176,38 @@ def select(x, ranks, omit_nonfinite: bool = False, group=None):
     return out
 
 
+#: samples of at least this many values try the one-pass bracketed selection first (exact; falls back when undecided)
+SELECT_BRACKET_MIN_N = 1 << 23
+
+
+def select_bracketed(x, ranks):
+    """``sorted(x)[ranks]`` for a LARGE NaN-free sample in one pass over ``x`` (``mcf_select_bracketed``): float64 device
+    tensor in the order of ``ranks``, or ``None`` when the one-pass form could not decide (the caller then runs the radix
+    selection).  At most 16 distinct ranks."""
+    torch = _torch()
+    lib = N.lib()
+    n = int(x.numel())
+    uniq = sorted({int(r) for r in ranks})
+    if n < SELECT_BRACKET_MIN_N or not uniq or len(uniq) > 16 or uniq[0] < 0 or uniq[-1] >= n:
+        return None
+    k = len(uniq)
+    nbytes = int(lib.mcf_select_workspace_bytes())
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    sbytes = int(lib.mcf_select_bracket_bytes(n))
+    scratch = torch.empty(sbytes, dtype=torch.uint8, device=x.device)
+    out = torch.empty(k + 1, dtype=torch.float64, device=x.device)  # [k] carries the "undecided" flag back in the same copy
+    flag = out[k:].view(torch.int32)
+    arr = (C.c_int64 * k)(*uniq)
+    rc = lib.mcf_select_bracketed(_ptr(x), n, arr, k, _ptr(out), _ptr(ws), nbytes, _ptr(scratch), sbytes, _ptr(flag), _stream_ptr())
+    N.check("mcf_select_bracketed", rc)
+    LAUNCHES["stats"] += 24 + 2 * int(lib.mcf_select_passes())
+    host = out.cpu()
+    if int(host[k:].view(torch.int32)[0]) != 0:
+        return None
+    pos = {r: i for i, r in enumerate(uniq)}
+    return host[:k][[pos[int(r)] for r in ranks]]
+
+
 def quantile_plan(n: int, percentiles):
     """NumPy's default ('linear') quantile definition as order-statistic ranks + interpolation weights
     (numpy/lib/_function_base_impl.py: 'linear' virtual index ``(n-1)*q``, ``_get_indexes``, ``_get_gamma``)."""
@@ -217,6 +249,11 @@ def percentiles(x, pcts, n_valid: int | None = None, has_nan: bool = False, omit
         return np.full(len(pcts), np.nan)
     prev, nxt, gamma = quantile_plan(n, pcts)
     ranks = np.concatenate([prev, nxt])
+    if group is None and not omit_nonfinite and n == int(x.numel()):  # large NaN-free samples: one pass over x
+        got = select_bracketed(x, ranks)
+        if got is not None:
+            vals = got.numpy()
+            return lerp_like_numpy(vals[:len(pcts)], vals[len(pcts):], gamma)
     out = np.empty(len(ranks), dtype=np.float64)
     for i in range(0, len(ranks), 32):  # MCF_SELECT_MAX_RANKS per launch
         out[i:i + 32] = select(x, ranks[i:i + 32], omit_nonfinite, group).cpu().numpy()

@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(256) moments_final_kernel(const MomentsPartial
 #define SEL_BITS 8
 #define SEL_BINS (1 << SEL_BITS)
 #define SEL_PASSES (64 / SEL_BITS)
+#define MCF_SELECT_SAMPLE (1 << 20)  // strided sub-sample that brackets the targets of mcf_select_bracketed
 
 struct SelectState {
     int32_t k, n_uniq, pass, pad;
@@ -382,6 +383,166 @@ __global__ void __launch_bounds__(512) select_compact_kernel(const double *__res
     }
 }
 __global__ void select_compact_done_kernel(SelectState *st) { st->compact_done = 1; }
+
+// ------------------------------------------------------------------------------------------- bracketed selection
+// Large samples: instead of two full radix passes (the second one bound by shared-memory atomics: every element is still
+// a candidate) plus a compaction pass, ONE pass over x suffices.  A strided sub-sample of 2^20 values brackets every
+// requested order statistic: for target rank r the sample's order statistics at r*m/n -+ delta (delta = 6 standard
+// deviations of the sampling error + slack) enclose it with overwhelming probability.  The pass over x counts, for each
+// bracket [L, H] (overlapping ones merged; at most 8), how many keys lie below L and inside it, and appends the inside
+// keys -- a few per cent of the data -- to `keys`.  The radix passes then run on those keys alone, with ranks rebased
+// to the candidate set.  The counts are exact, so the result is the exact order statistic or -- target outside its
+// bracket, scratch overflow (heavy ties) -- a flag that sends the caller to the plain radix path.  Nothing is
+// approximated.
+#define MCF_BRACKET_MAX 8
+struct BracketSet {
+    int32_t n_int, k, invalid, pad;
+    uint64_t lo[MCF_BRACKET_MAX], hi[MCF_BRACKET_MAX];   // merged key intervals, ascending, disjoint
+    int32_t interval_of[MCF_SELECT_MAX_RANKS];           // target rank -> interval
+    unsigned long long below[MCF_BRACKET_MAX], inside[MCF_BRACKET_MAX];
+};
+
+__global__ void select_sample_kernel(const double *__restrict__ x, int64_t stride, int64_t m, double *__restrict__ sample) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) sample[i] = __ldg(&x[i * stride]);
+}
+
+// one thread: bracket values (lo[0..k), hi[0..k) in target order, targets ascending) -> merged key intervals
+__global__ void select_bracket_build_kernel(const double *__restrict__ bvals, int k, const int32_t *__restrict__ open_lo,
+                                            const int32_t *__restrict__ open_hi, BracketSet *__restrict__ bs) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    BracketSet b;
+    memset(&b, 0, sizeof(b));
+    b.k = k;
+    int ni = 0;
+    for (int r = 0; r < k; r++) {
+        const uint64_t lo = open_lo[r] ? 0ULL : select_key(bvals[r], 0);
+        const uint64_t hi = open_hi[r] ? MCF_KEY_EXCLUDED : select_key(bvals[k + r], 0);
+        if (ni > 0 && lo <= b.hi[ni - 1]) {  // overlaps (or touches) the previous interval: merge
+            if (hi > b.hi[ni - 1]) b.hi[ni - 1] = hi;
+            if (lo < b.lo[ni - 1]) b.lo[ni - 1] = lo;
+        } else if (ni < MCF_BRACKET_MAX) {
+            b.lo[ni] = lo;
+            b.hi[ni] = hi;
+            ni++;
+        } else {
+            b.invalid = 1;  // more than MCF_BRACKET_MAX disjoint brackets: the caller takes the radix path
+        }
+        b.interval_of[r] = ni - 1;
+    }
+    b.n_int = ni;
+    *bs = b;
+}
+
+__global__ void __launch_bounds__(512) select_bracket_pass_kernel(const double *__restrict__ x, int64_t n,
+                                                                  BracketSet *__restrict__ bs, SelectState *__restrict__ st,
+                                                                  uint64_t *__restrict__ keys, int64_t cap) {
+    __shared__ uint64_t sh_lo[MCF_BRACKET_MAX], sh_hi[MCF_BRACKET_MAX];
+    __shared__ unsigned long long sh_below[MCF_BRACKET_MAX], sh_inside[MCF_BRACKET_MAX];
+    constexpr int UNROLL = 4;
+    __shared__ uint64_t stage[UNROLL * 512];
+    __shared__ unsigned sh_cnt;
+    __shared__ unsigned long long sh_base;
+    if (threadIdx.x < MCF_BRACKET_MAX) {
+        const bool live = (int)threadIdx.x < bs->n_int;
+        sh_lo[threadIdx.x] = live ? bs->lo[threadIdx.x] : MCF_KEY_EXCLUDED;  // dead intervals: nothing below, nothing inside
+        sh_hi[threadIdx.x] = live ? bs->hi[threadIdx.x] : 0ULL;
+        sh_below[threadIdx.x] = 0ULL;
+        sh_inside[threadIdx.x] = 0ULL;
+    }
+    __syncthreads();
+    uint64_t lo[MCF_BRACKET_MAX], hi[MCF_BRACKET_MAX];
+    unsigned below[MCF_BRACKET_MAX], inside[MCF_BRACKET_MAX];
+#pragma unroll
+    for (int j = 0; j < MCF_BRACKET_MAX; j++) {
+        lo[j] = sh_lo[j];
+        hi[j] = sh_hi[j];
+        below[j] = 0u;
+        inside[j] = 0u;
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t b0 = (int64_t)blockIdx.x * blockDim.x; b0 < n; b0 += UNROLL * nthr) {  // CTA-uniform trip count
+        if (threadIdx.x == 0) sh_cnt = 0u;
+        __syncthreads();
+        uint64_t key[UNROLL];
+#pragma unroll
+        for (int q = 0; q < UNROLL; q++) {
+            const int64_t i = b0 + threadIdx.x + q * nthr;
+            key[q] = i < n ? select_key(__ldg(&x[i]), 0) : MCF_KEY_EXCLUDED;
+        }
+#pragma unroll
+        for (int q = 0; q < UNROLL; q++) {
+            const int64_t i = b0 + threadIdx.x + q * nthr;
+            bool hit = false;
+            if (i < n) {
+#pragma unroll
+                for (int j = 0; j < MCF_BRACKET_MAX; j++) {
+                    const bool lt = key[q] < lo[j];
+                    const bool in = !lt && key[q] <= hi[j];
+                    below[j] += lt ? 1u : 0u;
+                    inside[j] += in ? 1u : 0u;
+                    hit |= in;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m == 0u) continue;
+            unsigned base = 0;
+            if (lane == __ffs(m) - 1) base = atomicAdd(&sh_cnt, (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (hit) stage[base + (unsigned)__popc(m & ((1u << lane) - 1u))] = key[q];
+        }
+        __syncthreads();
+        const unsigned cnt = sh_cnt;
+        if (threadIdx.x == 0 && cnt) sh_base = atomicAdd(&st->compact_n, (unsigned long long)cnt);
+        __syncthreads();
+        for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x)
+            if ((int64_t)(sh_base + j) < cap) keys[sh_base + j] = stage[j];
+    }
+#pragma unroll
+    for (int j = 0; j < MCF_BRACKET_MAX; j++) {
+        unsigned long long b = below[j], in = inside[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+            in += __shfl_xor_sync(0xffffffffu, in, o);
+        }
+        if (lane == 0) {
+            if (b) atomicAdd(&sh_below[j], b);
+            if (in) atomicAdd(&sh_inside[j], in);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < MCF_BRACKET_MAX) {
+        if (sh_below[threadIdx.x]) atomicAdd(&bs->below[threadIdx.x], sh_below[threadIdx.x]);
+        if (sh_inside[threadIdx.x]) atomicAdd(&bs->inside[threadIdx.x], sh_inside[threadIdx.x]);
+    }
+}
+
+// one thread: ranks relative to x -> ranks relative to the candidate set; anything that does not fit raises `invalid`
+__global__ void select_bracket_rebase_kernel(BracketSet *__restrict__ bs, SelectState *__restrict__ st, int64_t cap,
+                                             int32_t *__restrict__ invalid_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int bad = bs->invalid;
+    if ((int64_t)st->compact_n > cap) bad = 1;
+    unsigned long long before[MCF_BRACKET_MAX];
+    unsigned long long acc = 0ULL;
+    for (int j = 0; j < MCF_BRACKET_MAX; j++) {
+        before[j] = acc;
+        acc += bs->inside[j];
+    }
+    for (int r = 0; r < st->k && !bad; r++) {
+        const int j = bs->interval_of[r];
+        const unsigned long long rank = (unsigned long long)st->rank[r];
+        if (j < 0 || j >= bs->n_int || rank < bs->below[j] || rank >= bs->below[j] + bs->inside[j]) {
+            bad = 1;
+            break;
+        }
+        st->rank[r] = (int64_t)(rank - bs->below[j] + before[j]);
+    }
+    st->compact_done = 1;
+    *invalid_out = bad;
+}
 
 // one CTA: every rank walks the histogram of its prefix, picks its digit, then prefixes are re-uniqued
 __global__ void __launch_bounds__(1024) select_choose_kernel(SelectState *st, unsigned long long *hist) {
@@ -1200,15 +1361,17 @@ struct LsmPeers {
 __host__ __device__ inline size_t lsm_slot_index(int parity, int rank) {
     return ((size_t)parity * MCF_LSM_MAX_PEERS + (size_t)rank) * MCF_LSM_SLOT_DOUBLES;
 }
-__device__ __forceinline__ void lsm_exchange_sums(const LsmPeers &px, int parity, unsigned long long seq, double sums[8]) {
-    for (int p = 0; p < px.world; p++) {
-        volatile double *dst = px.slots[p] + lsm_slot_index(parity, px.rank);
+// thread p of the last CTA publishes this rank's sums to peer p (the eight NVLink round trips overlap) ...
+__device__ __forceinline__ void lsm_publish_sums(const LsmPeers &px, int peer, int parity, unsigned long long seq,
+                                                 const double *sums) {
+    volatile double *dst = px.slots[peer] + lsm_slot_index(parity, px.rank);
 #pragma unroll
-        for (int k = 0; k < 8; k++) dst[k] = sums[k];
-    }
+    for (int k = 0; k < 8; k++) dst[k] = sums[k];
     __threadfence_system();
-    for (int p = 0; p < px.world; p++)
-        *reinterpret_cast<volatile unsigned long long *>(px.slots[p] + lsm_slot_index(parity, px.rank) + 8) = seq;
+    *reinterpret_cast<volatile unsigned long long *>(px.slots[peer] + lsm_slot_index(parity, px.rank) + 8) = seq;
+}
+// ... and one thread waits for every rank's sums in its own buffer and adds them in rank order
+__device__ __forceinline__ void lsm_collect_sums(const LsmPeers &px, int parity, unsigned long long seq, double sums[8]) {
     double total[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (int src = 0; src < px.world; src++) {
         const double *mine = px.slots[px.rank] + lsm_slot_index(parity, src);
@@ -1365,14 +1528,17 @@ __global__ void __launch_bounds__(LSM_THREADS, MCF_LSM_CTAS)
         if (lane == 0) st_next->sums[wid] = v;
     }
     __syncthreads();
+    const unsigned long long seq = peers.seq_base + (unsigned long long)(n_steps - t + 1);
+    if (peers.world > 1) {  // this rank's sums go to every rank's exchange buffer, one thread per peer
+        if ((int)threadIdx.x < peers.world) lsm_publish_sums(peers, (int)threadIdx.x, t & 1, seq, st_next->sums);
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
         *counter = 0;
         double n_all = (double)n_paths;
-        if (peers.world > 1) {  // add the other ranks' sums (and receive theirs) before anybody solves
+        if (peers.world > 1) {  // add every rank's sums (same order everywhere) before anybody solves
             double sums[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) sums[k] = st_next->sums[k];
-            lsm_exchange_sums(peers, t & 1, peers.seq_base + (unsigned long long)(n_steps - t + 1), sums);
+            lsm_collect_sums(peers, t & 1, seq, sums);
 #pragma unroll
             for (int k = 0; k < 8; k++) st_next->sums[k] = sums[k];
             n_all = peers.n_paths_global;
@@ -1607,6 +1773,80 @@ int mcf_select_compacting(const double *d_x, int64_t n, int32_t omit_nonfinite, 
             MCF_CUDA_OK(cudaGetLastError());
         }
         rc = select_hist_launch(d_x, n, omit_nonfinite, d_workspace, p >= 2 ? keys : nullptr, cap, cuda_stream);
+        if (rc) return rc;
+        rc = mcf_select_choose(d_workspace, cuda_stream);
+        if (rc) return rc;
+    }
+    return mcf_select_finish(d_workspace, d_out, cuda_stream);
+}
+
+int64_t mcf_select_bracket_bytes(int64_t n) {
+    if (n <= 0) return MCF_ERR_BAD_ARG;
+    const SelectGeom g = select_geom();
+    // candidate keys | sample | second select workspace | bracket values | open flags | bracket set | flag
+    return align256((n / 8 + 1024) * 8) + align256((int64_t)MCF_SELECT_SAMPLE * 8) + g.total + align256(2 * MCF_SELECT_MAX_RANKS * 8) +
+           align256(2 * MCF_SELECT_MAX_RANKS * 4) + align256((int64_t)sizeof(BracketSet)) + 256;
+}
+
+// Exact order statistics of a LARGE sample without NaN handling (omit_nonfinite = 0 semantics; NaNs, if any, sort last):
+// h_ranks ascending, k <= 16.  *d_invalid (device int) != 0 afterwards means "not decided here": the caller runs
+// mcf_select_compacting instead (ties heavier than the scratch, more than 8 disjoint brackets, a 6-sigma sampling miss).
+int mcf_select_bracketed(const double *d_x, int64_t n, const int64_t *h_ranks, int32_t k, double *d_out, void *d_workspace,
+                         int64_t workspace_bytes, void *d_scratch, int64_t scratch_bytes, int32_t *d_invalid,
+                         void *cuda_stream) {
+    if (!d_x || !h_ranks || !d_out || !d_workspace || !d_scratch || !d_invalid || k < 1 || 2 * k > MCF_SELECT_MAX_RANKS ||
+        n < 4 * (int64_t)MCF_SELECT_SAMPLE)
+        return MCF_ERR_BAD_ARG;
+    if (scratch_bytes < mcf_select_bracket_bytes(n)) return MCF_ERR_WORKSPACE_TOO_SMALL;
+    for (int r = 0; r < k; r++)
+        if (h_ranks[r] < 0 || h_ranks[r] >= n || (r > 0 && h_ranks[r] < h_ranks[r - 1])) return MCF_ERR_BAD_ARG;
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    const SelectGeom g = select_geom();
+    char *sc = (char *)d_scratch;
+    const int64_t cap = n / 8 + 1024;
+    uint64_t *keys = (uint64_t *)sc;
+    sc += align256(cap * 8);
+    double *sample = (double *)sc;
+    sc += align256((int64_t)MCF_SELECT_SAMPLE * 8);
+    void *ws2 = sc;
+    sc += g.total;
+    double *bvals = (double *)sc;
+    sc += align256(2 * MCF_SELECT_MAX_RANKS * 8);
+    int32_t *open_flags = (int32_t *)sc;
+    sc += align256(2 * MCF_SELECT_MAX_RANKS * 4);
+    BracketSet *bs = (BracketSet *)sc;
+
+    // 1. strided sample and the sample ranks that bracket every target
+    const int64_t m = MCF_SELECT_SAMPLE, stride = n / m;
+    select_sample_kernel<<<(unsigned)((m + 255) / 256), 256, 0, cs>>>(d_x, stride, m, sample);
+    int64_t sranks[MCF_SELECT_MAX_RANKS];
+    int32_t h_open[2 * MCF_SELECT_MAX_RANKS];
+    for (int r = 0; r < k; r++) {
+        const double q = (double)h_ranks[r] / (double)n;
+        const double pos = q * (double)m;
+        const double delta = 6.0 * sqrt((double)m * q * (1.0 - q)) + 8.0;
+        int64_t lo = (int64_t)floor(pos - delta), hi = (int64_t)ceil(pos + delta);
+        h_open[r] = lo <= 0;          // nothing of the sample below: the bracket is open towards -inf
+        h_open[k + r] = hi >= m - 1;  // ... towards +inf (NaN keys included)
+        sranks[r] = lo < 0 ? 0 : lo;
+        sranks[k + r] = hi > m - 1 ? m - 1 : hi;
+    }
+    // the 2k sample order statistics, ascending per half (targets ascend, so do their brackets)
+    int rc = mcf_select(sample, m, 0, sranks, 2 * k, bvals, ws2, g.total, cuda_stream);
+    if (rc) return rc;
+    MCF_CUDA_OK(cudaMemcpyAsync(open_flags, h_open, sizeof(int32_t) * 2 * (size_t)k, cudaMemcpyHostToDevice, cs));
+    MCF_CUDA_OK(cudaStreamSynchronize(cs));  // h_open / sranks live on this stack frame
+    select_bracket_build_kernel<<<1, 32, 0, cs>>>(bvals, k, open_flags, open_flags + k, bs);
+    // 2. one pass over x: exact counts below / inside every bracket, inside keys appended
+    rc = mcf_select_begin(h_ranks, k, d_workspace, workspace_bytes, cuda_stream);
+    if (rc) return rc;
+    SelectState *st = (SelectState *)((char *)d_workspace + g.off_state);
+    select_bracket_pass_kernel<<<grid_cap(n, 512 * 8, MCF_SM_COUNT * 4), 512, 0, cs>>>(d_x, n, bs, st, keys, cap);
+    select_bracket_rebase_kernel<<<1, 32, 0, cs>>>(bs, st, cap, d_invalid);
+    MCF_CUDA_OK(cudaGetLastError());
+    // 3. radix passes over the candidate keys only
+    for (int p = 0; p < SEL_PASSES; p++) {
+        rc = select_hist_launch(d_x, n, 0, d_workspace, keys, cap, cuda_stream);
         if (rc) return rc;
         rc = mcf_select_choose(d_workspace, cuda_stream);
         if (rc) return rc;

@@ -382,3 +382,44 @@ def test_bootstrap_binned_path_is_the_same_index_stream(sd, n, B, shift, cs):
     assert g_dev.bit_generator.state == g_ref.bit_generator.state
     plain = sd.bootstrap_means(_dev_tensor(xi), B, g_dev2, binned=False, chunk_slots=cs).cpu().numpy() * n
     assert np.array_equal(np.rint(plain), want)
+
+
+@pytest.mark.parametrize("case", ["normal", "lognormal_heavy_tail", "half_zeros", "sorted", "constant", "with_infs", "few_levels"])
+def test_bracketed_selection_is_exact(sd, case):
+    """Large samples take the one-pass bracketed selection (mcf_select_bracketed: sample brackets, exact counts, radix
+    passes on the candidates only).  Bit-exact against np.percentile whatever the shape of the data; heavy ties and
+    constant data are the cases it hands back to the plain radix path (same answer either way)."""
+    n = 9_000_001
+    rng = np.random.default_rng(17)
+    if case == "normal":
+        x = rng.normal(5, 2, n)
+    elif case == "lognormal_heavy_tail":
+        x = np.exp(rng.normal(0, 3, n))
+    elif case == "half_zeros":  # option payoffs: a point mass at 0 heavier than the candidate scratch
+        x = np.maximum(rng.normal(0, 1, n), 0.0)
+    elif case == "sorted":
+        x = np.sort(rng.normal(0, 1, n))
+    elif case == "constant":
+        x = np.full(n, 3.25)
+    elif case == "with_infs":
+        x = rng.normal(0, 1, n)
+        x[::1000] = np.inf
+        x[5::1000] = -np.inf
+    else:
+        x = rng.integers(0, 7, n).astype(float)
+    xd = _dev_tensor(x)
+    pcts = (0, 0.001, 1, 5, 25, 50, 75, 95, 99, 99.999, 100)[:8] if case != "normal" else (1, 5, 25, 50, 75, 95, 99)
+    got = sd.percentiles(xd, pcts)
+    want = np.percentile(x, pcts)
+    assert np.array_equal(got, want, equal_nan=True), (case, got, want)  # (inf - inf in NumPy's lerp is NaN on both sides)
+    # the direct entry: order statistics at ranks including both ends
+    ranks = [0, 1, n // 3, n // 2, n - 2, n - 1]
+    direct = sd.select_bracketed(xd, ranks)
+    ref = np.sort(x)[ranks]
+    if direct is not None:
+        assert np.array_equal(direct.numpy(), ref), case
+    else:
+        assert case in ("half_zeros", "constant", "few_levels", "with_infs", "sorted", "lognormal_heavy_tail", "normal")
+    assert np.array_equal(sd.select(xd, ranks).cpu().numpy(), ref)
+    if case == "normal":  # the smooth case must really be decided by the one-pass form
+        assert sd.select_bracketed(xd, [n // 100, n // 2, (99 * n) // 100]) is not None
