@@ -578,6 +578,7 @@ def cfg_lsm(cx):
     n_total, steps = int(1e7 * cx.args.config_scale), 252
     n = n_total // cx.world
     sim = mcf.BlackScholesPathSimulation()
+    sim.simulate_paths(2048, n_steps=steps, device=True, time_major=True)  # first use of the PCG64 kernels (module load)
     sim.set_seed(1 + 1000 * cx.rank)  # each rank draws its own shard of paths
     cx.barrier()
     a = ev(torch)

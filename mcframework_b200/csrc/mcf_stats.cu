@@ -421,12 +421,12 @@ __global__ void select_bracket_build_kernel(const double *__restrict__ bvals, in
         if (ni > 0 && lo <= b.hi[ni - 1]) {  // overlaps (or touches) the previous interval: merge
             if (hi > b.hi[ni - 1]) b.hi[ni - 1] = hi;
             if (lo < b.lo[ni - 1]) b.lo[ni - 1] = lo;
-        } else if (ni < MCF_BRACKET_MAX) {
+        } else if (ni < MCF_BRACKET_MAX - 1) {  // the three-probe search of the pass kernel resolves 7 intervals
             b.lo[ni] = lo;
             b.hi[ni] = hi;
             ni++;
         } else {
-            b.invalid = 1;  // more than MCF_BRACKET_MAX disjoint brackets: the caller takes the radix path
+            b.invalid = 1;  // more than 7 disjoint brackets: the caller takes the radix path
         }
         b.interval_of[r] = ni - 1;
     }
@@ -437,29 +437,27 @@ __global__ void select_bracket_build_kernel(const double *__restrict__ bvals, in
 __global__ void __launch_bounds__(512) select_bracket_pass_kernel(const double *__restrict__ x, int64_t n,
                                                                   BracketSet *__restrict__ bs, SelectState *__restrict__ st,
                                                                   uint64_t *__restrict__ keys, int64_t cap) {
+    // interval search: p = #{j : lo[j] <= key} by three probes of a sorted 8-entry table (at most 7 live intervals, dead
+    // entries hold the maximum key), then one probe of hi[p-1]; per-thread counters live in shared memory, one column per
+    // thread (no atomics, no bank conflicts): hist[p] counts keys with exactly p interval starts at or below them.
     __shared__ uint64_t sh_lo[MCF_BRACKET_MAX], sh_hi[MCF_BRACKET_MAX];
-    __shared__ unsigned long long sh_below[MCF_BRACKET_MAX], sh_inside[MCF_BRACKET_MAX];
+    __shared__ unsigned short sh_hist[MCF_BRACKET_MAX][512], sh_in[MCF_BRACKET_MAX][512];  // < 2^16 elements per thread
     constexpr int UNROLL = 4;
     __shared__ uint64_t stage[UNROLL * 512];
     __shared__ unsigned sh_cnt;
     __shared__ unsigned long long sh_base;
     if (threadIdx.x < MCF_BRACKET_MAX) {
         const bool live = (int)threadIdx.x < bs->n_int;
-        sh_lo[threadIdx.x] = live ? bs->lo[threadIdx.x] : MCF_KEY_EXCLUDED;  // dead intervals: nothing below, nothing inside
+        sh_lo[threadIdx.x] = live ? bs->lo[threadIdx.x] : MCF_KEY_EXCLUDED;
         sh_hi[threadIdx.x] = live ? bs->hi[threadIdx.x] : 0ULL;
-        sh_below[threadIdx.x] = 0ULL;
-        sh_inside[threadIdx.x] = 0ULL;
     }
-    __syncthreads();
-    uint64_t lo[MCF_BRACKET_MAX], hi[MCF_BRACKET_MAX];
-    unsigned below[MCF_BRACKET_MAX], inside[MCF_BRACKET_MAX];
 #pragma unroll
     for (int j = 0; j < MCF_BRACKET_MAX; j++) {
-        lo[j] = sh_lo[j];
-        hi[j] = sh_hi[j];
-        below[j] = 0u;
-        inside[j] = 0u;
+        sh_hist[j][threadIdx.x] = 0;
+        sh_in[j][threadIdx.x] = 0;
     }
+    __syncthreads();
+    const bool top_open = bs->n_int > 0 && bs->hi[bs->n_int - 1] == MCF_KEY_EXCLUDED;  // a bracket open towards +inf
     const int lane = threadIdx.x & 31;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
     for (int64_t b0 = (int64_t)blockIdx.x * blockDim.x; b0 < n; b0 += UNROLL * nthr) {  // CTA-uniform trip count
@@ -476,14 +474,16 @@ __global__ void __launch_bounds__(512) select_bracket_pass_kernel(const double *
             const int64_t i = b0 + threadIdx.x + q * nthr;
             bool hit = false;
             if (i < n) {
-#pragma unroll
-                for (int j = 0; j < MCF_BRACKET_MAX; j++) {
-                    const bool lt = key[q] < lo[j];
-                    const bool in = !lt && key[q] <= hi[j];
-                    below[j] += lt ? 1u : 0u;
-                    inside[j] += in ? 1u : 0u;
-                    hit |= in;
-                }
+                // dead entries compare as "above every key" except for the maximum key itself (NaN), which an open
+                // top bracket must still catch: strict < on dead entries is what `lo <= key` gives for lo = MAX only
+                // when key = MAX, and then hi = 0 rejects it unless the live top bracket is open (handled below)
+                int p = sh_lo[3] <= key[q] ? 4 : 0;
+                p += sh_lo[p + 1] <= key[q] ? 2 : 0;
+                p += sh_lo[p] <= key[q] ? 1 : 0;
+                if (key[q] == MCF_KEY_EXCLUDED) p = top_open ? bs->n_int : p;  // NaN keys: the last live interval or none
+                hit = p > 0 && key[q] <= sh_hi[p - 1];
+                sh_hist[p][threadIdx.x] += 1;
+                if (hit) sh_in[p - 1][threadIdx.x] += 1;
             }
             const unsigned m = __ballot_sync(0xffffffffu, hit);
             if (m == 0u) continue;
@@ -499,23 +499,23 @@ __global__ void __launch_bounds__(512) select_bracket_pass_kernel(const double *
         for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x)
             if ((int64_t)(sh_base + j) < cap) keys[sh_base + j] = stage[j];
     }
-#pragma unroll
-    for (int j = 0; j < MCF_BRACKET_MAX; j++) {
-        unsigned long long b = below[j], in = inside[j];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            b += __shfl_xor_sync(0xffffffffu, b, o);
-            in += __shfl_xor_sync(0xffffffffu, in, o);
-        }
-        if (lane == 0) {
-            if (b) atomicAdd(&sh_below[j], b);
-            if (in) atomicAdd(&sh_inside[j], in);
-        }
-    }
     __syncthreads();
-    if (threadIdx.x < MCF_BRACKET_MAX) {
-        if (sh_below[threadIdx.x]) atomicAdd(&bs->below[threadIdx.x], sh_below[threadIdx.x]);
-        if (sh_inside[threadIdx.x]) atomicAdd(&bs->inside[threadIdx.x], sh_inside[threadIdx.x]);
+    // column sums: warp w adds rows w and w+... over the 512 columns
+    const int wid = threadIdx.x >> 5;
+    for (int row = wid; row < 2 * MCF_BRACKET_MAX; row += 16) {
+        const unsigned short *src = row < MCF_BRACKET_MAX ? sh_hist[row] : sh_in[row - MCF_BRACKET_MAX];
+        unsigned long long v = 0ULL;
+        for (int c = lane; c < 512; c += 32) v += src[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) {
+            if (row < MCF_BRACKET_MAX) {
+                // hist[p]: keys with p starts at or below them are BELOW the starts of intervals p, p+1, ...
+                for (int j = row; j < MCF_BRACKET_MAX; j++) atomicAdd(&bs->below[j], v);
+            } else {
+                atomicAdd(&bs->inside[row - MCF_BRACKET_MAX], v);
+            }
+        }
     }
 }
 
@@ -547,7 +547,9 @@ __global__ void select_bracket_rebase_kernel(BracketSet *__restrict__ bs, Select
 // one CTA: every rank walks the histogram of its prefix, picks its digit, then prefixes are re-uniqued
 __global__ void __launch_bounds__(1024) select_choose_kernel(SelectState *st, unsigned long long *hist) {
     __shared__ SelectState s;
-    if (threadIdx.x == 0) s = *st;
+    static_assert(sizeof(SelectState) % 8 == 0, "copied as 64-bit words");
+    for (int i = threadIdx.x; i < (int)(sizeof(SelectState) / 8); i += blockDim.x)  // (one thread copying 1.3 KB was a third of this kernel)
+        reinterpret_cast<uint64_t *>(&s)[i] = reinterpret_cast<const uint64_t *>(st)[i];
     __syncthreads();
     const int n_rows = s.n_uniq;
     // one warp per rank: 8 coalesced 32-bin loads + shuffle scans instead of 256 dependent global loads
@@ -610,9 +612,10 @@ __global__ void __launch_bounds__(1024) select_choose_kernel(SelectState *st, un
                 if (s.uniq[u] == s.prefix[r]) s.uniq_of[r] = u;
         s.n_uniq = nu;
         s.pass += 1;
-        *st = s;
     }
     __syncthreads();
+    for (int i = threadIdx.x; i < (int)(sizeof(SelectState) / 8); i += blockDim.x)
+        reinterpret_cast<uint64_t *>(st)[i] = reinterpret_cast<const uint64_t *>(&s)[i];
     for (int i = threadIdx.x; i < n_rows * SEL_BINS; i += blockDim.x) hist[i] = 0ULL;  // only the rows that were used
 }
 
@@ -1798,6 +1801,7 @@ int mcf_select_bracketed(const double *d_x, int64_t n, const int64_t *h_ranks, i
         n < 4 * (int64_t)MCF_SELECT_SAMPLE)
         return MCF_ERR_BAD_ARG;
     if (scratch_bytes < mcf_select_bracket_bytes(n)) return MCF_ERR_WORKSPACE_TOO_SMALL;
+    if (n / ((int64_t)grid_cap(n, 512 * 8, MCF_SM_COUNT * 4) * 512) >= 65000) return MCF_ERR_BAD_ARG;  // 16-bit per-thread counters
     for (int r = 0; r < k; r++)
         if (h_ranks[r] < 0 || h_ranks[r] >= n || (r > 0 && h_ranks[r] < h_ranks[r - 1])) return MCF_ERR_BAD_ARG;
     cudaStream_t cs = (cudaStream_t)cuda_stream;
