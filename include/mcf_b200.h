@@ -288,6 +288,25 @@ int mcf_bootstrap_accumulate(uint32_t gen_kind, const mcf_stream *d_stream, cons
                              int64_t n_resamples, uint64_t slot_lo, uint64_t slot_hi, int32_t chunk_slots,
                              uint64_t ordinal_base, const void *d_workspace, int64_t workspace_bytes, double *d_sums,
                              uint64_t *d_end_slot, void *cuda_stream);
+/* Single-pass form of the binned bootstrap.  The ordinal at slot s is s*(1-p) to within a few standard deviations of a
+ * binomial count, so a CTA whose estimated ordinal range (+- 8 sigma) lies strictly inside ONE resample -- 96 % of them at
+ * n = 1e8 -- bins into that resample in its only pass over its slots and counts what it accepted on the way; only the CTAs
+ * near resample boundaries and near the end of the draw are counted first and binned with exact ordinals.  phase1: safe
+ * CTAs (bin + gather, batch by batch), count of the others, prefix sums; *d_total = accepted slots of [slot_lo, slot_hi).
+ * phase2 (ordinal_base = accepted slots of all lower ranks): the exact CTAs, then every safe CTA is checked against its
+ * exact ordinal range: *d_flag != 0 (an 8-sigma miss) or *d_end_slot == 0 (window too small) => recompute with
+ * mcf_bootstrap_count + mcf_bootstrap_accumulate_binned.  slot_total: slots of ALL ranks (sets the margin).  Workspaces as
+ * for the two-pass form.  Both calls synchronise the stream. */
+int mcf_bootstrap_fused_phase1(uint32_t gen_kind, const mcf_stream *d_stream, const double *d_x, int64_t n, int64_t n_resamples,
+                               uint64_t slot_lo, uint64_t slot_hi, uint64_t slot_total, int32_t chunk_slots, void *d_workspace,
+                               int64_t workspace_bytes, int32_t resamples_per_batch, int32_t region_shift,
+                               void *d_bin_workspace, int64_t bin_workspace_bytes, double *d_sums, uint64_t *d_total,
+                               void *cuda_stream);
+int mcf_bootstrap_fused_phase2(uint32_t gen_kind, const mcf_stream *d_stream, const double *d_x, int64_t n, int64_t n_resamples,
+                               uint64_t slot_lo, uint64_t slot_hi, uint64_t slot_total, int32_t chunk_slots,
+                               uint64_t ordinal_base, void *d_workspace, int64_t workspace_bytes, int32_t resamples_per_batch,
+                               int32_t region_shift, void *d_bin_workspace, int64_t bin_workspace_bytes, double *d_sums,
+                               uint64_t *d_end_slot, int32_t *d_flag, void *cuda_stream);
 int mcf_bootstrap_finalize(double *d_sums, int64_t n_resamples, int64_t n, void *cuda_stream);
 /* Binned variant of mcf_bootstrap_accumulate for populations larger than L2 (a random 8-byte gather from HBM moves a
  * 128-byte line; from an L2-resident region it is 3-4x faster): the accepted indices of `resamples_per_batch`

@@ -99,6 +99,10 @@ SIGNATURES = {
     "mcf_bootstrap_binned_workspace_bytes": (_i64, [_i64, _i32, _i32]),
     "mcf_bootstrap_accumulate_binned": (C.c_int, [_u32, _vp, _vp, _i64, _i64, _u64, _u64, _i32, _u64, _vp, _i64, _vp, _i32, _i32,
                                                   _vp, _i64, _vp, _vp, _vp]),
+    "mcf_bootstrap_fused_phase1": (C.c_int, [_u32, _vp, _vp, _i64, _i64, C.c_uint64, C.c_uint64, C.c_uint64, _i32, _vp, _i64, _i32,
+                                             _i32, _vp, _i64, _vp, _vp, _vp]),
+    "mcf_bootstrap_fused_phase2": (C.c_int, [_u32, _vp, _vp, _i64, _i64, C.c_uint64, C.c_uint64, C.c_uint64, _i32, C.c_uint64, _vp,
+                                             _i64, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
     "mcf_count_less": (C.c_int, [_vp, _i64, _f64, _vp, _vp]),
     "mcf_compact_workspace_bytes": (_i64, [_i64]),
     "mcf_compact_finite": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp]),

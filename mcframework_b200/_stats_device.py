@@ -286,11 +286,71 @@ def rejection_probability(n: int) -> float:
 
 #: populations above this many elements use the binned (L2-resident regions) gather path
 BINNED_MIN_N = 12_000_000
+#: how many binned bootstraps were decided by the single-pass form / recomputed or run by the two-pass form (tests, bench)
+BOOT_FORMS = {"single_pass": 0, "two_pass": 0}
+
+
+def _slot_window(need: int, p: float, extra_sigma: float) -> int:
+    """Slots of the single index stream that hold ``need`` accepted ones, + ``extra_sigma`` standard deviations."""
+    if p <= 0:
+        return need
+    expect = need / (1.0 - p)
+    return int(math.ceil(expect + extra_sigma * math.sqrt(expect * p / max(1e-300, (1.0 - p))) + 64))
+
+
+def _bootstrap_single_pass(x, n, B, kind, d_rec, p, rank, world, group, chunk_slots, region_shift, resamples_per_batch,
+                           sums, end_slot) -> bool:
+    """Binned bootstrap without the count pass (``mcf_bootstrap_fused_phase1/2``): CTAs whose estimated ordinal range lies
+    inside one resample bin and count in one pass, the rest get exact ordinals.  False = undecided, nothing usable in
+    ``sums`` (the caller recomputes with the two-pass form)."""
+    torch = _torch()
+    lib = N.lib()
+    total_slots = _slot_window(B * n, p, 8.0)
+    lo, hi = total_slots * rank // world, total_slots * (rank + 1) // world
+    nslots = hi - lo
+    cs = chunk_slots or int(min(8192, max(64, (nslots // (148 * 2048 * 2)) // 8 * 8)))
+    if 256 * cs > n:
+        return False
+    nbytes = int(lib.mcf_bootstrap_workspace_bytes(nslots, cs))
+    bbytes = int(lib.mcf_bootstrap_binned_workspace_bytes(n, int(resamples_per_batch), int(region_shift)))
+    if nbytes < 0 or bbytes < 0:
+        return False
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    bws = torch.empty(bbytes, dtype=torch.uint8, device=x.device)
+    total = torch.zeros(1, dtype=torch.int64, device=x.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+    sp = _stream_ptr()
+    rc = lib.mcf_bootstrap_fused_phase1(kind, _ptr(d_rec), _ptr(x), n, B, lo, hi, total_slots, cs, _ptr(ws), nbytes,
+                                        int(resamples_per_batch), int(region_shift), _ptr(bws), bbytes, _ptr(sums), _ptr(total), sp)
+    ok = rc == N.OK
+    if group is not None:
+        import torch.distributed as dist
+
+        totals = [torch.empty_like(total) for _ in range(world)]
+        dist.all_gather(totals, total, group=group)
+        base = sum(int(t.item()) for t in totals[:rank])
+    else:
+        base = 0
+    if ok:
+        rc = lib.mcf_bootstrap_fused_phase2(kind, _ptr(d_rec), _ptr(x), n, B, lo, hi, total_slots, cs, base, _ptr(ws), nbytes,
+                                            int(resamples_per_batch), int(region_shift), _ptr(bws), bbytes, _ptr(sums),
+                                            _ptr(end_slot), _ptr(flag), sp)
+        ok = rc == N.OK
+    LAUNCHES["stats"] += 6
+    bad = torch.tensor([0 if ok else 1], dtype=torch.int32, device=x.device) + flag
+    if group is not None:
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(end_slot, op=dist.ReduceOp.MAX, group=group)
+    if int(bad.item()) != 0 or int(end_slot.item()) == 0:
+        return False
+    if group is not None:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    return True
 
 
 def bootstrap_means(x, n_resamples: int, gen: np.random.Generator, group=None, advance: bool = True,
                     chunk_slots: int | None = None, binned: bool | None = None, region_shift: int = 0,
-                    resamples_per_batch: int = 32):
+                    resamples_per_batch: int = 32, single_pass: bool = True):
     """``x[rng.integers(0, n, size=(B, n))].mean(axis=1)`` (stats_engine.py:1039-1041) without the index
     matrix: float64[B] device tensor.  ``gen`` is advanced exactly as NumPy would have advanced it.
 
@@ -319,6 +379,19 @@ def bootstrap_means(x, n_resamples: int, gen: np.random.Generator, group=None, a
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     sums = torch.zeros(B, dtype=torch.float64, device=x.device)
     end_slot = torch.zeros(1, dtype=torch.int64, device=x.device)
+    if binned is None:
+        binned = n >= BINNED_MIN_N
+    if binned and single_pass and p > 0:
+        done = _bootstrap_single_pass(x, n, B, kind, d_rec, p, rank, world, group, chunk_slots, region_shift,
+                                      resamples_per_batch, sums, end_slot)
+        if done:
+            BOOT_FORMS["single_pass"] += 1
+            N.check("mcf_bootstrap_finalize", lib.mcf_bootstrap_finalize(_ptr(sums), B, n, _stream_ptr()))
+            if advance:
+                _advance_generator(gen, int(end_slot.item()))
+            return sums
+        sums.zero_()  # undecided (an 8-sigma miss, a window too small): the two-pass form below recomputes everything
+        end_slot.zero_()
     extra_sigma = 8.0
     for _attempt in range(4):
         expect = need / (1.0 - p)
@@ -345,11 +418,10 @@ def bootstrap_means(x, n_resamples: int, gen: np.random.Generator, group=None, a
     else:
         raise N.NativeError("mcf_bootstrap_count", N.ERR_WINDOW_TOO_SMALL, "slot window too small after retries")
     base = sum(totals[:rank])
-    if binned is None:
-        binned = n >= BINNED_MIN_N
     if binned and 256 * cs > n:
         binned = False  # a CTA must not span more than two resamples
     if binned:
+        BOOT_FORMS["two_pass"] += 1
         nb = int(lib.mcf_bootstrap_blocks(nslots, cs))
         h_bb = np.empty(nb, dtype=np.uint64)
         N.check("mcf_bootstrap_block_base", lib.mcf_bootstrap_block_base(_ptr(ws), nslots, cs, h_bb.ctypes.data_as(C.c_void_p), _stream_ptr()))

@@ -14,7 +14,9 @@
 //               basis) + a 3x3 pseudo-inverse solve + one decision sweep; state per path is
 //               (exercise step, cash flow at exercise).
 #include <cuda_runtime.h>
+#include <vector>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "mcf_stats_device.cuh"
 
@@ -626,9 +628,10 @@ __global__ void select_finish_kernel(const SelectState *st, double *out) {
 // ===================================================================================== bootstrap
 struct BootGeom {
     int64_t n_chunks, n_blocks;
-    int64_t off_counts, off_bsum, off_bbase, off_total, total;
+    int64_t off_counts, off_bsum, off_bbase, off_total, off_list, total;
 };
 #define BOOT_THREADS 256
+#define BOOT_FINE 16  // the exact pass of the single-pass form cuts a CTA's slots into up to 16 finer CTAs
 static inline BootGeom boot_geom(int64_t n_slots, int32_t chunk_slots) {
     BootGeom g;
     g.n_chunks = (n_slots + chunk_slots - 1) / chunk_slots;
@@ -638,9 +641,12 @@ static inline BootGeom boot_geom(int64_t n_slots, int32_t chunk_slots) {
     o += 256;
     g.off_counts = o;
     o = align256(o + g.n_blocks * BOOT_THREADS * 4);
+    // (x BOOT_FINE: the single-pass form prefix-sums and lists FINE blocks -- see mcf_bootstrap_fused_phase1)
     g.off_bsum = o;
-    o = align256(o + g.n_blocks * 8);
+    o = align256(o + g.n_blocks * 8 * BOOT_FINE);
     g.off_bbase = o;
+    o = align256(o + g.n_blocks * 8 * BOOT_FINE);
+    g.off_list = o;  // block list of the single-pass form (CTAs that need exact ordinals)
     o = align256(o + g.n_blocks * 8);
     g.total = o;
     return g;
@@ -691,8 +697,11 @@ template <int KIND>
 __global__ void __launch_bounds__(BOOT_THREADS) boot_count_kernel(const mcf_stream *__restrict__ stream, uint32_t n,
                                                                   uint64_t slot_lo, uint64_t slot_hi, int chunk_slots,
                                                                   int64_t n_chunks, uint32_t *__restrict__ counts,
-                                                                  unsigned long long *__restrict__ block_sum) {
-    const int64_t chunk = (int64_t)blockIdx.x * BOOT_THREADS + threadIdx.x;
+                                                                  unsigned long long *__restrict__ block_sum,
+                                                                  const int64_t *__restrict__ block_list = nullptr) {
+    // block_list (may be NULL): the CTAs of this launch count the listed blocks instead of blocks 0 .. gridDim.x-1
+    const int64_t blk = block_list ? block_list[blockIdx.x] : (int64_t)blockIdx.x;
+    const int64_t chunk = blk * BOOT_THREADS + threadIdx.x;
     uint32_t cnt = 0;
     if (chunk < n_chunks) {
         const SlotRule rule = slot_rule(n);
@@ -716,7 +725,8 @@ __global__ void __launch_bounds__(BOOT_THREADS) boot_count_kernel(const mcf_stre
             }
         }
     }
-    counts[chunk] = cnt;  // counts[] is padded to n_blocks * BOOT_THREADS
+    // counts[] is padded to n_blocks * BOOT_THREADS; with a block list it is COMPACT (indexed by list position)
+    counts[block_list ? (int64_t)blockIdx.x * BOOT_THREADS + threadIdx.x : chunk] = cnt;
     __shared__ uint32_t sh[BOOT_THREADS / 32];
     uint32_t v = cnt;
 #pragma unroll
@@ -726,7 +736,7 @@ __global__ void __launch_bounds__(BOOT_THREADS) boot_count_kernel(const mcf_stre
     if (threadIdx.x == 0) {
         unsigned long long t = 0;
         for (int w2 = 0; w2 < BOOT_THREADS / 32; w2++) t += sh[w2];
-        block_sum[blockIdx.x] = t;
+        block_sum[blk] = t;
     }
 }
 
@@ -893,19 +903,20 @@ __global__ void __launch_bounds__(BOOT_THREADS) boot_bin_kernel(const mcf_stream
                                                                 const unsigned long long *__restrict__ block_base,
                                                                 uint32_t *__restrict__ queues,
                                                                 unsigned int *__restrict__ tails,
-                                                                unsigned long long *__restrict__ end_slot, int *overflow) {
+                                                                unsigned long long *__restrict__ end_slot, int *overflow,
+                                                                const int64_t *__restrict__ block_list = nullptr) {
     __shared__ uint32_t warp_tot[BOOT_THREADS / 32];
     // staging for the CTA's FIRST resample only; the few CTAs that straddle a resample boundary append the entries of
     // the second one directly (1 CTA in n / (256 * chunk_slots))
     __shared__ uint32_t sh_stage[BIN_MAX_REGIONS][BIN_STAGE_CAP];
     __shared__ unsigned int sh_cnt[BIN_MAX_REGIONS], sh_n[BIN_MAX_REGIONS], sh_base[BIN_MAX_REGIONS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t blk = block0 + blockIdx.x;
+    const int64_t blk = block_list ? block_list[block0 + blockIdx.x] : block0 + blockIdx.x;
     const int64_t chunk = blk * BOOT_THREADS + threadIdx.x;
     const uint32_t R = bp.n_regions;
     if (threadIdx.x < BIN_MAX_REGIONS) sh_cnt[threadIdx.x] = 0;
-    // block-exclusive scan of the per-chunk accepted counts (as in boot_accumulate_kernel)
-    const uint32_t cnt = counts[chunk];
+    // block-exclusive scan of the per-chunk accepted counts (as in boot_accumulate_kernel); compact with a block list
+    const uint32_t cnt = counts[block_list ? (block0 + (int64_t)blockIdx.x) * BOOT_THREADS + threadIdx.x : chunk];
     uint32_t incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -1029,6 +1040,144 @@ __global__ void __launch_bounds__(BOOT_THREADS) boot_bin_kernel(const mcf_stream
             }
         }
         if ((g % BIN_FLUSH_EVERY) == BIN_FLUSH_EVERY - 1 || g == groups - 1) flush();
+    }
+}
+
+// ------------------------------------------------------------------------------------ single-pass ("safe zone") form
+// The count pass exists only to give every CTA the ordinal of its first accepted slot -- i.e. the RESAMPLE its indices
+// belong to.  But the ordinal at slot s is s * (1 - p) to within a few standard deviations of a binomial count
+// (p = rejection probability): at 1e12 slots that is +-1.2e6 of 1e8 per resample.  A CTA whose estimated ordinal range,
+// widened by that margin, lies strictly inside ONE resample (96 % of them) needs no exact ordinal at all: it bins into
+// that resample in the first and only pass over its slots and counts what it accepted on the way
+// (boot_bin_safe_kernel).  Only the CTAs near resample boundaries and near the end of the draw are counted
+// (boot_count_kernel on a block list), prefix-summed together with the safe CTAs' counts, and binned with exact
+// ordinals by the general kernel.  A verification pass checks every safe CTA against its exact ordinal range
+// afterwards; a violation (an 8-sigma event) raises a flag and the caller recomputes with the two-pass form.
+struct FuseGeom {
+    uint64_t q;             // 2^32 - threshold: accepted values of a 32-bit slot
+    uint64_t margin;        // ordinals
+    uint64_t n, total_needed;
+    uint64_t S;             // slots per CTA
+    uint64_t slot_lo, slot_hi;
+};
+MCF_HD uint64_t fuse_est_ordinal(uint64_t s, uint64_t q) {  // floor(s * q / 2^32), exact
+    const uint64_t hi = mulhi64(s, q), lo = s * q;
+    return (hi << 32) | (lo >> 32);
+}
+// 1: safe (resample *b), 0: needs exact ordinals, -1: wholly beyond the end of the draw (nothing to do)
+MCF_HD int fuse_block_class(const FuseGeom &g, int64_t blk, uint64_t *b, uint64_t *b_min, uint64_t *b_max) {
+    const uint64_t s0 = g.slot_lo + (uint64_t)blk * g.S;
+    const uint64_t s1 = s0 + g.S < g.slot_hi ? s0 + g.S : g.slot_hi;
+    const uint64_t e0 = fuse_est_ordinal(s0, g.q), e1 = fuse_est_ordinal(s1, g.q);
+    const uint64_t lo = e0 > g.margin ? e0 - g.margin : 0ULL, hi = e1 + g.margin;
+    if (lo >= g.total_needed) return -1;
+    *b_min = lo / g.n;
+    *b_max = (hi < g.total_needed ? hi : g.total_needed - 1ULL) / g.n;
+    if (s1 - s0 < g.S || e0 < g.margin || hi >= g.total_needed || lo / g.n != hi / g.n) return 0;
+    *b = lo / g.n;
+    return 1;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(BOOT_THREADS) boot_bin_safe_kernel(const mcf_stream *__restrict__ stream, BinParams bp,
+                                                                     FuseGeom fg, int chunk_slots, int64_t block0, int fine,
+                                                                     unsigned long long *__restrict__ block_sum,
+                                                                     uint32_t *__restrict__ queues,
+                                                                     unsigned int *__restrict__ tails, int *overflow) {
+    __shared__ uint32_t sh_stage[BIN_MAX_REGIONS][BIN_STAGE_CAP];
+    __shared__ unsigned int sh_cnt[BIN_MAX_REGIONS], sh_n[BIN_MAX_REGIONS], sh_base[BIN_MAX_REGIONS];
+    __shared__ unsigned int sh_acc[BOOT_THREADS / 32];
+    const int64_t blk = block0 + blockIdx.x;
+    uint64_t b = 0, bmin = 0, bmax = 0;
+    const int cls = fuse_block_class(fg, blk, &b, &bmin, &bmax);
+    if (cls != 1 || b < bp.b_first || b - bp.b_first >= (uint64_t)bp.n_res_window) {
+        // not a safe CTA of this batch: its count comes from the exact pass (or it lies beyond the draw)
+        return;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t R = bp.n_regions;
+    if (threadIdx.x < BIN_MAX_REGIONS) sh_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const SlotRule rule = slot_rule(bp.n);
+    const mcf_stream st = *stream;
+    const int64_t chunk = blk * BOOT_THREADS + threadIdx.x;
+    const uint64_t s0 = fg.slot_lo + (uint64_t)chunk * (uint64_t)chunk_slots;
+    SlotWalker<KIND> w;
+    w.init(st, s0);
+    const uint32_t mask = (1u << bp.region_shift) - 1u;
+    const int groups = chunk_slots / 8;
+    const uint64_t q_row = (b - bp.b_first) * R;
+    auto flush = [&]() {
+        __syncthreads();
+        if (threadIdx.x < R) {
+            unsigned c = sh_cnt[threadIdx.x];
+            if (c > BIN_STAGE_CAP) c = BIN_STAGE_CAP;
+            sh_n[threadIdx.x] = c;
+            sh_base[threadIdx.x] = c ? atomicAdd(&tails[q_row + threadIdx.x], c) : 0u;
+            sh_cnt[threadIdx.x] = 0;
+        }
+        __syncthreads();
+        for (unsigned q = wid; q < R; q += BOOT_THREADS / 32) {
+            const unsigned c = sh_n[q], base = sh_base[q];
+            const uint64_t gq = q_row + q;
+            if (c && (uint64_t)base + c > bp.cap) atomicExch(overflow, 1);
+            for (unsigned j = lane; j < c; j += 32)
+                if ((uint64_t)base + j < bp.cap) queues[gq * bp.cap + base + j] = sh_stage[q][j];
+        }
+        __syncthreads();
+    };
+    unsigned cnt_addr = (unsigned)__cvta_generic_to_shared(sh_cnt);
+    unsigned stage_addr = (unsigned)__cvta_generic_to_shared(&sh_stage[0][0]);
+    unsigned shift = bp.region_shift, lowmask = mask;
+    asm volatile("" : "+r"(cnt_addr), "+r"(stage_addr), "+r"(shift), "+r"(lowmask));
+    unsigned accepted = 0;
+    for (int g = 0; g < groups; g++) {
+        uint32_t u[8];
+        w.get8(s0 + (uint64_t)g * 8, u);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            uint32_t idx;
+            if (slot_accept(rule, u[j], idx)) {
+                accepted++;
+                const unsigned q = idx >> shift;
+                unsigned pos;
+                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(cnt_addr + q * 4u) : "memory");
+                if (pos < BIN_STAGE_CAP) {
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(stage_addr + q * (BIN_STAGE_CAP * 4u) + pos * 4u),
+                                 "r"(idx & lowmask)
+                                 : "memory");
+                } else {  // staging full: append directly
+                    const uint64_t gq = q_row + q;
+                    const unsigned gp = atomicAdd(&tails[gq], 1u);
+                    if (gp < bp.cap)
+                        queues[gq * bp.cap + gp] = idx & lowmask;
+                    else
+                        atomicExch(overflow, 1);
+                }
+            }
+        }
+        if ((g % BIN_FLUSH_EVERY) == BIN_FLUSH_EVERY - 1 || g == groups - 1) flush();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) accepted += __shfl_xor_sync(0xffffffffu, accepted, o);
+    if (lane == 0) sh_acc[wid] = accepted;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w2 = 0; w2 < BOOT_THREADS / 32; w2++) t += sh_acc[w2];
+        block_sum[blk * fine] = t;  // the sums are kept per FINE block: a safe CTA owns the first of its `fine` entries
+    }
+}
+
+// every safe CTA against its exact ordinal range
+__global__ void boot_fuse_verify_kernel(FuseGeom fg, int64_t n_blocks, int fine, uint64_t ordinal_base,
+                                        const unsigned long long *__restrict__ block_base,
+                                        const unsigned long long *__restrict__ block_sum, int *__restrict__ flag) {
+    for (int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; blk < n_blocks; blk += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t b = 0, bmin = 0, bmax = 0;
+        if (fuse_block_class(fg, blk, &b, &bmin, &bmax) != 1) continue;
+        const uint64_t ord0 = ordinal_base + block_base[blk * fine], ord1 = ord0 + block_sum[blk * fine];
+        if (ord0 < b * fg.n || ord1 > (b + 1ULL) * fg.n || ord1 > fg.total_needed) atomicExch(flag, 1);
     }
 }
 
@@ -2089,6 +2238,267 @@ int mcf_bootstrap_accumulate_binned(uint32_t gen_kind, const mcf_stream *d_strea
     cudaMemcpyAsync(&h_over, overflow, 4, cudaMemcpyDeviceToHost, cs);
     const cudaError_t e1 = cudaStreamSynchronize(cs);
     if (overlap) cudaStreamSynchronize(side);
+    if (e1 != cudaSuccess || rc != MCF_OK) return MCF_ERR_CUDA;
+    return h_over ? MCF_ERR_WINDOW_TOO_SMALL : MCF_OK;
+}
+
+// ---- single-pass form of the binned bootstrap (see boot_bin_safe_kernel) ----
+static inline int fuse_fine(int32_t chunk_slots) {  // finer CTAs of the exact pass: chunk_slots / fine stays a multiple of 8
+    int fine = BOOT_FINE;
+    while (fine > 1 && (chunk_slots % (8 * fine)) != 0) fine >>= 1;
+    return fine;
+}
+static FuseGeom fuse_geom(int64_t n, int64_t n_resamples, uint64_t slot_lo, uint64_t slot_hi, uint64_t slot_total,
+                          int32_t chunk_slots) {
+    FuseGeom fg;
+    const SlotRule rule = slot_rule((uint32_t)n);
+    fg.q = (1ULL << 32) - (uint64_t)rule.threshold;
+    const double p = (double)rule.threshold / 4294967296.0;
+    // 8 standard deviations of the accepted count at the LAST slot of the whole draw (all ranks), + slack
+    fg.margin = (uint64_t)ceil(8.0 * sqrt((double)slot_total * p * (1.0 - p))) + 64ULL;
+    fg.n = (uint64_t)n;
+    fg.total_needed = (uint64_t)n_resamples * (uint64_t)n;
+    fg.S = (uint64_t)BOOT_THREADS * (uint64_t)chunk_slots;
+    fg.slot_lo = slot_lo;
+    fg.slot_hi = slot_hi;
+    return fg;
+}
+
+struct FuseQueues {
+    uint32_t *queues[2];
+    unsigned int *tails[2];
+    int *overflow;
+    int64_t R, cap, window;
+    uint32_t sh;
+};
+static FuseQueues fuse_queues(int64_t n, int32_t resamples_per_batch, int32_t region_shift, void *d_bin_workspace) {
+    FuseQueues q;
+    q.sh = bin_region_shift(n, region_shift);
+    q.R = (n + (1LL << q.sh) - 1) >> q.sh;
+    const int64_t region_len = 1LL << q.sh;
+    q.cap = region_len + 8 * (int64_t)sqrt((double)region_len) + 4096;
+    q.window = resamples_per_batch + 2;
+    char *bws = (char *)d_bin_workspace;
+    const int64_t set_bytes = bin_set_bytes(q.window, q.R, q.cap);
+    for (int b = 0; b < 2; b++) {
+        q.queues[b] = (uint32_t *)(bws + b * set_bytes);
+        q.tails[b] = (unsigned int *)(bws + b * set_bytes + align256(q.window * q.R * q.cap * 4));
+    }
+    q.overflow = (int *)(bws + 2 * set_bytes);
+    return q;
+}
+
+// Phase 1: every safe CTA bins (and counts) its slots; then the CTAs that need exact ordinals are counted and all block
+// sums are prefix-summed.  *d_total = accepted slots of this rank's range before the end of the draw.
+int mcf_bootstrap_fused_phase1(uint32_t gen_kind, const mcf_stream *d_stream, const double *d_x, int64_t n, int64_t n_resamples,
+                               uint64_t slot_lo, uint64_t slot_hi, uint64_t slot_total, int32_t chunk_slots, void *d_workspace,
+                               int64_t workspace_bytes, int32_t resamples_per_batch, int32_t region_shift,
+                               void *d_bin_workspace, int64_t bin_workspace_bytes, double *d_sums, uint64_t *d_total,
+                               void *cuda_stream) {
+    if (!d_stream || !d_x || n < 2 || n > 0xFFFFFFFFLL || n_resamples <= 0 || slot_hi <= slot_lo || slot_total < slot_hi ||
+        chunk_slots < 8 || (chunk_slots % 8) || !d_workspace || resamples_per_batch < 1 || !d_bin_workspace || !d_sums ||
+        (int64_t)BOOT_THREADS * chunk_slots > n)
+        return MCF_ERR_BAD_ARG;
+    const BootGeom g = boot_geom((int64_t)(slot_hi - slot_lo), chunk_slots);
+    if (workspace_bytes < g.total) return MCF_ERR_WORKSPACE_TOO_SMALL;
+    if (bin_workspace_bytes < mcf_bootstrap_binned_workspace_bytes(n, resamples_per_batch, region_shift))
+        return MCF_ERR_WORKSPACE_TOO_SMALL;
+    const FuseGeom fg = fuse_geom(n, n_resamples, slot_lo, slot_hi, slot_total, chunk_slots);
+    const FuseQueues Q = fuse_queues(n, resamples_per_batch, region_shift, d_bin_workspace);
+    char *ws = (char *)d_workspace;
+    uint32_t *counts = (uint32_t *)(ws + g.off_counts);
+    unsigned long long *bsum = (unsigned long long *)(ws + g.off_bsum), *bbase = (unsigned long long *)(ws + g.off_bbase);
+    unsigned long long *total = (unsigned long long *)(ws + g.off_total);
+    int64_t *d_list = (int64_t *)(ws + g.off_list);
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    // The exact pass runs on FINER CTAs (chunk_slots / fine slots per thread): the few CTAs that straddle a resample
+    // boundary take the slot-by-slot path of the general kernel, and alone in a launch a 2e6-slot straddler is a 7 ms
+    // critical path; cut 16 ways it is 0.45 ms and the launch has 16 times the CTAs.  Block sums and their prefix are
+    // kept per fine block (a safe CTA owns the first of its `fine` entries, the others stay zero).
+    const int fine = fuse_fine(chunk_slots);
+    const int64_t n_fine = g.n_blocks * fine;
+    MCF_CUDA_OK(cudaMemsetAsync(Q.overflow, 0, 4, cs));
+    MCF_CUDA_OK(cudaMemsetAsync(bsum, 0, (size_t)n_fine * 8, cs));
+    SideStream ss;
+    if (!ss.open(cs)) return MCF_ERR_CUDA;
+    // The gathers of a batch run on the CALLER's stream, after its bin kernel: overlapped with the next batch's bin
+    // kernel (as the two-pass form does) they take 26 ms per 32 resamples instead of 7.4 + 12.5 -- the safe kernel
+    // streams 13 GB of queue entries through L2 fast enough to evict the 32 MB region the gathers depend on.  Measured at
+    // n = 1e8, B = 512: 0.43 s overlapped, 0.32 s back to back.
+    const cudaStream_t side = cs;
+    // classify the CTAs once on the host (integer arithmetic shared with the kernels): safe ones by batch of resamples,
+    // the others into the exact list
+    std::vector<int64_t> exact;
+    int64_t blk = 0;
+    int k = 0;
+    int rc = MCF_OK;
+    while (blk < g.n_blocks) {
+        uint64_t b = 0, bmin = 0, bmax = 0, b_first = 0;
+        bool have_first = false;
+        int64_t end = blk;
+        for (; end < g.n_blocks; end++) {
+            const int cls = fuse_block_class(fg, end, &b, &bmin, &bmax);
+            if (cls == 0)
+                for (int f = 0; f < fine; f++)  // its fine blocks that still hold slots
+                    if (slot_lo + (uint64_t)(end * fine + f) * (fg.S / (uint64_t)fine) < slot_hi) exact.push_back(end * fine + f);
+            if (cls != 1) continue;
+            if (!have_first) {
+                have_first = true;
+                b_first = b;
+            } else if (b >= b_first + (uint64_t)resamples_per_batch) {
+                break;  // this CTA opens the next batch
+            }
+        }
+        if (have_first) {
+            BinParams bp;
+            bp.n = (uint32_t)n;
+            bp.region_shift = Q.sh;
+            bp.n_regions = (uint32_t)Q.R;
+            bp.n_res_window = (uint32_t)resamples_per_batch;  // safe CTAs never leave their batch
+            bp.b_first = b_first;
+            bp.cap = (uint64_t)Q.cap;
+            bp.n_resamples = (uint64_t)n_resamples;
+            const int buf = k & 1;
+            if (k >= 2) cudaStreamWaitEvent(cs, ss.ev_gat[buf], 0);  // this queue set has been drained
+            cudaMemsetAsync(Q.tails[buf], 0, (size_t)(Q.window * Q.R * 4), cs);
+            if (gen_kind == MCF_GEN_PCG64)
+                boot_bin_safe_kernel<MCF_GEN_PCG64><<<(unsigned)(end - blk), BOOT_THREADS, 0, cs>>>(
+                    d_stream, bp, fg, chunk_slots, blk, fine, bsum, Q.queues[buf], Q.tails[buf], Q.overflow);
+            else
+                boot_bin_safe_kernel<MCF_GEN_PHILOX><<<(unsigned)(end - blk), BOOT_THREADS, 0, cs>>>(
+                    d_stream, bp, fg, chunk_slots, blk, fine, bsum, Q.queues[buf], Q.tails[buf], Q.overflow);
+            cudaEventRecord(ss.ev_bin[buf], cs);
+            cudaStreamWaitEvent(side, ss.ev_bin[buf], 0);
+            bp.n_res_window = (uint32_t)Q.window;
+            for (uint32_t r = 0; r < (uint32_t)Q.R; r++) {
+                dim3 grid(64, (unsigned)resamples_per_batch);
+                boot_gather_kernel<<<grid, 256, 0, side>>>(d_x, bp, r, Q.queues[buf], Q.tails[buf], d_sums);
+            }
+            cudaEventRecord(ss.ev_gat[buf], side);
+            k++;
+        }
+        if (cudaGetLastError() != cudaSuccess) {
+            rc = MCF_ERR_CUDA;
+            break;
+        }
+        blk = end;
+    }
+    for (int b2 = 0; b2 < 2; b2++)
+        if (k > b2) cudaStreamWaitEvent(cs, ss.ev_gat[b2], 0);
+    if (rc != MCF_OK) return rc;
+    // the (fine) CTAs that need exact ordinals: count them, then prefix-sum ALL block sums.  The compact per-chunk counts
+    // and the list must fit the regions sized for the coarse geometry: more than 1/fine of the CTAs unsafe = undecided.
+    if ((int64_t)exact.size() > g.n_blocks) return MCF_ERR_WORKSPACE_TOO_SMALL;
+    const int cs_fine = chunk_slots / fine;
+    const int64_t n_chunks_fine = ((int64_t)(slot_hi - slot_lo) + cs_fine - 1) / cs_fine;
+    if (!exact.empty()) {
+        MCF_CUDA_OK(cudaMemcpyAsync(d_list, exact.data(), exact.size() * 8, cudaMemcpyHostToDevice, cs));
+        if (gen_kind == MCF_GEN_PCG64)
+            boot_count_kernel<MCF_GEN_PCG64><<<(unsigned)exact.size(), BOOT_THREADS, 0, cs>>>(
+                d_stream, (uint32_t)n, slot_lo, slot_hi, cs_fine, n_chunks_fine, counts, bsum, d_list);
+        else
+            boot_count_kernel<MCF_GEN_PHILOX><<<(unsigned)exact.size(), BOOT_THREADS, 0, cs>>>(
+                d_stream, (uint32_t)n, slot_lo, slot_hi, cs_fine, n_chunks_fine, counts, bsum, d_list);
+    }
+    scan_u64_kernel<<<1, 1024, 0, cs>>>(bsum, n_fine, bbase, total);
+    MCF_CUDA_OK(cudaGetLastError());
+    if (d_total) MCF_CUDA_OK(cudaMemcpyAsync(d_total, total, 8, cudaMemcpyDeviceToDevice, cs));
+    MCF_CUDA_OK(cudaStreamSynchronize(cs));  // `exact` is a host vector; the side stream is released on return
+    cudaStreamSynchronize(side);
+    return MCF_OK;
+}
+
+// Phase 2: the listed CTAs with exact ordinals (general kernel), batch by batch, then the verification of the safe ones.
+// *d_flag != 0 afterwards: a safe CTA was not where the estimate put it, or a queue overflowed -- recompute with the
+// two-pass form.  ordinal_base = accepted slots of all lower ranks.
+int mcf_bootstrap_fused_phase2(uint32_t gen_kind, const mcf_stream *d_stream, const double *d_x, int64_t n, int64_t n_resamples,
+                               uint64_t slot_lo, uint64_t slot_hi, uint64_t slot_total, int32_t chunk_slots,
+                               uint64_t ordinal_base, void *d_workspace, int64_t workspace_bytes, int32_t resamples_per_batch,
+                               int32_t region_shift, void *d_bin_workspace, int64_t bin_workspace_bytes, double *d_sums,
+                               uint64_t *d_end_slot, int32_t *d_flag, void *cuda_stream) {
+    if (!d_stream || !d_x || n < 2 || n_resamples <= 0 || slot_hi <= slot_lo || chunk_slots < 8 || !d_workspace ||
+        !d_bin_workspace || !d_sums || !d_end_slot || !d_flag)
+        return MCF_ERR_BAD_ARG;
+    const BootGeom g = boot_geom((int64_t)(slot_hi - slot_lo), chunk_slots);
+    if (workspace_bytes < g.total) return MCF_ERR_WORKSPACE_TOO_SMALL;
+    if (bin_workspace_bytes < mcf_bootstrap_binned_workspace_bytes(n, resamples_per_batch, region_shift))
+        return MCF_ERR_WORKSPACE_TOO_SMALL;
+    const FuseGeom fg = fuse_geom(n, n_resamples, slot_lo, slot_hi, slot_total, chunk_slots);
+    const FuseQueues Q = fuse_queues(n, resamples_per_batch, region_shift, d_bin_workspace);
+    char *ws = (char *)d_workspace;
+    const uint32_t *counts = (const uint32_t *)(ws + g.off_counts);
+    const unsigned long long *bsum = (const unsigned long long *)(ws + g.off_bsum);
+    const unsigned long long *bbase = (const unsigned long long *)(ws + g.off_bbase);
+    const int64_t *d_list = (const int64_t *)(ws + g.off_list);
+    cudaStream_t cs = (cudaStream_t)cuda_stream;
+    MCF_CUDA_OK(cudaMemsetAsync(d_flag, 0, 4, cs));
+    const int fine = fuse_fine(chunk_slots);
+    const int cs_fine = chunk_slots / fine;
+    const int64_t n_chunks_fine = ((int64_t)(slot_hi - slot_lo) + cs_fine - 1) / cs_fine;
+    // the same classification as phase 1 (the list on the device is in this order)
+    std::vector<uint64_t> lo_b, hi_b;
+    for (int64_t blk = 0; blk < g.n_blocks; blk++) {
+        uint64_t b = 0, bmin = 0, bmax = 0;
+        if (fuse_block_class(fg, blk, &b, &bmin, &bmax) == 0) {
+            for (int f = 0; f < fine; f++) {
+                if (slot_lo + (uint64_t)(blk * fine + f) * (fg.S / (uint64_t)fine) >= slot_hi) continue;
+                // exact ordinals lie within the margin of the estimate: one resample of slack on either side
+                lo_b.push_back(bmin > 0 ? bmin - 1 : 0);
+                hi_b.push_back(bmax + 1);
+            }
+        }
+    }
+    SideStream ss;
+    if (!ss.open(cs)) return MCF_ERR_CUDA;
+    const cudaStream_t side = ss.stream;
+    size_t i = 0;
+    int k = 0;
+    int rc = MCF_OK;
+    while (i < lo_b.size()) {
+        const uint64_t b_first = lo_b[i];
+        if (hi_b[i] >= b_first + (uint64_t)Q.window) return MCF_ERR_BAD_ARG;  // a CTA wider than the queue window
+        size_t end = i + 1;
+        while (end < lo_b.size() && hi_b[end] < b_first + (uint64_t)Q.window) end++;
+        BinParams bp;
+        bp.n = (uint32_t)n;
+        bp.region_shift = Q.sh;
+        bp.n_regions = (uint32_t)Q.R;
+        bp.n_res_window = (uint32_t)Q.window;
+        bp.b_first = b_first;
+        bp.cap = (uint64_t)Q.cap;
+        bp.n_resamples = (uint64_t)n_resamples;
+        const int buf = k & 1;
+        if (k >= 2) cudaStreamWaitEvent(cs, ss.ev_gat[buf], 0);
+        cudaMemsetAsync(Q.tails[buf], 0, (size_t)(Q.window * Q.R * 4), cs);
+        if (gen_kind == MCF_GEN_PCG64)
+            boot_bin_kernel<MCF_GEN_PCG64><<<(unsigned)(end - i), BOOT_THREADS, 0, cs>>>(
+                d_stream, bp, slot_lo, slot_hi, cs_fine, n_chunks_fine, (int64_t)i, ordinal_base, counts, bbase, Q.queues[buf],
+                Q.tails[buf], (unsigned long long *)d_end_slot, Q.overflow, d_list);
+        else
+            boot_bin_kernel<MCF_GEN_PHILOX><<<(unsigned)(end - i), BOOT_THREADS, 0, cs>>>(
+                d_stream, bp, slot_lo, slot_hi, cs_fine, n_chunks_fine, (int64_t)i, ordinal_base, counts, bbase, Q.queues[buf],
+                Q.tails[buf], (unsigned long long *)d_end_slot, Q.overflow, d_list);
+        cudaEventRecord(ss.ev_bin[buf], cs);
+        cudaStreamWaitEvent(side, ss.ev_bin[buf], 0);
+        for (uint32_t r = 0; r < (uint32_t)Q.R; r++) {
+            dim3 grid(16, (unsigned)Q.window);  // these queues hold a few per cent of a resample
+            boot_gather_kernel<<<grid, 256, 0, side>>>(d_x, bp, r, Q.queues[buf], Q.tails[buf], d_sums);
+        }
+        cudaEventRecord(ss.ev_gat[buf], side);
+        if (cudaGetLastError() != cudaSuccess) {
+            rc = MCF_ERR_CUDA;
+            break;
+        }
+        i = end;
+        k++;
+    }
+    for (int b2 = 0; b2 < 2; b2++)
+        if (k > b2) cudaStreamWaitEvent(cs, ss.ev_gat[b2], 0);
+    boot_fuse_verify_kernel<<<MCF_SM_COUNT * 2, 256, 0, cs>>>(fg, g.n_blocks, fine, ordinal_base, bbase, bsum, (int *)d_flag);
+    int h_over = 0;
+    cudaMemcpyAsync(&h_over, Q.overflow, 4, cudaMemcpyDeviceToHost, cs);
+    const cudaError_t e1 = cudaStreamSynchronize(cs);
+    cudaStreamSynchronize(side);
     if (e1 != cudaSuccess || rc != MCF_OK) return MCF_ERR_CUDA;
     return h_over ? MCF_ERR_WINDOW_TOO_SMALL : MCF_OK;
 }

@@ -376,10 +376,18 @@ def test_bootstrap_binned_path_is_the_same_index_stream(sd, n, B, shift, cs):
     xi = np.random.default_rng(2).integers(0, 1 << 20, n).astype(float)
     g_ref, g_dev, g_dev2 = (np.random.default_rng(5) for _ in range(3))
     want = np.stack([xi[g_ref.integers(0, n, size=n)].sum() for _ in range(B)])
+    before = dict(sd.BOOT_FORMS)
     got = sd.bootstrap_means(_dev_tensor(xi), B, g_dev, binned=True, region_shift=shift, chunk_slots=cs,
                              resamples_per_batch=7).cpu().numpy() * n
     assert np.array_equal(np.rint(got), want)
     assert g_dev.bit_generator.state == g_ref.bit_generator.state
+    # the single-pass form (safe CTAs bin without exact ordinals, the rest are counted first) decided this run ...
+    assert sd.BOOT_FORMS["single_pass"] == before["single_pass"] + 1 and sd.BOOT_FORMS["two_pass"] == before["two_pass"]
+    # ... and the two-pass form (count pass over every slot first) gives the same sums and the same generator state
+    g_two = np.random.default_rng(5)
+    two = sd.bootstrap_means(_dev_tensor(xi), B, g_two, binned=True, region_shift=shift, chunk_slots=cs, resamples_per_batch=7,
+                             single_pass=False).cpu().numpy() * n
+    assert np.array_equal(np.rint(two), want) and g_two.bit_generator.state == g_ref.bit_generator.state
     plain = sd.bootstrap_means(_dev_tensor(xi), B, g_dev2, binned=False, chunk_slots=cs).cpu().numpy() * n
     assert np.array_equal(np.rint(plain), want)
 

@@ -92,6 +92,17 @@ def main():
     check("slot-sharded bootstrap: integer sums exact, generator state equal",
           np.array_equal(np.rint(got), want_sums) and g_dev.bit_generator.state == g_ref.bit_generator.state)
 
+    # the same through the binned gather and its single-pass form (safe CTAs bin without exact ordinals)
+    xb = np.random.default_rng(3).integers(0, 1 << 20, 400_000).astype(float)
+    g_ref, g_dev = np.random.default_rng(6), np.random.default_rng(6)
+    want_b = np.stack([xb[g_ref.integers(0, xb.size, size=xb.size)].sum() for _ in range(24)])
+    before = SD.BOOT_FORMS["single_pass"]
+    got_b = SD.bootstrap_means(torch.from_numpy(xb).cuda(), 24, g_dev, group=dist.group.WORLD, binned=True, region_shift=15,
+                               chunk_slots=256, resamples_per_batch=5).cpu().numpy() * xb.size
+    check("slot-sharded BINNED bootstrap, single-pass form: integer sums exact, generator state equal",
+          np.array_equal(np.rint(got_b), want_b) and g_dev.bit_generator.state == g_ref.bit_generator.state
+          and SD.BOOT_FORMS["single_pass"] == before + 1)
+
     # LSM with paths sharded by rank
     ps = m.BlackScholesPathSimulation()
     ps.set_seed(1)
