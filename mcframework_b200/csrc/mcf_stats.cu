@@ -2243,11 +2243,6 @@ int mcf_bootstrap_accumulate_binned(uint32_t gen_kind, const mcf_stream *d_strea
 }
 
 // ---- single-pass form of the binned bootstrap (see boot_bin_safe_kernel) ----
-static inline int fuse_fine(int32_t chunk_slots) {  // finer CTAs of the exact pass: chunk_slots / fine stays a multiple of 8
-    int fine = BOOT_FINE;
-    while (fine > 1 && (chunk_slots % (8 * fine)) != 0) fine >>= 1;
-    return fine;
-}
 static FuseGeom fuse_geom(int64_t n, int64_t n_resamples, uint64_t slot_lo, uint64_t slot_hi, uint64_t slot_total,
                           int32_t chunk_slots) {
     FuseGeom fg;
@@ -2262,6 +2257,19 @@ static FuseGeom fuse_geom(int64_t n, int64_t n_resamples, uint64_t slot_lo, uint
     fg.slot_lo = slot_lo;
     fg.slot_hi = slot_hi;
     return fg;
+}
+
+// Finer CTAs of the exact pass: chunk_slots / fine stays a multiple of 8, and the listed fine blocks must fit the list and
+// the compact per-chunk counts, both sized for the coarse geometry (n_blocks entries) -- small populations, where a third of
+// the CTAs straddle a resample boundary, get a smaller factor instead of giving up on the single-pass form.
+static int fuse_fine(const FuseGeom &fg, int64_t n_blocks, int32_t chunk_slots) {
+    int fine = BOOT_FINE;
+    while (fine > 1 && (chunk_slots % (8 * fine)) != 0) fine >>= 1;
+    int64_t unsafe = 0;
+    uint64_t b = 0, bmin = 0, bmax = 0;
+    for (int64_t blk = 0; blk < n_blocks; blk++) unsafe += fuse_block_class(fg, blk, &b, &bmin, &bmax) == 0;
+    while (fine > 1 && unsafe * fine > n_blocks) fine >>= 1;
+    return fine;
 }
 
 struct FuseQueues {
@@ -2315,7 +2323,7 @@ int mcf_bootstrap_fused_phase1(uint32_t gen_kind, const mcf_stream *d_stream, co
     // boundary take the slot-by-slot path of the general kernel, and alone in a launch a 2e6-slot straddler is a 7 ms
     // critical path; cut 16 ways it is 0.45 ms and the launch has 16 times the CTAs.  Block sums and their prefix are
     // kept per fine block (a safe CTA owns the first of its `fine` entries, the others stay zero).
-    const int fine = fuse_fine(chunk_slots);
+    const int fine = fuse_fine(fg, g.n_blocks, chunk_slots);
     const int64_t n_fine = g.n_blocks * fine;
     MCF_CUDA_OK(cudaMemsetAsync(Q.overflow, 0, 4, cs));
     MCF_CUDA_OK(cudaMemsetAsync(bsum, 0, (size_t)n_fine * 8, cs));
@@ -2387,7 +2395,7 @@ int mcf_bootstrap_fused_phase1(uint32_t gen_kind, const mcf_stream *d_stream, co
         if (k > b2) cudaStreamWaitEvent(cs, ss.ev_gat[b2], 0);
     if (rc != MCF_OK) return rc;
     // the (fine) CTAs that need exact ordinals: count them, then prefix-sum ALL block sums.  The compact per-chunk counts
-    // and the list must fit the regions sized for the coarse geometry: more than 1/fine of the CTAs unsafe = undecided.
+    // and the list fit the regions sized for the coarse geometry (fuse_fine chose the factor accordingly).
     if ((int64_t)exact.size() > g.n_blocks) return MCF_ERR_WORKSPACE_TOO_SMALL;
     const int cs_fine = chunk_slots / fine;
     const int64_t n_chunks_fine = ((int64_t)(slot_hi - slot_lo) + cs_fine - 1) / cs_fine;
@@ -2432,7 +2440,7 @@ int mcf_bootstrap_fused_phase2(uint32_t gen_kind, const mcf_stream *d_stream, co
     const int64_t *d_list = (const int64_t *)(ws + g.off_list);
     cudaStream_t cs = (cudaStream_t)cuda_stream;
     MCF_CUDA_OK(cudaMemsetAsync(d_flag, 0, 4, cs));
-    const int fine = fuse_fine(chunk_slots);
+    const int fine = fuse_fine(fg, g.n_blocks, chunk_slots);
     const int cs_fine = chunk_slots / fine;
     const int64_t n_chunks_fine = ((int64_t)(slot_hi - slot_lo) + cs_fine - 1) / cs_fine;
     // the same classification as phase 1 (the list on the device is in this order)
