@@ -1,3 +1,7 @@
+#!/bin/bash
+# Multi-GPU run of one box: parity checks of the sharded paths, the sharded LSM A/B, and bench.py (weak scaling with every
+# config, strong scaling, and the root-gather A/B of the headline).  Usage (from the repo root, under gpurun --gpus N):
+#   bash tools/run_multi_gpu.sh N        -> gpurun_out/bench_r2_${N}gpu*.json
 N=${1:-2}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
 timeout 600 $TR tools/multi_gpu_check.py 2>&1 | grep -v "INFO\|Warning\|warn" | tail -12
@@ -9,7 +13,7 @@ python - <<PY
 import json
 for f in ("bench_r2_${N}gpu.json","bench_r2_${N}gpu_strong.json","bench_r2_${N}gpu_rootgather.json"):
     try:
-        j=json.load(open("gpurun_out/"+f))
+        j=json.loads([l for l in open("gpurun_out/"+f) if l.startswith("{")][-1])
     except Exception as e:
         print(f, "FAILED", e); continue
     print(f, "value %.4e ms %.1f e2e %.4e e2e_ms %.1f scaling %s parity %s"%(j["value"], j["ms_per_step"], j["e2e"]["value"], j["e2e"]["ms_per_step"], j["scaling"], j["checks"].get("sharded_parity")))
