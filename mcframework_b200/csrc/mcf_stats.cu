@@ -14,6 +14,7 @@
 //               basis) + a 3x3 pseudo-inverse solve + one decision sweep; state per path is
 //               (exercise step, cash flow at exercise).
 #include <cuda_runtime.h>
+#include <type_traits>
 #include <vector>
 #include <stdio.h>
 #include <stdlib.h>
@@ -1544,101 +1545,193 @@ __device__ __forceinline__ void lsm_collect_sums(const LsmPeers &px, int parity,
 // co-resident wave of CTAs: what the previous launch touched last is what this one touches first, and S_t -- dead after
 // this launch -- is loaded with the evict-first policy so that it does not push the reusable lines out.
 #ifndef MCF_LSM_PPT
-#define MCF_LSM_PPT 4  // paths per thread and loop trip (3 independent loads each)
+#define MCF_LSM_PPT 8  // paths per thread and loop trip (MCF_LSM_PPT / VEC loads of S_t, S_{t-1} and the cash flows each)
 #endif
 #ifndef MCF_LSM_CTAS
-#define MCF_LSM_CTAS 3  // resident CTAs per SM (register budget 65536 / (256 * CTAS))
+#define MCF_LSM_CTAS 2  // resident CTAs per SM (register budget 65536 / (256 * CTAS))
 #endif
+// A thread moves VEC paths per load: 2 (16-byte loads) when the path count is even and the columns are 16-byte aligned.
+template <int VEC> struct LsmVec;
+template <> struct LsmVec<1> {
+    typedef double T;
+    static __device__ __forceinline__ void unpack(const T &v, double *o) { o[0] = v; }
+    static __device__ __forceinline__ T pack(const double *o) { return o[0]; }
+};
+template <> struct LsmVec<2> {
+    typedef double2 T;
+    static __device__ __forceinline__ void unpack(const T &v, double *o) {
+        o[0] = v.x;
+        o[1] = v.y;
+    }
+    static __device__ __forceinline__ T pack(const double *o) { return make_double2(o[0], o[1]); }
+};
+// L2 residency of the cash flows.  They are read by every step and a sixth of them is rewritten by every step (deep
+// in-the-money paths exercise again and again on the way back), 80 MB at 1e7 paths: inside the 126 MB L2 they cost no HBM
+// traffic at all, neither the reads nor the write-backs.  Plain LRU loses them to the 160 MB of path columns streaming
+// through per step, so their loads and stores carry an evict-last policy for the first `keep_bytes` of the array (the
+// size of the device's set-aside for persisting lines, lsm_l2_keep_bytes below) -- measured 10.36 -> 9.29 ms per sweep.
+__device__ __forceinline__ unsigned long long lsm_keep_policy(const void *base, uint32_t keep_bytes, uint32_t total_bytes) {
+    unsigned long long pol;
+    if (keep_bytes)
+        asm volatile("createpolicy.range.global.L2::evict_last.L2::evict_unchanged.b64 %0, [%1], %2, %3;"
+                     : "=l"(pol)
+                     : "l"(base), "r"(keep_bytes), "r"(total_bytes));
+    else
+        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// after the sweep: the lines go back to normal priority (stream-ordered; an untouched persisting line would otherwise
+// stay in the set-aside for an undetermined time)
+__global__ void lsm_release_lines_kernel(const char *base, size_t bytes) {
+    for (size_t o = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 128; o < bytes; o += (size_t)gridDim.x * blockDim.x * 128)
+        asm volatile("applypriority.global.L2::evict_normal [%0], 128;" ::"l"(base + o) : "memory");
+}
+__device__ __forceinline__ double lsm_ld_keep(const double *p, unsigned long long pol) {
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double2 lsm_ld_keep(const double2 *p, unsigned long long pol) {
+    double2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void lsm_st_keep(double *p, double v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void lsm_st_keep(double2 *p, double2 v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+// The step kernel is issue-bound before it is HBM-bound (round-2 ncu: 107 thread instructions per path, issue slots 58 %
+// busy at 52 % of DRAM peak), so everything that is the same for every path of a launch is a template parameter --
+// MODE bit 0: t == n_steps (the cash flows are initialised, not read), bit 1: t == 1 (no regression, the cash flows are
+// summed); HAS_EX: exercise steps are recorded -- the loop runs without bounds checks except for the one trip that holds
+// the last (partial) band, and a path is straight-line code: the intrinsic value is +-(S - K) (a sign flip in the high
+// word; "in the money" is `> 0`, no max()), out-of-the-money paths enter the regression sums as exact zeros, the count
+// of in-the-money paths is an integer.  Values per path are those of the branchy form bit for bit.
+template <int MODE, bool HAS_EX, int VEC>
 __global__ void __launch_bounds__(LSM_THREADS, MCF_LSM_CTAS)
     lsm_fused_step_kernel(const double *__restrict__ s_t, const double *__restrict__ s_prev, int64_t n_paths, int32_t t,
                           int32_t n_steps, double K, int is_put, double disc_t, double grow_prev,
                           const LsmState *__restrict__ st_cur, LsmState *__restrict__ st_next,
                           int32_t *__restrict__ ex, double *__restrict__ cf, double *__restrict__ partials,
                           unsigned int *__restrict__ counter, double *__restrict__ price_out, int reverse,
-                          const __grid_constant__ LsmPeers peers) {
-    const bool init = t == n_steps, last_step = t == 1;
+                          uint32_t keep_bytes, const __grid_constant__ LsmPeers peers) {
+    constexpr bool init = (MODE & 1) != 0, last_step = (MODE & 2) != 0;
+    typedef typename LsmVec<VEC>::T V;
+    constexpr int TRIP = MCF_LSM_PPT / VEC;  // loads per array and trip
     // Programmatic dependent launch: this grid may start while the previous step's grid is still finishing (its last
     // CTA is adding the partial sums and solving).  The path columns do not depend on it, so the first trip's loads of
     // S_t / S_{t-1} are issued BEFORE `griddepcontrol.wait`; the coefficients and the cash flows are read after it.
 #ifndef MCF_LSM_NO_PDL
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
-    bool have_fit = false, waited = false;
-    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    bool waited = false;
+    double c0 = __longlong_as_double(0x7ff0000000000000LL), c1 = 0.0, c2 = 0.0;  // no fit: nothing exceeds +inf
     auto wait_for_previous_step = [&]() {
         if (waited) return;
         waited = true;
 #ifndef MCF_LSM_NO_PDL
         asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
-        have_fit = !init && st_cur->have_fit;
-        if (have_fit) {
+        if (!init && st_cur->have_fit) {
             c0 = st_cur->coef[0];
             c1 = st_cur->coef[1];
             c2 = st_cur->coef[2];
         }
     };
     const double invK = 1.0 / K;
-    double a[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) a[k] = 0.0;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    auto one = [&](int64_t i, double s, double c, double sp) {
-        const double intr = lsm_intrinsic(s, K, is_put);
+    const int flip = is_put ? (int)0x80000000 : 0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0;
+    int n_itm = 0;
+    // one path: decide step t (c = its cash flow discounted to time 0), then its terms of the regression of step t-1
+    auto one = [&](double s, double sp, double &c) -> bool {
+        const double d = s - K;
+        const double gap = __hiloint2double(__double2hiint(d) ^ flip, __double2loint(d));  // K - S for a put
+        bool exercised;
         if (init) {
-            c = intr * disc_t;
-            cf[i] = c;
-            if (ex) ex[i] = t;
-        } else if (have_fit && intr > 0.0) {
-            const double u = (s - K) * invK;
+            exercised = true;
+            c = gap > 0.0 ? gap * disc_t : 0.0;
+        } else {
+            const double u = d * invK;
             const double fitted = fma(fma(c2, u, c1), u, c0);
-            if (intr > fitted) {
-                c = intr * disc_t;
-                cf[i] = c;
-                if (ex) ex[i] = t;
-            }
+            exercised = gap > 0.0 && gap > fitted;
+            c = exercised ? gap * disc_t : c;
         }
         if (last_step) {
-            a[0] += c;
-        } else if (lsm_intrinsic(sp, K, is_put) > 0.0) {
-            const double y = c * grow_prev;
-            const double u = (sp - K) * invK, u2 = u * u;
-            a[0] += 1.0;
-            a[1] += u;
-            a[2] += u2;
-            a[3] = fma(u2, u, a[3]);
-            a[4] = fma(u2, u2, a[4]);
-            a[5] += y;
-            a[6] = fma(u, y, a[6]);
-            a[7] = fma(u2, y, a[7]);
+            a0 += c;
+        } else {
+            const double dp = sp - K;
+            const double gap_p = __hiloint2double(__double2hiint(dp) ^ flip, __double2loint(dp));
+            const bool itm = gap_p > 0.0;
+            const double u = itm ? dp * invK : 0.0, y = itm ? c * grow_prev : 0.0, u2 = u * u;
+            n_itm += itm ? 1 : 0;
+            a1 += u;
+            a2 += u2;
+            a3 = fma(u2, u, a3);
+            a4 = fma(u2, u2, a4);
+            a5 += y;
+            a6 = fma(u, y, a6);
+            a7 = fma(u2, y, a7);
         }
+        return exercised;
     };
-    // bands of `stride` paths; a thread owns one path of every band.  Forward: band 0, 1, ...; reverse: last band first.
+    // bands of `stride` units (a unit = VEC neighbouring paths); a thread owns one unit of every band.  Forward: band 0,
+    // 1, ...; reverse: last band first.
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t lane_i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t bands = (n_paths + stride - 1) / stride;
-    for (int64_t b0 = 0; b0 < bands; b0 += MCF_LSM_PPT) {
-        double s[MCF_LSM_PPT], p[MCF_LSM_PPT], c[MCF_LSM_PPT];
-        int64_t idx[MCF_LSM_PPT];
+    const int64_t n_units = n_paths / VEC;
+    const int64_t bands = (n_units + stride - 1) / stride;
+    const V *sv_t = reinterpret_cast<const V *>(s_t), *sv_prev = reinterpret_cast<const V *>(s_prev);
+    V *cfv = reinterpret_cast<V *>(cf);
+    const unsigned long long keep = lsm_keep_policy(cf, keep_bytes, (uint32_t)(n_paths * 8));  // (0 when n_paths * 8 >= 4 GB)
+    auto trip = [&](auto checked_tag, int64_t lo_band) {
+        constexpr bool CHECKED = decltype(checked_tag)::value;
+        V s[TRIP], p[TRIP], c[TRIP];
+        int64_t unit[TRIP];
+        bool on[TRIP];
 #pragma unroll
-        for (int q = 0; q < MCF_LSM_PPT; q++) {
-            const int64_t b = b0 + q;
-            const int64_t band = reverse ? bands - 1 - b : b;
-            idx[q] = (b < bands && band * stride + lane_i < n_paths) ? band * stride + lane_i : -1;
-        }
-#pragma unroll
-        for (int q = 0; q < MCF_LSM_PPT; q++) {  // all loads of the trip are issued before the first use
-            const bool on = idx[q] >= 0;
-            s[q] = on ? __ldcs(&s_t[idx[q]]) : 0.0;
-            p[q] = (on && !last_step) ? __ldg(&s_prev[idx[q]]) : 0.0;
+        for (int q = 0; q < TRIP; q++) {  // all loads of the trip are issued before the first use
+            const int64_t band = lo_band + q;
+            unit[q] = band * stride + lane_i;
+            on[q] = !CHECKED || (band >= 0 && band < bands && unit[q] < n_units);
+            if (on[q]) {
+                s[q] = __ldcs(sv_t + unit[q]);
+                if (!last_step) p[q] = __ldg(sv_prev + unit[q]);
+            }
         }
         wait_for_previous_step();
+        if (!init) {
 #pragma unroll
-        for (int q = 0; q < MCF_LSM_PPT; q++) c[q] = (idx[q] >= 0 && !init) ? cf[idx[q]] : 0.0;
+            for (int q = 0; q < TRIP; q++)
+                if (on[q]) c[q] = lsm_ld_keep(cfv + unit[q], keep);
+        }
 #pragma unroll
-        for (int q = 0; q < MCF_LSM_PPT; q++)
-            if (idx[q] >= 0) one(idx[q], s[q], c[q], p[q]);
+        for (int q = 0; q < TRIP; q++) {
+            if (!on[q]) continue;
+            double se[VEC], pe[VEC], ce[VEC];
+            LsmVec<VEC>::unpack(s[q], se);
+            if (!last_step) LsmVec<VEC>::unpack(p[q], pe);
+            if (!init) LsmVec<VEC>::unpack(c[q], ce);
+            bool any = false;
+#pragma unroll
+            for (int e = 0; e < VEC; e++) {
+                const bool exercised = one(se[e], last_step ? 0.0 : pe[e], ce[e]);
+                any |= exercised;
+                if (HAS_EX && exercised) ex[unit[q] * VEC + e] = t;
+            }
+            if (any) lsm_st_keep(cfv + unit[q], LsmVec<VEC>::pack(ce), keep);  // (an unchanged neighbour keeps its value)
+        }
+    };
+    for (int64_t b0 = 0; b0 < bands; b0 += TRIP) {
+        const int64_t lo_band = reverse ? bands - TRIP - b0 : b0;
+        if (lo_band >= 0 && lo_band + TRIP < bands)  // every band of the trip is complete
+            trip(std::false_type(), lo_band);
+        else
+            trip(std::true_type(), lo_band);
     }
     wait_for_previous_step();  // (a grid with no band still orders itself behind the previous step)
+    double a[8] = {last_step ? a0 : (double)n_itm, a1, a2, a3, a4, a5, a6, a7};
 
     __shared__ double sh[LSM_THREADS / 32][8];
     __shared__ bool is_last;
@@ -2612,6 +2705,54 @@ int mcf_lsm_finish(int64_t n_paths, double r, double dt, void *d_workspace, doub
     return MCF_OK;
 }
 
+#ifdef MCF_LSM_NOREV  // (development: every step sweeps front to back)
+#define MCF_LSM_REVERSE(k) 0
+#else
+#define MCF_LSM_REVERSE(k) (int)((k) & 1)
+#endif
+typedef void (*LsmStepKernel)(const double *, const double *, int64_t, int32_t, int32_t, double, int, double, double,
+                              const LsmState *, LsmState *, int32_t *, double *, double *, unsigned int *, double *, int,
+                              uint32_t, const LsmPeers);
+static LsmStepKernel lsm_step_kernel_for(int mode, bool has_ex, int vec) {
+#define MCF_LSM_PICK(M)                                                                                          \
+    case M:                                                                                                      \
+        return vec == 2 ? (has_ex ? lsm_fused_step_kernel<M, true, 2> : lsm_fused_step_kernel<M, false, 2>)      \
+                        : (has_ex ? lsm_fused_step_kernel<M, true, 1> : lsm_fused_step_kernel<M, false, 1>);
+    switch (mode) {
+        MCF_LSM_PICK(0)
+        MCF_LSM_PICK(1)
+        MCF_LSM_PICK(2)
+    default:
+        MCF_LSM_PICK(3)
+    }
+#undef MCF_LSM_PICK
+}
+
+// Bytes of the cash-flow array that are kept in L2: all of it or nothing.  A partial window is worse than none -- at 2e7
+// paths a 79 MB window over the 160 MB array: 21.9 ms against 20.9 ms without, a 48 MB window at 1e7 paths: 11.1 ms against
+// 10.4 -- because it takes the capacity that the alternating sweep direction would have used for both arrays.  The
+// device's set-aside for persisting lines is raised to what the array needs (device maximum: 79 of 126 MB on a B200): a
+// context-wide limit, changed only when it is too small and never lowered again; it matters only while persisting lines
+// exist, and the sweep releases its own when it is done.  MCF_LSM_L2_PERSIST=0 leaves the device alone.
+static uint32_t lsm_l2_keep_bytes(size_t cf_bytes) {
+    const char *e = getenv("MCF_LSM_L2_PERSIST");
+    if (e && e[0] == '0') return 0;
+    int dev = 0, max_persist = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess ||
+        cf_bytes > (size_t)(max_persist > 0 ? max_persist : 0))
+        return 0;
+    size_t cur = 0;
+    if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) != cudaSuccess) return 0;
+    if (cur < cf_bytes) {  // (the driver rounds the request to its own granularity: ask for a little more)
+        size_t want = cf_bytes + cf_bytes / 8;
+        if (want > (size_t)max_persist) want = (size_t)max_persist;
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) (void)cudaGetLastError();
+        if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) != cudaSuccess) return 0;
+    }
+    return cur >= cf_bytes ? (uint32_t)cf_bytes : 0;
+}
+
 static int lsm_sweep(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K, double r, double dt, int32_t is_put,
                      void *d_workspace, int64_t workspace_bytes, double *d_price, int32_t *d_exercise_times,
                      const LsmPeers &peers, void *cuda_stream) {
@@ -2628,6 +2769,9 @@ static int lsm_sweep(const double *d_paths_tm, int64_t n_paths, int64_t n_steps,
     // slots the workspace was sized for
     int grid = MCF_SM_COUNT * MCF_LSM_CTAS;
     if (grid > g.n_blocks) grid = g.n_blocks;
+    const uint32_t keep_bytes = lsm_l2_keep_bytes((size_t)n_paths * 8);
+    // 16-byte loads (two paths per load) when every column S_t and the cash flows are 16-byte aligned
+    const int vec = (n_paths % 2 == 0 && ((uintptr_t)d_paths_tm & 15) == 0 && ((uintptr_t)cf & 15) == 0) ? 2 : 1;
     // t = n_steps: initialise cash flows and fit step n_steps-1; t = n_steps-1 .. 1: decide step t, fit step t-1
     for (int64_t t = n_steps; t >= 1; t--) {
         const double *s_t = d_paths_tm + (size_t)t * (size_t)n_paths;
@@ -2642,11 +2786,13 @@ static int lsm_sweep(const double *d_paths_tm, int64_t n_paths, int64_t n_steps,
         cfg.attrs = attr;
         cfg.numAttrs = t == n_steps ? 0 : 1;  // the first step follows a memset, not a kernel of this chain
 #endif
-        MCF_CUDA_OK(cudaLaunchKernelEx(&cfg, lsm_fused_step_kernel, s_t, s_t - n_paths, n_paths, (int32_t)t, (int32_t)n_steps, K,
-                                       (int)is_put, exp(-r * dt * (double)t), exp(r * dt * (double)(t - 1)),
-                                       (const LsmState *)(st + (t & 1)), st + ((t - 1) & 1), d_exercise_times, cf, partials,
-                                       counter, d_price, (int)((n_steps - t) & 1), peers));
+        const int mode = (t == n_steps ? 1 : 0) | (t == 1 ? 2 : 0);
+        MCF_CUDA_OK(cudaLaunchKernelEx(&cfg, lsm_step_kernel_for(mode, d_exercise_times != nullptr, vec), s_t, s_t - n_paths,
+                                       n_paths, (int32_t)t, (int32_t)n_steps, K, (int)is_put, exp(-r * dt * (double)t),
+                                       exp(r * dt * (double)(t - 1)), (const LsmState *)(st + (t & 1)), st + ((t - 1) & 1),
+                                       d_exercise_times, cf, partials, counter, d_price, MCF_LSM_REVERSE(n_steps - t), keep_bytes, peers));
     }
+    if (keep_bytes) lsm_release_lines_kernel<<<MCF_SM_COUNT * 4, 256, 0, cs>>>((const char *)cf, (size_t)keep_bytes);
     MCF_CUDA_OK(cudaGetLastError());
     return MCF_OK;
 }
