@@ -1572,19 +1572,10 @@ template <> struct LsmVec<2> {
 // size of the device's set-aside for persisting lines, lsm_l2_keep_bytes below) -- measured 10.36 -> 9.29 ms per sweep.
 __device__ __forceinline__ unsigned long long lsm_keep_policy(const void *base, uint32_t keep_bytes, uint32_t total_bytes) {
     unsigned long long pol;
-    if (keep_bytes)
-        asm volatile("createpolicy.range.global.L2::evict_last.L2::evict_unchanged.b64 %0, [%1], %2, %3;"
-                     : "=l"(pol)
-                     : "l"(base), "r"(keep_bytes), "r"(total_bytes));
-    else
-        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("createpolicy.range.global.L2::evict_last.L2::evict_unchanged.b64 %0, [%1], %2, %3;"
+                 : "=l"(pol)
+                 : "l"(base), "r"(keep_bytes), "r"(total_bytes));
     return pol;
-}
-// after the sweep: the lines go back to normal priority (stream-ordered; an untouched persisting line would otherwise
-// stay in the set-aside for an undetermined time)
-__global__ void lsm_release_lines_kernel(const char *base, size_t bytes) {
-    for (size_t o = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 128; o < bytes; o += (size_t)gridDim.x * blockDim.x * 128)
-        asm volatile("applypriority.global.L2::evict_normal [%0], 128;" ::"l"(base + o) : "memory");
 }
 __device__ __forceinline__ double lsm_ld_keep(const double *p, unsigned long long pol) {
     double v;
@@ -1609,7 +1600,7 @@ __device__ __forceinline__ void lsm_st_keep(double2 *p, double2 v, unsigned long
 // the last (partial) band, and a path is straight-line code: the intrinsic value is +-(S - K) (a sign flip in the high
 // word; "in the money" is `> 0`, no max()), out-of-the-money paths enter the regression sums as exact zeros, the count
 // of in-the-money paths is an integer.  Values per path are those of the branchy form bit for bit.
-template <int MODE, bool HAS_EX, int VEC>
+template <int MODE, bool HAS_EX, int VEC, bool KEEP>
 __global__ void __launch_bounds__(LSM_THREADS, MCF_LSM_CTAS)
     lsm_fused_step_kernel(const double *__restrict__ s_t, const double *__restrict__ s_prev, int64_t n_paths, int32_t t,
                           int32_t n_steps, double K, int is_put, double disc_t, double grow_prev,
@@ -1684,7 +1675,8 @@ __global__ void __launch_bounds__(LSM_THREADS, MCF_LSM_CTAS)
     const int64_t bands = (n_units + stride - 1) / stride;
     const V *sv_t = reinterpret_cast<const V *>(s_t), *sv_prev = reinterpret_cast<const V *>(s_prev);
     V *cfv = reinterpret_cast<V *>(cf);
-    const unsigned long long keep = lsm_keep_policy(cf, keep_bytes, (uint32_t)(n_paths * 8));  // (0 when n_paths * 8 >= 4 GB)
+    // (a policy-hinted access is never the default: with an evict-normal policy the sweep at 2e7 paths took 39 ms, not 21)
+    const unsigned long long keep = KEEP ? lsm_keep_policy(cf, keep_bytes, (uint32_t)(n_paths * 8)) : 0ULL;
     auto trip = [&](auto checked_tag, int64_t lo_band) {
         constexpr bool CHECKED = decltype(checked_tag)::value;
         V s[TRIP], p[TRIP], c[TRIP];
@@ -1696,15 +1688,15 @@ __global__ void __launch_bounds__(LSM_THREADS, MCF_LSM_CTAS)
             unit[q] = band * stride + lane_i;
             on[q] = !CHECKED || (band >= 0 && band < bands && unit[q] < n_units);
             if (on[q]) {
-                s[q] = __ldcs(sv_t + unit[q]);
-                if (!last_step) p[q] = __ldg(sv_prev + unit[q]);
+                s[q] = __ldcs(sv_t + unit[q]);  // S_t is dead after this launch: evict-first
+                if (!last_step) p[q] = KEEP ? __ldcg(sv_prev + unit[q]) : __ldg(sv_prev + unit[q]);
             }
         }
         wait_for_previous_step();
         if (!init) {
 #pragma unroll
             for (int q = 0; q < TRIP; q++)
-                if (on[q]) c[q] = lsm_ld_keep(cfv + unit[q], keep);
+                if (on[q]) c[q] = KEEP ? lsm_ld_keep(cfv + unit[q], keep) : cfv[unit[q]];
         }
 #pragma unroll
         for (int q = 0; q < TRIP; q++) {
@@ -1720,7 +1712,12 @@ __global__ void __launch_bounds__(LSM_THREADS, MCF_LSM_CTAS)
                 any |= exercised;
                 if (HAS_EX && exercised) ex[unit[q] * VEC + e] = t;
             }
-            if (any) lsm_st_keep(cfv + unit[q], LsmVec<VEC>::pack(ce), keep);  // (an unchanged neighbour keeps its value)
+            if (any) {  // (an unchanged neighbour is rewritten with its own value)
+                if (KEEP)
+                    lsm_st_keep(cfv + unit[q], LsmVec<VEC>::pack(ce), keep);
+                else
+                    cfv[unit[q]] = LsmVec<VEC>::pack(ce);
+            }
         }
     };
     for (int64_t b0 = 0; b0 < bands; b0 += TRIP) {
@@ -2426,6 +2423,8 @@ int mcf_bootstrap_fused_phase1(uint32_t gen_kind, const mcf_stream *d_stream, co
     // kernel (as the two-pass form does) they take 26 ms per 32 resamples instead of 7.4 + 12.5 -- the safe kernel
     // streams 13 GB of queue entries through L2 fast enough to evict the 32 MB region the gathers depend on.  Measured at
     // n = 1e8, B = 512: 0.43 s overlapped, 0.32 s back to back.
+    // (Also measured: the same overlap with the region's lines loaded evict-last into the persisting set-aside of L2, so
+    // that the queue traffic cannot evict them: 0.43 s again -- the two kernels contend for more than the region.)
     const cudaStream_t side = cs;
     // classify the CTAs once on the host (integer arithmetic shared with the kernels): safe ones by batch of resamples,
     // the others into the exact list
@@ -2713,11 +2712,12 @@ int mcf_lsm_finish(int64_t n_paths, double r, double dt, void *d_workspace, doub
 typedef void (*LsmStepKernel)(const double *, const double *, int64_t, int32_t, int32_t, double, int, double, double,
                               const LsmState *, LsmState *, int32_t *, double *, double *, unsigned int *, double *, int,
                               uint32_t, const LsmPeers);
-static LsmStepKernel lsm_step_kernel_for(int mode, bool has_ex, int vec) {
-#define MCF_LSM_PICK(M)                                                                                          \
-    case M:                                                                                                      \
-        return vec == 2 ? (has_ex ? lsm_fused_step_kernel<M, true, 2> : lsm_fused_step_kernel<M, false, 2>)      \
-                        : (has_ex ? lsm_fused_step_kernel<M, true, 1> : lsm_fused_step_kernel<M, false, 1>);
+static LsmStepKernel lsm_step_kernel_for(int mode, bool has_ex, int vec, bool keep) {
+#define MCF_LSM_PICK2(M, E, V) (keep ? lsm_fused_step_kernel<M, E, V, true> : lsm_fused_step_kernel<M, E, V, false>)
+#define MCF_LSM_PICK(M) \
+    case M:             \
+        return vec == 2 ? (has_ex ? MCF_LSM_PICK2(M, true, 2) : MCF_LSM_PICK2(M, false, 2)) \
+                        : (has_ex ? MCF_LSM_PICK2(M, true, 1) : MCF_LSM_PICK2(M, false, 1));
     switch (mode) {
         MCF_LSM_PICK(0)
         MCF_LSM_PICK(1)
@@ -2726,32 +2726,49 @@ static LsmStepKernel lsm_step_kernel_for(int mode, bool has_ex, int vec) {
         MCF_LSM_PICK(3)
     }
 #undef MCF_LSM_PICK
+#undef MCF_LSM_PICK2
 }
 
-// Bytes of the cash-flow array that are kept in L2: all of it or nothing.  A partial window is worse than none -- at 2e7
-// paths a 79 MB window over the 160 MB array: 21.9 ms against 20.9 ms without, a 48 MB window at 1e7 paths: 11.1 ms against
-// 10.4 -- because it takes the capacity that the alternating sweep direction would have used for both arrays.  The
-// device's set-aside for persisting lines is raised to what the array needs (device maximum: 79 of 126 MB on a B200): a
-// context-wide limit, changed only when it is too small and never lowered again; it matters only while persisting lines
-// exist, and the sweep releases its own when it is done.  MCF_LSM_L2_PERSIST=0 leaves the device alone.
-static uint32_t lsm_l2_keep_bytes(size_t cf_bytes) {
-    const char *e = getenv("MCF_LSM_L2_PERSIST");
-    if (e && e[0] == '0') return 0;
-    int dev = 0, max_persist = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess ||
-        cf_bytes > (size_t)(max_persist > 0 ? max_persist : 0))
-        return 0;
-    size_t cur = 0;
-    if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) != cudaSuccess) return 0;
-    if (cur < cf_bytes) {  // (the driver rounds the request to its own granularity: ask for a little more)
-        size_t want = cf_bytes + cf_bytes / 8;
-        if (want > (size_t)max_persist) want = (size_t)max_persist;
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) (void)cudaGetLastError();
-        if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) != cudaSuccess) return 0;
+// L2 set-aside for the cash flows, held for the duration of one sweep: all of the array or nothing.  A partial window is
+// worse than none -- a 79 MB window over the 160 MB array of 2e7 paths: 21.9 ms against 20.9 ms, a 48 MB window at 1e7
+// paths: 11.1 ms against 10.4 -- because it takes the capacity that the alternating sweep direction would have used for
+// both arrays.  And the set-aside must not outlive the sweep: the limit is context-wide and an enabled set-aside costs
+// every other kernel its share of L2 whether persisting lines exist or not (a 2e7-path sweep, which cannot use it, took
+// 40 ms instead of 21 with the 79 MB set-aside of an earlier sweep still in place).  So: raise the limit to what the
+// array needs (device maximum: 79 of 126 MB on a B200), sweep, wait for the stream, reset the persisting lines and put
+// the limit back.  A sweep that uses the set-aside therefore returns when it has finished.  MCF_LSM_L2_PERSIST=0 leaves
+// the device alone (and the call asynchronous).
+struct LsmL2Reservation {
+    size_t before = 0;
+    uint32_t keep_bytes = 0;  // 0 = no residency
+    void acquire(size_t cf_bytes) {
+        const char *e = getenv("MCF_LSM_L2_PERSIST");
+        if ((e && e[0] == '0') || cf_bytes >= (1ULL << 32)) return;
+        int dev = 0, max_persist = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess ||
+            max_persist <= 0 || cf_bytes > (size_t)max_persist)
+            return;
+        if (cudaDeviceGetLimit(&before, cudaLimitPersistingL2CacheSize) != cudaSuccess) return;
+        size_t ask = cf_bytes + cf_bytes / 8, now = 0;  // (the driver rounds the request to its own granularity)
+        if (ask > (size_t)max_persist) ask = (size_t)max_persist;
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ask) != cudaSuccess ||
+            cudaDeviceGetLimit(&now, cudaLimitPersistingL2CacheSize) != cudaSuccess || now < cf_bytes) {
+            (void)cudaGetLastError();
+            (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, before);
+            return;
+        }
+        keep_bytes = (uint32_t)cf_bytes;
     }
-    return cur >= cf_bytes ? (uint32_t)cf_bytes : 0;
-}
+    int release(cudaStream_t cs) {
+        if (!keep_bytes) return MCF_OK;
+        keep_bytes = 0;
+        const cudaError_t e1 = cudaStreamSynchronize(cs);
+        (void)cudaCtxResetPersistingL2Cache();
+        (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, before);
+        return e1 == cudaSuccess ? MCF_OK : MCF_ERR_CUDA;
+    }
+};
 
 static int lsm_sweep(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K, double r, double dt, int32_t is_put,
                      void *d_workspace, int64_t workspace_bytes, double *d_price, int32_t *d_exercise_times,
@@ -2769,7 +2786,9 @@ static int lsm_sweep(const double *d_paths_tm, int64_t n_paths, int64_t n_steps,
     // slots the workspace was sized for
     int grid = MCF_SM_COUNT * MCF_LSM_CTAS;
     if (grid > g.n_blocks) grid = g.n_blocks;
-    const uint32_t keep_bytes = lsm_l2_keep_bytes((size_t)n_paths * 8);
+    LsmL2Reservation l2;
+    l2.acquire((size_t)n_paths * 8);
+    const uint32_t keep_bytes = l2.keep_bytes;
     // 16-byte loads (two paths per load) when every column S_t and the cash flows are 16-byte aligned
     const int vec = (n_paths % 2 == 0 && ((uintptr_t)d_paths_tm & 15) == 0 && ((uintptr_t)cf & 15) == 0) ? 2 : 1;
     // t = n_steps: initialise cash flows and fit step n_steps-1; t = n_steps-1 .. 1: decide step t, fit step t-1
@@ -2787,14 +2806,19 @@ static int lsm_sweep(const double *d_paths_tm, int64_t n_paths, int64_t n_steps,
         cfg.numAttrs = t == n_steps ? 0 : 1;  // the first step follows a memset, not a kernel of this chain
 #endif
         const int mode = (t == n_steps ? 1 : 0) | (t == 1 ? 2 : 0);
-        MCF_CUDA_OK(cudaLaunchKernelEx(&cfg, lsm_step_kernel_for(mode, d_exercise_times != nullptr, vec), s_t, s_t - n_paths,
+        const cudaError_t le = cudaLaunchKernelEx(&cfg, lsm_step_kernel_for(mode, d_exercise_times != nullptr, vec, keep_bytes != 0), s_t, s_t - n_paths,
                                        n_paths, (int32_t)t, (int32_t)n_steps, K, (int)is_put, exp(-r * dt * (double)t),
                                        exp(r * dt * (double)(t - 1)), (const LsmState *)(st + (t & 1)), st + ((t - 1) & 1),
-                                       d_exercise_times, cf, partials, counter, d_price, MCF_LSM_REVERSE(n_steps - t), keep_bytes, peers));
+                                       d_exercise_times, cf, partials, counter, d_price, MCF_LSM_REVERSE(n_steps - t), keep_bytes, peers);
+        if (le != cudaSuccess) {
+            (void)l2.release(cs);
+            return MCF_ERR_CUDA;
+        }
     }
-    if (keep_bytes) lsm_release_lines_kernel<<<MCF_SM_COUNT * 4, 256, 0, cs>>>((const char *)cf, (size_t)keep_bytes);
-    MCF_CUDA_OK(cudaGetLastError());
-    return MCF_OK;
+    const cudaError_t launched = cudaGetLastError();
+    const int released = l2.release(cs);
+    if (launched != cudaSuccess) return MCF_ERR_CUDA;
+    return released;
 }
 
 int mcf_lsm(const double *d_paths_tm, int64_t n_paths, int64_t n_steps, double K, double r, double dt, int32_t is_put,

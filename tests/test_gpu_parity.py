@@ -296,8 +296,11 @@ def test_bootstrap_philox_generator(sd):
     assert np.array_equal(g_dev.integers(0, 1 << 30, 5), g_ref.integers(0, 1 << 30, 5))
 
 
-@pytest.mark.parametrize("n_paths,n_steps,put", [(100, 50, True), (100, 50, False), (20_000, 252, True), (3, 10, True), (5000, 12, False)])
+@pytest.mark.parametrize("n_paths,n_steps,put", [(100, 50, True), (100, 50, False), (20_000, 252, True), (3, 10, True), (5000, 12, False),
+                                                 (800_001, 8, True), (1_000_000, 6, False)])
 def test_lsm_vs_oracle(sd, n_paths, n_steps, put):
+    """Odd path counts take the 8-byte form of the step kernel, even ones the 16-byte form; the two large cases span several
+    bands per thread (unchecked full trips, the partial last band, both sweep directions)."""
     from oracle import np_port
     rng = np.random.default_rng(42)
     T, r, sigma, S0, K = 1.0, 0.05, 0.2, 100.0, 100.0

@@ -12,3 +12,4 @@ for k, v in j["configs"].items():
 PY
 python -c "
 import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+for n in 5e6 1e7 2e7; do AB_PATHS=$n python tools/ab_lsm.py lsm_$n 2>/dev/null | grep "^{"; done
