@@ -599,6 +599,12 @@ def cfg_lsm(cx):
                                        "lsm_fused_step_kernel (the ranks' sums meet inside the kernel, over peer memory)"),
            "tensor_pipe_note": "3-column regression (8 sums per path): not tensor-core shaped, FP64 FMA; HBM binds",
            "checks": {"american_put_price": float(price.cpu()[0]), "reference_1e6_path_price": 6.053948135228681}}
+    if n * 8 <= 79 * (1 << 20):  # the cash flows fit the L2 set-aside (mcf_stats.cu, LsmL2Reservation)
+        out["roofline"]["note"] = ("frac counts all 24 algorithmic bytes per path and step against the HBM peak; the 8 bytes of "
+                                   "cash flows are kept L2-resident for the sweep (evict-last set-aside), so only the two path "
+                                   "columns have to cross HBM and frac can exceed 1; hbm_frac_of_16_bytes is the same time "
+                                   "against those 16 bytes")
+        out["roofline"]["hbm_frac_of_16_bytes"] = (steps - 1) * n * 16 / t / 1e9 / cx.hbm_peak
     del paths
     if cx.world == 1 and not cx.args.no_cpu_baseline:
         import bench_reference as R

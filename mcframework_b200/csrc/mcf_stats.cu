@@ -1498,9 +1498,9 @@ __global__ void __launch_bounds__(LSM_THREADS) lsm_apply_kernel(const double *__
 // t == 1 accumulates the price sum instead of regression sums.
 // Paths sharded over the GPUs of one box: the 8 sums of a step are exchanged INSIDE the step kernel, over peer memory.
 // Every rank owns a small exchange buffer that all ranks have mapped (CUDA IPC over NVLink): the CTA that finishes last
-// stores its rank's 8 sums into slot [parity][rank] of EVERY rank's buffer, then a sequence number (system-scope
-// release), waits until all slots of its own buffer carry this step's number, adds them in rank order (the same order
-// on every rank: identical coefficients everywhere, deterministic) and solves.  No collective library call, no extra
+// stores its rank's 8 sums into slot [parity][rank] of EVERY rank's buffer (each 8-byte word tagged with the step's
+// sequence number, see lsm_publish_word), waits until all slots of its own buffer carry this step's number, adds them in
+// rank order (the same order on every rank: identical coefficients everywhere, deterministic) and solves.  No collective library call, no extra
 // launch, no host: a step of the sharded sweep is the single-GPU step plus one NVLink round trip.  Ranks can be at most
 // one step apart (nobody passes a step without everybody's sums), hence two slot sets by step parity.
 #define MCF_LSM_MAX_PEERS 8
@@ -1510,32 +1510,36 @@ struct LsmPeers {
     unsigned long long seq_base;       // sequence numbers of this sweep are seq_base + 1 .. seq_base + n_steps
     double n_paths_global;
 };
-#define MCF_LSM_SLOT_DOUBLES 16  // 8 sums, the sequence number, padding to 128 bytes
+#define MCF_LSM_SLOT_DOUBLES 16  // 16 words of 8 bytes: half a double + the sequence number each (128 bytes)
 __host__ __device__ inline size_t lsm_slot_index(int parity, int rank) {
     return ((size_t)parity * MCF_LSM_MAX_PEERS + (size_t)rank) * MCF_LSM_SLOT_DOUBLES;
 }
-// thread p of the last CTA publishes this rank's sums to peer p (the eight NVLink round trips overlap) ...
-__device__ __forceinline__ void lsm_publish_sums(const LsmPeers &px, int peer, int parity, unsigned long long seq,
+// A slot is 16 words of 8 bytes, each carrying HALF a double and the low 32 bits of the step's sequence number (word 2k:
+// low half of sum k, word 2k+1: high half).  An 8-byte store is atomic over NVLink, so a word whose upper half shows the
+// expected sequence number carries valid data: no fence, no separate flag, one NVLink store latency per step (the form
+// with 8 stores, a system-scope fence and a flag store cost a round trip more).  16 threads per peer store the 16 words
+// at once; the same 16 x world threads then poll this rank's own buffer.
+__device__ __forceinline__ void lsm_publish_word(const LsmPeers &px, int peer, int w, int parity, unsigned seq32,
                                                  const double *sums) {
-    volatile double *dst = px.slots[peer] + lsm_slot_index(parity, px.rank);
-#pragma unroll
-    for (int k = 0; k < 8; k++) dst[k] = sums[k];
-    __threadfence_system();
-    *reinterpret_cast<volatile unsigned long long *>(px.slots[peer] + lsm_slot_index(parity, px.rank) + 8) = seq;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(sums[w >> 1]);
+    const unsigned half = (w & 1) ? (unsigned)(bits >> 32) : (unsigned)bits;
+    volatile unsigned long long *dst =
+        reinterpret_cast<volatile unsigned long long *>(px.slots[peer] + lsm_slot_index(parity, px.rank)) + w;
+    *dst = ((unsigned long long)seq32 << 32) | half;
 }
-// ... and one thread waits for every rank's sums in its own buffer and adds them in rank order
-__device__ __forceinline__ void lsm_collect_sums(const LsmPeers &px, int parity, unsigned long long seq, double sums[8]) {
-    double total[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int src = 0; src < px.world; src++) {
-        const double *mine = px.slots[px.rank] + lsm_slot_index(parity, src);
-        const volatile unsigned long long *flag = reinterpret_cast<const volatile unsigned long long *>(mine + 8);
-        while (*flag != seq) __nanosleep(20);
-        __threadfence_system();
-#pragma unroll
-        for (int k = 0; k < 8; k++) total[k] += reinterpret_cast<const volatile double *>(mine)[k];
+// false: the word did not arrive within ~2 s (a peer died); the caller poisons the sums instead of hanging the GPU
+__device__ __forceinline__ bool lsm_collect_word(const LsmPeers &px, int src, int w, int parity, unsigned seq32, unsigned *half) {
+    const volatile unsigned long long *p =
+        reinterpret_cast<const volatile unsigned long long *>(px.slots[px.rank] + lsm_slot_index(parity, src)) + w;
+    const long long t0 = clock64();
+    for (;;) {
+        const unsigned long long v = *p;
+        if ((unsigned)(v >> 32) == seq32) {
+            *half = (unsigned)v;
+            return true;
+        }
+        if (clock64() - t0 > (1LL << 32)) return false;
     }
-#pragma unroll
-    for (int k = 0; k < 8; k++) sums[k] = total[k];
 }
 
 // Sweep direction.  Column S_{t-1} is read here for the regression and again by the NEXT launch for its decision, and
@@ -1770,21 +1774,31 @@ __global__ void __launch_bounds__(LSM_THREADS, MCF_LSM_CTAS)
         if (lane == 0) st_next->sums[wid] = v;
     }
     __syncthreads();
-    const unsigned long long seq = peers.seq_base + (unsigned long long)(n_steps - t + 1);
-    if (peers.world > 1) {  // this rank's sums go to every rank's exchange buffer, one thread per peer
-        if ((int)threadIdx.x < peers.world) lsm_publish_sums(peers, (int)threadIdx.x, t & 1, seq, st_next->sums);
+    if (peers.world > 1) {  // the ranks' sums meet here: publish to every rank, collect from every rank, add in rank order
+        __shared__ unsigned sh_half[MCF_LSM_MAX_PEERS][16];
+        __shared__ int sh_lost;
+        const unsigned seq32 = (unsigned)(peers.seq_base + (unsigned long long)(n_steps - t + 1));
+        const int peer = (int)threadIdx.x >> 4, w = (int)threadIdx.x & 15;
+        if (threadIdx.x == 0) sh_lost = 0;
+        __syncthreads();
+        if (peer < peers.world) {
+            lsm_publish_word(peers, peer, w, t & 1, seq32, st_next->sums);
+            unsigned half = 0;
+            if (!lsm_collect_word(peers, peer, w, t & 1, seq32, &half)) sh_lost = 1;
+            sh_half[peer][w] = half;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) {  // the same order on every rank: identical coefficients everywhere
+            double total = 0.0;
+            for (int src = 0; src < peers.world; src++)
+                total += __hiloint2double((int)sh_half[src][2 * threadIdx.x + 1], (int)sh_half[src][2 * threadIdx.x]);
+            st_next->sums[threadIdx.x] = sh_lost ? __longlong_as_double(0x7ff8000000000000LL) : total;
+        }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         *counter = 0;
-        double n_all = (double)n_paths;
-        if (peers.world > 1) {  // add every rank's sums (same order everywhere) before anybody solves
-            double sums[8];
-            lsm_collect_sums(peers, t & 1, seq, sums);
-#pragma unroll
-            for (int k = 0; k < 8; k++) st_next->sums[k] = sums[k];
-            n_all = peers.n_paths_global;
-        }
+        const double n_all = peers.world > 1 ? peers.n_paths_global : (double)n_paths;
         if (last_step) {
             if (price_out) *price_out = st_next->sums[0] / n_all;
         } else {
