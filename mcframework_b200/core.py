@@ -22,6 +22,7 @@ import logging
 import multiprocessing as mp
 import sys
 import time
+import weakref
 from abc import ABC, abstractmethod
 from concurrent.futures import ProcessPoolExecutor, ThreadPoolExecutor, as_completed
 from dataclasses import dataclass, field
@@ -56,6 +57,16 @@ def _worker_run_chunk(sim: "MonteCarloSimulation", chunk_size: int, seed_seq: np
 def make_blocks(n: int, block_size: int = 10_000) -> list[tuple[int, int]]:
     """Half-open ``(start, stop)`` blocks covering ``range(n)`` (:107-134)."""
     return [(lo, min(lo + block_size, n)) for lo in range(0, n, block_size)] if n > 0 else []
+
+
+# Page-locked host memory held by results the caller has not released yet (bytes), and the budget beyond which new
+# results are copied into pageable memory instead (a caller that keeps hundreds of large results must not pin them all).
+PINNED_RESULT_BUDGET = 16 << 30
+_PINNED_LIVE = [0]
+
+
+def _unpin_accounting(nbytes: int) -> None:
+    _PINNED_LIVE[0] -= nbytes
 
 
 class DeviceResults:
@@ -334,7 +345,13 @@ class MonteCarloSimulation(ABC):
         allocator recycles the buffer once the previous result is released): ~50 GB/s instead of ~2 GB/s pageable."""
         import torch
 
-        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=t.numel() >= (1 << 20))
+        nbytes = int(t.numel()) * int(t.element_size())
+        # results the caller still holds stay page-locked: beyond the budget further ones are pageable (slower, unbounded)
+        pin = t.numel() >= (1 << 20) and _PINNED_LIVE[0] + nbytes <= PINNED_RESULT_BUDGET
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=pin)
+        if pin:
+            _PINNED_LIVE[0] += nbytes
+            weakref.finalize(host, _unpin_accounting, nbytes)
         host.copy_(t, non_blocking=False)
         return host.numpy()
 

@@ -376,3 +376,18 @@ def test_child_philox_keys_equal_numpy_generate_state():
     rec = S.philox_records(kids, blocks)
     assert np.array_equal(rec["s"][:, :2], np.array([c.generate_state(2, np.uint64) for c in kids]))
     assert rec["first_sim"].tolist() == [a for a, _ in blocks] and rec["n_sims"].tolist() == [10] * 40
+
+
+def test_result_copies_beyond_the_pinned_budget_are_pageable(monkeypatch):
+    """Results the caller keeps stay page-locked only up to core.PINNED_RESULT_BUDGET; past it the copy goes to pageable
+    memory (here: budget 0, so a large vector must not ask for pinned memory -- which a CPU-only torch could not give)."""
+    import torch
+
+    from mcframework_b200 import core
+
+    monkeypatch.setattr(core, "PINNED_RESULT_BUDGET", 0)
+    before = core._PINNED_LIVE[0]
+    t = torch.arange(float(1 << 20), dtype=torch.float64)
+    out = core.MonteCarloSimulation._to_host(t)
+    assert isinstance(out, np.ndarray) and out.shape == (1 << 20,) and out[-1] == float((1 << 20) - 1)
+    assert core._PINNED_LIVE[0] == before
