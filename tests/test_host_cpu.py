@@ -391,3 +391,24 @@ def test_result_copies_beyond_the_pinned_budget_are_pageable(monkeypatch):
     out = core.MonteCarloSimulation._to_host(t)
     assert isinstance(out, np.ndarray) and out.shape == (1 << 20,) and out[-1] == float((1 << 20) - 1)
     assert core._PINNED_LIVE[0] == before
+
+
+def test_bootstrap_batch_size_follows_free_memory(monkeypatch):
+    """The binned bootstrap bins 64 resamples per batch when its two queue sets fit a third of the free device memory,
+    else 32, else 16; never more than there are resamples."""
+    import torch
+
+    from mcframework_b200 import _stats_device as SD
+
+    class Lib:
+        @staticmethod
+        def mcf_bootstrap_binned_workspace_bytes(n, rpb, shift):
+            return 8 * n * (rpb + 2)  # two sets of 4-byte queues, window = rpb + 2
+
+    class X:
+        is_cuda, device = True, "cuda:0"
+
+    n = 100_000_000
+    for free, B, want in [(180e9, 10_000, 64), (100e9, 10_000, 32), (60e9, 10_000, 16), (180e9, 40, 40), (180e9, 5, 5), (1e9, 5, 5)]:
+        monkeypatch.setattr(torch.cuda, "mem_get_info", lambda dev=None, free=free: (int(free), int(180e9)))
+        assert SD._default_resamples_per_batch(Lib, X, n, B, 0) == want, (free, B)
