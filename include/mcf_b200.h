@@ -200,11 +200,15 @@ int mcf_probe_issue_rate(int32_t kind, double *warp_inst_per_s, void *cuda_strea
 
 /* Paths sharded over the GPUs of ONE box (world <= 8): the same fused step kernel as mcf_lsm, with the exchange of the 8
  * sums of a step done inside the kernel over peer memory -- the last CTA of every rank stores its sums into a slot of
- * every rank's exchange buffer, waits for the others' and adds them in rank order (no collective call per step).
+ * every rank's exchange buffer (8-byte words, each tagged with the low 32 bits of the step's sequence number: no fence, no
+ * separate flag), waits for the others' and adds them in rank order (no collective call per step).
  * mcf_peer_buffer_create allocates one exchange buffer (mcf_lsm_exchange_bytes()) and returns its 64-byte CUDA IPC
  * handle; the handles are exchanged by the caller (torch.distributed), opened with mcf_peer_buffer_open, and passed as
  * peer_buffers[world] (entry [rank] = the local buffer).  sequence_base: any number that grows by more than n_steps
- * from one sweep to the next (stale slots never match); the caller orders successive sweeps with a stream barrier. */
+ * from one sweep to the next (stale slots never match); the caller orders successive sweeps with a stream barrier.
+ * mcf_lsm and mcf_lsm_sharded keep the cash flows L2-resident when they fit the device's persisting set-aside (see
+ * INTEGRATION.md): such a call raises cudaLimitPersistingL2CacheSize for its duration, restores it, and returns when the
+ * sweep has finished; MCF_LSM_L2_PERSIST=0 in the environment turns that off. */
 int64_t mcf_lsm_exchange_bytes(void);
 int mcf_peer_buffer_create(int64_t bytes, void **d_ptr, void *handle64);
 int mcf_peer_buffer_open(const void *handle64, void **d_ptr);
