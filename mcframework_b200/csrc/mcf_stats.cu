@@ -2820,10 +2820,11 @@ static int lsm_sweep(const double *d_paths_tm, int64_t n_paths, int64_t n_steps,
         cfg.numAttrs = t == n_steps ? 0 : 1;  // the first step follows a memset, not a kernel of this chain
 #endif
         const int mode = (t == n_steps ? 1 : 0) | (t == 1 ? 2 : 0);
-        const cudaError_t le = cudaLaunchKernelEx(&cfg, lsm_step_kernel_for(mode, d_exercise_times != nullptr, vec, keep_bytes != 0), s_t, s_t - n_paths,
-                                       n_paths, (int32_t)t, (int32_t)n_steps, K, (int)is_put, exp(-r * dt * (double)t),
-                                       exp(r * dt * (double)(t - 1)), (const LsmState *)(st + (t & 1)), st + ((t - 1) & 1),
-                                       d_exercise_times, cf, partials, counter, d_price, MCF_LSM_REVERSE(n_steps - t), keep_bytes, peers);
+        const LsmStepKernel kernel = lsm_step_kernel_for(mode, d_exercise_times != nullptr, vec, keep_bytes != 0);
+        const cudaError_t le = cudaLaunchKernelEx(
+            &cfg, kernel, s_t, s_t - n_paths, n_paths, (int32_t)t, (int32_t)n_steps, K, (int)is_put, exp(-r * dt * (double)t),
+            exp(r * dt * (double)(t - 1)), (const LsmState *)(st + (t & 1)), st + ((t - 1) & 1), d_exercise_times, cf, partials,
+            counter, d_price, MCF_LSM_REVERSE(n_steps - t), keep_bytes, peers);
         if (le != cudaSuccess) {
             (void)l2.release(cs);
             return MCF_ERR_CUDA;
